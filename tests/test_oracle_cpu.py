@@ -1,0 +1,144 @@
+"""Pin the oracle: restatements vs the third-party ops called as the reference calls them,
+and vs fixtures produced by the reference modules themselves (tests/golden/make_golden.py)."""
+import numpy as np
+import torch
+
+from conftest import load_golden
+from oracle import ctc_oracle as CO
+from oracle import transducer_oracle as TO
+
+
+def T(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def _w(fx, prefix):
+    return {k[len(prefix):]: T(v) for k, v in fx.items() if k.startswith(prefix)}
+
+
+def test_lattice_restated_matches_torchaudio_and_golden():
+    fx = load_golden("rnnt_small.npz")
+    logits, tgt, tl, ul = T(fx["logits"]), T(fx["tgt"]), T(fx["tl"]), T(fx["ul"])
+    blank = int(fx["blank"])
+    for tag, clamp in (("n", -1.0), ("c", float(fx["clamp"]))):
+        r = TO.rnnt_lattice_restated(logits, tgt, tl, ul, blank, clamp)
+        np.testing.assert_allclose(r["costs"].numpy(), fx[f"{tag}_costs"], rtol=2e-6)
+        np.testing.assert_allclose(r["costs"].mean().item(), fx[f"{tag}_loss"], rtol=2e-6)
+        # reference gradient is d(mean)/dlogits = grads / B
+        np.testing.assert_allclose(r["grads"].numpy() / logits.size(0), fx[f"{tag}_dlogits"], atol=2e-6)
+        # padded cells carry exactly zero gradient
+        assert np.all(r["grads"][1, 9:].numpy() == 0) and np.all(r["grads"][1, :, 4:].numpy() == 0)
+    live = TO.rnnt_loss_reference_call(logits, tgt, tl, ul, blank, -1.0, "none")
+    np.testing.assert_allclose(live.numpy(), fx["n_costs"], rtol=1e-6)
+
+
+def test_fused_joint_rnnt_restated_matches_reference_grads():
+    fx = load_golden("rnnt_small.npz")
+    w = _w(fx, "w_")
+    r = TO.fused_joint_rnnt_restated(T(fx["enc"]), T(fx["pred"]), w, T(fx["tgt"]), T(fx["tl"]), T(fx["ul"]),
+                                     int(fx["blank"]))
+    np.testing.assert_allclose(r["loss"].item(), fx["n_loss"], rtol=2e-6)
+    np.testing.assert_allclose(r["d_enc_out"].numpy(), fx["n_d_enc"], atol=3e-6)
+    np.testing.assert_allclose(r["d_pred_out"].numpy(), fx["n_d_pred"], atol=3e-6)
+    for k in w:
+        np.testing.assert_allclose(r["d_" + k].numpy(), fx["n_d_" + k], atol=1e-5, rtol=1e-4)
+
+
+def test_cfg1_example1_loss():
+    """BASELINE.json configs[0]: reference TransducerModel on example1.pt[:2]."""
+    fx = load_golden("cfg1_example1.npz")
+    jw = _w(fx, "joint.")
+    enc, pred = T(fx["encoder_out"]), T(fx["predictor_out"])
+    tl, ul = T(fx["encoder_out_lens"]), T(fx["text_lens"])
+    r = TO.fused_joint_rnnt_restated(enc, pred, jw, T(fx["texts"]), tl, ul, int(fx["blank"]))
+    np.testing.assert_allclose(r["loss"].item(), fx["loss_rnnt"], rtol=1e-5)
+    loss_ctc, _ = CO.ctc_head_reference_call(enc, tl, T(fx["texts"]), ul, T(fx["ctc.ctc_lo.weight"]),
+                                             T(fx["ctc.ctc_lo.bias"]), int(fx["blank"]), "offline")
+    np.testing.assert_allclose(loss_ctc.item(), fx["loss_ctc"], rtol=1e-5)
+    np.testing.assert_allclose(0.7 * r["loss"].item() + 0.3 * loss_ctc.item(), fx["loss"], rtol=1e-5)
+    # d loss / d joint params = 0.7 * d rnnt / d params
+    # (the reference is fp32: its own rounding noise vs this fp64 restatement is ~6e-5 rel-L2)
+    for k in ("ffn_out.weight", "ffn_out.bias", "enc_ffn.weight", "pred_ffn.weight"):
+        assert rel_l2(0.7 * r["d_" + k].numpy(), fx["d_" + k]) < 1e-4
+
+
+def test_ctc_restated_matches_reference_heads():
+    fx = load_golden("ctc_small.npz")
+    hs, hl, ys, yl = T(fx["hs"]), T(fx["hl"]), T(fx["ys"]), T(fx["yl"])
+    blank = int(fx["blank"])
+    for mode, tag in (("offline", "off"), ("online", "on")):
+        w, b = T(fx[f"{tag}_w"]), T(fx[f"{tag}_b"])
+        loss, ys_hat = CO.ctc_head_reference_call(hs, hl, ys, yl, w, b, blank, mode)
+        np.testing.assert_allclose(loss.item(), fx[f"{tag}_loss"], rtol=1e-6)
+        np.testing.assert_allclose(ys_hat.numpy(), fx[f"{tag}_ys_hat"], atol=1e-6)
+        nll, g = CO.ctc_loss_restated(ys_hat.numpy(), ys.numpy(), hl.numpy(), yl.numpy(), blank)
+        B = hs.size(0)
+        if mode == "offline":
+            want = nll.sum() / B
+            scale = np.full(B, 1.0 / B)
+        else:
+            want = (nll / np.maximum(yl.numpy(), 1)).mean()
+            scale = 1.0 / np.maximum(yl.numpy(), 1) / B
+        np.testing.assert_allclose(want, fx[f"{tag}_loss"], rtol=1e-5)
+        dlogits = g * scale[:, None, None]
+        d_hs = dlogits @ w.numpy().astype(np.float64)
+        np.testing.assert_allclose(d_hs, fx[f"{tag}_d_hs"], atol=2e-6)
+        assert nll[2] == 0.0 and np.all(g[2] == 0)            # infeasible -> zero_infinity
+
+
+def test_example2_known_answers():
+    """3.ipynb:87,159 and 3_v2.ipynb:150 record the frame argmax / collapsed ids of utts 0,1."""
+    fx = load_golden("example2.npz")
+    pre, lens, blank = T(fx["pre"]), fx["lens"], int(fx["blank"])
+    hyps = CO.ctc_greedy_search(pre, lens, blank)
+    res = CO.ctc_prefix_beam_search(pre, lens, int(fx["beam"]), blank)
+    # collapsed sequences recorded in the notebooks (utt 0: 3_v2.ipynb:150, utt 1: 3.ipynb:159)
+    assert hyps[0] == [2, 40, 188, 227, 247, 243, 375, 360, 32, 87, 251, 291, 282, 32, 141, 243, 55, 317, 3]
+    assert hyps[1] == [2, 323, 296, 75, 243, 278, 394, 51, 247, 360, 364, 57, 238, 122, 65, 167, 271, 142, 68, 3]
+    for i, r in enumerate(res):
+        assert r["tokens"] == fx[f"best_{i}"].tolist()
+        np.testing.assert_allclose(r["score"], fx[f"score_{i}"], rtol=1e-9, atol=1e-9)
+        assert r["times"] == fx[f"times_{i}"].tolist()
+        np.testing.assert_allclose(r["nbest_scores"], fx[f"nbest_scores_{i}"], rtol=1e-9, atol=1e-9)
+        assert [t for x in r["nbest"] for t in x] == fx[f"nbest_flat_{i}"].tolist()
+        assert [t for x in r["nbest_times"] for t in x] == fx[f"nbest_times_flat_{i}"].tolist()
+    assert res[0]["tokens"] == hyps[0] and res[1]["tokens"] == hyps[1]
+
+
+def test_decoders_match_reference():
+    fx = load_golden("decode_small.npz")
+    pw, jw = _w(fx, "predictor."), _w(fx, "joint.")
+    enc, elens, blank = T(fx["enc"]), T(fx["elens"]), int(fx["blank"])
+    hy = TO.greedy_search_offline(pw, jw, blank, enc, elens, 64)
+    for b in range(3):
+        assert hy[b] == fx[f"a5_hyp_{b}"].tolist()
+    hy = TO.greedy_search_offline(pw, jw, blank, enc, elens, 2)
+    for b in range(3):
+        assert hy[b] == fx[f"a5cap2_hyp_{b}"].tolist()
+    assert TO.greedy_search_offline(pw, jw, blank, enc[:1], elens[:1], 64)[0] == fx["a6w_hyp_0"].tolist()
+    toks, st, last = [], None, blank
+    for s in range(0, 37, 8):
+        c, st, last = TO.greedy_chunk_streaming(pw, jw, blank, enc[0, s:s + 8], st, last, 10)
+        toks += c
+    assert toks == fx["a6_hyp_0"].tolist() and last == int(fx["a6_last"])
+    np.testing.assert_allclose(st[0].numpy(), fx["a6_h"], atol=1e-5)
+    for beam in (4, 10):
+        hyps = None
+        for s in range(0, 37, 8):
+            hyps = TO.beam_chunk_online(pw, jw, blank, enc[0, s:s + 8], hyps, beam, 10)
+        assert len(hyps) == int(fx[f"a7_b{beam}_n"])
+        for i, h in enumerate(hyps):
+            assert h.tokens == fx[f"a7_b{beam}_tok_{i}"].tolist()
+            np.testing.assert_allclose(h.log_prob, fx[f"a7_b{beam}_lp_{i}"], atol=1e-4)
+    ctc_logp = torch.log_softmax(enc[0] @ T(fx["ctc.ctc_lo.weight"]).T + T(fx["ctc.ctc_lo.bias"]), dim=-1)
+    for beam in (5, 10):
+        out = TO.prefix_beam_search_wenet(pw, jw, blank, enc[0], ctc_logp, beam)
+        assert len(out) == int(fx[f"a8_b{beam}_n"])
+        for i, (hyp, sc) in enumerate(out):
+            assert hyp == fx[f"a8_b{beam}_tok_{i}"].tolist()
+            np.testing.assert_allclose(sc, fx[f"a8_b{beam}_sc_{i}"], atol=1e-4)
