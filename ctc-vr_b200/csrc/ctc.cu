@@ -1,0 +1,251 @@
+// CTC head tail on B200: log_softmax rows, CTC loss (alpha/beta + gradient wrt logits) and CTC greedy.
+//   F.log_softmax(ctc_lo(x)) + nn.CTCLoss(blank, zero_infinity=True):
+//     model/rnnt_model.py:52-58, model/online_rnnt_model.py:27-31, model/model.py:289-293
+//   ctc_greedy_search: model/rnnt_model.py:188-210, model/online_rnnt_model.py:647-671,
+//     wenet/transformer/search.py:107-122
+// Algorithmic HBM bytes of the loss: read log-probs once (fwd gather is a subset), write the gradient
+// once, alpha scratch written+read: B*T*(2*V + 2*S)*4 B.  The kernel is bound by its T dependent steps.
+#include "common.cuh"
+
+namespace ctcvr {
+
+// ---------------------------------------------------------------- log_softmax: one warp per row
+__global__ void log_softmax_kernel(const float* __restrict__ x, float* __restrict__ y, long rows, int V) {
+  long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  int lane = threadIdx.x & 31;
+  const float* xr = x + r * V;
+  float* yr = y + r * V;
+  float m = kNegInf;
+  for (int v = lane; v < V; v += 32) m = fmaxf(m, xr[v]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int v = lane; v < V; v += 32) s += expf(xr[v] - m);
+  s = warp_sum(s);
+  float l = m + logf(s);
+  for (int v = lane; v < V; v += 32) yr[v] = xr[v] - l;
+}
+
+int log_softmax(const float* x, float* y, long rows, int V, cudaStream_t st) {
+  if (rows == 0) return 0;
+  log_softmax_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, y, rows, V);
+  CTCVR_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- CTC loss: one CTA per utterance
+// thread s owns extended-label state s (S = 2U+1).  alpha is kept in the workspace [B][T][Sp].
+__global__ void ctc_loss_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targets,
+                                const int32_t* __restrict__ in_lens, const int32_t* __restrict__ tgt_lens,
+                                const float* __restrict__ grad_scale, float* __restrict__ nll_out,
+                                float* __restrict__ grad, float* __restrict__ alpha_ws, int T, int V, int Umax,
+                                int Sp, int blank, int zero_infinity) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, s = threadIdx.x, nthr = blockDim.x;
+  const int Tb = min(in_lens[b], T), Ub = tgt_lens[b];
+  const int S = 2 * Ub + 1;
+  float* cur = sm;                  // [Sp] alpha_{t} / beta_{t} exchange
+  float* ab = cur + Sp;             // [Sp] alpha+beta at time t
+  float* lc = ab + Sp;              // [Sp] per-leader log-sum of alpha+beta
+  float* red = lc + Sp;             // [32]
+  int* slot = reinterpret_cast<int*>(red + 32);    // [V] label -> leader state (-1: not in l')
+  int* nxt = slot + V;              // [Sp] next state with the same label (-1: none)
+  const float* lpb = lp + (size_t)b * T * V;
+  float* ga = alpha_ws + (size_t)b * T * Sp;
+  float* gb = grad ? grad + (size_t)b * T * V : nullptr;
+
+  int lab = blank;
+  if (s < S && (s & 1)) lab = (int)targets[(size_t)b * Umax + (s >> 1)];
+  bool skip_ok = false;             // may take the s-2 transition
+  if (s < S && (s & 1) && s >= 2) skip_ok = (lab != (int)targets[(size_t)b * Umax + (s >> 1) - 1]);
+
+  // label -> leader map, same-label chains (leader = lowest state carrying the label)
+  for (int v = s; v < V; v += nthr) slot[v] = -1;
+  if (s < Sp) nxt[s] = -1;
+  __syncthreads();
+  if (s == 0) {
+    slot[blank] = 0;                // all even states: handled by a block reduction, leader 0
+    for (int q = 1; q < S; q += 2) {
+      int l = (int)targets[(size_t)b * Umax + (q >> 1)];
+      if (slot[l] < 0) slot[l] = q;
+      else { int p = slot[l]; while (nxt[p] >= 0) p = nxt[p]; nxt[p] = q; }
+    }
+  }
+  __syncthreads();
+
+  float nll;
+  if (Tb == 0) {
+    nll = (Ub == 0) ? 0.f : INFINITY;
+  } else {
+    // ---- alpha
+    float a = kNegInf;
+    if (s < S && s < 2) a = lpb[lab];
+    if (s < Sp) { cur[s] = a; ga[s] = a; }
+    float lnext = (s < S && Tb > 1) ? lpb[(size_t)V + lab] : 0.f;
+    __syncthreads();
+    for (int t = 1; t < Tb; ++t) {
+      float lcur = lnext;
+      if (s < S && t + 1 < Tb) lnext = lpb[(size_t)(t + 1) * V + lab];
+      float v = kNegInf;
+      if (s < S) {
+        v = cur[s];
+        if (s >= 1) v = log_add_exp(v, cur[s - 1]);
+        if (skip_ok) v = log_add_exp(v, cur[s - 2]);
+        v = (v == kNegInf) ? kNegInf : v + lcur;
+      }
+      __syncthreads();
+      if (s < Sp) { cur[s] = v; ga[(size_t)t * Sp + s] = v; }
+      __syncthreads();
+    }
+    float ll = cur[S - 1];
+    if (S > 1) ll = log_add_exp(ll, cur[S - 2]);
+    nll = -ll;
+  }
+  bool inf = !(nll < INFINITY);
+  if (inf && zero_infinity) nll = 0.f;
+  if (s == 0) nll_out[b] = nll;
+  if (!gb) return;
+  const float scale = grad_scale ? grad_scale[b] : 1.f;
+  if (inf || Tb == 0) {            // zero gradient everywhere (ATen zero_infinity semantics)
+    for (size_t i = s; i < (size_t)T * V; i += nthr) gb[i] = 0.f;
+    return;
+  }
+  // ---- beta + gradient, t descending
+  bool skip_fwd = false;           // may take the s+2 transition
+  if (s < S && (s & 1) && s + 2 < S) skip_fwd = (lab != (int)targets[(size_t)b * Umax + (s >> 1) + 1]);
+  __syncthreads();
+  float bprev = kNegInf;
+  for (int t = Tb - 1; t >= 0; --t) {
+    float lcur = (s < S) ? lpb[(size_t)t * V + lab] : 0.f;
+    float v = kNegInf;
+    if (s < S) {
+      if (t == Tb - 1) v = (s >= S - 2) ? lcur : kNegInf;
+      else {
+        v = cur[s];
+        if (s + 1 < S) v = log_add_exp(v, cur[s + 1]);
+        if (skip_fwd) v = log_add_exp(v, cur[s + 2]);
+        v = (v == kNegInf) ? kNegInf : v + lcur;
+      }
+    }
+    (void)bprev;
+    __syncthreads();                // everyone has read cur (beta_{t+1})
+    if (s < Sp) {
+      cur[s] = v;
+      ab[s] = (s < S) ? ga[(size_t)t * Sp + s] + v : kNegInf;
+    }
+    __syncthreads();
+    // leaders gather log-sum over their label's states
+    if (s < S && (s & 1) && slot[lab] == s) {
+      float acc = ab[s];
+      for (int q = nxt[s]; q >= 0; q = nxt[q]) acc = log_add_exp(acc, ab[q]);
+      lc[s] = acc;
+    }
+    {   // blank: block log-sum-exp over even states
+      float m = (s < S && !(s & 1)) ? ab[s] : kNegInf;
+      float wm = warp_max(m);
+      if ((s & 31) == 0) red[s >> 5] = wm;
+      __syncthreads();
+      float bm = kNegInf;
+      for (int w = 0; w < (nthr >> 5); ++w) bm = fmaxf(bm, red[w]);
+      __syncthreads();
+      float e = (s < S && !(s & 1) && bm != kNegInf) ? expf(ab[s] - bm) : 0.f;
+      float ws_ = warp_sum(e);
+      if ((s & 31) == 0) red[s >> 5] = ws_;
+      __syncthreads();
+      if (s == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < (nthr >> 5); ++w) tot += red[w];
+        lc[0] = (bm == kNegInf) ? kNegInf : bm + logf(tot);
+      }
+      __syncthreads();
+    }
+    const float* lrow = lpb + (size_t)t * V;
+    float* grow = gb + (size_t)t * V;
+    for (int vv = s; vv < V; vv += nthr) {
+      float l = lrow[vv];
+      float g = expf(l);
+      int q = slot[vv];
+      if (q >= 0 && lc[q] != kNegInf) g -= expf(lc[q] - l + nll);
+      grow[vv] = g * scale;
+    }
+  }
+  for (size_t i = (size_t)Tb * V + s; i < (size_t)T * V; i += nthr) gb[i] = 0.f;
+}
+
+size_t ctc_loss_ws_bytes(int B, int T, int Umax) {
+  int Sp = (2 * Umax + 1 + 31) / 32 * 32;
+  return (size_t)B * T * Sp * sizeof(float) + 256;
+}
+
+int ctc_loss(const float* lp, const int64_t* targets, const int32_t* in_lens, const int32_t* tgt_lens,
+             const float* grad_scale, float* nll, float* grad, int B, int T, int V, int Umax, int blank,
+             int zero_infinity, void* ws, size_t ws_bytes, cudaStream_t st) {
+  int Sp = (2 * Umax + 1 + 31) / 32 * 32;
+  CTCVR_REQUIRE(Sp <= 1024, "ctc_loss: target length %d too long (2U+1 must be <= 1024)", Umax);
+  CTCVR_REQUIRE(ws_bytes >= ctc_loss_ws_bytes(B, T, Umax), "ctc_loss: workspace too small");
+  int threads = Sp < 64 ? 64 : Sp;
+  size_t smem = (size_t)(3 * Sp + 32) * sizeof(float) + (size_t)(V + Sp) * sizeof(int);
+  CTCVR_REQUIRE(smem <= 200 * 1024, "ctc_loss: vocabulary %d too large", V);
+  CTCVR_CHECK_CUDA(cudaFuncSetAttribute(ctc_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ctc_loss_kernel<<<B, threads, smem, st>>>(lp, targets, in_lens, tgt_lens, grad_scale, nll, grad,
+                                            reinterpret_cast<float*>(ws), T, V, Umax, Sp, blank, zero_infinity);
+  CTCVR_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- CTC greedy: one CTA per utterance
+__global__ void ctc_greedy_kernel(const float* __restrict__ scores, const int32_t* __restrict__ lens,
+                                  int32_t* __restrict__ out_tokens, int32_t* __restrict__ out_lens, int T, int V,
+                                  int blank) {
+  extern __shared__ int ids[];      // [T]
+  const int b = blockIdx.x;
+  const int Tb = min(lens[b], T);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int t = warp; t < Tb; t += nw) {
+    const float* x = scores + ((size_t)b * T + t) * V;
+    float best = kNegInf;
+    int bi = V;
+    for (int v = lane; v < V; v += 32) {
+      float xv = x[v];
+      if (xv > best) { best = xv; bi = v; }          // first maximum within the lane (ascending v)
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) ids[t] = bi;
+  }
+  __syncthreads();
+  if (warp == 0) {                  // keep[t] = id!=blank && id!=id[t-1]; ordered compaction by ballot
+    int count = 0;
+    for (int t0 = 0; t0 < Tb; t0 += 32) {
+      int t = t0 + lane;
+      bool keep = false;
+      int id = 0;
+      if (t < Tb) {
+        id = ids[t];
+        int prev = (t > 0) ? ids[t - 1] : -1;
+        keep = (id != blank) && (id != prev);
+      }
+      unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) out_tokens[(size_t)b * T + count + __popc(m & ((1u << lane) - 1))] = id;
+      count += __popc(m);
+    }
+    if (lane == 0) out_lens[b] = count;
+  }
+}
+
+int ctc_greedy(const float* scores, const int32_t* lens, int32_t* out_tokens, int32_t* out_lens, int B, int T, int V,
+               int blank, cudaStream_t st) {
+  if (B == 0) return 0;
+  size_t smem = (size_t)T * sizeof(int);
+  CTCVR_REQUIRE(smem <= 200 * 1024, "ctc_greedy: T=%d too long", T);
+  CTCVR_CHECK_CUDA(cudaFuncSetAttribute(ctc_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ctc_greedy_kernel<<<B, 256, smem, st>>>(scores, lens, out_tokens, out_lens, T, V, blank);
+  CTCVR_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ctcvr

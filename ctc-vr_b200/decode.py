@@ -1,0 +1,152 @@
+"""On-device RNN-T decoders behind the reference's decode call surface.
+
+  basic_greedy_search(model, encoder_out, encoder_out_lens, n_steps=64) -> List[List[int]]
+      model/component/transducer.py:22-70 (and wenet/transducer/search/greedy_search.py:6-54)
+  greedy_chunk(model_parts, encoder_out_chunk, states, prev_token, n_steps=10)
+      the loop of OnlineRNNTModel._decode_chunk_streaming_logic (model/online_rnnt_model.py:193-222)
+  beam_chunk_online(...)   model/online_rnnt_model.py:389-522        (A7)
+  prefix_beam_search(...)  wenet/transducer/search/prefix_beam_search.py:42-148  (A8)
+
+`model` only needs `.predictor` (embed, rnn, projection), `.joint` (enc_ffn, pred_ffn, ffn_out) and
+`.blank` / `.blank_id`, i.e. the reference's own modules work as well as the mirrors in this package.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import DecoderWeights, call, ptr, query, stream
+
+
+class PreparedDecoder:
+    """Device-side weight layouts of `ctcvr_decoder_weights` (include/ctcvr.h), derived once per
+    parameter version (re-derived automatically after an optimizer step / load_state_dict)."""
+
+    def __init__(self, predictor, joint):
+        self.predictor, self.joint = predictor, joint
+        self._key = None
+        self._keep = None
+        self.struct = None
+
+    def _version_key(self):
+        ps = list(self.predictor.parameters()) + list(self.joint.parameters())
+        return tuple((p.data_ptr(), p._version) for p in ps)
+
+    @torch.no_grad()
+    def get(self) -> DecoderWeights:
+        key = self._version_key()
+        if key == self._key:
+            return self.struct
+        p, j = self.predictor, self.joint
+        rnn = p.rnn
+        L, H = rnn.num_layers, rnn.hidden_size
+        f = lambda t: t.detach().float().contiguous()
+        emb = f(p.embed.weight)
+        if not emb.is_cuda:
+            raise RuntimeError("ctcvr_b200 decoders run on CUDA (B200) only; move the model to the GPU")
+        bias = lambda l, n: (f(getattr(rnn, f"{n}_l{l}")) if rnn.bias else torch.zeros(4 * H, device=emb.device))
+        gate_tok = torch.addmm(bias(0, "bias_ih") + bias(0, "bias_hh"), emb, f(rnn.weight_ih_l0).t()).contiguous()
+        w_hh_t = torch.stack([f(getattr(rnn, f"weight_hh_l{l}")).t().contiguous() for l in range(L)]).contiguous()
+        if L > 1:
+            w_ih_t = torch.stack([f(getattr(rnn, f"weight_ih_l{l}")).t().contiguous() for l in range(1, L)]).contiguous()
+            b_gate = torch.stack([bias(l, "bias_ih") + bias(l, "bias_hh") for l in range(1, L)]).contiguous()
+        else:
+            w_ih_t = b_gate = None
+        proj_t, proj_b = f(p.projection.weight).t().contiguous(), f(p.projection.bias)
+        if j.pred_ffn is not None:
+            pf_t, pf_b = f(j.pred_ffn.weight).t().contiguous(), f(j.pred_ffn.bias)
+        else:   # prejoin_linear=False: identity
+            P = proj_t.shape[1]
+            pf_t, pf_b = torch.eye(P, device=emb.device), torch.zeros(P, device=emb.device)
+        out_t, out_b = f(j.ffn_out.weight).t().contiguous(), f(j.ffn_out.bias)
+        self._keep = (gate_tok, w_hh_t, w_ih_t, b_gate, proj_t, proj_b, pf_t, pf_b, out_t, out_b)
+        s = DecoderWeights()
+        for name, t in zip(("gate_tok", "w_hh_t", "w_ih_t", "b_gate", "proj_t", "proj_b", "pred_ffn_t",
+                            "pred_ffn_b", "out_t", "out_b"), self._keep):
+            setattr(s, name, None if t is None else t.data_ptr())
+        s.V, s.H, s.L, s.P, s.D = out_t.shape[1], H, L, proj_t.shape[1], out_t.shape[0]
+        self.struct, self._key = s, key
+        return s
+
+
+def _prepared(model) -> PreparedDecoder:
+    pd = getattr(model, "_ctcvr_prepared", None)
+    if pd is None or pd.predictor is not model.predictor or pd.joint is not model.joint:
+        pd = PreparedDecoder(model.predictor, model.joint)
+        try:
+            object.__setattr__(model, "_ctcvr_prepared", pd)
+        except Exception:
+            pass
+    return pd
+
+
+def _blank_of(model) -> int:
+    return int(model.blank if hasattr(model, "blank") else model.blank_id)
+
+
+def _enc_proj(model, encoder_out):
+    j = model.joint
+    x = encoder_out.float()
+    if getattr(j, "enc_ffn", None) is not None:
+        x = torch.nn.functional.linear(x, j.enc_ffn.weight, j.enc_ffn.bias)
+    return x.contiguous()
+
+
+@torch.no_grad()
+def greedy_batch(model, encoder_out, encoder_out_lens, n_steps: int, h=None, c=None, last_token=None):
+    """Run the greedy walk for N utterances/streams at once.  Returns (hyps, h, c, last_token) with the
+    predictor state after the walk ([L,N,H]) and the last emitted token per stream."""
+    w = _prepared(model).get()
+    blank = _blank_of(model)
+    ep = _enc_proj(model, encoder_out)
+    N, T, D = ep.shape
+    dev = ep.device
+    lens = encoder_out_lens.to(device=dev, dtype=torch.int32).contiguous()
+    if h is None:
+        h = torch.zeros((w.L, N, w.H), dtype=torch.float32, device=dev)
+        c = torch.zeros_like(h)
+    else:
+        h, c = h.detach().float().contiguous().clone(), c.detach().float().contiguous().clone()
+    if last_token is None:
+        last_token = torch.full((N,), blank, dtype=torch.int32, device=dev)
+    else:
+        last_token = last_token.to(device=dev, dtype=torch.int32).contiguous().clone()
+    max_out = T * n_steps
+    toks = torch.empty((N, max_out), dtype=torch.int32, device=dev)
+    nout = torch.empty((N,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        call("ctcvr_rnnt_greedy", ctypes.byref(w), ptr(ep), ptr(lens), ptr(h), ptr(c), ptr(last_token), ptr(toks),
+             ptr(nout), N, T, max_out, blank, int(n_steps), None, 0, stream())
+    nh = nout.cpu()
+    width = int(nh.max()) if N > 0 else 0
+    th = toks[:, :max(width, 1)].cpu()
+    hyps = [th[i, :int(nh[i])].tolist() for i in range(N)]
+    return hyps, h, c, last_token
+
+
+def basic_greedy_search(model, encoder_out: torch.Tensor, encoder_out_lens: torch.Tensor,
+                        n_steps: int = 64) -> List[List[int]]:
+    """Drop-in for model/component/transducer.py:22-70: all utterances decoded by one kernel launch,
+    one device->host copy of the hypotheses at the end (the reference syncs once per step)."""
+    return greedy_batch(model, encoder_out, encoder_out_lens, n_steps)[0]
+
+
+@torch.no_grad()
+def greedy_chunk(model, encoder_out_chunk: torch.Tensor, predictor_states: Optional[List[torch.Tensor]],
+                 prev_token: int, n_steps: int = 10) -> Tuple[List[int], List[torch.Tensor], int]:
+    """The search loop of model/online_rnnt_model.py:193-222 for one encoder chunk [1,Tc,H]:
+    returns (tokens, [h,c], last_token)."""
+    dev = encoder_out_chunk.device
+    Tc = encoder_out_chunk.size(1)
+    if predictor_states is None:
+        predictor_states = model.predictor.init_state(batch_size=1, device=dev)
+    if Tc == 0:
+        return [], predictor_states, prev_token
+    lens = torch.tensor([Tc], dtype=torch.int32, device=dev)
+    last = torch.tensor([prev_token], dtype=torch.int32, device=dev)
+    hyps, h, c, last = greedy_batch(model, encoder_out_chunk, lens, n_steps, predictor_states[0],
+                                    predictor_states[1], last)
+    return hyps[0], [h, c], int(last.item())

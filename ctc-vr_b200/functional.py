@@ -1,0 +1,254 @@
+"""Autograd ops over the C-ABI kernels.
+
+  fused_joint_rnnt_loss  — the fused seam of SURVEY.md §8b: everything between the predictor output and
+                           the per-utterance cost (model/component/transducer.py:172-187,
+                           model/online_rnnt_model.py:243-255) as one op; logits never reach HBM.
+  rnnt_loss              — drop-in for torchaudio.functional.rnnt_loss on dense logits
+                           (site-packages/torchaudio/functional/functional.py:1747-1800).
+  ctc_loss               — drop-in for F.log_softmax + nn.CTCLoss(zero_infinity=True) tails
+                           (model/rnnt_model.py:55-58, model/online_rnnt_model.py:29-30).
+  joint_logits           — dense TransducerJoint tail (model/component/joint.py:57-68).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, query, stream
+
+F32, BF16 = 0, 1
+_PREC = {"fp32": F32, "f32": F32, "bf16": BF16, F32: F32, BF16: BF16}
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _i32c(t, device):
+    return t.detach().to(device=device, dtype=torch.int32).contiguous()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+class _FusedJointRnnt(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, enc_proj, pred_proj, w_out, b_out, targets, t_len, u_len, blank, clamp, precision):
+        _lib.require_cuda(enc_proj, pred_proj, w_out, b_out)
+        dev = enc_proj.device
+        e, p, w, b = _f32c(enc_proj), _f32c(pred_proj), _f32c(w_out), _f32c(b_out)
+        B, T, D = e.shape
+        U1 = p.shape[1]
+        V = w.shape[0]
+        if p.shape[0] != B or p.shape[2] != D or w.shape[1] != D or b.shape[0] != V:
+            raise RuntimeError("fused_joint_rnnt_loss: inconsistent shapes")
+        tg = _i32c(targets, dev)
+        if tg.dim() != 2 or tg.shape[0] != B or tg.shape[1] != U1 - 1:
+            raise RuntimeError("fused_joint_rnnt_loss: targets must be [B, U] with U == pred_out.size(1) - 1")
+        tl, ul = _i32c(t_len, dev), _i32c(u_len, dev)
+        lse = torch.empty((B, T, U1), dtype=torch.float32, device=dev)
+        lpb, lpl = torch.empty_like(lse), torch.empty_like(lse)
+        alpha, beta = torch.empty_like(lse), torch.empty_like(lse)
+        costs = torch.empty((B,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _ws(query("ctcvr_joint_rnnt_fwd_ws_bytes", B, T, U1, D, V, precision), dev)
+            call("ctcvr_joint_rnnt_fwd", ptr(e), ptr(p), ptr(w), ptr(b), ptr(tg), ptr(tl), ptr(ul), ptr(lse),
+                 ptr(lpb), ptr(lpl), B, T, U1, D, V, blank, precision, ptr(ws), ws.numel(), stream())
+            call("ctcvr_rnnt_lattice", ptr(lpb), ptr(lpl), ptr(tl), ptr(ul), ptr(alpha), ptr(beta), ptr(costs),
+                 B, T, U1, stream())
+        ctx.save_for_backward(e, p, w, b, tg, tl, ul, lse, alpha, beta, costs)
+        ctx.cfg = (blank, float(clamp), precision)
+        return costs
+
+    @staticmethod
+    def backward(ctx, grad_costs):
+        e, p, w, b, tg, tl, ul, lse, alpha, beta, costs = ctx.saved_tensors
+        blank, clamp, precision = ctx.cfg
+        B, T, D = e.shape
+        U1, V = p.shape[1], w.shape[0]
+        dev = e.device
+        gc = _f32c(grad_costs)
+        d_e, d_p = torch.empty_like(e), torch.empty_like(p)
+        d_w, d_b = torch.empty_like(w), torch.empty_like(b)
+        with torch.cuda.device(dev):
+            ws = _ws(query("ctcvr_joint_rnnt_bwd_ws_bytes", B, T, U1, D, V, precision), dev)
+            call("ctcvr_joint_rnnt_bwd", ptr(e), ptr(p), ptr(w), ptr(b), ptr(tg), ptr(tl), ptr(ul), ptr(lse),
+                 ptr(alpha), ptr(beta), ptr(costs), ptr(gc), clamp, ptr(d_e), ptr(d_p), ptr(d_w), ptr(d_b),
+                 B, T, U1, D, V, blank, precision, ptr(ws), ws.numel(), stream())
+        return d_e, d_p, d_w, d_b, None, None, None, None, None, None
+
+
+def fused_joint_rnnt_loss(enc_proj, pred_proj, w_out, b_out, targets, logit_lengths, target_lengths,
+                          blank: int, clamp: float = -1.0, reduction: str = "mean", precision="bf16"):
+    """costs_b = RNN-T negative log-likelihood of utterance b for
+    logits = ffn_out(tanh(enc_proj[:, :, None] + pred_proj[:, None])) without materialising them.
+    enc_proj [B,T,D] / pred_proj [B,U+1,D] are the enc_ffn / pred_ffn outputs (joint.py:54-55)."""
+    costs = _FusedJointRnnt.apply(enc_proj, pred_proj, w_out, b_out, targets, logit_lengths, target_lengths,
+                                  int(blank), float(clamp), _PREC[precision])
+    return _reduce(costs, reduction)
+
+
+def _reduce(costs, reduction):
+    if reduction == "mean":
+        return costs.mean()
+    if reduction == "sum":
+        return costs.sum()
+    if reduction == "none":
+        return costs
+    raise ValueError('reduction should be one of "none", "mean", or "sum"')
+
+
+class _RnntLossDense(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets, t_len, u_len, blank, clamp):
+        B, T, U1, V = logits.shape
+        dev = logits.device
+        costs = torch.empty((B,), dtype=torch.float32, device=dev)
+        grads = torch.empty_like(logits) if logits.requires_grad else None
+        with torch.cuda.device(dev):
+            ws = _ws(query("ctcvr_rnnt_loss_dense_ws_bytes", B, T, U1), dev)
+            call("ctcvr_rnnt_loss_dense", ptr(logits), ptr(targets), ptr(t_len), ptr(u_len), ptr(costs), ptr(grads),
+                 B, T, U1, V, blank, clamp, ptr(ws), ws.numel(), stream())
+        ctx.grads = grads
+        return costs
+
+    @staticmethod
+    def backward(ctx, dy):
+        g = ctx.grads
+        return (g * dy.view(-1, 1, 1, 1) if g is not None else None), None, None, None, None, None
+
+
+def rnnt_loss(logits, targets, logit_lengths, target_lengths, blank: int = -1, clamp: float = -1,
+              reduction: str = "mean", fused_log_softmax: bool = True):
+    """Same signature and checks as torchaudio.functional.rnnt_loss (functional.py:1747-1800); the
+    validation errors of rnnt/cpu/compute.cpp:36-84 are raised as RuntimeError."""
+    if reduction not in ("none", "mean", "sum"):
+        raise ValueError('reduction should be one of "none", "mean", or "sum"')
+    _lib.require_cuda(logits)
+    if not fused_log_softmax:
+        raise RuntimeError("rnnt_loss: only fused_log_softmax=True is supported (the only mode the reference uses)")
+    if logits.dtype != torch.float32:
+        raise RuntimeError("rnnt_loss: logits must be float32")
+    if targets.dtype != torch.int32 or logit_lengths.dtype != torch.int32 or target_lengths.dtype != torch.int32:
+        raise RuntimeError("rnnt_loss: targets, logit_lengths and target_lengths must be int32")
+    if logits.dim() != 4 or targets.dim() != 2 or logit_lengths.dim() != 1 or target_lengths.dim() != 1:
+        raise RuntimeError("rnnt_loss: logits must be 4-D, targets 2-D, lengths 1-D")
+    if not (logits.is_contiguous() and targets.is_contiguous()):
+        raise RuntimeError("rnnt_loss: logits and targets must be contiguous")
+    B, T, U1, V = logits.shape
+    if blank < 0:
+        blank = V + blank
+    if not (0 <= blank < V):
+        raise RuntimeError("rnnt_loss: blank must be within [0, logits.shape[-1])")
+    if targets.shape[0] != B or logit_lengths.shape[0] != B or target_lengths.shape[0] != B:
+        raise RuntimeError("rnnt_loss: batch dimension mismatch")
+    # torchaudio also rejects non-max shapes (one host sync, as in the reference op)
+    if int(logit_lengths.max()) != T:
+        raise RuntimeError("rnnt_loss: input length mismatch")
+    if int(target_lengths.max()) != U1 - 1 or targets.shape[1] != U1 - 1:
+        raise RuntimeError("rnnt_loss: output length mismatch")
+    dev = logits.device
+    costs = _RnntLossDense.apply(logits, targets.to(dev), logit_lengths.to(dev).contiguous(),
+                                 target_lengths.to(dev).contiguous(), int(blank), float(clamp))
+    return _reduce(costs, reduction)
+
+
+class _JointLogits(torch.autograd.Function):
+    """Dense joint tail; backward through plain matmuls (not the hot path: the fused op is)."""
+    @staticmethod
+    def forward(ctx, enc_proj, pred_proj, w_out, b_out):
+        e, p, w, b = _f32c(enc_proj), _f32c(pred_proj), _f32c(w_out), _f32c(b_out)
+        B, T, D = e.shape
+        U1, V = p.shape[1], w.shape[0]
+        out = torch.empty((B, T, U1, V), dtype=torch.float32, device=e.device)
+        with torch.cuda.device(e.device):
+            call("ctcvr_joint_logits", ptr(e), ptr(p), ptr(w), ptr(b), ptr(out), B, T, U1, D, V, stream())
+        ctx.save_for_backward(e, p, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        e, p, w = ctx.saved_tensors
+        z = torch.tanh(e.unsqueeze(2) + p.unsqueeze(1))
+        g2 = g.reshape(-1, g.shape[-1])
+        dz = (g2 @ w).view_as(z) * (1 - z * z)
+        return dz.sum(2), dz.sum(1), g2.t() @ z.reshape(-1, z.shape[-1]), g2.sum(0)
+
+
+def joint_logits(enc_proj, pred_proj, w_out, b_out):
+    """logits[b,t,u,:] = W_out tanh(enc_proj[b,t] + pred_proj[b,u]) + b_out (joint.py:57-68)."""
+    _lib.require_cuda(enc_proj, pred_proj, w_out, b_out)
+    return _JointLogits.apply(enc_proj, pred_proj, w_out, b_out)
+
+
+def log_softmax_rows(x):
+    """F.log_softmax(x, dim=-1) for fp32 CUDA input (forward only; used inside ctc_loss)."""
+    xc = _f32c(x)
+    y = torch.empty_like(xc)
+    with torch.cuda.device(xc.device):
+        call("ctcvr_log_softmax", ptr(xc), ptr(y), xc.numel() // xc.shape[-1], xc.shape[-1], stream())
+    return y
+
+
+class _CtcFromLogits(torch.autograd.Function):
+    """logits [B,T,V] -> (nll [B], log_probs [B,T,V]).  As torchaudio does for rnnt_loss, the gradient
+    wrt logits is produced by the same launch as the loss and scaled by dL/dnll in backward."""
+    @staticmethod
+    def forward(ctx, logits, targets, in_lens, tgt_lens, blank, zero_infinity):
+        x = _f32c(logits)
+        B, T, V = x.shape
+        dev = x.device
+        lp = torch.empty_like(x)
+        nll = torch.empty((B,), dtype=torch.float32, device=dev)
+        tg = targets.detach().to(device=dev, dtype=torch.int64).contiguous()
+        Umax = tg.shape[1] if tg.dim() == 2 else 0
+        il, tl = _i32c(in_lens, dev), _i32c(tgt_lens, dev)
+        grad = torch.empty_like(x) if logits.requires_grad else None
+        with torch.cuda.device(dev):
+            call("ctcvr_log_softmax", ptr(x), ptr(lp), B * T, V, stream())
+            ws = _ws(query("ctcvr_ctc_loss_ws_bytes", B, T, Umax), dev)
+            call("ctcvr_ctc_loss", ptr(lp), ptr(tg), ptr(il), ptr(tl), None, ptr(nll), ptr(grad), B, T, V, Umax,
+                 blank, int(zero_infinity), ptr(ws), ws.numel(), stream())
+        ctx.grad = grad
+        ctx.mark_non_differentiable(lp)
+        return nll, lp
+
+    @staticmethod
+    def backward(ctx, g_nll, _g_lp):
+        g = ctx.grad
+        return (g * g_nll.view(-1, 1, 1) if g is not None else None), None, None, None, None, None
+
+
+def ctc_loss_from_logits(logits, targets, input_lengths, target_lengths, blank: int, reduction: str = "sum",
+                         zero_infinity: bool = True):
+    """F.log_softmax(logits, -1) followed by nn.CTCLoss(blank, reduction, zero_infinity) on [B,T,V] logits.
+    Returns (loss, log_probs [B,T,V]).  reduction semantics are ATen's: 'mean' divides each nll by
+    clamp_min(target_length, 1) and averages over the batch."""
+    _lib.require_cuda(logits)
+    nll, lp = _CtcFromLogits.apply(logits, targets, input_lengths, target_lengths, int(blank), bool(zero_infinity))
+    if reduction == "sum":
+        loss = nll.sum()
+    elif reduction == "mean":
+        tl = target_lengths.to(device=nll.device, dtype=torch.float32).clamp_min(1)
+        loss = (nll / tl).mean()
+    elif reduction == "none":
+        loss = nll
+    else:
+        raise ValueError(f"{reduction} is not a valid value for reduction")
+    return loss, lp
+
+
+def ctc_greedy_search(scores, lens, blank: int):
+    """Per-frame argmax + collapse (model/rnnt_model.py:188-210).  scores [B,T,V] logits or log-probs."""
+    _lib.require_cuda(scores)
+    x = _f32c(scores)
+    B, T, V = x.shape
+    dev = x.device
+    ln = _i32c(lens, dev)
+    toks = torch.empty((B, T), dtype=torch.int32, device=dev)
+    n = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        call("ctcvr_ctc_greedy", ptr(x), ptr(ln), ptr(toks), ptr(n), B, T, V, int(blank), stream())
+    toks_h, n_h = toks.cpu(), n.cpu()
+    return [toks_h[b, :int(n_h[b])].tolist() for b in range(B)]

@@ -1,0 +1,72 @@
+"""TransducerJoint — same constructor, parameter names and forward signature as
+model/component/joint.py:9-69 (and wenet/transducer/joint.py:62-92), so checkpoints load unchanged
+(state_dict keys enc_ffn.*, pred_ffn.*, ffn_out.*[, post_ffn.*])."""
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import functional as CF
+
+
+class TransducerJoint(nn.Module):
+    def __init__(self, vocab_size: int, enc_output_size: int, pred_output_size: int, join_dim: int,
+                 prejoin_linear: bool = True, postjoin_linear: bool = False, joint_mode: str = "add",
+                 activation: str = "tanh"):
+        super().__init__()
+        self.activation_name = activation if activation in ("tanh", "relu", "gelu") else "tanh"
+        self.activation = {"tanh": nn.Tanh(), "relu": nn.ReLU(), "gelu": nn.GELU()}[self.activation_name]
+        self.prejoin_linear = prejoin_linear
+        self.postjoin_linear = postjoin_linear
+        self.joint_mode = joint_mode
+        if not self.prejoin_linear and not self.postjoin_linear:
+            assert enc_output_size == pred_output_size == join_dim
+        self.enc_ffn: Optional[nn.Linear] = None
+        self.pred_ffn: Optional[nn.Linear] = None
+        if self.prejoin_linear:
+            self.enc_ffn = nn.Linear(enc_output_size, join_dim)
+            self.pred_ffn = nn.Linear(pred_output_size, join_dim)
+        self.post_ffn: Optional[nn.Linear] = None
+        if self.postjoin_linear:
+            self.post_ffn = nn.Linear(join_dim, join_dim)
+        self.ffn_out = nn.Linear(join_dim, vocab_size)
+
+    @property
+    def fusable(self) -> bool:
+        """True for the configuration both reference models build (add + tanh, no post-join linear)."""
+        return self.activation_name == "tanh" and not self.postjoin_linear and self.joint_mode == "add"
+
+    def project(self, enc_out, pred_out, pre_project: bool = True):
+        """enc_ffn / pred_ffn (joint.py:52-55): two small library GEMMs."""
+        if pre_project and self.prejoin_linear and self.enc_ffn is not None and self.pred_ffn is not None:
+            enc_out = self.enc_ffn(enc_out)
+            pred_out = self.pred_ffn(pred_out)
+        return enc_out, pred_out
+
+    def forward(self, enc_out: torch.Tensor, pred_out: torch.Tensor, pre_project: bool = True) -> torch.Tensor:
+        """Dense logits [B,T,U,V] (joint.py:48-69).  The training path does not call this: it uses
+        `rnnt_loss_fused`, which never materialises the logits."""
+        enc_out, pred_out = self.project(enc_out, pred_out, pre_project)
+        if self.fusable and enc_out.is_cuda and enc_out.dim() == 3 and pred_out.dim() == 3:
+            return CF.joint_logits(enc_out, pred_out, self.ffn_out.weight, self.ffn_out.bias)
+        if not enc_out.is_cuda:
+            raise RuntimeError("ctcvr_b200.TransducerJoint runs on CUDA (B200) tensors only; there is no CPU path")
+        # non-default configurations (relu/gelu, post-join linear) keep the reference data flow
+        if enc_out.ndim != 4:
+            enc_out = enc_out.unsqueeze(2)
+        if pred_out.ndim != 4:
+            pred_out = pred_out.unsqueeze(1)
+        out = enc_out + pred_out
+        if self.postjoin_linear and self.post_ffn is not None:
+            out = self.post_ffn(out)
+        return self.ffn_out(self.activation(out))
+
+    def rnnt_loss_fused(self, enc_out, pred_out, targets, logit_lengths, target_lengths, blank: int,
+                        clamp: float = -1.0, reduction: str = "mean", precision: str = "bf16",
+                        pre_project: bool = True):
+        """joint + log-softmax + RNN-T lattice loss in one op (the seam of transducer.py:172-187)."""
+        if not self.fusable:
+            raise RuntimeError("rnnt_loss_fused: only joint_mode='add', activation='tanh', postjoin_linear=False")
+        e, p = self.project(enc_out, pred_out, pre_project)
+        return CF.fused_joint_rnnt_loss(e, p, self.ffn_out.weight, self.ffn_out.bias, targets, logit_lengths,
+                                        target_lengths, blank, clamp, reduction, precision)

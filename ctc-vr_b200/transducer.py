@@ -1,0 +1,83 @@
+"""Transducer wrapper with the reference's constructor, attributes and method signatures
+(model/component/transducer.py:73-189); `_compute_rnnt_loss` is the fused seam."""
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from . import decode as D
+
+
+def add_blank(text: torch.Tensor, blank: int, ignore_id: int) -> torch.Tensor:
+    """model/component/transducer.py:8-19: prepend blank (ignore_id is NOT remapped there)."""
+    ys_in = torch.zeros((text.size(0), text.size(1) + 1), dtype=text.dtype, device=text.device)
+    ys_in[:, 0] = blank
+    ys_in[:, 1:] = text
+    return ys_in
+
+
+basic_greedy_search = D.basic_greedy_search
+
+
+class Transducer(nn.Module):
+    def __init__(self, vocab_size: int, blank: int, encoder: nn.Module, predictor: nn.Module, joint: nn.Module,
+                 ctc: Optional[nn.Module] = None, ctc_weight: float = 0.3, ignore_id: int = -1,
+                 transducer_weight: float = 0.7, precision: str = "bf16") -> None:
+        super().__init__()
+        assert ctc_weight + transducer_weight == 1.0
+        self.vocab_size = vocab_size
+        self.blank = blank
+        self.ignore_id = ignore_id
+        self.ctc_weight = ctc_weight
+        self.transducer_weight = transducer_weight
+        self.encoder = encoder
+        self.predictor = predictor
+        self.joint = joint
+        self.ctc = ctc
+        self.precision = precision
+
+    def forward(self, batch: dict, device: torch.device) -> Dict[str, Optional[torch.Tensor]]:
+        speech = batch["feats"].to(device)
+        speech_lengths = batch["feats_lengths"].to(device)
+        text = batch["target"].to(device)
+        text_lengths = batch["target_lengths"].to(device)
+        encoder_out, encoder_mask = self.encoder(speech, speech_lengths)
+        encoder_out_lens = encoder_mask.squeeze(1).sum(1)
+        loss_rnnt = self._compute_rnnt_loss(encoder_out, encoder_out_lens, text, text_lengths)
+        loss = self.transducer_weight * loss_rnnt
+        loss_ctc: Optional[torch.Tensor] = None
+        if self.ctc_weight != 0.0 and self.ctc is not None:
+            loss_ctc, _ = self.ctc(encoder_out, encoder_out_lens, text, text_lengths)
+            loss = loss + self.ctc_weight * loss_ctc.sum()
+        return {"loss": loss, "loss_ctc": loss_ctc, "loss_rnnt": loss_rnnt}
+
+    def greedy_search(self, speech, speech_lengths, decoding_chunk_size: int = -1,
+                      num_decoding_left_chunks: int = -1, n_steps: int = 64) -> List[List[int]]:
+        assert speech.shape[0] == speech_lengths.shape[0]
+        encoder_out, encoder_mask = self.encoder(speech, speech_lengths)
+        encoder_out_lens = encoder_mask.squeeze(1).sum(1)
+        return basic_greedy_search(self, encoder_out, encoder_out_lens, n_steps=n_steps)
+
+    def _compute_rnnt_loss(self, encoder_out, encoder_out_lens, text, text_lengths) -> torch.Tensor:
+        """transducer.py:161-189 with joint + log-softmax + lattice + gradients fused."""
+        return compute_rnnt_loss(self, encoder_out, encoder_out_lens, text, text_lengths)
+
+
+def compute_rnnt_loss(self, encoder_out, encoder_out_lens, text, text_lengths, clamp: float = -1.0):
+    """Body shared with patch.install(): works on the reference's own Transducer instance too."""
+    ys_in_pad = add_blank(text, self.blank, self.ignore_id)
+    predictor_out = self.predictor(ys_in_pad)
+    rnnt_text = text.to(torch.int64)
+    rnnt_text = torch.where(rnnt_text == self.ignore_id, 0, rnnt_text).to(torch.int32)
+    joint = self.joint
+    precision = getattr(self, "precision", "bf16")
+    from . import functional as CF
+    j_ok = getattr(joint, "prejoin_linear", True) and not getattr(joint, "postjoin_linear", False) and \
+        isinstance(getattr(joint, "activation", None), nn.Tanh)
+    if not j_ok:
+        raise RuntimeError("ctcvr_b200: fused RNN-T loss needs the add/tanh joint both reference models build")
+    e = joint.enc_ffn(encoder_out)
+    p = joint.pred_ffn(predictor_out)
+    return CF.fused_joint_rnnt_loss(e, p, joint.ffn_out.weight, joint.ffn_out.bias, rnnt_text,
+                                    encoder_out_lens.to(torch.int32), text_lengths.to(torch.int32),
+                                    self.blank, clamp, "mean", precision)

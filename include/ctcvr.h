@@ -1,0 +1,174 @@
+/*
+ * ctcvr.h — C-ABI of libctcvr.so: the B200 (sm_100a) transducer hot path of CentaureaHO/CTC-VR.
+ *
+ * The reference has NO plugin / FFI layer for this path: the boundary is a set of Python call
+ * sites into third-party wheels.  Each entry point below names the reference
+ * call site it replaces (paths relative to the reference tree; `site-packages/` = installed
+ * torchaudio / torch).  The reference-side binding is a ctypes stub: see INTEGRATION.md and
+ * ctc-vr_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named h_*.
+ *   - the caller owns every buffer (PyTorch allocates); kernels are enqueued on `stream`
+ *     (a cudaStream_t passed as void*); no entry point synchronises, allocates device memory
+ *     or reads device data on the host.
+ *   - return 0 on success, non-zero on error; `ctcvr_last_error()` gives the message; the Python
+ *     shim raises RuntimeError (rnnt_train.py:139 relies on `except RuntimeError`).
+ *   - all tensors are dense row-major ("contiguous"); T = max encoder frames, U1 = max target
+ *     length + 1, D = joint dim, V = vocabulary size; lengths are int32.
+ *   - precision: CTCVR_F32 = fp32 SIMT path (1e-4 parity path), CTCVR_BF16 = tcgen05 path
+ *     (bf16 operands, fp32 accumulate / softmax / lattice).
+ */
+#ifndef CTCVR_H_
+#define CTCVR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTCVR_F32 0
+#define CTCVR_BF16 1
+
+const char* ctcvr_last_error(void);
+int ctcvr_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long ctcvr_launch_count(void);
+
+/* ---- A1: TransducerJoint.forward dense logits — model/component/joint.py:57-68
+ * logits[b,t,u,:] = W_out · tanh(enc_proj[b,t,:] + pred_proj[b,u,:]) + b_out.
+ * enc_proj/pred_proj are the outputs of enc_ffn/pred_ffn (joint.py:54-55). */
+int ctcvr_joint_logits(const float* enc_proj, const float* pred_proj, const float* w_out,
+                       const float* b_out, float* logits, int B, int T, int U1, int D, int V,
+                       void* stream);
+
+/* ---- A1+A2 fused forward — model/component/joint.py:57-68 followed by the log-softmax /
+ * log-prob gather of torchaudio.functional.rnnt_loss as called at
+ * model/component/transducer.py:180-187 and model/online_rnnt_model.py:247-255.
+ * Emits only lse, lp_blank, lp_label [B,T,U1]; logits never reach HBM.
+ * targets [B,U1-1] int32.  Cells with t>=t_len[b] or u>u_len[b] are not written. */
+size_t ctcvr_joint_rnnt_fwd_ws_bytes(int B, int T, int U1, int D, int V, int precision);
+int ctcvr_joint_rnnt_fwd(const float* enc_proj, const float* pred_proj, const float* w_out,
+                         const float* b_out, const int32_t* targets, const int32_t* t_len,
+                         const int32_t* u_len, float* lse, float* lp_blank, float* lp_label,
+                         int B, int T, int U1, int D, int V, int blank, int precision,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* ---- A2 lattice — the alpha/beta recursion and costs of torchaudio rnnt_loss
+ * (site-packages/torchaudio/functional/functional.py:1725).
+ * alpha, beta [B,T,U1]; costs [B] = -beta(0,0). */
+int ctcvr_rnnt_lattice(const float* lp_blank, const float* lp_label, const int32_t* t_len,
+                       const int32_t* u_len, float* alpha, float* beta, float* costs,
+                       int B, int T, int U1, void* stream);
+
+/* ---- A1+A2 fused backward — replaces RnntLoss.backward (functional.py:1730-1734) + the
+ * autograd backward of joint.py:57-68.  Recomputes logits tiles; grad_costs [B] is dL/dcost_b
+ * (1/B for reduction='mean').  Outputs are OVERWRITTEN: d_enc_proj [B,T,D], d_pred_proj
+ * [B,U1,D], d_w_out [V,D], d_b_out [V]. */
+size_t ctcvr_joint_rnnt_bwd_ws_bytes(int B, int T, int U1, int D, int V, int precision);
+int ctcvr_joint_rnnt_bwd(const float* enc_proj, const float* pred_proj, const float* w_out,
+                         const float* b_out, const int32_t* targets, const int32_t* t_len,
+                         const int32_t* u_len, const float* lse, const float* alpha,
+                         const float* beta, const float* costs, const float* grad_costs,
+                         float clamp, float* d_enc_proj, float* d_pred_proj, float* d_w_out,
+                         float* d_b_out, int B, int T, int U1, int D, int V, int blank,
+                         int precision, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- A2 on dense logits — torch.ops.torchaudio.rnnt_loss_forward
+ * (site-packages/torchaudio/functional/functional.py:1725,1737-1744), fused_log_softmax=True.
+ * logits [B,T,U1,V] fp32; costs [B]; grads [B,T,U1,V] (may be NULL) = d cost_b / d logits,
+ * exact zeros at padded cells, clamped to +-clamp when clamp > 0.
+ * ws: 5*B*T*U1 floats (ctcvr_rnnt_loss_dense_ws_bytes). */
+size_t ctcvr_rnnt_loss_dense_ws_bytes(int B, int T, int U1);
+int ctcvr_rnnt_loss_dense(const float* logits, const int32_t* targets, const int32_t* t_len,
+                          const int32_t* u_len, float* costs, float* grads, int B, int T,
+                          int U1, int V, int blank, float clamp, void* ws, size_t ws_bytes,
+                          void* stream);
+
+/* ---- A4 CTC head tail — F.log_softmax + nn.CTCLoss(blank, zero_infinity=True) as used at
+ * model/rnnt_model.py:55-58, model/online_rnnt_model.py:29-30, model/model.py:289-293.
+ * ctcvr_log_softmax: y[r,:] = log_softmax(x[r,:]) over rows x V.
+ * ctcvr_ctc_loss: log_probs [B,T,V]; targets [B,Umax] int64 (as the reference passes them);
+ * nll [B] (inf -> 0 when zero_infinity); grad_logits [B,T,V] (may be NULL) = d nll_b/d logits
+ * scaled by grad_scale[b]; ws: ctcvr_ctc_loss_ws_bytes. */
+int ctcvr_log_softmax(const float* x, float* y, long rows, int V, void* stream);
+size_t ctcvr_ctc_loss_ws_bytes(int B, int T, int Umax);
+int ctcvr_ctc_loss(const float* log_probs, const int64_t* targets, const int32_t* in_lens,
+                   const int32_t* tgt_lens, const float* grad_scale, float* nll,
+                   float* grad_logits, int B, int T, int V, int Umax, int blank,
+                   int zero_infinity, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- A10 CTC greedy — model/rnnt_model.py:188-210, model/online_rnnt_model.py:647-671,
+ * wenet/transformer/search.py:107-122: per-frame argmax, collapse repeats, drop blank.
+ * scores [B,T,V] (logits or log-probs); out_tokens [B,T] int32; out_lens [B] int32. */
+int ctcvr_ctc_greedy(const float* scores, const int32_t* lens, int32_t* out_tokens,
+                     int32_t* out_lens, int B, int T, int V, int blank, void* stream);
+
+/* Predictor + joint weights for the on-device decoders, in the layouts the kernels stream
+ * (all fp32, device).  Source parameters: model/component/predictor.py:27-38 /
+ * wenet/transducer/predictor.py:60-89 (embed, rnn.weight_ih_l*, rnn.weight_hh_l*, rnn.bias_*,
+ * projection) and model/component/joint.py:38-46 (pred_ffn, ffn_out).  The host shim
+ * (ctc-vr_b200/decode.py::prepare_decoder_weights) derives them once per weight version:
+ * "_t" = transposed so that consecutive threads (output rows) read consecutive addresses. */
+typedef struct {
+  const float* gate_tok;   /* [V,4H]     embed . W_ih_l0^T + b_ih_l0 + b_hh_l0 (gate order i,f,g,o) */
+  const float* w_hh_t;     /* [L][H,4H]  W_hh_l^T */
+  const float* w_ih_t;     /* [L-1][H,4H] W_ih_l^T for layers >= 1 (NULL when L == 1) */
+  const float* b_gate;     /* [L-1][4H]  b_ih_l + b_hh_l for layers >= 1 (NULL when L == 1) */
+  const float* proj_t;     /* [H,P]      projection.weight^T */
+  const float* proj_b;     /* [P] */
+  const float* pred_ffn_t; /* [P,D]      joint.pred_ffn.weight^T */
+  const float* pred_ffn_b; /* [D] */
+  const float* out_t;      /* [D,V]      joint.ffn_out.weight^T */
+  const float* out_b;      /* [V] */
+  int V, H, L, P, D;
+} ctcvr_decoder_weights;
+
+/* ---- A5/A6/A6' greedy — model/component/transducer.py:22-70 (n_steps=64, fresh state),
+ * model/online_rnnt_model.py:166-222 (n_steps=10, state carried across chunks),
+ * wenet/transducer/search/greedy_search.py:6-54.
+ * enc_proj [N,T,D] = enc_ffn(encoder_out); lens [N]; h,c [L,N,H] in/out; last_token [N]
+ * in/out; out_tokens [N,max_out] int32; out_lens [N]. No host sync per step. */
+size_t ctcvr_rnnt_greedy_ws_bytes(const ctcvr_decoder_weights* w, int N);
+int ctcvr_rnnt_greedy(const ctcvr_decoder_weights* w, const float* enc_proj,
+                      const int32_t* lens, float* h, float* c, int32_t* last_token,
+                      int32_t* out_tokens, int32_t* out_lens, int N, int T, int max_out,
+                      int blank, int n_steps, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- A7 online beam — model/online_rnnt_model.py:389-522.  One stream (batch 1), beam state
+ * carried across chunks in `beam_state` (opaque, ctcvr_rnnt_beam_state_bytes).  After the
+ * call: out_n hyps, out_tokens [beam,max_out], out_lens [beam], out_scores [beam] fp64, and
+ * out_h/out_c [beam,L,H] predictor states, ordered as the reference's list. */
+size_t ctcvr_rnnt_beam_state_bytes(const ctcvr_decoder_weights* w, int beam, int n_steps, int max_out);
+int ctcvr_rnnt_beam_reset(void* beam_state, const ctcvr_decoder_weights* w, int beam, int n_steps,
+                          int max_out, void* stream);
+int ctcvr_rnnt_beam_chunk(const ctcvr_decoder_weights* w, const float* enc_proj, int T,
+                          void* beam_state, int beam, int n_steps, int max_out, int blank,
+                          int32_t* out_n, int32_t* out_tokens, int32_t* out_lens,
+                          double* out_scores, float* out_h, float* out_c, void* stream);
+
+/* ---- A8 wenet transducer prefix beam with CTC shallow fusion —
+ * wenet/transducer/search/prefix_beam_search.py:42-148.  enc_proj [T,D]; ctc_logp [T,V]. */
+size_t ctcvr_rnnt_prefix_beam_ws_bytes(const ctcvr_decoder_weights* w, int beam, int T);
+int ctcvr_rnnt_prefix_beam(const ctcvr_decoder_weights* w, const float* enc_proj,
+                           const float* ctc_logp, int T, int beam, int blank, float ctc_weight,
+                           float transducer_weight, int32_t* out_n, int32_t* out_tokens,
+                           int32_t* out_lens, double* out_scores, void* ws, size_t ws_bytes,
+                           void* stream);
+
+/* ---- A9 CTC prefix beam search — wenet/transformer/search.py:125-247 (context_graph=None).
+ * ctc_probs [B,T,V] log-probs; per utterance up to `beam` hyps: out_tokens [B,beam,T],
+ * out_lens [B,beam], out_scores [B,beam] fp64 (log_add(s,ns)), out_times [B,beam,T],
+ * out_n [B]. */
+size_t ctcvr_ctc_prefix_beam_ws_bytes(int B, int T, int V, int beam);
+int ctcvr_ctc_prefix_beam(const float* ctc_probs, const int32_t* lens, int B, int T, int V,
+                          int beam, int blank, int32_t* out_n, int32_t* out_tokens,
+                          int32_t* out_lens, double* out_scores, int32_t* out_times,
+                          void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTCVR_H_ */

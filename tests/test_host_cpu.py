@@ -1,0 +1,154 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/ctcvr.h declares, the
+host shims fail loudly without a GPU (no silent fallback), and the data-parallel step's host logic
+(utterance sharding + gradient all-reduce) reproduces the single-process gradients under gloo."""
+import os
+import re
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctcvr_b200
+    from ctcvr_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "ctcvr.h")).read()
+    declared = set(re.findall(r"\b(ctcvr_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    l = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(l, name), f"libctcvr.so does not export {name}"
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert l.ctcvr_version() >= 100
+    assert ctcvr_b200.__version__
+
+
+def test_ws_queries_need_no_gpu():
+    from ctcvr_b200._lib import query
+    assert query("ctcvr_rnnt_loss_dense_ws_bytes", 2, 10, 5) == 5 * 2 * 10 * 5 * 4
+    assert query("ctcvr_ctc_loss_ws_bytes", 2, 10, 5) > 0
+    assert query("ctcvr_joint_rnnt_bwd_ws_bytes", 32, 250, 41, 512, 412, 0) > 0
+    assert query("ctcvr_joint_rnnt_bwd_ws_bytes", 32, 250, 41, 512, 412, 1) > 0
+
+
+def test_no_cpu_fallback():
+    import ctcvr_b200 as C
+    j = C.TransducerJoint(11, 8, 8, 8)
+    e, p = torch.randn(1, 3, 8), torch.randn(1, 2, 8)
+    with pytest.raises(RuntimeError):
+        j(e, p)
+    with pytest.raises(RuntimeError):
+        j.rnnt_loss_fused(e, p, torch.zeros(1, 1, dtype=torch.int32), torch.tensor([3]), torch.tensor([1]), 5)
+    with pytest.raises(RuntimeError):
+        C.rnnt_loss(torch.randn(1, 3, 2, 11), torch.zeros(1, 1, dtype=torch.int32), torch.tensor([3], dtype=torch.int32),
+                    torch.tensor([1], dtype=torch.int32), blank=5)
+    with pytest.raises(RuntimeError):
+        C.ctc_loss_from_logits(torch.randn(1, 3, 11), torch.zeros(1, 1, dtype=torch.long), torch.tensor([3]),
+                               torch.tensor([1]), 5)
+    with pytest.raises(RuntimeError):
+        C.ctc_prefix_beam_search(torch.randn(1, 3, 11), torch.tensor([3]), 2, blank_id=5)
+    # argument errors of the C ABI surface as RuntimeError with the library's message
+    from ctcvr_b200._lib import call
+    with pytest.raises(RuntimeError, match="bad dims"):
+        call("ctcvr_rnnt_lattice", None, None, None, None, None, None, None, 0, 0, 0, None)
+
+
+def test_module_surface_matches_reference_names():
+    import ctcvr_b200 as C
+    j = C.TransducerJoint(412, 256, 256, 256)
+    assert list(j.state_dict()) == ["enc_ffn.weight", "enc_ffn.bias", "pred_ffn.weight", "pred_ffn.bias",
+                                    "ffn_out.weight", "ffn_out.bias"]
+    assert list(C.CTC(412, 256, 0.1, True, 5).state_dict()) == ["ctc_lo.weight", "ctc_lo.bias"]
+    assert list(C.OnlineCTC(412, 256, 0.1, 5).state_dict()) == ["ctc_lo.weight", "ctc_lo.bias"]
+    p = C.RNNPredictor(412, 256, 256, 0.1, 256, 1)
+    assert list(p.state_dict()) == ["embed.weight", "rnn.weight_ih_l0", "rnn.weight_hh_l0", "rnn.bias_ih_l0",
+                                    "rnn.bias_hh_l0", "projection.weight", "projection.bias"]
+    ys = C.add_blank(torch.tensor([[7, 8, 0]]), 5, -1)
+    assert ys.tolist() == [[5, 7, 8, 0]]
+
+
+def test_shard_bounds():
+    from ctcvr_b200.dist import shard_bounds
+    for n, w in ((256, 8), (10, 4), (3, 8)):
+        cover = []
+        for r in range(w):
+            lo, hi = shard_bounds(n, w, r)
+            cover += list(range(lo, hi))
+        assert cover == list(range(n))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ctcvr_b200.dist import GradAllReducer, dp_loss_and_backward, shard_bounds
+    from oracle import transducer_oracle as TO
+    torch.manual_seed(0)
+    B, T, U, D, V, blank = 5, 9, 4, 12, 17, 5          # uneven shards: 3 + 2
+    lin = {k: torch.nn.Linear(i, o) for k, (i, o) in {"enc_ffn": (D, D), "pred_ffn": (D, D), "ffn_out": (D, V)}.items()}
+    params = {f"{k}.{n}": p for k, m in lin.items() for n, p in m.named_parameters()}
+    enc, pred = torch.randn(B, T, D), torch.randn(B, U + 1, D)
+    tgt = torch.randint(6, V, (B, U), dtype=torch.int32)
+    tl = torch.tensor([9, 7, 5, 9, 3], dtype=torch.int32)
+    ul = torch.tensor([4, 0, 2, 4, 1], dtype=torch.int32)
+    lo, hi = shard_bounds(B, world, rank)
+
+    def costs_fn():      # stand-in for the CUDA op: same math through the oracle's differentiable call
+        logits = TO.joint_forward(enc[lo:hi], pred[lo:hi], params)
+        return TO.rnnt_loss_reference_call(logits, tgt[lo:hi], tl[lo:hi], ul[lo:hi], blank, -1.0, "none")
+
+    red = GradAllReducer(params.values())
+    total = dp_loss_and_backward(costs_fn, B, red)
+    if rank == 0:
+        q.put((total.item(), {k: p.grad.numpy().tolist() for k, p in params.items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_step_matches_single_process_gloo():
+    """N-rank loss/grad == 1-rank loss/grad on the concatenated batch."""
+    from oracle import transducer_oracle as TO
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    import time
+    deadline = time.time() + 120
+    while q.empty() and time.time() < deadline and any(p.is_alive() for p in procs):
+        time.sleep(0.2)
+    if q.empty():
+        for p in procs:
+            p.kill()
+        pytest.fail("data-parallel workers died or timed out")
+    total, grads = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    B, T, U, D, V, blank = 5, 9, 4, 12, 17, 5
+    lin = {k: torch.nn.Linear(i, o) for k, (i, o) in {"enc_ffn": (D, D), "pred_ffn": (D, D), "ffn_out": (D, V)}.items()}
+    params = {f"{k}.{n}": p for k, m in lin.items() for n, p in m.named_parameters()}
+    enc, pred = torch.randn(B, T, D), torch.randn(B, U + 1, D)
+    tgt = torch.randint(6, V, (B, U), dtype=torch.int32)
+    tl = torch.tensor([9, 7, 5, 9, 3], dtype=torch.int32)
+    ul = torch.tensor([4, 0, 2, 4, 1], dtype=torch.int32)
+    loss = TO.rnnt_loss_reference_call(TO.joint_forward(enc, pred, params), tgt, tl, ul, blank, -1.0, "mean")
+    loss.backward()
+    assert abs(total - loss.item()) < 1e-5 * abs(loss.item())
+    for k, p in params.items():
+        torch.testing.assert_close(torch.tensor(grads[k]), p.grad, rtol=1e-4, atol=1e-6)
