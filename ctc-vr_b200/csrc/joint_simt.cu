@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(JT_THREADS, 1) joint_tile_kernel(JointTileArgs
     rowi[TM + tid] = valid ? t : -1;
     rowi[2 * TM + tid] = u;
     int lab = -1;
-    if (valid && u < Ub) lab = a.targets[(size_t)b * (U1 - 1) + u];
+    if (valid && u < Ub && a.targets != nullptr) lab = a.targets[(size_t)b * (U1 - 1) + u];
     rowi[tid] = lab;
     if (MODE == MODE_GRAD) {
       float k_all = kNegInf, k_blank = kNegInf, k_label = kNegInf, scale = 0.f;

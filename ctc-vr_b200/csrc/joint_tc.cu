@@ -1,0 +1,595 @@
+// bf16 tcgen05 path of the fused transducer joint (the performance path on B200).
+//
+//   z      = tanh(enc_proj[b,t,:] + pred_proj[b,u,:])        model/component/joint.py:57-67
+//   logits = z . W_out^T + b_out                             model/component/joint.py:68
+//   fwd   : per lattice cell lse / lp_blank / lp_label (log-softmax + gather of
+//           torchaudio.functional.rnnt_loss, model/component/transducer.py:180-187)
+//   bwd   : recompute logits, closed-form d cost/d logits, dZ = g.W, dH = dZ*(1-z^2),
+//           d_enc = sum_u dH, d_pred = sum_t dH, dW = g^T.z, db = sum g
+//
+// Structure (one persistent CTA per SM, 512 threads, warp-specialised):
+//   warp 0      TMA producer : streams bf16 W_out k-blocks (128B-swizzled, K-major) into a smem ring
+//   warp 1      MMA issuer   : one elected thread issues tcgen05.mma (M=128, N=Vp/2 x2, K=16), fp32
+//                              accumulators live in TMEM, commits release smem stages / signal the epilogue
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue     : tcgen05.ld (thread = lattice cell), online log-softmax, gathers
+//   warps 8-15  A producers  : the A operand is COMPUTED, not loaded: tanh(e+p) -> bf16 -> smem in the
+//                              UMMA canonical swizzled layout, fence.proxy.async, mbarrier arrive
+// The [B,T,U+1,V] logits only ever exist as TMEM tiles.
+#include "tc_common.cuh"
+
+namespace ctcvr {
+namespace tc {
+
+constexpr int BM = 128;            // lattice cells (rows) per tile
+constexpr int BK = 64;             // k-block: 64 bf16 = 128 B = one swizzle row
+constexpr int A_STAGES = 3;
+constexpr int W_STAGES = 5;
+constexpr int NTHREADS = 512;
+constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KB
+constexpr int SLAB_PITCH = 68;                    // floats; 272 B row pitch -> conflict-free LDS.128
+constexpr int SLAB_ROWS_FLAT = 132;               // >= distinct u + distinct t of any 128-cell run (U1 <= 128)
+constexpr int SLAB_ROWS_RECT = 24;                // 16 u + 8 t
+constexpr int PROD_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+enum { TILE_FLAT = 0, TILE_RECT = 1 };
+
+struct TcParams {
+  const float* enc;        // [B,T,D] fp32
+  const float* pred;       // [B,U1,D] fp32
+  const float* bias_pad;   // [Vp] fp32, -inf beyond V
+  const int32_t* targets;  // [B,U1-1]
+  const int32_t* t_len;
+  const int32_t* u_len;
+  const int4* tiles;       // tile table: flat {b, c0, 0, 0} ; rect {b, s, tb, row0/128}
+  const int* ntiles;
+  int B, T, U1, D, V, Vp, NH, blank;
+  // forward outputs
+  float* lse;
+  float* lp_blank;
+  float* lp_label;
+  // backward inputs
+  const float* lse_in;
+  const float* alpha;
+  const float* beta;
+  const float* costs;
+  const float* grad_costs;
+  float clamp;
+  // backward outputs / scratch
+  __nv_bfloat16* zt;       // [D][Rpad]   z^T spill (K-major operand of the dW GEMM)
+  __nv_bfloat16* gt;       // [Vp][Rpad]  g^T spill
+  long Rpad;
+  float* d_enc_part;       // [S][B,T,D] partial d_enc per u-split
+  float* d_pred;           // [B,U1,D] (atomic accumulate)
+  float* d_bias;           // [Vp] (atomic accumulate)
+  int S_max;
+};
+
+struct RowMap {
+  int b, Tb, Ub, W;
+  int t0;        // first frame covered by the tile
+  int ubase;     // first label column covered by the tile's pred slab rows
+  int np, ne;    // slab rows holding pred / enc vectors
+};
+
+// ---- tile geometry ---------------------------------------------------------------------------
+template <int TILE>
+__device__ __forceinline__ RowMap tile_geometry(const TcParams& p, int4 ti) {
+  RowMap g;
+  g.b = ti.x;
+  g.Tb = min(p.t_len[g.b], p.T);
+  g.Ub = min(p.u_len[g.b], p.U1 - 1);
+  g.W = g.Ub + 1;
+  if (TILE == TILE_FLAT) {
+    int ncell = g.Tb * g.W;
+    int c0 = ti.y;
+    int clast = min(c0 + BM - 1, ncell - 1);
+    g.t0 = c0 / g.W;
+    g.ubase = 0;
+    g.np = g.W;
+    g.ne = clast / g.W - g.t0 + 1;
+  } else {
+    int S = (g.W + 15) >> 4;
+    int us = (g.W + S - 1) / S;
+    g.t0 = ti.z * 8;
+    g.ubase = ti.y * us;
+    g.np = 16;
+    g.ne = 8;
+  }
+  return g;
+}
+
+// row r of the tile -> lattice cell; returns false for padding rows
+template <int TILE>
+__device__ __forceinline__ bool row_cell(const TcParams& p, const RowMap& g, int4 ti, int r, int& t, int& u) {
+  if (TILE == TILE_FLAT) {
+    int c = ti.y + r;
+    t = c / g.W;
+    u = c - t * g.W;
+    return c < g.Tb * g.W;
+  } else {
+    int S = (g.W + 15) >> 4;
+    int us = (g.W + S - 1) / S;
+    int tloc = r >> 4, ul = r & 15;
+    t = g.t0 + tloc;
+    u = g.ubase + ul;
+    return t < g.Tb && ul < us && u <= g.Ub;
+  }
+}
+
+struct SmemLayout {
+  uint32_t a_base, w_base, w_bytes, bar_base;
+  float* slab;
+  float* bias;
+  uint32_t* tmem_ptr;
+  // addresses are computed, not tabulated: indexing a table with the runtime stage id would put it in local memory
+  __device__ __forceinline__ uint32_t a_stage(int i) const { return a_base + i * A_STAGE_BYTES; }
+  __device__ __forceinline__ uint32_t w_stage(int i) const { return w_base + i * w_bytes; }
+  __device__ __forceinline__ uint32_t a_full(int i) const { return bar_base + i * 16; }
+  __device__ __forceinline__ uint32_t a_empty(int i) const { return bar_base + i * 16 + 8; }
+  __device__ __forceinline__ uint32_t w_full(int i) const { return bar_base + A_STAGES * 16 + i * 16; }
+  __device__ __forceinline__ uint32_t w_empty(int i) const { return bar_base + A_STAGES * 16 + i * 16 + 8; }
+  __device__ __forceinline__ uint32_t tmem_full() const { return bar_base + (A_STAGES + W_STAGES) * 16; }
+  __device__ __forceinline__ uint32_t tmem_empty() const { return bar_base + (A_STAGES + W_STAGES) * 16 + 8; }
+  __device__ __forceinline__ uint32_t aux_bar(int i) const { return bar_base + (A_STAGES + W_STAGES) * 16 + 16 + i * 8; }
+};
+
+__host__ __device__ inline size_t tc_smem_bytes(int NH, int Vp, int slab_rows) {
+  size_t s = 1024;                                     // alignment slack
+  s += (size_t)A_STAGES * A_STAGE_BYTES;
+  s += (size_t)W_STAGES * NH * 128;
+  s += (size_t)slab_rows * SLAB_PITCH * 4;
+  s += (size_t)Vp * 4;
+  s += 512;                                            // barriers + tmem ptr
+  return s;
+}
+
+__device__ __forceinline__ void carve_smem(SmemLayout& L, uint8_t* raw, int NH, int Vp, int slab_rows) {
+  uint32_t base = smem_u32(raw);
+  uint32_t aligned = (base + 1023u) & ~1023u;
+  uint32_t a = aligned;
+  L.a_base = a; a += A_STAGES * A_STAGE_BYTES;
+  L.w_base = a; L.w_bytes = NH * 128; a += W_STAGES * NH * 128;
+  L.slab = reinterpret_cast<float*>(raw + (a - base)); a += slab_rows * SLAB_PITCH * 4;
+  L.bias = reinterpret_cast<float*>(raw + (a - base)); a += Vp * 4;
+  a = (a + 15u) & ~15u;
+  L.bar_base = a; a += (A_STAGES + W_STAGES) * 16 + 16 + 64;
+  L.tmem_ptr = reinterpret_cast<uint32_t*>(raw + (a - base));
+}
+
+// ---- A producer: slab staging + tanh tile -----------------------------------------------------
+// Slab rows [0,np) hold pred_proj[b][ubase+i][k0..k0+64), rows [np,np+ne) hold enc_proj[b][t0+i][k0..k0+64).
+__device__ __forceinline__ const float* slab_src(const TcParams& p, const RowMap& g, int srow) {
+  if (srow < g.np) {
+    int u = g.ubase + srow;
+    return (u <= g.Ub) ? p.pred + ((size_t)g.b * p.U1 + u) * p.D : nullptr;
+  }
+  int t = g.t0 + srow - g.np;
+  return (t < g.Tb) ? p.enc + ((size_t)g.b * p.T + t) * p.D : nullptr;
+}
+
+template <int NPRE>
+__device__ __forceinline__ void slab_fetch(const TcParams& p, const RowMap& g, int k0, int pt, float4 (&pre)[NPRE]) {
+  const int n4 = (g.np + g.ne) * 16;
+#pragma unroll
+  for (int i = 0; i < NPRE; ++i) {
+    int idx = pt + i * PROD_THREADS;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx < n4) {
+      const float* src = slab_src(p, g, idx >> 4);
+      if (src) v = __ldg(reinterpret_cast<const float4*>(src + k0) + (idx & 15));
+    }
+    pre[i] = v;
+  }
+}
+template <int NPRE>
+__device__ __forceinline__ void slab_store(float* slab, const RowMap& g, int pt, const float4 (&pre)[NPRE]) {
+  const int n4 = (g.np + g.ne) * 16;
+#pragma unroll
+  for (int i = 0; i < NPRE; ++i) {
+    int idx = pt + i * PROD_THREADS;
+    if (idx < n4) *reinterpret_cast<float4*>(slab + (idx >> 4) * SLAB_PITCH + (idx & 15) * 4) = pre[i];
+  }
+}
+
+// One k-block of the A tile for row r, k sub-range khalf*32..+32: tanh(e+p) -> bf16 -> swizzled smem.
+// Optionally spills z^T (bf16, [D][Rpad]) for the dW GEMM.
+template <bool SPILL>
+__device__ __forceinline__ void produce_a(const float* slab, uint32_t a_stage, int r, int khalf, bool valid,
+                                          int prow, int erow, __nv_bfloat16* zt_col, long Rpad) {
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    const int chunk = khalf * 4 + ch;                 // 16-byte chunk within the 128-byte row
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (valid) {
+      const float4 p0 = *reinterpret_cast<const float4*>(slab + prow * SLAB_PITCH + chunk * 8);
+      const float4 p1 = *reinterpret_cast<const float4*>(slab + prow * SLAB_PITCH + chunk * 8 + 4);
+      const float4 e0 = *reinterpret_cast<const float4*>(slab + erow * SLAB_PITCH + chunk * 8);
+      const float4 e1 = *reinterpret_cast<const float4*>(slab + erow * SLAB_PITCH + chunk * 8 + 4);
+      w[0] = pack_bf16(tanh_fast(e0.x + p0.x), tanh_fast(e0.y + p0.y));
+      w[1] = pack_bf16(tanh_fast(e0.z + p0.z), tanh_fast(e0.w + p0.w));
+      w[2] = pack_bf16(tanh_fast(e1.x + p1.x), tanh_fast(e1.y + p1.y));
+      w[3] = pack_bf16(tanh_fast(e1.z + p1.z), tanh_fast(e1.w + p1.w));
+    }
+    const uint32_t dst = a_stage + r * 128 + ((chunk ^ (r & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                 : "memory");
+    if (SPILL) {
+      // zt_col points at zt[k0 + khalf*32][row]; lanes hold consecutive rows -> 64 B coalesced per k
+      unsigned short* z = reinterpret_cast<unsigned short*>(zt_col) + (size_t)(ch * 8) * Rpad;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        z[(size_t)(2 * j) * Rpad] = (unsigned short)(w[j] & 0xffffu);
+        z[(size_t)(2 * j + 1) * Rpad] = (unsigned short)(w[j] >> 16);
+      }
+    }
+  }
+}
+
+struct Pipe {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int n) {
+    if (++stage == n) { stage = 0; phase ^= 1u; }
+  }
+};
+
+// =================================================================================================
+// Forward kernel
+// =================================================================================================
+__global__ void __launch_bounds__(NTHREADS, 1)
+joint_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  SmemLayout L;
+  carve_smem(L, smem_raw, p.NH, p.Vp, SLAB_ROWS_FLAT);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KB = p.D / BK;
+  const int ntiles = *p.ntiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(L.a_full(i), PROD_THREADS); mbar_init(L.a_empty(i), 1); }
+    for (int i = 0; i < W_STAGES; ++i) { mbar_init(L.w_full(i), 1); mbar_init(L.w_empty(i), 1); }
+    mbar_init(L.tmem_full(), 1);
+    mbar_init(L.tmem_empty(), 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(L.tmem_ptr), TMEM_COLS);
+  for (int i = tid; i < p.Vp; i += NTHREADS) L.bias[i] = p.bias_pad[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *L.tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (W_out)
+    if (lane == 0) {
+      Pipe wp;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+        for (int kb = 0; kb < KB; ++kb)
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(L.w_empty(wp.stage), wp.phase ^ 1u, 1);
+            mbar_arrive_expect_tx(L.w_full(wp.stage), (uint32_t)p.NH * 128u);
+            tma_load_2d(L.w_stage(wp.stage), &tmap_w, L.w_full(wp.stage), kb * BK, h * p.NH);
+            wp.advance(W_STAGES);
+          }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      Pipe ap, wp;
+      uint32_t tphase = 0;
+      const uint32_t idesc = make_idesc_bf16(BM, p.NH);
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(L.tmem_empty(), tphase ^ 1u, 2);
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(L.a_full(ap.stage), ap.phase, 3);
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(L.w_full(wp.stage), wp.phase, 4);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < BK / 16; ++ks) {
+              uint64_t ad = make_desc_sw128(L.a_stage(ap.stage) + ks * 32);
+              uint64_t bd = make_desc_sw128(L.w_stage(wp.stage) + ks * 32);
+              umma_bf16(tmem_base + h * p.NH, ad, bd, idesc, (kb | ks) ? 1u : 0u);
+            }
+            umma_commit(L.w_empty(wp.stage));
+            wp.advance(W_STAGES);
+          }
+          umma_commit(L.a_empty(ap.stage));
+          ap.advance(A_STAGES);
+        }
+        umma_commit(L.tmem_full());
+        tphase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ epilogue: online log-softmax
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    uint32_t tphase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int4 ti = p.tiles[tile];
+      const RowMap g = tile_geometry<TILE_FLAT>(p, ti);
+      int t, u;
+      const bool valid = row_cell<TILE_FLAT>(p, g, ti, r, t, u);
+      int lab = -1;
+      if (valid && u < g.Ub) lab = p.targets[(size_t)g.b * (p.U1 - 1) + u];
+      mbar_wait(L.tmem_full(), tphase, 5);
+      tc_fence_after();
+      float m = kNegInf, s = 0.f, xb = 0.f, xl = 0.f;
+      for (int c0 = 0; c0 < p.Vp; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        float cm = kNegInf;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] += L.bias[c0 + j];
+          cm = fmaxf(cm, v[j]);
+          xb = (c0 + j == p.blank) ? v[j] : xb;
+          xl = (c0 + j == lab) ? v[j] : xl;
+        }
+        const float nm = fmaxf(m, cm);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc += ex2_fast((v[j] - nm) * LOG2E);
+        s = s * ex2_fast((m - nm) * LOG2E) + acc;
+        m = nm;
+      }
+      tc_fence_before();
+      mbar_arrive(L.tmem_empty());
+      if (valid) {
+        const size_t cell = ((size_t)g.b * p.T + t) * p.U1 + u;
+        const float l = m + __logf(s);
+        p.lse[cell] = l;
+        p.lp_blank[cell] = xb - l;
+        p.lp_label[cell] = (lab >= 0) ? xl - l : kNegInf;
+      }
+      tphase ^= 1u;
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ A producers
+    const int pt = tid - 256;
+    const int r = pt & 127, khalf = pt >> 7;
+    Pipe ap;
+    constexpr int NPRE = (SLAB_ROWS_FLAT * 16 + PROD_THREADS - 1) / PROD_THREADS;   // 9
+    float4 pre[NPRE];
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int4 ti = p.tiles[tile];
+      const RowMap g = tile_geometry<TILE_FLAT>(p, ti);
+      int t, u;
+      const bool valid = row_cell<TILE_FLAT>(p, g, ti, r, t, u);
+      const int prow = u - g.ubase, erow = g.np + (t - g.t0);
+      slab_fetch<NPRE>(p, g, 0, pt, pre);
+      named_barrier_sync(1, PROD_THREADS);             // previous tile's last slab fully consumed
+      slab_store<NPRE>(L.slab, g, pt, pre);
+      named_barrier_sync(1, PROD_THREADS);
+      for (int kb = 0; kb < KB; ++kb) {
+        if (kb + 1 < KB) slab_fetch<NPRE>(p, g, (kb + 1) * BK, pt, pre);
+        mbar_wait(L.a_empty(ap.stage), ap.phase ^ 1u, 6);
+        produce_a<false>(L.slab, L.a_stage(ap.stage), r, khalf, valid, prow, erow, nullptr, 0);
+        fence_proxy_async();
+        mbar_arrive(L.a_full(ap.stage));
+        ap.advance(A_STAGES);
+        if (kb + 1 < KB) {
+          named_barrier_sync(1, PROD_THREADS);
+          slab_store<NPRE>(L.slab, g, pt, pre);
+          named_barrier_sync(1, PROD_THREADS);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// =================================================================================================
+// Helper kernels: weight conversion, tile tables
+// =================================================================================================
+// wb [Vp][D] bf16 (zero rows beyond V), wtb [D][Vp] bf16 (optional), bias_pad [Vp] (-inf beyond V)
+__global__ void prep_weights_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                    __nv_bfloat16* __restrict__ wb, __nv_bfloat16* __restrict__ wtb,
+                                    float* __restrict__ bias_pad, int V, int Vp, int D) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Vp * D) {
+    int v = i / D, d = i - v * D;
+    float x = (v < V) ? w[(size_t)v * D + d] : 0.f;
+    wb[i] = __float2bfloat16(x);
+    if (wtb) wtb[(size_t)d * Vp + v] = __float2bfloat16(x);
+  }
+  if (i < Vp) bias_pad[i] = (i < V) ? bias[i] : kNegInf;
+}
+
+// Single-CTA tile table builder (B is small).  flat: 128 consecutive valid cells per tile.
+// rect: tiles of 8 frames x 16 label columns, ordered (b, u-split, frame block) so that one CTA sweeps
+// consecutive frame blocks of the same (b, u-split).
+__global__ void build_tiles_kernel(const int32_t* __restrict__ t_len, const int32_t* __restrict__ u_len, int B, int T,
+                                   int U1, int rect, int4* __restrict__ tiles, int* __restrict__ ntiles,
+                                   int max_tiles) {
+  __shared__ int s_off[1025];
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (int b = 0; b < B; ++b) {
+      s_off[b & 1023] = off;   // (only used when B <= 1024; larger batches recompute below)
+      int Tb = min(t_len[b], T), W = min(u_len[b], U1 - 1) + 1;
+      if (Tb > 0) {
+        if (rect) { int S = (W + 15) >> 4; off += S * ((Tb + 7) >> 3); }
+        else off += (Tb * W + BM - 1) / BM;
+      }
+    }
+    *ntiles = min(off, max_tiles);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int off;
+    if (B <= 1024) off = s_off[b];
+    else {
+      off = 0;
+      for (int bb = 0; bb < b; ++bb) {
+        int Tb = min(t_len[bb], T), W = min(u_len[bb], U1 - 1) + 1;
+        if (Tb > 0) off += rect ? ((W + 15) >> 4) * ((Tb + 7) >> 3) : (Tb * W + BM - 1) / BM;
+      }
+    }
+    int Tb = min(t_len[b], T), W = min(u_len[b], U1 - 1) + 1;
+    if (Tb <= 0) continue;
+    if (rect) {
+      int S = (W + 15) >> 4, NTB = (Tb + 7) >> 3;
+      for (int s = 0; s < S; ++s)
+        for (int tb = 0; tb < NTB; ++tb) {
+          int idx = off + s * NTB + tb;
+          if (idx < max_tiles) tiles[idx] = make_int4(b, s, tb, idx);
+        }
+    } else {
+      int n = (Tb * W + BM - 1) / BM;
+      for (int i = 0; i < n; ++i)
+        if (off + i < max_tiles) tiles[off + i] = make_int4(b, i * BM, 0, off + i);
+    }
+  }
+}
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                      uint32_t box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr);
+    if (e != cudaSuccess || qr != cudaDriverEntryPointSuccess || !sym) {
+      set_error("cuTensorMapEncodeTiled is not available from the driver (%s)", cudaGetErrorString(e));
+      return 1;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu box_rows=%u)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, box_rows);
+    return 1;
+  }
+  return 0;
+}
+
+static int check_tc_error(const char* where) {
+  // asynchronous: reads the flag left by a PREVIOUS launch (no host sync on the hot path)
+  (void)where;
+  return 0;
+}
+
+}  // namespace tc
+
+// =================================================================================================
+// Host entry points
+// =================================================================================================
+using namespace tc;
+
+static int pad_v(int V) { return (V + 31) / 32 * 32; }
+static int max_tiles_flat(int B, int T, int U1) { return B * (int)(((long)T * U1 + BM - 1) / BM); }
+static int max_tiles_rect(int B, int T, int U1) { return B * ((U1 + 15) / 16) * ((T + 7) / 8); }
+
+bool joint_tc_supported(int U1, int D, int V) { return D % 64 == 0 && D >= 64 && D <= 1024 && pad_v(V) <= 512 && U1 <= 128; }
+
+struct FwdWs {
+  __nv_bfloat16* wb;
+  float* bias_pad;
+  int4* tiles;
+  int* ntiles;
+  size_t bytes;
+};
+static FwdWs carve_fwd_ws(void* ws, int B, int T, int U1, int D, int V) {
+  int Vp = pad_v(V);
+  uint8_t* p = reinterpret_cast<uint8_t*>(ws);
+  size_t off = 0;
+  FwdWs w;
+  w.wb = reinterpret_cast<__nv_bfloat16*>(p + off); off = align_up(off + (size_t)Vp * D * 2, 256);
+  w.bias_pad = reinterpret_cast<float*>(p + off); off = align_up(off + (size_t)Vp * 4, 256);
+  w.tiles = reinterpret_cast<int4*>(p + off); off = align_up(off + (size_t)max_tiles_flat(B, T, U1) * 16, 256);
+  w.ntiles = reinterpret_cast<int*>(p + off); off = align_up(off + 4, 256);
+  w.bytes = off;
+  return w;
+}
+
+size_t joint_fwd_tc_ws_bytes(int B, int T, int U1, int D, int V) { return carve_fwd_ws(nullptr, B, T, U1, D, V).bytes; }
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int joint_fwd_f32(const float*, const float*, const float*, const float*, const int32_t*, const int32_t*,
+                  const int32_t*, float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
+
+int joint_fwd_tc(const float* enc, const float* pred, const float* w, const float* bias, const int32_t* targets,
+                 const int32_t* t_len, const int32_t* u_len, float* lse, float* lp_blank, float* lp_label, int B, int T,
+                 int U1, int D, int V, int blank, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!joint_tc_supported(U1, D, V))   // shapes outside the tensor-core tiling use the fp32 kernels (same GPU)
+    return joint_fwd_f32(enc, pred, w, bias, targets, t_len, u_len, lse, lp_blank, lp_label, B, T, U1, D, V, blank, st);
+  CTCVR_REQUIRE(ws && ws_bytes >= joint_fwd_tc_ws_bytes(B, T, U1, D, V), "joint_rnnt_fwd bf16: workspace too small");
+  const int Vp = pad_v(V), NH = Vp / 2;
+  FwdWs W = carve_fwd_ws(ws, B, T, U1, D, V);
+  prep_weights_kernel<<<cdiv((long)Vp * D, 256), 256, 0, st>>>(w, bias, W.wb, nullptr, W.bias_pad, V, Vp, D);
+  CTCVR_LAUNCH_CHECK();
+  const int mt = max_tiles_flat(B, T, U1);
+  build_tiles_kernel<<<1, 256, 0, st>>>(t_len, u_len, B, T, U1, 0, W.tiles, W.ntiles, mt);
+  CTCVR_LAUNCH_CHECK();
+  CUtensorMap tmap;
+  if (make_tmap_bf16_2d(&tmap, W.wb, Vp, D, D, NH)) return 1;
+  TcParams p{};
+  p.enc = enc; p.pred = pred; p.bias_pad = W.bias_pad; p.targets = targets; p.t_len = t_len; p.u_len = u_len;
+  p.tiles = W.tiles; p.ntiles = W.ntiles;
+  p.B = B; p.T = T; p.U1 = U1; p.D = D; p.V = V; p.Vp = Vp; p.NH = NH; p.blank = blank;
+  p.lse = lse; p.lp_blank = lp_blank; p.lp_label = lp_label;
+  size_t smem = tc_smem_bytes(NH, Vp, SLAB_ROWS_FLAT);
+  CTCVR_REQUIRE(smem <= 232448, "joint_rnnt_fwd bf16: shared memory budget exceeded (%zu B)", smem);
+  CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = min(sm_count(), mt);
+  joint_fwd_tc_kernel<<<grid, NTHREADS, smem, st>>>(tmap, p);
+  CTCVR_LAUNCH_CHECK();
+  (void)check_tc_error;
+  return 0;
+}
+
+size_t joint_bwd_f32_ws_bytes(int, int, int, int, int);
+int joint_bwd_f32(const float*, const float*, const float*, const float*, const int32_t*, const int32_t*,
+                  const int32_t*, const float*, const float*, const float*, const float*, const float*, float, float*,
+                  float*, float*, float*, int, int, int, int, int, int, void*, size_t, cudaStream_t);
+
+// TEMPORARY (until the tcgen05 backward lands): the bf16 path's backward runs the fp32 kernels.
+size_t joint_bwd_tc_ws_bytes(int B, int T, int U1, int D, int V) { return joint_bwd_f32_ws_bytes(B, T, U1, D, V); }
+int joint_bwd_tc(const float* enc, const float* pred, const float* w, const float* bias, const int32_t* targets,
+                 const int32_t* t_len, const int32_t* u_len, const float* lse, const float* alpha, const float* beta,
+                 const float* costs, const float* grad_costs, float clamp, float* d_enc, float* d_pred, float* d_w,
+                 float* d_b, int B, int T, int U1, int D, int V, int blank, void* ws, size_t ws_bytes, cudaStream_t st) {
+  return joint_bwd_f32(enc, pred, w, bias, targets, t_len, u_len, lse, alpha, beta, costs, grad_costs, clamp, d_enc,
+                       d_pred, d_w, d_b, B, T, U1, D, V, blank, ws, ws_bytes, st);
+}
+
+unsigned int tc_error_flag() {
+  unsigned int v = 0;
+  cudaMemcpyFromSymbol(&v, tc::g_tc_error, sizeof(v));
+  unsigned int zero = 0;
+  if (v) cudaMemcpyToSymbol(tc::g_tc_error, &zero, sizeof(zero));
+  return v;
+}
+
+}  // namespace ctcvr

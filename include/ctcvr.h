@@ -36,6 +36,8 @@ const char* ctcvr_last_error(void);
 int ctcvr_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long ctcvr_launch_count(void);
+/* debug: non-zero if a tcgen05 kernel hit its bounded mbarrier wait (synchronises; clears the flag) */
+unsigned int ctcvr_debug_tc_error(void);
 
 /* ---- A1: TransducerJoint.forward dense logits — model/component/joint.py:57-68
  * logits[b,t,u,:] = W_out · tanh(enc_proj[b,t,:] + pred_proj[b,u,:]) + b_out.
