@@ -393,6 +393,502 @@ joint_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p
 }
 
 // =================================================================================================
+// Backward kernel 1: recompute logits -> g = d cost/d logits -> dZ^T = W^T g^T -> dH -> d_enc / d_pred
+// Tiles are rectangles of 8 frames x 16 label columns (row = tloc*16 + ul) so that, with the transposed
+// GEMM (TMEM lane = joint dim d, TMEM column = tile row), both reductions are thread-local and static:
+//   d_enc[t]  = sum over the 16 columns of one tcgen05.ld.x16
+//   d_pred[u] = sum over the 8 frame slots, kept in registers across the tiles of one (b, u-split) sweep
+// Phases of one tile (TMEM is 512 columns, so logits [128 x Vp] and dZ^T [D x 128] cannot coexist):
+//   P1 producers: tanh tile (+ z^T spill) | TMA: W_out k-blocks | MMA: logits -> TMEM
+//   P2 epilogue : TMEM -> g (bf16) -> smem G tile (K-major over v) + g^T spill
+//   P3 TMA: W_out^T tiles | MMA: dZ^T[mb] = W^T[mb] . G^T -> TMEM ; producers: column sums of G (d_bias)
+//   P4 epilogue : TMEM -> dH = dZ*(1-z^2) -> d_enc partial (store), d_pred (registers)
+// The smem of P2-P4 (G tile, W^T ring) overlays the smem of P1 (A ring, W ring, slab).
+// =================================================================================================
+constexpr int WT_STAGES = 6;
+constexpr int WT_STAGE_BYTES = 128 * 128;          // [128 d][64 v] bf16
+
+struct BwdSmem {
+  uint32_t base;          // 1024-aligned
+  uint32_t a_base, w_base, w_bytes, g_base, wt_base, bar_base;
+  float* slab;
+  float* bias;
+  uint32_t* tmem_ptr;
+  __device__ __forceinline__ uint32_t a_stage(int i) const { return a_base + i * A_STAGE_BYTES; }
+  __device__ __forceinline__ uint32_t w_stage(int i) const { return w_base + i * w_bytes; }
+  __device__ __forceinline__ uint32_t g_kblock(int i) const { return g_base + i * A_STAGE_BYTES; }
+  __device__ __forceinline__ uint32_t wt_stage(int i) const { return wt_base + i * WT_STAGE_BYTES; }
+  __device__ __forceinline__ uint32_t a_full(int i) const { return bar_base + i * 16; }
+  __device__ __forceinline__ uint32_t a_empty(int i) const { return bar_base + i * 16 + 8; }
+  __device__ __forceinline__ uint32_t w_full(int i) const { return bar_base + A_STAGES * 16 + i * 16; }
+  __device__ __forceinline__ uint32_t w_empty(int i) const { return bar_base + A_STAGES * 16 + i * 16 + 8; }
+  __device__ __forceinline__ uint32_t wt_full(int i) const { return bar_base + (A_STAGES + W_STAGES) * 16 + i * 16; }
+  __device__ __forceinline__ uint32_t wt_empty(int i) const { return bar_base + (A_STAGES + W_STAGES) * 16 + i * 16 + 8; }
+  __device__ __forceinline__ uint32_t misc(int i) const { return bar_base + (A_STAGES + W_STAGES + WT_STAGES) * 16 + i * 8; }
+  __device__ __forceinline__ uint32_t tmem_full() const { return misc(0); }    // logits complete
+  __device__ __forceinline__ uint32_t g_full() const { return misc(1); }       // G tile written (128 arrivals)
+  __device__ __forceinline__ uint32_t dz_full() const { return misc(2); }      // dZ^T complete, smem free again
+  __device__ __forceinline__ uint32_t tmem_empty() const { return misc(3); }   // epilogue done with TMEM (128)
+};
+
+__host__ __device__ inline size_t bwd_smem_bytes(int NH, int Vp) {
+  size_t r1 = (size_t)A_STAGES * A_STAGE_BYTES + (size_t)W_STAGES * NH * 128 + (size_t)SLAB_ROWS_RECT * SLAB_PITCH * 4;
+  size_t kbg = (Vp + 63) / 64;
+  size_t r2 = kbg * A_STAGE_BYTES + (size_t)WT_STAGES * WT_STAGE_BYTES;
+  size_t s = 1024 + (r1 > r2 ? r1 : r2);
+  s = (s + 15) / 16 * 16;
+  s += (size_t)Vp * 4 + 512;
+  return s;
+}
+
+__device__ __forceinline__ void carve_bwd(BwdSmem& L, uint8_t* raw, int NH, int Vp) {
+  uint32_t base = smem_u32(raw);
+  uint32_t al = (base + 1023u) & ~1023u;
+  L.base = al;
+  L.a_base = al;
+  L.w_base = al + A_STAGES * A_STAGE_BYTES;
+  L.w_bytes = NH * 128;
+  uint32_t slab_off = A_STAGES * A_STAGE_BYTES + W_STAGES * NH * 128;
+  L.slab = reinterpret_cast<float*>(raw + (al - base) + slab_off);
+  uint32_t r1 = slab_off + SLAB_ROWS_RECT * SLAB_PITCH * 4;
+  uint32_t kbg = (Vp + 63) / 64;
+  L.g_base = al;
+  L.wt_base = al + kbg * A_STAGE_BYTES;
+  uint32_t r2 = kbg * A_STAGE_BYTES + WT_STAGES * WT_STAGE_BYTES;
+  uint32_t a = al + (r1 > r2 ? r1 : r2);
+  a = (a + 15u) & ~15u;
+  L.bias = reinterpret_cast<float*>(raw + (a - base));
+  a += Vp * 4;
+  a = (a + 15u) & ~15u;
+  L.bar_base = a;
+  a += (A_STAGES + W_STAGES + WT_STAGES) * 16 + 4 * 8;
+  L.tmem_ptr = reinterpret_cast<uint32_t*>(raw + (a - base));
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+joint_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_wt,
+                    const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  BwdSmem L;
+  carve_bwd(L, smem_raw, p.NH, p.Vp);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KB = p.D / BK;                 // k-blocks of the logits GEMM
+  const int KBG = (p.Vp + 63) / 64;        // k-blocks (over v) of the dZ GEMM
+  const int MB = p.D / 128;                // 128-lane blocks of dZ^T
+  const int ntiles = *p.ntiles;
+  const int tile_begin = (int)(((long)ntiles * blockIdx.x) / gridDim.x);
+  const int tile_end = (int)(((long)ntiles * (blockIdx.x + 1)) / gridDim.x);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_wt);
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(L.a_full(i), PROD_THREADS); mbar_init(L.a_empty(i), 1); }
+    for (int i = 0; i < W_STAGES; ++i) { mbar_init(L.w_full(i), 1); mbar_init(L.w_empty(i), 1); }
+    for (int i = 0; i < WT_STAGES; ++i) { mbar_init(L.wt_full(i), 1); mbar_init(L.wt_empty(i), 1); }
+    mbar_init(L.tmem_full(), 1);
+    mbar_init(L.g_full(), 128);
+    mbar_init(L.dz_full(), 1);
+    mbar_init(L.tmem_empty(), 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(L.tmem_ptr), TMEM_COLS);
+  for (int i = tid; i < p.Vp; i += NTHREADS) L.bias[i] = p.bias_pad[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *L.tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      Pipe wp, tp;
+      uint32_t ph = 0;       // parity of tmem_full / dz_full for the current tile
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        if (tile > tile_begin) mbar_wait(L.dz_full(), ph ^ 1u, 10);       // previous tile released the overlay
+        for (int kb = 0; kb < KB; ++kb)
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(L.w_empty(wp.stage), wp.phase ^ 1u, 11);
+            mbar_arrive_expect_tx(L.w_full(wp.stage), (uint32_t)p.NH * 128u);
+            tma_load_2d(L.w_stage(wp.stage), &tmap_w, L.w_full(wp.stage), kb * BK, h * p.NH);
+            wp.advance(W_STAGES);
+          }
+        mbar_wait(L.tmem_full(), ph, 12);                                  // logits done: W ring is dead
+        for (int mb = 0; mb < MB; ++mb)
+          for (int kb = 0; kb < KBG; ++kb) {
+            mbar_wait(L.wt_empty(tp.stage), tp.phase ^ 1u, 13);
+            mbar_arrive_expect_tx(L.wt_full(tp.stage), (uint32_t)WT_STAGE_BYTES);
+            tma_load_2d(L.wt_stage(tp.stage), &tmap_wt, L.wt_full(tp.stage), kb * 64, mb * 128);
+            tp.advance(WT_STAGES);
+          }
+        ph ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      Pipe ap, wp, tp;
+      uint32_t ph = 0;
+      const uint32_t idesc1 = make_idesc_bf16(BM, p.NH);
+      const uint32_t idesc2 = make_idesc_bf16(128, BM);
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        mbar_wait(L.tmem_empty(), ph ^ 1u, 20);
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(L.a_full(ap.stage), ap.phase, 21);
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(L.w_full(wp.stage), wp.phase, 22);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < BK / 16; ++ks)
+              umma_bf16(tmem_base + h * p.NH, make_desc_sw128(L.a_stage(ap.stage) + ks * 32),
+                        make_desc_sw128(L.w_stage(wp.stage) + ks * 32), idesc1, (kb | ks) ? 1u : 0u);
+            umma_commit(L.w_empty(wp.stage));
+            wp.advance(W_STAGES);
+          }
+          umma_commit(L.a_empty(ap.stage));
+          ap.advance(A_STAGES);
+        }
+        umma_commit(L.tmem_full());
+        // ---- P3: dZ^T[mb] (128 d x 128 rows) = W^T[mb] (128 x Vp) . G^T (Vp x 128)
+        mbar_wait(L.g_full(), ph, 23);
+        tc_fence_after();
+        for (int mb = 0; mb < MB; ++mb)
+          for (int kb = 0; kb < KBG; ++kb) {
+            mbar_wait(L.wt_full(tp.stage), tp.phase, 24);
+            tc_fence_after();
+            const int nks = min(4, (p.Vp - kb * 64) / 16);
+            for (int ks = 0; ks < nks; ++ks)
+              umma_bf16(tmem_base + mb * 128, make_desc_sw128(L.wt_stage(tp.stage) + ks * 32),
+                        make_desc_sw128(L.g_kblock(kb) + ks * 32), idesc2, (kb | ks) ? 1u : 0u);
+            umma_commit(L.wt_empty(tp.stage));
+            tp.advance(WT_STAGES);
+          }
+        umma_commit(L.dz_full());
+        ph ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;
+    const int r = q * 32 + lane;               // P2: tile row ; P4: lane of the d block
+    uint32_t ph = 0;
+    float pacc[4][16];                          // d_pred partial sums: [d block][label slot]
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pacc[i][j] = 0.f;
+    int cur_b = -1, cur_ubase = 0;
+    auto flush_pred = [&]() {
+      if (cur_b < 0) return;
+      const int Ub = min(p.u_len[cur_b], p.U1 - 1);
+#pragma unroll
+      for (int mb = 0; mb < 4; ++mb) {
+        if (mb < MB) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int u = cur_ubase + j;
+            if (u <= Ub) atomicAdd(p.d_pred + ((size_t)cur_b * p.U1 + u) * p.D + mb * 128 + r, pacc[mb][j]);
+            pacc[mb][j] = 0.f;
+          }
+        }
+      }
+    };
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int4 ti = p.tiles[tile];
+      const RowMap g = tile_geometry<TILE_RECT>(p, ti);
+      if (g.b != cur_b || g.ubase != cur_ubase) { flush_pred(); cur_b = g.b; cur_ubase = g.ubase; }
+      const size_t row0 = (size_t)ti.w * BM;
+      // ---------------- P2: g = d cost / d logits for row r
+      int t, u;
+      const bool valid = row_cell<TILE_RECT>(p, g, ti, r, t, u);
+      float k_all = kNegInf, k_blank = kNegInf, k_label = kNegInf, scale = 0.f;
+      int lab = -1;
+      if (valid) {
+        const size_t cell = ((size_t)g.b * p.T + t) * p.U1 + u;
+        const float al = p.alpha[cell], be = p.beta[cell], cost = p.costs[g.b], l = p.lse_in[cell];
+        k_all = al + be + cost - l;
+        float bnext = kNegInf;
+        if (t + 1 < g.Tb) bnext = p.beta[cell + p.U1];
+        else if (u == g.Ub) bnext = 0.f;
+        k_blank = al + bnext + cost - l;
+        if (u < g.Ub) { k_label = al + p.beta[cell + 1] + cost - l; lab = p.targets[(size_t)g.b * (p.U1 - 1) + u]; }
+        scale = p.grad_costs[g.b];
+      }
+      mbar_wait(L.tmem_full(), ph, 30);
+      tc_fence_after();
+      for (int c0 = 0; c0 < p.Vp; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float gg[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = c0 + j + e;
+            const float x = v[j + e] + L.bias[col];
+            float gv = ex2_fast((x + k_all) * LOG2E);
+            if (col == p.blank) gv -= ex2_fast((x + k_blank) * LOG2E);
+            if (col == lab) gv -= ex2_fast((x + k_label) * LOG2E);
+            if (p.clamp > 0.f) gv = fminf(fmaxf(gv, -p.clamp), p.clamp);
+            gg[e] = valid ? gv * scale : 0.f;
+          }
+          pk[j >> 1] = pack_bf16(gg[0], gg[1]);
+        }
+        // G tile: k-block c0/64, row r, 16-byte chunks (c0%64)/8 .. +3, 128B swizzle
+        const uint32_t gb = L.g_kblock(c0 >> 6) + r * 128;
+        const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t dst = gb + (((ch0 + i) ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
+                       "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3]) : "memory");
+        }
+        // g^T spill: gt[col][row0 + r] (lanes = consecutive rows -> 64 B per column)
+        unsigned short* gt = reinterpret_cast<unsigned short*>(p.gt) + (size_t)c0 * p.Rpad + row0 + r;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          gt[(size_t)(2 * j) * p.Rpad] = (unsigned short)(pk[j] & 0xffffu);
+          gt[(size_t)(2 * j + 1) * p.Rpad] = (unsigned short)(pk[j] >> 16);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(L.g_full());
+      // ---------------- P4: dH = dZ * (1 - z^2); reductions
+      mbar_wait(L.dz_full(), ph, 31);
+      tc_fence_after();
+#pragma unroll
+      for (int mb = 0; mb < 4; ++mb) {
+        if (mb < MB) {
+          const int d = mb * 128 + r;
+          const __nv_bfloat16* zrow = p.zt + (size_t)d * p.Rpad + row0;
+#pragma unroll
+          for (int tloc = 0; tloc < 8; ++tloc) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + mb * 128 + tloc * 16, v);
+            const uint4 z0 = __ldcg(reinterpret_cast<const uint4*>(zrow + tloc * 16));
+            const uint4 z1 = __ldcg(reinterpret_cast<const uint4*>(zrow + tloc * 16 + 8));
+            tmem_ld_wait();
+            const uint32_t zw[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+            float esum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float za = __uint_as_float(zw[j] << 16), zb = __uint_as_float(zw[j] & 0xffff0000u);
+              const float ha = v[2 * j] * (1.f - za * za), hb = v[2 * j + 1] * (1.f - zb * zb);
+              esum += ha + hb;
+              pacc[mb][2 * j] += ha;
+              pacc[mb][2 * j + 1] += hb;
+            }
+            const int tt = g.t0 + tloc;
+            if (tt < g.Tb) p.d_enc_part[(((size_t)ti.y * p.B + g.b) * p.T + tt) * p.D + d] = esum;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(L.tmem_empty());
+      ph ^= 1u;
+    }
+    flush_pred();
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ A producers (+ d_bias column sums)
+    const int pt = tid - 256;
+    const int r = pt & 127, khalf = pt >> 7;
+    Pipe ap;
+    uint32_t ph = 0;
+    constexpr int NPRE = (SLAB_ROWS_RECT * 16 + PROD_THREADS - 1) / PROD_THREADS;   // 2
+    float4 pre[NPRE];
+    float db0 = 0.f, db1 = 0.f;                  // columns pt and pt + 256
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int4 ti = p.tiles[tile];
+      const RowMap g = tile_geometry<TILE_RECT>(p, ti);
+      const size_t row0 = (size_t)ti.w * BM;
+      int t, u;
+      const bool valid = row_cell<TILE_RECT>(p, g, ti, r, t, u);
+      const int prow = r & 15, erow = 16 + (r >> 4);
+      slab_fetch<NPRE>(p, g, 0, pt, pre);
+      if (tile > tile_begin) mbar_wait(L.dz_full(), ph ^ 1u, 40);          // overlay (G tile / W^T ring) released
+      named_barrier_sync(1, PROD_THREADS);
+      slab_store<NPRE>(L.slab, g, pt, pre);
+      named_barrier_sync(1, PROD_THREADS);
+      for (int kb = 0; kb < KB; ++kb) {
+        if (kb + 1 < KB) slab_fetch<NPRE>(p, g, (kb + 1) * BK, pt, pre);
+        mbar_wait(L.a_empty(ap.stage), ap.phase ^ 1u, 41);
+        produce_a<true>(L.slab, L.a_stage(ap.stage), r, khalf, valid, prow, erow,
+                        p.zt + (size_t)(kb * BK + khalf * 32) * p.Rpad + row0 + r, p.Rpad);
+        fence_proxy_async();
+        mbar_arrive(L.a_full(ap.stage));
+        ap.advance(A_STAGES);
+        if (kb + 1 < KB) {
+          named_barrier_sync(1, PROD_THREADS);
+          slab_store<NPRE>(L.slab, g, pt, pre);
+          named_barrier_sync(1, PROD_THREADS);
+        }
+      }
+      // d_bias: column sums of the bf16 G tile (written by the epilogue warps)
+      mbar_wait(L.g_full(), ph, 42);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col = pt + c * 256;
+        if (col < p.Vp) {
+          const uint32_t gb = L.g_kblock(col >> 6) + (col & 7) * 2;
+          const int ch = (col & 63) >> 3;
+          float acc = 0.f;
+          for (int rr = 0; rr < BM; ++rr) {
+            unsigned short hv;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(gb + rr * 128 + ((ch ^ (rr & 7)) << 4)));
+            acc += __uint_as_float((uint32_t)hv << 16);
+          }
+          if (c == 0) db0 += acc; else db1 += acc;
+        }
+      }
+      ph ^= 1u;
+    }
+    if (pt < p.V && tile_end > tile_begin) atomicAdd(p.d_bias + pt, db0);
+    if (pt + 256 < p.V && tile_end > tile_begin) atomicAdd(p.d_bias + pt + 256, db1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// d_enc[b,t,:] = sum over the u-splits of the partial sums (zero for padded frames)
+__global__ void reduce_denc_kernel(const float* __restrict__ part, const int32_t* __restrict__ t_len,
+                                   const int32_t* __restrict__ u_len, float* __restrict__ d_enc, int B, int T, int U1,
+                                   int D) {
+  const int bt = blockIdx.x;
+  const int b = bt / T, t = bt - b * T;
+  const int Tb = min(t_len[b], T), W = min(u_len[b], U1 - 1) + 1;
+  const int S = (W + 15) >> 4;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float s = 0.f;
+    if (t < Tb)
+      for (int i = 0; i < S; ++i) s += part[(((size_t)i * B + b) * T + t) * D + d];
+    d_enc[((size_t)b * T + t) * D + d] = s;
+  }
+}
+
+// =================================================================================================
+// Backward kernel 2: dW^T[d][v] = sum_rows z^T[d][row] * g^T[v][row]  (plain TMA-fed tcgen05 GEMM, split-K)
+// =================================================================================================
+constexpr int DW_STAGES = 3;
+constexpr int DW_THREADS = 256;
+
+__global__ void __launch_bounds__(DW_THREADS, 1)
+dw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_zt, const __grid_constant__ CUtensorMap tmap_gt,
+               const int* __restrict__ ntiles_ptr, float* __restrict__ partials, int D, int Vp, int NH, int KS) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  const uint32_t al = (base + 1023u) & ~1023u;
+  const uint32_t stage_bytes = A_STAGE_BYTES + 2 * NH * 128;
+  const uint32_t bar = al + DW_STAGES * stage_bytes;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem_raw + (bar + 128 - base));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mb = blockIdx.x, ks = blockIdx.y;
+  const int kblocks = (*ntiles_ptr) * 2;                      // 64-row k-blocks actually written by kernel 1
+  const int kb_begin = (int)(((long)kblocks * ks) / KS), kb_end = (int)(((long)kblocks * (ks + 1)) / KS);
+  auto full = [&](int i) { return bar + i * 16; };
+  auto empty = [&](int i) { return bar + i * 16 + 8; };
+  const uint32_t done = bar + DW_STAGES * 16;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_zt);
+    tma_prefetch_desc(&tmap_gt);
+    for (int i = 0; i < DW_STAGES; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_ptr), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      Pipe sp;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(empty(sp.stage), sp.phase ^ 1u, 50);
+        const uint32_t st = al + sp.stage * stage_bytes;
+        mbar_arrive_expect_tx(full(sp.stage), stage_bytes);
+        tma_load_2d(st, &tmap_zt, full(sp.stage), kb * 64, mb * 128);
+        tma_load_2d(st + A_STAGE_BYTES, &tmap_gt, full(sp.stage), kb * 64, 0);
+        tma_load_2d(st + A_STAGE_BYTES + NH * 128, &tmap_gt, full(sp.stage), kb * 64, NH);
+        sp.advance(DW_STAGES);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      Pipe sp;
+      const uint32_t idesc = make_idesc_bf16(128, NH);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(full(sp.stage), sp.phase, 51);
+        tc_fence_after();
+        const uint32_t st = al + sp.stage * stage_bytes;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_bf16(tmem_base + h * NH, make_desc_sw128(st + k4 * 32),
+                      make_desc_sw128(st + A_STAGE_BYTES + h * NH * 128 + k4 * 32), idesc,
+                      (kb > kb_begin || k4 > 0) ? 1u : 0u);
+        umma_commit(empty(sp.stage));
+        sp.advance(DW_STAGES);
+      }
+      umma_commit(done);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int d = mb * 128 + q * 32 + lane;
+    float* out = partials + ((size_t)ks * D + d) * Vp;
+    if (kb_end > kb_begin) {
+      mbar_wait(done, 0, 52);
+      tc_fence_after();
+      for (int c0 = 0; c0 < Vp; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        if (d < D) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+    } else if (d < D) {
+      for (int c0 = 0; c0 < Vp; c0 += 4) *reinterpret_cast<float4*>(out + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// d_w[v][d] = sum_ks partials[ks][d][v]
+__global__ void reduce_dw_kernel(const float* __restrict__ partials, float* __restrict__ d_w, int D, int V, int Vp,
+                                 int KS) {
+  __shared__ float tile[32][33];
+  const int d0 = blockIdx.x * 32, v0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int d = d0 + i, v = v0 + tx;
+    float s = 0.f;
+    if (d < D && v < Vp)
+      for (int k = 0; k < KS; ++k) s += partials[((size_t)k * D + d) * Vp + v];
+    tile[i][tx] = s;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int v = v0 + i, d = d0 + tx;
+    if (v < V && d < D) d_w[(size_t)v * D + d] = tile[tx][i];
+  }
+}
+
+// =================================================================================================
 // Helper kernels: weight conversion, tile tables
 // =================================================================================================
 // wb [Vp][D] bf16 (zero rows beyond V), wtb [D][Vp] bf16 (optional), bias_pad [Vp] (-inf beyond V)
@@ -574,14 +1070,98 @@ int joint_bwd_f32(const float*, const float*, const float*, const float*, const 
                   const int32_t*, const float*, const float*, const float*, const float*, const float*, float, float*,
                   float*, float*, float*, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 
-// TEMPORARY (until the tcgen05 backward lands): the bf16 path's backward runs the fp32 kernels.
-size_t joint_bwd_tc_ws_bytes(int B, int T, int U1, int D, int V) { return joint_bwd_f32_ws_bytes(B, T, U1, D, V); }
+static bool joint_tc_bwd_supported(int U1, int D, int V) {
+  return joint_tc_supported(U1, D, V) && D % 128 == 0 && D <= 512;
+}
+
+struct BwdWs {
+  __nv_bfloat16 *wb, *wtb, *zt, *gt;
+  float *bias_pad, *d_enc_part, *partials;
+  int4* tiles;
+  int* ntiles;
+  long Rpad;
+  int KS, S_max;
+  size_t bytes;
+};
+static BwdWs carve_bwd_ws(void* ws, int B, int T, int U1, int D, int V) {
+  const int Vp = pad_v(V);
+  uint8_t* p = reinterpret_cast<uint8_t*>(ws);
+  size_t off = 0;
+  BwdWs w;
+  const int mt = max_tiles_rect(B, T, U1);
+  w.Rpad = (long)mt * BM;
+  w.S_max = (U1 + 15) / 16;
+  const int MB = D / 128;
+  w.KS = MB > 0 ? sm_count() / MB : 1;
+  if (w.KS < 1) w.KS = 1;
+  auto take = [&](size_t n) { void* r = p + off; off = align_up(off + n, 1024); return r; };
+  w.wb = reinterpret_cast<__nv_bfloat16*>(take((size_t)Vp * D * 2));
+  w.wtb = reinterpret_cast<__nv_bfloat16*>(take((size_t)Vp * D * 2));
+  w.bias_pad = reinterpret_cast<float*>(take((size_t)Vp * 4));
+  w.tiles = reinterpret_cast<int4*>(take((size_t)mt * 16));
+  w.ntiles = reinterpret_cast<int*>(take(4));
+  w.zt = reinterpret_cast<__nv_bfloat16*>(take((size_t)D * w.Rpad * 2));
+  w.gt = reinterpret_cast<__nv_bfloat16*>(take((size_t)Vp * w.Rpad * 2));
+  w.d_enc_part = reinterpret_cast<float*>(take((size_t)w.S_max * B * T * D * 4));
+  w.partials = reinterpret_cast<float*>(take((size_t)w.KS * D * Vp * 4));
+  w.bytes = off;
+  return w;
+}
+
+size_t joint_bwd_tc_ws_bytes(int B, int T, int U1, int D, int V) {
+  if (!joint_tc_bwd_supported(U1, D, V)) return joint_bwd_f32_ws_bytes(B, T, U1, D, V);
+  return carve_bwd_ws(nullptr, B, T, U1, D, V).bytes;
+}
+
 int joint_bwd_tc(const float* enc, const float* pred, const float* w, const float* bias, const int32_t* targets,
                  const int32_t* t_len, const int32_t* u_len, const float* lse, const float* alpha, const float* beta,
                  const float* costs, const float* grad_costs, float clamp, float* d_enc, float* d_pred, float* d_w,
                  float* d_b, int B, int T, int U1, int D, int V, int blank, void* ws, size_t ws_bytes, cudaStream_t st) {
-  return joint_bwd_f32(enc, pred, w, bias, targets, t_len, u_len, lse, alpha, beta, costs, grad_costs, clamp, d_enc,
-                       d_pred, d_w, d_b, B, T, U1, D, V, blank, ws, ws_bytes, st);
+  if (!joint_tc_bwd_supported(U1, D, V))   // shapes outside the tensor-core tiling use the fp32 kernels (same GPU)
+    return joint_bwd_f32(enc, pred, w, bias, targets, t_len, u_len, lse, alpha, beta, costs, grad_costs, clamp, d_enc,
+                         d_pred, d_w, d_b, B, T, U1, D, V, blank, ws, ws_bytes, st);
+  CTCVR_REQUIRE(ws && ws_bytes >= joint_bwd_tc_ws_bytes(B, T, U1, D, V), "joint_rnnt_bwd bf16: workspace too small");
+  const int Vp = pad_v(V), NH = Vp / 2, MB = D / 128;
+  BwdWs W = carve_bwd_ws(ws, B, T, U1, D, V);
+  prep_weights_kernel<<<cdiv((long)Vp * D, 256), 256, 0, st>>>(w, bias, W.wb, W.wtb, W.bias_pad, V, Vp, D);
+  CTCVR_LAUNCH_CHECK();
+  const int mt = max_tiles_rect(B, T, U1);
+  build_tiles_kernel<<<1, 256, 0, st>>>(t_len, u_len, B, T, U1, 1, W.tiles, W.ntiles, mt);
+  CTCVR_LAUNCH_CHECK();
+  CTCVR_CHECK_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)B * U1 * D * sizeof(float), st));
+  CTCVR_CHECK_CUDA(cudaMemsetAsync(d_b, 0, (size_t)V * sizeof(float), st));
+  CUtensorMap tmap_w, tmap_wt, tmap_zt, tmap_gt;
+  if (make_tmap_bf16_2d(&tmap_w, W.wb, Vp, D, D, NH)) return 1;
+  if (make_tmap_bf16_2d(&tmap_wt, W.wtb, D, Vp, Vp, 128)) return 1;
+  if (make_tmap_bf16_2d(&tmap_zt, W.zt, D, W.Rpad, W.Rpad, 128)) return 1;
+  if (make_tmap_bf16_2d(&tmap_gt, W.gt, Vp, W.Rpad, W.Rpad, NH)) return 1;
+  TcParams p{};
+  p.enc = enc; p.pred = pred; p.bias_pad = W.bias_pad; p.targets = targets; p.t_len = t_len; p.u_len = u_len;
+  p.tiles = W.tiles; p.ntiles = W.ntiles;
+  p.B = B; p.T = T; p.U1 = U1; p.D = D; p.V = V; p.Vp = Vp; p.NH = NH; p.blank = blank;
+  p.lse_in = lse; p.alpha = alpha; p.beta = beta; p.costs = costs; p.grad_costs = grad_costs; p.clamp = clamp;
+  p.zt = W.zt; p.gt = W.gt; p.Rpad = W.Rpad; p.d_enc_part = W.d_enc_part; p.d_pred = d_pred; p.d_bias = d_b;
+  p.S_max = W.S_max;
+  {
+    size_t smem = bwd_smem_bytes(NH, Vp);
+    CTCVR_REQUIRE(smem <= 232448, "joint_rnnt_bwd bf16: shared memory budget exceeded (%zu B)", smem);
+    CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = min(sm_count(), mt);
+    joint_bwd_tc_kernel<<<grid, NTHREADS, smem, st>>>(tmap_w, tmap_wt, p);
+    CTCVR_LAUNCH_CHECK();
+  }
+  reduce_denc_kernel<<<B * T, 128, 0, st>>>(W.d_enc_part, t_len, u_len, d_enc, B, T, U1, D);
+  CTCVR_LAUNCH_CHECK();
+  {
+    size_t smem = 1024 + (size_t)DW_STAGES * (A_STAGE_BYTES + 2 * NH * 128) + 256;
+    CTCVR_REQUIRE(smem <= 232448, "dW GEMM: shared memory budget exceeded (%zu B)", smem);
+    CTCVR_CHECK_CUDA(cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dw_gemm_kernel<<<dim3(MB, W.KS), DW_THREADS, smem, st>>>(tmap_zt, tmap_gt, W.ntiles, W.partials, D, Vp, NH, W.KS);
+    CTCVR_LAUNCH_CHECK();
+  }
+  reduce_dw_kernel<<<dim3(cdiv(D, 32), cdiv(Vp, 32)), 256, 0, st>>>(W.partials, d_w, D, V, Vp, W.KS);
+  CTCVR_LAUNCH_CHECK();
+  return 0;
 }
 
 unsigned int tc_error_flag() {
