@@ -36,6 +36,16 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
 enum { TILE_FLAT = 0, TILE_RECT = 1 };
+constexpr int PROF_CAP = 2048;
+// timeline probe for CTA 0 (one lane per role); compiled in always, active only when p.prof != nullptr
+#define TC_PROF(role, tag)                                                                         \
+  do {                                                                                             \
+    if (p.prof != nullptr && blockIdx.x == 0) {                                                    \
+      int _n = prof_n++;                                                                           \
+      if (_n < PROF_CAP) p.prof[(role)*PROF_CAP + _n] = ((long long)(tag) << 48) | (clock64() & 0xffffffffffffLL); \
+    }                                                                                              \
+  } while (0)
+
 
 struct TcParams {
   const float* enc;        // [B,T,D] fp32
@@ -66,6 +76,7 @@ struct TcParams {
   float* d_pred;           // [B,U1,D] (atomic accumulate)
   float* d_bias;           // [Vp] (atomic accumulate)
   int S_max;
+  long long* prof;   // optional timeline buffer (debug): [4 roles][PROF_CAP] of (tag<<48 | clock)
 };
 
 struct RowMap {
@@ -74,6 +85,11 @@ struct RowMap {
   int ubase;     // first label column covered by the tile's pred slab rows
   int np, ne;    // slab rows holding pred / enc vectors
 };
+
+// Opaque identity: stops the compiler from re-deriving a per-tile value from global memory inside the
+// k-block loops (it otherwise rematerialises the tile-table / length loads there, a chain of two L2
+// round trips in front of every operand fetch).
+__device__ __forceinline__ void pin(int& x) { asm volatile("" : "+r"(x)); }
 
 // ---- tile geometry ---------------------------------------------------------------------------
 template <int TILE>
@@ -99,6 +115,7 @@ __device__ __forceinline__ RowMap tile_geometry(const TcParams& p, int4 ti) {
     g.np = 16;
     g.ne = 8;
   }
+  pin(g.b); pin(g.Tb); pin(g.Ub); pin(g.W); pin(g.t0); pin(g.ubase); pin(g.np); pin(g.ne);
   return g;
 }
 
@@ -268,10 +285,12 @@ joint_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p
     // ------------------------------------------------------------------ TMA producer (W_out)
     if (lane == 0) {
       Pipe wp;
+      int prof_n = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
         for (int kb = 0; kb < KB; ++kb)
           for (int h = 0; h < 2; ++h) {
             mbar_wait(L.w_empty(wp.stage), wp.phase ^ 1u, 1);
+            TC_PROF(0, kb * 2 + h);
             mbar_arrive_expect_tx(L.w_full(wp.stage), (uint32_t)p.NH * 128u);
             tma_load_2d(L.w_stage(wp.stage), &tmap_w, L.w_full(wp.stage), kb * BK, h * p.NH);
             wp.advance(W_STAGES);
@@ -283,14 +302,19 @@ joint_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p
     if (lane == 0) {
       Pipe ap, wp;
       uint32_t tphase = 0;
+      int prof_n = 0;
       const uint32_t idesc = make_idesc_bf16(BM, p.NH);
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        TC_PROF(1, 100);
         mbar_wait(L.tmem_empty(), tphase ^ 1u, 2);
+        TC_PROF(1, 101);
         tc_fence_after();
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(L.a_full(ap.stage), ap.phase, 3);
+          TC_PROF(1, kb);
           for (int h = 0; h < 2; ++h) {
             mbar_wait(L.w_full(wp.stage), wp.phase, 4);
+            TC_PROF(1, 50 + kb * 2 + h);
             tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < BK / 16; ++ks) {
@@ -314,37 +338,48 @@ joint_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p
     const int q = warp & 3;
     const int r = q * 32 + lane;
     uint32_t tphase = 0;
+    int prof_n = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int4 ti = p.tiles[tile];
+      int4 ti = p.tiles[tile];
+      pin(ti.x); pin(ti.y); pin(ti.z); pin(ti.w);
       const RowMap g = tile_geometry<TILE_FLAT>(p, ti);
       int t, u;
       const bool valid = row_cell<TILE_FLAT>(p, g, ti, r, t, u);
       int lab = -1;
       if (valid && u < g.Ub) lab = p.targets[(size_t)g.b * (p.U1 - 1) + u];
       mbar_wait(L.tmem_full(), tphase, 5);
+      if (tid == 128) TC_PROF(2, 1);
       tc_fence_after();
       float m = kNegInf, s = 0.f, xb = 0.f, xl = 0.f;
       for (int c0 = 0; c0 < p.Vp; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
         tmem_ld_wait();
-        float cm = kNegInf;
+        float cm[4] = {kNegInf, kNegInf, kNegInf, kNegInf};
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] += L.bias[c0 + j];
-          cm = fmaxf(cm, v[j]);
-          xb = (c0 + j == p.blank) ? v[j] : xb;
-          xl = (c0 + j == lab) ? v[j] : xl;
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bj = *reinterpret_cast<const float4*>(L.bias + c0 + j);
+          v[j] += bj.x; v[j + 1] += bj.y; v[j + 2] += bj.z; v[j + 3] += bj.w;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            cm[e] = fmaxf(cm[e], v[j + e]);
+            xb = (c0 + j + e == p.blank) ? v[j + e] : xb;
+            xl = (c0 + j + e == lab) ? v[j + e] : xl;
+          }
         }
-        const float nm = fmaxf(m, cm);
-        float acc = 0.f;
+        const float nm = fmaxf(m, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
+        const float nml = nm * LOG2E;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc += ex2_fast((v[j] - nm) * LOG2E);
-        s = s * ex2_fast((m - nm) * LOG2E) + acc;
+        for (int j = 0; j < 32; j += 4)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[e] += ex2_fast(fmaf(v[j + e], LOG2E, -nml));
+        s = s * ex2_fast((m - nm) * LOG2E) + ((acc[0] + acc[1]) + (acc[2] + acc[3]));
         m = nm;
       }
       tc_fence_before();
       mbar_arrive(L.tmem_empty());
+      if (tid == 128) TC_PROF(2, 2);
       if (valid) {
         const size_t cell = ((size_t)g.b * p.T + t) * p.U1 + u;
         const float l = m + __logf(s);
@@ -359,29 +394,38 @@ joint_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p
     const int pt = tid - 256;
     const int r = pt & 127, khalf = pt >> 7;
     Pipe ap;
+    int prof_n = 0;
     constexpr int NPRE = (SLAB_ROWS_FLAT * 16 + PROD_THREADS - 1) / PROD_THREADS;   // 9
     float4 pre[NPRE];
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int4 ti = p.tiles[tile];
+      int4 ti = p.tiles[tile];
+      pin(ti.x); pin(ti.y); pin(ti.z); pin(ti.w);
       const RowMap g = tile_geometry<TILE_FLAT>(p, ti);
       int t, u;
       const bool valid = row_cell<TILE_FLAT>(p, g, ti, r, t, u);
       const int prow = u - g.ubase, erow = g.np + (t - g.t0);
+      if (pt == 0) TC_PROF(3, 200);
       slab_fetch<NPRE>(p, g, 0, pt, pre);
       named_barrier_sync(1, PROD_THREADS);             // previous tile's last slab fully consumed
       slab_store<NPRE>(L.slab, g, pt, pre);
       named_barrier_sync(1, PROD_THREADS);
+      if (pt == 0) TC_PROF(3, 201);
       for (int kb = 0; kb < KB; ++kb) {
         if (kb + 1 < KB) slab_fetch<NPRE>(p, g, (kb + 1) * BK, pt, pre);
         mbar_wait(L.a_empty(ap.stage), ap.phase ^ 1u, 6);
+        if (pt == 0) TC_PROF(3, kb);
         produce_a<false>(L.slab, L.a_stage(ap.stage), r, khalf, valid, prow, erow, nullptr, 0);
+        if (pt == 0) TC_PROF(3, 20 + kb);
         fence_proxy_async();
         mbar_arrive(L.a_full(ap.stage));
+        if (pt == 0) TC_PROF(3, 40 + kb);
         ap.advance(A_STAGES);
         if (kb + 1 < KB) {
           named_barrier_sync(1, PROD_THREADS);
+          if (pt == 0) TC_PROF(3, 60 + kb);
           slab_store<NPRE>(L.slab, g, pt, pre);
           named_barrier_sync(1, PROD_THREADS);
+          if (pt == 0) TC_PROF(3, 80 + kb);
         }
       }
     }
@@ -502,9 +546,12 @@ joint_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       Pipe wp, tp;
+      int prof_n = 0;
       uint32_t ph = 0;       // parity of tmem_full / dz_full for the current tile
       for (int tile = tile_begin; tile < tile_end; ++tile) {
+        TC_PROF(0, 1);
         if (tile > tile_begin) mbar_wait(L.dz_full(), ph ^ 1u, 10);       // previous tile released the overlay
+        TC_PROF(0, 2);
         for (int kb = 0; kb < KB; ++kb)
           for (int h = 0; h < 2; ++h) {
             mbar_wait(L.w_empty(wp.stage), wp.phase ^ 1u, 11);
@@ -512,7 +559,9 @@ joint_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
             tma_load_2d(L.w_stage(wp.stage), &tmap_w, L.w_full(wp.stage), kb * BK, h * p.NH);
             wp.advance(W_STAGES);
           }
+        TC_PROF(0, 3);
         mbar_wait(L.tmem_full(), ph, 12);                                  // logits done: W ring is dead
+        TC_PROF(0, 4);
         for (int mb = 0; mb < MB; ++mb)
           for (int kb = 0; kb < KBG; ++kb) {
             mbar_wait(L.wt_empty(tp.stage), tp.phase ^ 1u, 13);
@@ -520,6 +569,7 @@ joint_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
             tma_load_2d(L.wt_stage(tp.stage), &tmap_wt, L.wt_full(tp.stage), kb * 64, mb * 128);
             tp.advance(WT_STAGES);
           }
+        TC_PROF(0, 5);
         ph ^= 1u;
       }
     }
@@ -528,11 +578,14 @@ joint_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       Pipe ap, wp, tp;
+      int prof_n = 0;
       uint32_t ph = 0;
       const uint32_t idesc1 = make_idesc_bf16(BM, p.NH);
       const uint32_t idesc2 = make_idesc_bf16(128, BM);
       for (int tile = tile_begin; tile < tile_end; ++tile) {
+        TC_PROF(1, 1);
         mbar_wait(L.tmem_empty(), ph ^ 1u, 20);
+        TC_PROF(1, 2);
         tc_fence_after();
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(L.a_full(ap.stage), ap.phase, 21);
@@ -550,8 +603,10 @@ joint_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
           ap.advance(A_STAGES);
         }
         umma_commit(L.tmem_full());
+        TC_PROF(1, 3);
         // ---- P3: dZ^T[mb] (128 d x 128 rows) = W^T[mb] (128 x Vp) . G^T (Vp x 128)
         mbar_wait(L.g_full(), ph, 23);
+        TC_PROF(1, 4);
         tc_fence_after();
         for (int mb = 0; mb < MB; ++mb)
           for (int kb = 0; kb < KBG; ++kb) {
@@ -565,6 +620,7 @@ joint_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
             tp.advance(WT_STAGES);
           }
         umma_commit(L.dz_full());
+        TC_PROF(1, 5);
         ph ^= 1u;
       }
     }
@@ -574,6 +630,7 @@ joint_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     const int q = warp & 3;
     const int r = q * 32 + lane;               // P2: tile row ; P4: lane of the d block
     uint32_t ph = 0;
+    int prof_n = 0;
     float pacc[4][16];                          // d_pred partial sums: [d block][label slot]
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -596,7 +653,8 @@ joint_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
       }
     };
     for (int tile = tile_begin; tile < tile_end; ++tile) {
-      const int4 ti = p.tiles[tile];
+      int4 ti = p.tiles[tile];
+      pin(ti.x); pin(ti.y); pin(ti.z); pin(ti.w);
       const RowMap g = tile_geometry<TILE_RECT>(p, ti);
       if (g.b != cur_b || g.ubase != cur_ubase) { flush_pred(); cur_b = g.b; cur_ubase = g.ubase; }
       const size_t row0 = (size_t)ti.w * BM;
@@ -616,12 +674,15 @@ joint_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
         if (u < g.Ub) { k_label = al + p.beta[cell + 1] + cost - l; lab = p.targets[(size_t)g.b * (p.U1 - 1) + u]; }
         scale = p.grad_costs[g.b];
       }
+      if (tid == 128) TC_PROF(2, 1);
       mbar_wait(L.tmem_full(), ph, 30);
+      if (tid == 128) TC_PROF(2, 2);
       tc_fence_after();
       for (int c0 = 0; c0 < p.Vp; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
         tmem_ld_wait();
+        if (tid == 128) TC_PROF(2, 10);
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
@@ -638,6 +699,7 @@ joint_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
           }
           pk[j >> 1] = pack_bf16(gg[0], gg[1]);
         }
+        if (tid == 128) TC_PROF(2, 11);
         // G tile: k-block c0/64, row r, 16-byte chunks (c0%64)/8 .. +3, 128B swizzle
         const uint32_t gb = L.g_kblock(c0 >> 6) + r * 128;
         const int ch0 = (c0 & 63) >> 3;
@@ -654,42 +716,55 @@ joint_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
           gt[(size_t)(2 * j) * p.Rpad] = (unsigned short)(pk[j] & 0xffffu);
           gt[(size_t)(2 * j + 1) * p.Rpad] = (unsigned short)(pk[j] >> 16);
         }
+        if (tid == 128) TC_PROF(2, 12);
       }
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(L.g_full());
+      if (tid == 128) TC_PROF(2, 3);
       // ---------------- P4: dH = dZ * (1 - z^2); reductions
       mbar_wait(L.dz_full(), ph, 31);
+      if (tid == 128) TC_PROF(2, 4);
       tc_fence_after();
 #pragma unroll
       for (int mb = 0; mb < 4; ++mb) {
         if (mb < MB) {
           const int d = mb * 128 + r;
-          const __nv_bfloat16* zrow = p.zt + (size_t)d * p.Rpad + row0;
+          const uint4* zrow = reinterpret_cast<const uint4*>(p.zt + (size_t)d * p.Rpad + row0);
+          uint4 zn0 = __ldcg(zrow), zn1 = __ldcg(zrow + 1);
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + mb * 128, v);
 #pragma unroll
           for (int tloc = 0; tloc < 8; ++tloc) {
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + mb * 128 + tloc * 16, v);
-            const uint4 z0 = __ldcg(reinterpret_cast<const uint4*>(zrow + tloc * 16));
-            const uint4 z1 = __ldcg(reinterpret_cast<const uint4*>(zrow + tloc * 16 + 8));
+            const uint4 z0 = zn0, z1 = zn1;
             tmem_ld_wait();
+            float w[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = v[j];
+            if (tloc < 7) {      // software pipeline: next frame slot's z row and TMEM columns are in flight
+              zn0 = __ldcg(zrow + 2 * (tloc + 1));
+              zn1 = __ldcg(zrow + 2 * (tloc + 1) + 1);
+              tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + mb * 128 + (tloc + 1) * 16, v);
+            }
             const uint32_t zw[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
-            float esum = 0.f;
+            float es0 = 0.f, es1 = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float za = __uint_as_float(zw[j] << 16), zb = __uint_as_float(zw[j] & 0xffff0000u);
-              const float ha = v[2 * j] * (1.f - za * za), hb = v[2 * j + 1] * (1.f - zb * zb);
-              esum += ha + hb;
+              const float ha = w[2 * j] * fmaf(-za, za, 1.f), hb = w[2 * j + 1] * fmaf(-zb, zb, 1.f);
+              es0 += ha;
+              es1 += hb;
               pacc[mb][2 * j] += ha;
               pacc[mb][2 * j + 1] += hb;
             }
             const int tt = g.t0 + tloc;
-            if (tt < g.Tb) p.d_enc_part[(((size_t)ti.y * p.B + g.b) * p.T + tt) * p.D + d] = esum;
+            if (tt < g.Tb) p.d_enc_part[(((size_t)ti.y * p.B + g.b) * p.T + tt) * p.D + d] = es0 + es1;
           }
         }
       }
       tc_fence_before();
       mbar_arrive(L.tmem_empty());
+      if (tid == 128) TC_PROF(2, 5);
       ph ^= 1u;
     }
     flush_pred();
@@ -699,18 +774,22 @@ joint_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     const int r = pt & 127, khalf = pt >> 7;
     Pipe ap;
     uint32_t ph = 0;
+    int prof_n = 0;
     constexpr int NPRE = (SLAB_ROWS_RECT * 16 + PROD_THREADS - 1) / PROD_THREADS;   // 2
     float4 pre[NPRE];
     float db0 = 0.f, db1 = 0.f;                  // columns pt and pt + 256
     for (int tile = tile_begin; tile < tile_end; ++tile) {
-      const int4 ti = p.tiles[tile];
+      int4 ti = p.tiles[tile];
+      pin(ti.x); pin(ti.y); pin(ti.z); pin(ti.w);
       const RowMap g = tile_geometry<TILE_RECT>(p, ti);
       const size_t row0 = (size_t)ti.w * BM;
       int t, u;
       const bool valid = row_cell<TILE_RECT>(p, g, ti, r, t, u);
       const int prow = r & 15, erow = 16 + (r >> 4);
+      if (pt == 0) TC_PROF(3, 1);
       slab_fetch<NPRE>(p, g, 0, pt, pre);
-      if (tile > tile_begin) mbar_wait(L.dz_full(), ph ^ 1u, 40);          // overlay (G tile / W^T ring) released
+      if (tile > tile_begin) mbar_wait(L.dz_full(), ph ^ 1u, 40);
+      if (pt == 0) TC_PROF(3, 2);          // overlay (G tile / W^T ring) released
       named_barrier_sync(1, PROD_THREADS);
       slab_store<NPRE>(L.slab, g, pt, pre);
       named_barrier_sync(1, PROD_THREADS);
@@ -729,7 +808,9 @@ joint_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
         }
       }
       // d_bias: column sums of the bf16 G tile (written by the epilogue warps)
+      if (pt == 0) TC_PROF(3, 3);
       mbar_wait(L.g_full(), ph, 42);
+      if (pt == 0) TC_PROF(3, 4);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int col = pt + c * 256;
@@ -745,6 +826,7 @@ joint_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
           if (c == 0) db0 += acc; else db1 += acc;
         }
       }
+      if (pt == 0) TC_PROF(3, 5);
       ph ^= 1u;
     }
     if (pt < p.V && tile_end > tile_begin) atomicAdd(p.d_bias + pt, db0);
@@ -993,6 +1075,7 @@ static int check_tc_error(const char* where) {
 // =================================================================================================
 using namespace tc;
 
+static long long* g_prof_buf = nullptr;
 static int pad_v(int V) { return (V + 31) / 32 * 32; }
 static int max_tiles_flat(int B, int T, int U1) { return B * (int)(((long)T * U1 + BM - 1) / BM); }
 static int max_tiles_rect(int B, int T, int U1) { return B * ((U1 + 15) / 16) * ((T + 7) / 8); }
@@ -1055,6 +1138,7 @@ int joint_fwd_tc(const float* enc, const float* pred, const float* w, const floa
   p.tiles = W.tiles; p.ntiles = W.ntiles;
   p.B = B; p.T = T; p.U1 = U1; p.D = D; p.V = V; p.Vp = Vp; p.NH = NH; p.blank = blank;
   p.lse = lse; p.lp_blank = lp_blank; p.lp_label = lp_label;
+  p.prof = g_prof_buf;
   size_t smem = tc_smem_bytes(NH, Vp, SLAB_ROWS_FLAT);
   CTCVR_REQUIRE(smem <= 232448, "joint_rnnt_fwd bf16: shared memory budget exceeded (%zu B)", smem);
   CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1142,6 +1226,7 @@ int joint_bwd_tc(const float* enc, const float* pred, const float* w, const floa
   p.lse_in = lse; p.alpha = alpha; p.beta = beta; p.costs = costs; p.grad_costs = grad_costs; p.clamp = clamp;
   p.zt = W.zt; p.gt = W.gt; p.Rpad = W.Rpad; p.d_enc_part = W.d_enc_part; p.d_pred = d_pred; p.d_bias = d_b;
   p.S_max = W.S_max;
+  p.prof = g_prof_buf;
   {
     size_t smem = bwd_smem_bytes(NH, Vp);
     CTCVR_REQUIRE(smem <= 232448, "joint_rnnt_bwd bf16: shared memory budget exceeded (%zu B)", smem);
@@ -1163,6 +1248,8 @@ int joint_bwd_tc(const float* enc, const float* pred, const float* w, const floa
   CTCVR_LAUNCH_CHECK();
   return 0;
 }
+
+void tc_set_prof(void* buf) { g_prof_buf = reinterpret_cast<long long*>(buf); }
 
 unsigned int tc_error_flag() {
   unsigned int v = 0;

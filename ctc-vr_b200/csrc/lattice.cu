@@ -18,6 +18,14 @@ namespace ctcvr {
 
 constexpr int LAT_THREADS = 128;
 
+// log(exp(a)+exp(b)) on the MUFU fast path (ex2/lg2.approx): the wavefront is a chain of T+U dependent
+// steps, so the latency of this function IS the kernel time.  Absolute error ~1e-7 per step.
+__device__ __forceinline__ float lae_fast(float a, float b) {
+  const float m = fmaxf(a, b);
+  const float r = m + __logf(1.f + __expf(-fabsf(a - b)));
+  return (m == kNegInf) ? kNegInf : r;
+}
+
 template <int NJ>
 __global__ void __launch_bounds__(LAT_THREADS) rnnt_lattice_kernel(
     const float* __restrict__ lp_blank, const float* __restrict__ lp_label, const int32_t* __restrict__ t_len,
@@ -55,24 +63,34 @@ __global__ void __launch_bounds__(LAT_THREADS) rnnt_lattice_kernel(
   if (warp == 0) {
     // ---------------- alpha: alpha(t,u) = LSE(alpha(t-1,u)+lpb(t-1,u), alpha(t,u-1)+lpl(t,u-1))
     float* ab = alpha + base;
+    // log-probs needed by the NEXT diagonal are fetched from smem before the dependent chain of this one
+    float nb[NJ], nl[NJ];
+    auto fetch_a = [&](int d) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int u = lane + 32 * j, t = d - u;
+        const bool ok = (u <= Ub && t >= 0 && t < Tb);
+        nb[j] = (ok && t > 0) ? sb[(t - 1) * sp + u] : kNegInf;
+        nl[j] = (ok && u > 0) ? sl[t * sp + u - 1] : kNegInf;
+      }
+    };
+    fetch_a(0);
     for (int d = 0; d < ndiag; ++d) {
+      float cb[NJ], cl[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { cb[j] = nb[j]; cl[j] = nl[j]; }
+      if (d + 1 < ndiag) fetch_a(d + 1);
       float cur[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int u = lane + 32 * j;
         const int t = d - u;
-        // value of column u-1 on the previous diagonal (same t)
         float left = __shfl_up_sync(0xffffffffu, prev[j], 1);
         float wrap = __shfl_sync(0xffffffffu, prev[j > 0 ? j - 1 : 0], 31);
         if (lane == 0) left = (j > 0) ? wrap : kNegInf;
         float v = kNegInf;
         if (u <= Ub && t >= 0 && t < Tb) {
-          if (d == 0) v = 0.f;
-          else {
-            float a = (t > 0) ? prev[j] + sb[(t - 1) * sp + u] : kNegInf;
-            float c = (u > 0) ? left + sl[t * sp + u - 1] : kNegInf;
-            v = log_add_exp(a, c);
-          }
+          v = (d == 0) ? 0.f : lae_fast(prev[j] + cb[j], left + cl[j]);
           ab[t * U1 + u] = v;
         }
         cur[j] = v;
@@ -83,24 +101,36 @@ __global__ void __launch_bounds__(LAT_THREADS) rnnt_lattice_kernel(
   } else {
     // ---------------- beta: beta(t,u) = LSE(beta(t+1,u)+lpb(t,u), beta(t,u+1)+lpl(t,u))
     float* bb = beta + base;
+    float nb[NJ], nl[NJ];
+    auto fetch_b = [&](int d) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int u = lane + 32 * j, t = d - u;
+        const bool ok = (u <= Ub && t >= 0 && t < Tb);
+        nb[j] = ok ? sb[t * sp + u] : kNegInf;
+        nl[j] = (ok && u < Ub) ? sl[t * sp + u] : kNegInf;
+      }
+    };
+    fetch_b(ndiag - 1);
     for (int d = ndiag - 1; d >= 0; --d) {
+      float cb[NJ], cl[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { cb[j] = nb[j]; cl[j] = nl[j]; }
+      if (d > 0) fetch_b(d - 1);
       float cur[NJ];
 #pragma unroll
       for (int j = NJ - 1; j >= 0; --j) {
         const int u = lane + 32 * j;
         const int t = d - u;
-        // value of column u+1 on the previous (d+1) diagonal (same t)
         float right = __shfl_down_sync(0xffffffffu, prev[j], 1);
         float wrap = __shfl_sync(0xffffffffu, prev[(j + 1 < NJ) ? j + 1 : j], 0);
         if (lane == 31) right = (j + 1 < NJ) ? wrap : kNegInf;
         float v = kNegInf;
         if (u <= Ub && t >= 0 && t < Tb) {
-          float lb = sb[t * sp + u];
-          if (t == Tb - 1 && u == Ub) v = lb;
+          if (t == Tb - 1 && u == Ub) v = cb[j];
           else {
-            float a = (t + 1 < Tb) ? prev[j] + lb : kNegInf;
-            float c = (u < Ub) ? right + sl[t * sp + u] : kNegInf;
-            v = log_add_exp(a, c);
+            const float a = (t + 1 < Tb) ? prev[j] + cb[j] : kNegInf;
+            v = lae_fast(a, right + cl[j]);
           }
           bb[t * U1 + u] = v;
         }

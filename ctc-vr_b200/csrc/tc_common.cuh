@@ -51,15 +51,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait; `site` identifies the call site in the error flag.
+// Bounded wait; `site` identifies the call site in the error flag.  The hot path touches no global
+// memory: the error flag is only consulted / written after ~2^20 failed probes (each probe already
+// suspends the warp in hardware for a while), so a protocol bug degrades into a slow, flagged exit.
+__device__ __noinline__ bool mbar_timeout(uint32_t site) {
+  atomicCAS(&g_tc_error, 0u, 0x80000000u | (site << 16) | (blockIdx.x & 0xffffu));
+  return true;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t site) {
-  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
-  const uint32_t limit = (*(volatile unsigned int*)&g_tc_error) ? 64u : (1u << 24);
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > limit) {
-      atomicCAS(&g_tc_error, 0u, 0x80000000u | (site << 16) | (blockIdx.x & 0xffffu));
-      return;
+    // every 4096 failed probes: give up if this wait is hopeless or another wait already timed out
+    if ((++spins & 4095u) == 0u && (spins > (1u << 20) || *(volatile unsigned int*)&g_tc_error != 0u)) {
+      if (mbar_timeout(site)) return;
     }
   }
 }

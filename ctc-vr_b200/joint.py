@@ -67,6 +67,11 @@ class TransducerJoint(nn.Module):
         """joint + log-softmax + RNN-T lattice loss in one op (the seam of transducer.py:172-187)."""
         if not self.fusable:
             raise RuntimeError("rnnt_loss_fused: only joint_mode='add', activation='tanh', postjoin_linear=False")
-        e, p = self.project(enc_out, pred_out, pre_project)
+        if precision in ("bf16", CF.BF16) and enc_out.is_cuda:
+            # bf16 path: the two pre-projections are plain library GEMMs; run them on the tensor cores too
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                e, p = self.project(enc_out, pred_out, pre_project)
+        else:
+            e, p = self.project(enc_out, pred_out, pre_project)
         return CF.fused_joint_rnnt_loss(e, p, self.ffn_out.weight, self.ffn_out.bias, targets, logit_lengths,
                                         target_lengths, blank, clamp, reduction, precision)

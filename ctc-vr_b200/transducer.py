@@ -76,8 +76,11 @@ def compute_rnnt_loss(self, encoder_out, encoder_out_lens, text, text_lengths, c
         isinstance(getattr(joint, "activation", None), nn.Tanh)
     if not j_ok:
         raise RuntimeError("ctcvr_b200: fused RNN-T loss needs the add/tanh joint both reference models build")
-    e = joint.enc_ffn(encoder_out)
-    p = joint.pred_ffn(predictor_out)
+    if precision == "bf16" and encoder_out.is_cuda:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            e, p = joint.enc_ffn(encoder_out), joint.pred_ffn(predictor_out)
+    else:
+        e, p = joint.enc_ffn(encoder_out), joint.pred_ffn(predictor_out)
     return CF.fused_joint_rnnt_loss(e, p, joint.ffn_out.weight, joint.ffn_out.bias, rnnt_text,
                                     encoder_out_lens.to(torch.int32), text_lengths.to(torch.int32),
                                     self.blank, clamp, "mean", precision)

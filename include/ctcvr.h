@@ -38,6 +38,8 @@ int ctcvr_version(void);
 unsigned long long ctcvr_launch_count(void);
 /* debug: non-zero if a tcgen05 kernel hit its bounded mbarrier wait (synchronises; clears the flag) */
 unsigned int ctcvr_debug_tc_error(void);
+/* debug: device buffer of 4*2048 int64 receiving a per-role timeline of CTA 0 of the next tcgen05 forward (NULL = off) */
+void ctcvr_debug_set_prof(void* device_buf);
 
 /* ---- A1: TransducerJoint.forward dense logits — model/component/joint.py:57-68
  * logits[b,t,u,:] = W_out · tanh(enc_proj[b,t,:] + pred_proj[b,u,:]) + b_out.
