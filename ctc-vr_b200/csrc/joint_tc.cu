@@ -16,6 +16,9 @@
 //   warps 8-15  A producers  : the A operand is COMPUTED, not loaded: tanh(e+p) -> bf16 -> smem in the
 //                              UMMA canonical swizzled layout, fence.proxy.async, mbarrier arrive
 // The [B,T,U+1,V] logits only ever exist as TMEM tiles.
+#include <algorithm>
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace ctcvr {
@@ -93,11 +96,11 @@ __device__ __forceinline__ void pin(int& x) { asm volatile("" : "+r"(x)); }
 
 // ---- tile geometry ---------------------------------------------------------------------------
 template <int TILE>
-__device__ __forceinline__ RowMap tile_geometry(const TcParams& p, int4 ti) {
+__device__ __forceinline__ RowMap tile_geometry(const int32_t* t_len, const int32_t* u_len, int T, int U1, int4 ti) {
   RowMap g;
   g.b = ti.x;
-  g.Tb = min(p.t_len[g.b], p.T);
-  g.Ub = min(p.u_len[g.b], p.U1 - 1);
+  g.Tb = min(t_len[g.b], T);
+  g.Ub = min(u_len[g.b], U1 - 1);
   g.W = g.Ub + 1;
   if (TILE == TILE_FLAT) {
     int ncell = g.Tb * g.W;
@@ -118,10 +121,14 @@ __device__ __forceinline__ RowMap tile_geometry(const TcParams& p, int4 ti) {
   pin(g.b); pin(g.Tb); pin(g.Ub); pin(g.W); pin(g.t0); pin(g.ubase); pin(g.np); pin(g.ne);
   return g;
 }
+template <int TILE>
+__device__ __forceinline__ RowMap tile_geometry(const TcParams& p, int4 ti) {
+  return tile_geometry<TILE>(p.t_len, p.u_len, p.T, p.U1, ti);
+}
 
 // row r of the tile -> lattice cell; returns false for padding rows
 template <int TILE>
-__device__ __forceinline__ bool row_cell(const TcParams& p, const RowMap& g, int4 ti, int r, int& t, int& u) {
+__device__ __forceinline__ bool row_cell(const RowMap& g, int4 ti, int r, int& t, int& u) {
   if (TILE == TILE_FLAT) {
     int c = ti.y + r;
     t = c / g.W;
@@ -135,6 +142,10 @@ __device__ __forceinline__ bool row_cell(const TcParams& p, const RowMap& g, int
     u = g.ubase + ul;
     return t < g.Tb && ul < us && u <= g.Ub;
   }
+}
+template <int TILE>
+__device__ __forceinline__ bool row_cell(const TcParams&, const RowMap& g, int4 ti, int r, int& t, int& u) {
+  return row_cell<TILE>(g, ti, r, t, u);
 }
 
 struct SmemLayout {
@@ -254,8 +265,15 @@ struct Pipe {
   }
 };
 
+}  // namespace tc
+}  // namespace ctcvr
+#include "joint_tc_fwd.cuh"
+#include "joint_tc_bwd.cuh"
+namespace ctcvr {
+namespace tc {
+
 // =================================================================================================
-// Forward kernel
+// Forward kernel (v1, kept for A/B runs: CTCVR_FWD_V1=1)
 // =================================================================================================
 __global__ void __launch_bounds__(NTHREADS, 1)
 joint_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p) {
@@ -1034,6 +1052,86 @@ __global__ void build_tiles_kernel(const int32_t* __restrict__ t_len, const int3
   }
 }
 
+// fp32 -> bf16 copies of the activations (n4 float4 groups each); the bf16 path rounds enc_proj / pred_proj
+// to bf16 (under autocast they already are bf16 values, so this is lossless there).
+__global__ void to_bf16_kernel(const float4* __restrict__ a, uint2* __restrict__ ab, long na4,
+                               const float4* __restrict__ b, uint2* __restrict__ bb, long nb4) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < na4 + nb4; i += stride) {
+    const bool first = i < na4;
+    const float4 v = first ? __ldg(a + i) : __ldg(b + (i - na4));
+    const uint2 o = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    if (first) ab[i] = o; else bb[i - na4] = o;
+  }
+}
+
+// wb [Vp][D] bf16 (zero rows beyond V), wtb [D][Vp] bf16 (optional), bias_pad [Vp] (-inf beyond V),
+// bias_l2 [Vp] = bias * log2(e) (-inf beyond V)
+__global__ void prep_weights2_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                     __nv_bfloat16* __restrict__ wb, __nv_bfloat16* __restrict__ wtb,
+                                     float* __restrict__ bias_pad, float* __restrict__ bias_l2, int V, int Vp, int D) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Vp * D) {
+    int v = i / D, d = i - v * D;
+    float x = (v < V) ? w[(size_t)v * D + d] : 0.f;
+    wb[i] = __float2bfloat16(x);
+    if (wtb) wtb[(size_t)d * Vp + v] = __float2bfloat16(x);
+  }
+  if (i < Vp) {
+    if (bias_pad) bias_pad[i] = (i < V) ? bias[i] : kNegInf;
+    if (bias_l2) bias_l2[i] = (i < V) ? bias[i] * LOG2E : kNegInf;
+  }
+}
+
+// Forward tile table (see joint_tc_fwd.cuh): one thread per utterance, block-wide exclusive scan of the
+// per-utterance tile counts (B is processed in chunks of blockDim.x with a running base).
+__global__ void build_tiles_fwd_kernel(const int32_t* __restrict__ t_len, const int32_t* __restrict__ u_len, int B,
+                                       int T, int U1, int4* __restrict__ tiles, int* __restrict__ ntiles,
+                                       int max_tiles) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < B; b0 += blockDim.x) {
+    const int b = b0 + threadIdx.x;
+    int Tb = 0, W = 1, n = 0;
+    if (b < B) {
+      Tb = min(t_len[b], T);
+      W = min(u_len[b], U1 - 1) + 1;
+      n = fwd_tiles_of(Tb, W);
+    }
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int x = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += x;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int i = 0; i < warp; ++i) woff += s_warp[i];
+    int total = 0;
+    for (int i = 0; i < nwarp; ++i) total += s_warp[i];
+    const int off = s_base + woff + incl - n;
+    if (n > 0) {
+      const int nb32 = (Tb + 31) >> 5, n4 = (W >> 2) * nb32;
+      const int n2 = (W & 2) ? ((Tb + 63) >> 6) : 0;
+      for (int i = 0; i < n; ++i) {
+        int4 e;
+        if (i < n4) { const int g = i / nb32; e = make_int4(b, 4 * g, 32 * (i - g * nb32), 4); }
+        else if (i < n4 + n2) e = make_int4(b, (W >> 2) * 4, 64 * (i - n4), 2);
+        else e = make_int4(b, W - 1, 128 * (i - n4 - n2), 1);
+        if (off + i < max_tiles) tiles[off + i] = e;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *ntiles = min(s_base, max_tiles);
+}
+
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                       uint32_t box_rows) {
   static EncodeTiledFn fn = nullptr;
@@ -1082,9 +1180,13 @@ static int max_tiles_rect(int B, int T, int U1) { return B * ((U1 + 15) / 16) * 
 
 bool joint_tc_supported(int U1, int D, int V) { return D % 64 == 0 && D >= 64 && D <= 1024 && pad_v(V) <= 512 && U1 <= 128; }
 
+static int max_tiles_fwd2(int B, int T, int U1) {
+  return B * ((U1 >> 2) * ((T + 31) / 32) + (T + 63) / 64 + (T + 127) / 128);
+}
+
 struct FwdWs {
-  __nv_bfloat16* wb;
-  float* bias_pad;
+  __nv_bfloat16 *wb, *eb, *pb;
+  float *bias_pad, *bias_l2;
   int4* tiles;
   int* ntiles;
   size_t bytes;
@@ -1094,10 +1196,15 @@ static FwdWs carve_fwd_ws(void* ws, int B, int T, int U1, int D, int V) {
   uint8_t* p = reinterpret_cast<uint8_t*>(ws);
   size_t off = 0;
   FwdWs w;
-  w.wb = reinterpret_cast<__nv_bfloat16*>(p + off); off = align_up(off + (size_t)Vp * D * 2, 256);
-  w.bias_pad = reinterpret_cast<float*>(p + off); off = align_up(off + (size_t)Vp * 4, 256);
-  w.tiles = reinterpret_cast<int4*>(p + off); off = align_up(off + (size_t)max_tiles_flat(B, T, U1) * 16, 256);
-  w.ntiles = reinterpret_cast<int*>(p + off); off = align_up(off + 4, 256);
+  auto take = [&](size_t n) { void* r = p + off; off = align_up(off + n, 1024); return r; };
+  w.wb = reinterpret_cast<__nv_bfloat16*>(take((size_t)Vp * D * 2));
+  w.eb = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * T * D * 2));
+  w.pb = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * U1 * D * 2));
+  w.bias_pad = reinterpret_cast<float*>(take((size_t)Vp * 4));
+  w.bias_l2 = reinterpret_cast<float*>(take((size_t)Vp * 4));
+  const int mt = max_tiles_flat(B, T, U1) > max_tiles_fwd2(B, T, U1) ? max_tiles_flat(B, T, U1) : max_tiles_fwd2(B, T, U1);
+  w.tiles = reinterpret_cast<int4*>(take((size_t)mt * 16));
+  w.ntiles = reinterpret_cast<int*>(take(4));
   w.bytes = off;
   return w;
 }
@@ -1115,15 +1222,18 @@ static int sm_count() {
   return n;
 }
 
+static bool env_flag(const char* name) {
+  const char* v = getenv(name);
+  return v && v[0] && v[0] != '0';
+}
+
 int joint_fwd_f32(const float*, const float*, const float*, const float*, const int32_t*, const int32_t*,
                   const int32_t*, float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
 
-int joint_fwd_tc(const float* enc, const float* pred, const float* w, const float* bias, const int32_t* targets,
-                 const int32_t* t_len, const int32_t* u_len, float* lse, float* lp_blank, float* lp_label, int B, int T,
-                 int U1, int D, int V, int blank, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (!joint_tc_supported(U1, D, V))   // shapes outside the tensor-core tiling use the fp32 kernels (same GPU)
-    return joint_fwd_f32(enc, pred, w, bias, targets, t_len, u_len, lse, lp_blank, lp_label, B, T, U1, D, V, blank, st);
-  CTCVR_REQUIRE(ws && ws_bytes >= joint_fwd_tc_ws_bytes(B, T, U1, D, V), "joint_rnnt_fwd bf16: workspace too small");
+static int joint_fwd_tc_v1(const float* enc, const float* pred, const float* w, const float* bias,
+                           const int32_t* targets, const int32_t* t_len, const int32_t* u_len, float* lse,
+                           float* lp_blank, float* lp_label, int B, int T, int U1, int D, int V, int blank, void* ws,
+                           cudaStream_t st) {
   const int Vp = pad_v(V), NH = Vp / 2;
   FwdWs W = carve_fwd_ws(ws, B, T, U1, D, V);
   prep_weights_kernel<<<cdiv((long)Vp * D, 256), 256, 0, st>>>(w, bias, W.wb, nullptr, W.bias_pad, V, Vp, D);
@@ -1145,7 +1255,51 @@ int joint_fwd_tc(const float* enc, const float* pred, const float* w, const floa
   int grid = min(sm_count(), mt);
   joint_fwd_tc_kernel<<<grid, NTHREADS, smem, st>>>(tmap, p);
   CTCVR_LAUNCH_CHECK();
-  (void)check_tc_error;
+  return 0;
+}
+
+int joint_fwd_tc(const float* enc, const float* pred, const float* w, const float* bias, const int32_t* targets,
+                 const int32_t* t_len, const int32_t* u_len, float* lse, float* lp_blank, float* lp_label, int B, int T,
+                 int U1, int D, int V, int blank, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!joint_tc_supported(U1, D, V))   // shapes outside the tensor-core tiling use the fp32 kernels (same GPU)
+    return joint_fwd_f32(enc, pred, w, bias, targets, t_len, u_len, lse, lp_blank, lp_label, B, T, U1, D, V, blank, st);
+  CTCVR_REQUIRE(ws && ws_bytes >= joint_fwd_tc_ws_bytes(B, T, U1, D, V), "joint_rnnt_fwd bf16: workspace too small");
+  CTCVR_REQUIRE(((uintptr_t)enc & 15) == 0 && ((uintptr_t)pred & 15) == 0, "joint_rnnt_fwd bf16: enc_proj / pred_proj must be 16-byte aligned");
+  if (env_flag("CTCVR_FWD_V1"))
+    return joint_fwd_tc_v1(enc, pred, w, bias, targets, t_len, u_len, lse, lp_blank, lp_label, B, T, U1, D, V, blank, ws, st);
+  const int Vp = pad_v(V), NH = Vp / 2;
+  FwdWs W = carve_fwd_ws(ws, B, T, U1, D, V);
+  prep_weights2_kernel<<<cdiv((long)Vp * D, 256), 256, 0, st>>>(w, bias, W.wb, nullptr, nullptr, W.bias_l2, V, Vp, D);
+  CTCVR_LAUNCH_CHECK();
+  {
+    const long na4 = (long)B * T * D / 4, nb4 = (long)B * U1 * D / 4;
+    const int blocks = (int)std::min<long>((na4 + nb4 + 255) / 256, 148L * 8);
+    to_bf16_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(enc), reinterpret_cast<uint2*>(W.eb), na4,
+                                           reinterpret_cast<const float4*>(pred), reinterpret_cast<uint2*>(W.pb), nb4);
+    CTCVR_LAUNCH_CHECK();
+  }
+  const int mt = max_tiles_fwd2(B, T, U1);
+  build_tiles_fwd_kernel<<<1, 256, 0, st>>>(t_len, u_len, B, T, U1, W.tiles, W.ntiles, mt);
+  CTCVR_LAUNCH_CHECK();
+  CUtensorMap tmap_w, tmap_e, tmap_p;
+  if (make_tmap_bf16_2d(&tmap_w, W.wb, Vp, D, D, NH)) return 1;
+  if (make_tmap_bf16_2d(&tmap_e, W.eb, (uint64_t)B * T, D, D, 32)) return 1;
+  if (make_tmap_bf16_2d(&tmap_p, W.pb, (uint64_t)B * U1, D, D, 4)) return 1;
+  FwdParams p{};
+  p.bias = bias; p.bias_l2 = W.bias_l2; p.targets = targets; p.t_len = t_len; p.u_len = u_len;
+  p.tiles = W.tiles; p.ntiles = W.ntiles;
+  p.B = B; p.T = T; p.U1 = U1; p.D = D; p.V = V; p.Vp = Vp; p.NH = NH; p.blank = blank;
+  p.lse = lse; p.lp_blank = lp_blank; p.lp_label = lp_label;
+  p.prof = g_prof_buf;
+  int ws_n = F_MAX_W_STAGES;
+  while (ws_n > 2 && fwd2_smem_bytes(NH, Vp, ws_n) > 232448) --ws_n;
+  p.w_stages = ws_n;
+  const size_t smem = fwd2_smem_bytes(NH, Vp, ws_n);
+  CTCVR_REQUIRE(smem <= 232448, "joint_rnnt_fwd bf16: shared memory budget exceeded (%zu B)", smem);
+  CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = min(sm_count(), mt);
+  joint_fwd2_kernel<<<grid, NTHREADS, smem, st>>>(tmap_w, tmap_e, tmap_p, p);
+  CTCVR_LAUNCH_CHECK();
   return 0;
 }
 
@@ -1159,12 +1313,12 @@ static bool joint_tc_bwd_supported(int U1, int D, int V) {
 }
 
 struct BwdWs {
-  __nv_bfloat16 *wb, *wtb, *zt, *gt;
-  float *bias_pad, *d_enc_part, *partials;
+  __nv_bfloat16 *wb, *wtb, *zt, *gt, *eb, *pb;
+  float *bias_pad, *bias_l2, *d_enc_part, *partials;
   int4* tiles;
   int* ntiles;
   long Rpad;
-  int KS, S_max;
+  int KS, S_max, mt;
   size_t bytes;
 };
 static BwdWs carve_bwd_ws(void* ws, int B, int T, int U1, int D, int V) {
@@ -1172,8 +1326,8 @@ static BwdWs carve_bwd_ws(void* ws, int B, int T, int U1, int D, int V) {
   uint8_t* p = reinterpret_cast<uint8_t*>(ws);
   size_t off = 0;
   BwdWs w;
-  const int mt = max_tiles_rect(B, T, U1);
-  w.Rpad = (long)mt * BM;
+  w.mt = max_tiles_rect(B, T, U1);
+  w.Rpad = (long)(w.mt + 1) * BM;           // + one scratch row tile for the dummy iterations of the lock-step loop
   w.S_max = (U1 + 15) / 16;
   const int MB = D / 128;
   w.KS = MB > 0 ? sm_count() / MB : 1;
@@ -1181,8 +1335,11 @@ static BwdWs carve_bwd_ws(void* ws, int B, int T, int U1, int D, int V) {
   auto take = [&](size_t n) { void* r = p + off; off = align_up(off + n, 1024); return r; };
   w.wb = reinterpret_cast<__nv_bfloat16*>(take((size_t)Vp * D * 2));
   w.wtb = reinterpret_cast<__nv_bfloat16*>(take((size_t)Vp * D * 2));
+  w.eb = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * T * D * 2));
+  w.pb = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * U1 * D * 2));
   w.bias_pad = reinterpret_cast<float*>(take((size_t)Vp * 4));
-  w.tiles = reinterpret_cast<int4*>(take((size_t)mt * 16));
+  w.bias_l2 = reinterpret_cast<float*>(take((size_t)Vp * 4));
+  w.tiles = reinterpret_cast<int4*>(take((size_t)w.mt * 16));
   w.ntiles = reinterpret_cast<int*>(take(4));
   w.zt = reinterpret_cast<__nv_bfloat16*>(take((size_t)D * w.Rpad * 2));
   w.gt = reinterpret_cast<__nv_bfloat16*>(take((size_t)Vp * w.Rpad * 2));
@@ -1205,34 +1362,64 @@ int joint_bwd_tc(const float* enc, const float* pred, const float* w, const floa
     return joint_bwd_f32(enc, pred, w, bias, targets, t_len, u_len, lse, alpha, beta, costs, grad_costs, clamp, d_enc,
                          d_pred, d_w, d_b, B, T, U1, D, V, blank, ws, ws_bytes, st);
   CTCVR_REQUIRE(ws && ws_bytes >= joint_bwd_tc_ws_bytes(B, T, U1, D, V), "joint_rnnt_bwd bf16: workspace too small");
+  CTCVR_REQUIRE(((uintptr_t)enc & 15) == 0 && ((uintptr_t)pred & 15) == 0, "joint_rnnt_bwd bf16: enc_proj / pred_proj must be 16-byte aligned");
   const int Vp = pad_v(V), NH = Vp / 2, MB = D / 128;
   BwdWs W = carve_bwd_ws(ws, B, T, U1, D, V);
-  prep_weights_kernel<<<cdiv((long)Vp * D, 256), 256, 0, st>>>(w, bias, W.wb, W.wtb, W.bias_pad, V, Vp, D);
+  const bool v1 = env_flag("CTCVR_BWD_V1");
+  prep_weights2_kernel<<<cdiv((long)Vp * D, 256), 256, 0, st>>>(w, bias, W.wb, W.wtb, W.bias_pad, W.bias_l2, V, Vp, D);
   CTCVR_LAUNCH_CHECK();
-  const int mt = max_tiles_rect(B, T, U1);
+  const int mt = W.mt;
   build_tiles_kernel<<<1, 256, 0, st>>>(t_len, u_len, B, T, U1, 1, W.tiles, W.ntiles, mt);
   CTCVR_LAUNCH_CHECK();
   CTCVR_CHECK_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)B * U1 * D * sizeof(float), st));
   CTCVR_CHECK_CUDA(cudaMemsetAsync(d_b, 0, (size_t)V * sizeof(float), st));
-  CUtensorMap tmap_w, tmap_wt, tmap_zt, tmap_gt;
-  if (make_tmap_bf16_2d(&tmap_w, W.wb, Vp, D, D, NH)) return 1;
-  if (make_tmap_bf16_2d(&tmap_wt, W.wtb, D, Vp, Vp, 128)) return 1;
+  CUtensorMap tmap_zt, tmap_gt;
   if (make_tmap_bf16_2d(&tmap_zt, W.zt, D, W.Rpad, W.Rpad, 128)) return 1;
   if (make_tmap_bf16_2d(&tmap_gt, W.gt, Vp, W.Rpad, W.Rpad, NH)) return 1;
-  TcParams p{};
-  p.enc = enc; p.pred = pred; p.bias_pad = W.bias_pad; p.targets = targets; p.t_len = t_len; p.u_len = u_len;
-  p.tiles = W.tiles; p.ntiles = W.ntiles;
-  p.B = B; p.T = T; p.U1 = U1; p.D = D; p.V = V; p.Vp = Vp; p.NH = NH; p.blank = blank;
-  p.lse_in = lse; p.alpha = alpha; p.beta = beta; p.costs = costs; p.grad_costs = grad_costs; p.clamp = clamp;
-  p.zt = W.zt; p.gt = W.gt; p.Rpad = W.Rpad; p.d_enc_part = W.d_enc_part; p.d_pred = d_pred; p.d_bias = d_b;
-  p.S_max = W.S_max;
-  p.prof = g_prof_buf;
-  {
+  if (v1) {
+    CUtensorMap tmap_w, tmap_wt;
+    if (make_tmap_bf16_2d(&tmap_w, W.wb, Vp, D, D, NH)) return 1;
+    if (make_tmap_bf16_2d(&tmap_wt, W.wtb, D, Vp, Vp, 128)) return 1;
+    TcParams p{};
+    p.enc = enc; p.pred = pred; p.bias_pad = W.bias_pad; p.targets = targets; p.t_len = t_len; p.u_len = u_len;
+    p.tiles = W.tiles; p.ntiles = W.ntiles;
+    p.B = B; p.T = T; p.U1 = U1; p.D = D; p.V = V; p.Vp = Vp; p.NH = NH; p.blank = blank;
+    p.lse_in = lse; p.alpha = alpha; p.beta = beta; p.costs = costs; p.grad_costs = grad_costs; p.clamp = clamp;
+    p.zt = W.zt; p.gt = W.gt; p.Rpad = W.Rpad; p.d_enc_part = W.d_enc_part; p.d_pred = d_pred; p.d_bias = d_b;
+    p.S_max = W.S_max;
+    p.prof = g_prof_buf;
     size_t smem = bwd_smem_bytes(NH, Vp);
     CTCVR_REQUIRE(smem <= 232448, "joint_rnnt_bwd bf16: shared memory budget exceeded (%zu B)", smem);
     CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = min(sm_count(), mt);
     joint_bwd_tc_kernel<<<grid, NTHREADS, smem, st>>>(tmap_w, tmap_wt, p);
+    CTCVR_LAUNCH_CHECK();
+  } else {
+    {
+      const long na4 = (long)B * T * D / 4, nb4 = (long)B * U1 * D / 4;
+      const int blocks = (int)std::min<long>((na4 + nb4 + 255) / 256, 148L * 8);
+      to_bf16_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(enc), reinterpret_cast<uint2*>(W.eb), na4,
+                                             reinterpret_cast<const float4*>(pred), reinterpret_cast<uint2*>(W.pb), nb4);
+      CTCVR_LAUNCH_CHECK();
+    }
+    const int grid = min(sm_count(), mt);
+    CUtensorMap tmap_w, tmap_wt, tmap_e, tmap_p;
+    if (make_tmap_bf16_2d(&tmap_w, W.wb, Vp, D, D, NH)) return 1;
+    if (make_tmap_bf16_2d(&tmap_wt, W.wtb, D, Vp, Vp, 128)) return 1;
+    if (make_tmap_bf16_2d(&tmap_e, W.eb, (uint64_t)B * T, D, D, 8)) return 1;
+    if (make_tmap_bf16_2d(&tmap_p, W.pb, (uint64_t)B * U1, D, D, 16)) return 1;
+    BwdParams p{};
+    p.bias = bias; p.bias_l2 = W.bias_l2; p.targets = targets; p.t_len = t_len; p.u_len = u_len;
+    p.tiles = W.tiles; p.ntiles = W.ntiles;
+    p.B = B; p.T = T; p.U1 = U1; p.D = D; p.V = V; p.Vp = Vp; p.NH = NH; p.blank = blank;
+    p.lse = lse; p.alpha = alpha; p.beta = beta; p.costs = costs; p.grad_costs = grad_costs; p.clamp = clamp;
+    p.zt = W.zt; p.gt = W.gt; p.Rpad = W.Rpad; p.scratch_tile = mt;
+    p.d_enc_part = W.d_enc_part; p.d_pred = d_pred; p.d_bias = d_b;
+    p.prof = g_prof_buf;
+    const size_t smem = bwd2_smem_bytes(NH, Vp, D);
+    CTCVR_REQUIRE(smem <= 232448, "joint_rnnt_bwd bf16: shared memory budget exceeded (%zu B)", smem);
+    CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    joint_bwd2_kernel<<<grid, NTHREADS, smem, st>>>(tmap_w, tmap_wt, tmap_e, tmap_p, tmap_zt, p);
     CTCVR_LAUNCH_CHECK();
   }
   reduce_denc_kernel<<<B * T, 128, 0, st>>>(W.d_enc_part, t_len, u_len, d_enc, B, T, U1, D);

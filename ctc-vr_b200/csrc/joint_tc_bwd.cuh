@@ -1,0 +1,569 @@
+// Backward kernel 1 of the bf16 tcgen05 path (included by joint_tc.cu):
+//   recompute logits -> g = d cost / d logits -> dZ^T = W^T g^T -> dH = dZ (1 - z^2) -> d_enc / d_pred partials,
+//   d_bias, and the bf16 spills z^T, g^T consumed by the dW GEMM (kernel 2).
+//
+// Tiles are rectangles of 8 frames x 16 label columns of one utterance (row = tloc*16 + ul).  With the
+// transposed second GEMM (TMEM lane = joint dim d, TMEM column = tile row) both reductions are thread-local:
+//   d_enc[t]  = sum over the 16 columns of one tcgen05.ld.x16
+//   d_pred[u] = sum over the frame slots, kept in registers across the tiles of one (b, u-split) sweep
+// TMEM holds 512 columns, so the logits [128 x Vp] and dZ^T [D x 128] cannot coexist: a tile runs four phases
+//   P1  producers: tanh tile (+ z^T spill) | TMA: W_out k-blocks | MMA: logits -> TMEM
+//   P2  12 warps : TMEM -> g (bf16) -> smem G tile (K-major over v) + g^T spill; exact fp32 blank/label entries
+//   P3  TMA: W_out^T blocks | MMA: dZ^T[mb] = W^T[mb] . G^T -> TMEM ; the 12 warps: column sums of G (d_bias)
+//   P4  12 warps : TMEM -> dH -> d_enc partial (store), d_pred (registers)
+// W_out / W_out^T stream through ONE smem ring.  With CL = 2 the two CTAs of a cluster run in lock step and
+// each loads half of every ring stage, multicast to both (halves the L2 -> SM traffic, the P1/P3 bound).
+//
+// Roles (512 threads): warp 0 TMA ring | warp 1 MMA issuer | warp 2 TMEM alloc | warp 3 TMA slabs |
+// warps 4-15 P2/P4 workers | warps 8-15 also the P1 A producers.
+#pragma once
+#include "tc_common.cuh"
+
+namespace ctcvr {
+namespace tc {
+
+constexpr int B_A_STAGES = 3;
+constexpr int B_S_STAGES = 3;
+constexpr int B_R1_STAGES = 3;                 // W_out ring view   (P1): NH x 128 B per stage
+constexpr int B_R3_STAGES = 5;                 // W_out^T ring view (P3): 16 KB per stage, same memory
+constexpr int B_SLAB_BYTES = 2048 + 1024;      // 16 pred rows + 8 enc rows, 128 B each
+constexpr int WORKERS = 384;
+
+struct BwdParams {
+  const float* bias;        // [V]
+  const float* bias_l2;     // [Vp] bias*log2e, -inf beyond V
+  const int32_t* targets;
+  const int32_t* t_len;
+  const int32_t* u_len;
+  const int4* tiles;        // {b, u-split, frame block, tile index}
+  const int* ntiles;
+  int B, T, U1, D, V, Vp, NH, blank;
+  const float* lse;
+  const float* alpha;
+  const float* beta;
+  const float* costs;
+  const float* grad_costs;
+  float clamp;
+  __nv_bfloat16* zt;        // [D][Rpad]
+  __nv_bfloat16* gt;        // [Vp][Rpad]
+  long Rpad;
+  int scratch_tile;         // unused row tile (kept for layout compatibility)
+  float* d_enc_part;        // [S][B,T,D]
+  float* d_pred;            // [B,U1,D] atomic accumulate
+  float* d_bias;            // [V] atomic accumulate
+  long long* prof;
+};
+
+// Shared memory: [GZ region: G tile (P2/P3) = A ring (P1) = z^T tile (P4)] [weight ring: 3 W stages = 5 W^T stages]
+// [slab ring] [bias] [column-sum partials] [barriers]
+struct Bwd2Smem {
+  uint32_t g_base, r_base, r1_bytes, s_base, bar_base;
+  float* bias_l2;
+  float* dbp;               // [4][Vp] column-sum partials
+  uint32_t* tmem_ptr;
+  __device__ __forceinline__ uint32_t a_stage(int i) const { return g_base + i * A_STAGE_BYTES; }
+  __device__ __forceinline__ uint32_t g_kblock(int i) const { return g_base + i * A_STAGE_BYTES; }
+  __device__ __forceinline__ uint32_t z_box(int i) const { return g_base + i * A_STAGE_BYTES; }    // (mb*2 + half)
+  __device__ __forceinline__ uint32_t r1_stage(int i) const { return r_base + i * r1_bytes; }
+  __device__ __forceinline__ uint32_t r3_stage(int i) const { return r_base + i * 16384; }
+  __device__ __forceinline__ uint32_t s_stage(int i) const { return s_base + i * B_SLAB_BYTES; }
+  __device__ __forceinline__ uint32_t a_full(int i) const { return bar_base + i * 16; }
+  __device__ __forceinline__ uint32_t a_empty(int i) const { return bar_base + i * 16 + 8; }
+  __device__ __forceinline__ uint32_t s_full(int i) const { return bar_base + 48 + i * 16; }
+  __device__ __forceinline__ uint32_t s_empty(int i) const { return bar_base + 48 + i * 16 + 8; }
+  __device__ __forceinline__ uint32_t r1_full(int i) const { return bar_base + 96 + i * 16; }
+  __device__ __forceinline__ uint32_t r1_empty(int i) const { return bar_base + 96 + i * 16 + 8; }
+  __device__ __forceinline__ uint32_t r3_full(int i) const { return bar_base + 144 + i * 16; }
+  __device__ __forceinline__ uint32_t r3_empty(int i) const { return bar_base + 144 + i * 16 + 8; }
+  __device__ __forceinline__ uint32_t z_full(int i) const { return bar_base + 224 + i * 8; }
+  __device__ __forceinline__ uint32_t tmem_full() const { return bar_base + 256; }
+  __device__ __forceinline__ uint32_t g_full() const { return bar_base + 264; }
+  __device__ __forceinline__ uint32_t dz_full() const { return bar_base + 272; }
+  __device__ __forceinline__ uint32_t tmem_empty() const { return bar_base + 280; }
+  __device__ __forceinline__ uint32_t gs_done() const { return bar_base + 288; }   // column sums have read G
+};
+
+__host__ __device__ inline uint32_t bwd2_ring_bytes(int NH) {
+  uint32_t a = (uint32_t)B_R1_STAGES * (uint32_t)NH * 128u, b = (uint32_t)B_R3_STAGES * 16384u;
+  return a > b ? a : b;
+}
+__host__ __device__ inline uint32_t bwd2_gz_blocks(int Vp, int D) {
+  const uint32_t kbg = (Vp + 63) / 64, zb = 2 * (D / 128);
+  return kbg > zb ? kbg : zb;
+}
+
+__host__ __device__ inline size_t bwd2_smem_bytes(int NH, int Vp, int D) {
+  size_t s = 1024;
+  s += (size_t)bwd2_gz_blocks(Vp, D) * A_STAGE_BYTES;
+  s += bwd2_ring_bytes(NH);
+  s = (s + 1023) / 1024 * 1024;
+  s += (size_t)B_S_STAGES * B_SLAB_BYTES;
+  s += (size_t)Vp * 4 + (size_t)4 * Vp * 4;
+  s += 304 + 16 + 16;
+  return s;
+}
+
+__device__ __forceinline__ void carve_bwd2(Bwd2Smem& L, uint8_t* raw, int NH, int Vp, int D) {
+  const uint32_t base = smem_u32(raw);
+  uint32_t a = (base + 1023u) & ~1023u;
+  L.g_base = a; a += bwd2_gz_blocks(Vp, D) * A_STAGE_BYTES;
+  L.r_base = a; L.r1_bytes = (uint32_t)NH * 128u; a += bwd2_ring_bytes(NH);
+  a = (a + 1023u) & ~1023u;
+  L.s_base = a; a += B_S_STAGES * B_SLAB_BYTES;
+  L.bias_l2 = reinterpret_cast<float*>(raw + (a - base)); a += Vp * 4;
+  L.dbp = reinterpret_cast<float*>(raw + (a - base)); a += 4 * Vp * 4;
+  a = (a + 15u) & ~15u;
+  L.bar_base = a; a += 304;
+  L.tmem_ptr = reinterpret_cast<uint32_t*>(raw + (a - base));
+}
+
+// tanh(a + b) on packed bf16 pairs: one packed add and one packed MUFU op per two elements.  The sum is rounded to
+// bf16 before the tanh (error <= 2^-9 |x| (1 - z^2) <= 9e-4, below the bf16 rounding of z itself).
+__device__ __forceinline__ uint32_t tanh_add_bf16x2_packed(uint32_t a, uint32_t b) {
+  uint32_t s, r;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(s) : "r"(a), "r"(b));
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(r) : "r"(s));
+  return r;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_wt,
+                  const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_p,
+                  const __grid_constant__ CUtensorMap tmap_zt, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  Bwd2Smem L;
+  carve_bwd2(L, smem_raw, p.NH, p.Vp, p.D);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KB = p.D / BK;                 // k-blocks of the logits GEMM
+  const int KBG = (p.Vp + 63) / 64;        // k-blocks (over v) of the dZ GEMM
+  const int MB = p.D / 128;                // 128-lane blocks of dZ^T
+  const int ntiles = *p.ntiles;
+  const int tile_begin = (int)(((long)ntiles * blockIdx.x) / gridDim.x);
+  const int tile_end = (int)(((long)ntiles * (blockIdx.x + 1)) / gridDim.x);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_wt);
+    tma_prefetch_desc(&tmap_e);
+    tma_prefetch_desc(&tmap_p);
+    tma_prefetch_desc(&tmap_zt);
+    for (int i = 0; i < B_A_STAGES; ++i) { mbar_init(L.a_full(i), PROD_THREADS); mbar_init(L.a_empty(i), 1); }
+    for (int i = 0; i < B_S_STAGES; ++i) { mbar_init(L.s_full(i), 1); mbar_init(L.s_empty(i), PROD_THREADS); }
+    for (int i = 0; i < B_R1_STAGES; ++i) { mbar_init(L.r1_full(i), 1); mbar_init(L.r1_empty(i), 1); }
+    for (int i = 0; i < B_R3_STAGES; ++i) { mbar_init(L.r3_full(i), 1); mbar_init(L.r3_empty(i), 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(L.z_full(i), 1);
+    mbar_init(L.tmem_full(), 1);
+    mbar_init(L.g_full(), WORKERS);
+    mbar_init(L.dz_full(), 1);
+    mbar_init(L.tmem_empty(), 256);
+    mbar_init(L.gs_done(), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(L.tmem_ptr), TMEM_COLS);
+  for (int i = tid; i < p.Vp; i += NTHREADS) L.bias_l2[i] = p.bias_l2[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *L.tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA: W_out (P1), W_out^T (P3), z^T tile (P4)
+    if (lane == 0) {
+      Pipe r1, r3;
+      int prof_n = 0;
+      uint32_t ph = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const size_t row0 = (size_t)p.tiles[tile].w * BM;
+        TC_PROF(0, 1);
+        // the ring is drained here: the previous tile's dz_full was observed below
+        for (int kb = 0; kb < KB; ++kb)
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(L.r1_empty(r1.stage), r1.phase ^ 1u, 11);
+            mbar_arrive_expect_tx(L.r1_full(r1.stage), (uint32_t)p.NH * 128u);
+            tma_load_2d(L.r1_stage(r1.stage), &tmap_w, L.r1_full(r1.stage), kb * BK, h * p.NH);
+            r1.advance(B_R1_STAGES);
+          }
+        TC_PROF(0, 2);
+        mbar_wait(L.tmem_full(), ph, 12);           // every P1 MMA has completed: the W view of the ring is dead
+        TC_PROF(0, 3);
+        for (int mb = 0; mb < MB; ++mb)
+          for (int kb = 0; kb < KBG; ++kb) {
+            mbar_wait(L.r3_empty(r3.stage), r3.phase ^ 1u, 13);
+            mbar_arrive_expect_tx(L.r3_full(r3.stage), 16384u);
+            tma_load_2d(L.r3_stage(r3.stage), &tmap_wt, L.r3_full(r3.stage), kb * 64, mb * 128);
+            r3.advance(B_R3_STAGES);
+          }
+        TC_PROF(0, 4);
+        mbar_wait(L.dz_full(), ph, 14);             // every P3 MMA has completed: G tile and the W^T view are dead
+        mbar_wait(L.gs_done(), ph, 16);             // ... and the d_bias column sums have read G
+        TC_PROF(0, 5);
+        fence_proxy_async_global();                 // z^T was written with st.global by this CTA's producers
+        TC_PROF(0, 6);
+        for (int mb = 0; mb < MB; ++mb) {
+          mbar_arrive_expect_tx(L.z_full(mb), 32768u);
+          tma_load_2d(L.z_box(2 * mb), &tmap_zt, L.z_full(mb), (int)row0, mb * 128);
+          tma_load_2d(L.z_box(2 * mb + 1), &tmap_zt, L.z_full(mb), (int)row0 + 64, mb * 128);
+        }
+        ph ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ TMA: enc / pred slabs
+    if (lane == 0) {
+      Pipe sp;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int4 ti = p.tiles[tile];
+        const int b = ti.x;
+        const int W = min(p.u_len[b], p.U1 - 1) + 1;
+        const int S = (W + 15) >> 4, us = (W + S - 1) / S;
+        const int prow = b * p.U1 + ti.y * us;
+        const int erow = b * p.T + ti.z * 8;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(L.s_empty(sp.stage), sp.phase ^ 1u, 15);
+          const uint32_t st = L.s_stage(sp.stage);
+          mbar_arrive_expect_tx(L.s_full(sp.stage), (uint32_t)B_SLAB_BYTES);
+          tma_load_2d(st, &tmap_p, L.s_full(sp.stage), kb * BK, prow);
+          tma_load_2d(st + 2048, &tmap_e, L.s_full(sp.stage), kb * BK, erow);
+          sp.advance(B_S_STAGES);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      Pipe ap, r1, r3;
+      int prof_n = 0;
+      uint32_t ph = 0;
+      const uint32_t idesc1 = make_idesc_bf16(BM, p.NH);
+      const uint32_t idesc2 = make_idesc_bf16(128, BM);
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        TC_PROF(1, 1);
+        mbar_wait(L.tmem_empty(), ph ^ 1u, 20);
+        TC_PROF(1, 2);
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(L.a_full(ap.stage), ap.phase, 21);
+          TC_PROF(1, 50 + kb);
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(L.r1_full(r1.stage), r1.phase, 22);
+            TC_PROF(1, 100 + kb * 2 + h);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < BK / 16; ++ks)
+              umma_bf16(tmem_base + h * p.NH, make_desc_sw128(L.a_stage(ap.stage) + ks * 32),
+                        make_desc_sw128(L.r1_stage(r1.stage) + ks * 32), idesc1, (kb | ks) ? 1u : 0u);
+            umma_commit(L.r1_empty(r1.stage));
+            r1.advance(B_R1_STAGES);
+          }
+          umma_commit(L.a_empty(ap.stage));
+          ap.advance(B_A_STAGES);
+        }
+        umma_commit(L.tmem_full());
+        TC_PROF(1, 3);
+        // ---- P3: dZ^T[mb] (128 d x 128 rows) = W^T[mb] (128 x Vp) . G^T (Vp x 128)
+        mbar_wait(L.g_full(), ph, 23);
+        TC_PROF(1, 4);
+        tc_fence_after();
+        for (int mb = 0; mb < MB; ++mb)
+          for (int kb = 0; kb < KBG; ++kb) {
+            mbar_wait(L.r3_full(r3.stage), r3.phase, 24);
+            TC_PROF(1, 200 + mb * KBG + kb);
+            tc_fence_after();
+            const int nks = min(4, (p.Vp - kb * 64) / 16);
+            for (int ks = 0; ks < nks; ++ks)
+              umma_bf16(tmem_base + mb * 128, make_desc_sw128(L.r3_stage(r3.stage) + ks * 32),
+                        make_desc_sw128(L.g_kblock(kb) + ks * 32), idesc2, (kb | ks) ? 1u : 0u);
+            umma_commit(L.r3_empty(r3.stage));
+            r3.advance(B_R3_STAGES);
+          }
+        umma_commit(L.dz_full());
+        TC_PROF(1, 5);
+        ph ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ workers (warps 4-15), producers (8-15)
+    const int q = warp & 3;
+    const int wg = (warp - 4) >> 2;            // 0..2
+    const int wt = tid - 128;                  // 0..383
+    const int r = q * 32 + lane;               // P2: tile row ; P4: lane of the d block
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool producer = warp >= 8;
+    const int pc = (warp - 8) & 7;             // producer: 16-byte chunk of the k-block handled by this warp
+    uint32_t ph = 0;
+    int prof_n = 0;
+    Pipe ap, sp;
+    float db0 = 0.f, db1 = 0.f;                // d_bias of columns wt and wt + 384
+    float pacc[2][16];                         // d_pred sums of d blocks 2wg, 2wg+1 over the tiles of one (b, u-split) sweep
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pacc[i][j] = 0.f;
+    int cur_b = -1, cur_ubase = 0;
+    auto flush_pred = [&]() {
+      if (cur_b < 0 || wg >= 2) return;
+      const int Ub = min(p.u_len[cur_b], p.U1 - 1);
+#pragma unroll
+      for (int mbl = 0; mbl < 2; ++mbl) {
+        const int mb = 2 * wg + mbl;
+        if (mb < MB) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int u = cur_ubase + j;
+            if (u <= Ub) atomicAdd(p.d_pred + ((size_t)cur_b * p.U1 + u) * p.D + mb * 128 + r, pacc[mbl][j]);
+            pacc[mbl][j] = 0.f;
+          }
+        }
+      }
+    };
+    // producer addressing (rows lane, lane+32, lane+64, lane+96 of the tile; row = tloc*16 + ul)
+    const int ul_p = lane & 15;
+    const uint32_t p_off = (uint32_t)ul_p * 128u + (uint32_t)((pc ^ (ul_p & 7)) << 4);
+    uint32_t e_off[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int tloc = (lane >> 4) + 2 * j;
+      e_off[j] = 2048u + (uint32_t)tloc * 128u + (uint32_t)((pc ^ tloc) << 4);
+    }
+    const uint32_t a_off = (uint32_t)lane * 128u + (uint32_t)((pc ^ (lane & 7)) << 4);
+
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      int4 ti = p.tiles[tile];
+      pin(ti.x); pin(ti.y); pin(ti.z); pin(ti.w);
+      const RowMap g = tile_geometry<TILE_RECT>(p.t_len, p.u_len, p.T, p.U1, ti);
+      if (g.b != cur_b || g.ubase != cur_ubase) { flush_pred(); cur_b = g.b; cur_ubase = g.ubase; }
+      const size_t row0 = (size_t)ti.w * BM;
+
+      // ---------------- P1 (warps 8-15): A tile k-blocks + z^T spill
+      if (producer) {
+        // the A ring overlays the z^T tile of the previous iteration: wait until its readers (P4) are done
+        mbar_wait(L.tmem_empty(), ph ^ 1u, 40);
+        if (tid == 256) TC_PROF(3, 1);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(L.s_full(sp.stage), sp.phase, 41);
+          mbar_wait(L.a_empty(ap.stage), ap.phase ^ 1u, 42);
+          const uint32_t sb = L.s_stage(sp.stage);
+          const uint32_t ab = L.a_stage(ap.stage) + a_off;
+          const uint4 pv = lds128(sb + p_off);
+          unsigned short* z = reinterpret_cast<unsigned short*>(p.zt) + (size_t)(kb * BK + pc * 8) * p.Rpad + row0 + lane;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 ev = lds128(sb + e_off[j]);
+            uint32_t w[4];
+            w[0] = tanh_add_bf16x2_packed(ev.x, pv.x);
+            w[1] = tanh_add_bf16x2_packed(ev.y, pv.y);
+            w[2] = tanh_add_bf16x2_packed(ev.z, pv.z);
+            w[3] = tanh_add_bf16x2_packed(ev.w, pv.w);
+            sts128(ab + j * 4096, w[0], w[1], w[2], w[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              z[(size_t)(2 * e) * p.Rpad + 32 * j] = (unsigned short)(w[e] & 0xffffu);
+              z[(size_t)(2 * e + 1) * p.Rpad + 32 * j] = (unsigned short)(w[e] >> 16);
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(L.a_full(ap.stage));
+          mbar_arrive(L.s_empty(sp.stage));
+          ap.advance(B_A_STAGES);
+          sp.advance(B_S_STAGES);
+        }
+        if (tid == 256) TC_PROF(3, 2);
+        fence_proxy_async_global();                  // z^T (st.global above) is read back by the P4 TMA load
+        if (tid == 256) TC_PROF(3, 3);
+      }
+
+      // ---------------- P2: g = d cost / d logits for row r, column chunks wg, wg+3, ...
+      int t, u;
+      const bool valid = row_cell<TILE_RECT>(g, ti, r, t, u);
+      float k_all = kNegInf, k_blank = kNegInf, k_label = kNegInf, scale = 0.f;
+      int lab = -1;
+      if (valid) {
+        const size_t cell = ((size_t)g.b * p.T + t) * p.U1 + u;
+        const float al = p.alpha[cell], be = p.beta[cell], cost = p.costs[g.b], l = p.lse[cell];
+        k_all = al + be + cost - l;
+        float bnext = kNegInf;
+        if (t + 1 < g.Tb) bnext = p.beta[cell + p.U1];
+        else if (u == g.Ub) bnext = 0.f;
+        k_blank = al + bnext + cost - l;
+        if (u < g.Ub) { k_label = al + p.beta[cell + 1] + cost - l; lab = p.targets[(size_t)g.b * (p.U1 - 1) + u]; }
+        scale = p.grad_costs[g.b];
+      }
+      // fast path: no clamp and a positive cost gradient (uniform per tile): fold log2(scale) into the exponent
+      const float sc_tile = p.grad_costs[g.b];
+      const bool fast = !(p.clamp > 0.f) && sc_tile > 0.f;
+      const float kr = (valid && fast) ? fmaf(k_all, LOG2E, lg2_fast(scale)) : kNegInf;
+      if (tid == 128) TC_PROF(2, 1);
+      mbar_wait(L.tmem_full(), ph, 30);
+      if (tid == 128) TC_PROF(2, 2);
+      tc_fence_after();
+      for (int c0 = wg * 32; c0 < p.Vp; c0 += 96) {
+        float v[32];
+        tmem_ld32(tq + c0, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+        if (fast) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bj = *reinterpret_cast<const float4*>(L.bias_l2 + c0 + j);
+            const float g0 = ex2_fast(fmaf(v[j], LOG2E, bj.x) + kr);
+            const float g1 = ex2_fast(fmaf(v[j + 1], LOG2E, bj.y) + kr);
+            const float g2 = ex2_fast(fmaf(v[j + 2], LOG2E, bj.z) + kr);
+            const float g3 = ex2_fast(fmaf(v[j + 3], LOG2E, bj.w) + kr);
+            pk[j >> 1] = pack_bf16(g0, g1);
+            pk[(j >> 1) + 1] = pack_bf16(g2, g3);
+          }
+        } else {
+          const float ka2 = k_all * LOG2E;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float gg[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              float gv = ex2_fast(fmaf(v[j + e], LOG2E, L.bias_l2[c0 + j + e]) + ka2);
+              if (p.clamp > 0.f) gv = fminf(gv, p.clamp);
+              gg[e] = valid ? gv * scale : 0.f;
+            }
+            pk[j >> 1] = pack_bf16(gg[0], gg[1]);
+          }
+        }
+        // G tile: k-block c0/64, row r, 16-byte chunks (c0%64)/8 .. +3, 128B swizzle
+        const uint32_t gb = L.g_kblock(c0 >> 6) + r * 128;
+        const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          sts128(gb + (((ch0 + i) ^ (r & 7)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        // g^T spill: gt[col][row0 + r] (lanes = consecutive rows -> 64 B per column)
+        unsigned short* gt = reinterpret_cast<unsigned short*>(p.gt) + (size_t)c0 * p.Rpad + row0 + r;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          gt[(size_t)(2 * j) * p.Rpad] = (unsigned short)(pk[j] & 0xffffu);
+          gt[(size_t)(2 * j + 1) * p.Rpad] = (unsigned short)(pk[j] >> 16);
+        }
+      }
+      named_barrier_sync(2, WORKERS);            // every generic entry of G / g^T is written
+      if (wg == 0) {
+        // exact (fp32, single rounding) blank and label entries of row r
+        const float xb = tmem_ld1(tq + p.blank);
+        float xl = 0.f;
+        for (int i = 0; i < 16; ++i) {
+          const int ui = g.ubase + i;
+          int col = 0;
+          if (ui < g.Ub) col = p.targets[(size_t)g.b * (p.U1 - 1) + ui];
+          const float xi = tmem_ld1(tq + col);
+          if ((r & 15) == i) xl = xi;
+        }
+        tmem_ld_wait();
+        if (valid) {
+          auto entry = [&](float x, float kc1, float kc2) {
+            float gv = __expf(x + k_all) - __expf(x + kc1);
+            if (kc2 != kNegInf) gv -= __expf(x + kc2);
+            if (p.clamp > 0.f) gv = fminf(fmaxf(gv, -p.clamp), p.clamp);
+            return gv * scale;
+          };
+          auto put = [&](int col, float val) {
+            const unsigned short h = __bfloat16_as_ushort(__float2bfloat16(val));
+            const uint32_t a = L.g_kblock(col >> 6) + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4) + (col & 7) * 2;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(h) : "memory");
+            reinterpret_cast<unsigned short*>(p.gt)[(size_t)col * p.Rpad + row0 + r] = h;
+          };
+          const float xbb = xb + __ldg(p.bias + p.blank);
+          put(p.blank, entry(xbb, k_blank, (lab == p.blank) ? k_label : kNegInf));
+          if (lab >= 0 && lab != p.blank) put(lab, entry(xl + __ldg(p.bias + lab), k_label, kNegInf));
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(L.g_full());
+      if (tid == 128) TC_PROF(2, 3);
+
+      // ---------------- P3 (MMA busy): d_bias = column sums of the final G tile
+      mbar_wait(L.g_full(), ph, 31);
+      {
+        const int nchunk = p.Vp >> 3;
+        if (wt < 4 * nchunk) {
+          const int rg = wt / nchunk, c = wt - rg * nchunk;
+          const uint32_t gb = L.g_kblock(c >> 3) + (uint32_t)(rg * 32) * 128u;
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            const uint4 x = lds128(gb + rr * 128 + ((((c & 7) ^ (rr & 7))) << 4));
+            acc[0] += __uint_as_float(x.x << 16); acc[1] += __uint_as_float(x.x & 0xffff0000u);
+            acc[2] += __uint_as_float(x.y << 16); acc[3] += __uint_as_float(x.y & 0xffff0000u);
+            acc[4] += __uint_as_float(x.z << 16); acc[5] += __uint_as_float(x.z & 0xffff0000u);
+            acc[6] += __uint_as_float(x.w << 16); acc[7] += __uint_as_float(x.w & 0xffff0000u);
+          }
+          float* o = L.dbp + rg * p.Vp + c * 8;
+          *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+        named_barrier_sync(2, WORKERS);
+        if (wt == 0) mbar_arrive(L.gs_done());
+        if (wt < p.Vp) db0 += (L.dbp[wt] + L.dbp[p.Vp + wt]) + (L.dbp[2 * p.Vp + wt] + L.dbp[3 * p.Vp + wt]);
+        if (wt + WORKERS < p.Vp)
+          db1 += (L.dbp[wt + WORKERS] + L.dbp[p.Vp + wt + WORKERS]) + (L.dbp[2 * p.Vp + wt + WORKERS] + L.dbp[3 * p.Vp + wt + WORKERS]);
+      }
+
+      // ---------------- P4 (warps 4-11): dH = dZ * (1 - z^2); reductions.  Warp group wg owns d blocks 2wg, 2wg+1.
+      // z^T arrives in shared memory (TMA, issued after dz_full): box (mb, half) = [128 d][64 rows], 128B swizzle.
+      if (wg < 2) {
+        mbar_wait(L.dz_full(), ph, 32);
+        if (tid == 128) TC_PROF(2, 4);
+        tc_fence_after();
+#pragma unroll
+        for (int mbl = 0; mbl < 2; ++mbl) {
+          const int mb = 2 * wg + mbl;
+          if (mb < MB) {
+            mbar_wait(L.z_full(mb), ph, 33);
+            if (tid == 128) TC_PROF(2, 40 + mb);
+            const int d = mb * 128 + r;
+            float v[16];
+            tmem_ld16(tq + mb * 128, v);
+#pragma unroll
+            for (int tloc = 0; tloc < 8; ++tloc) {
+              const uint32_t zb = L.z_box(2 * mb + (tloc >> 2)) + (uint32_t)r * 128u;
+              const uint4 z0 = lds128(zb + ((((tloc & 3) * 2) ^ (r & 7)) << 4));
+              const uint4 z1 = lds128(zb + ((((tloc & 3) * 2 + 1) ^ (r & 7)) << 4));
+              tmem_ld_wait();
+              float w[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) w[j] = v[j];
+              if (tloc < 7) tmem_ld16(tq + mb * 128 + (tloc + 1) * 16, v);
+              const uint32_t zw[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+              float es0 = 0.f, es1 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float za = __uint_as_float(zw[j] << 16), zb2 = __uint_as_float(zw[j] & 0xffff0000u);
+                const float ha = w[2 * j] * fmaf(-za, za, 1.f), hb = w[2 * j + 1] * fmaf(-zb2, zb2, 1.f);
+                es0 += ha;
+                es1 += hb;
+                pacc[mbl][2 * j] += ha;
+                pacc[mbl][2 * j + 1] += hb;
+              }
+              const int tt = g.t0 + tloc;
+              if (tt < g.Tb) p.d_enc_part[(((size_t)ti.y * p.B + g.b) * p.T + tt) * p.D + d] = es0 + es1;
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(L.tmem_empty());
+        if (tid == 128) TC_PROF(2, 5);
+      }
+      ph ^= 1u;
+    }
+    flush_pred();
+    if (tile_end > tile_begin) {
+      if (wt < p.V) atomicAdd(p.d_bias + wt, db0);
+      if (wt + WORKERS < p.V) atomicAdd(p.d_bias + wt + WORKERS, db1);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace tc
+}  // namespace ctcvr

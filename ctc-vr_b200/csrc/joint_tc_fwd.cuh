@@ -1,0 +1,313 @@
+// Forward kernel of the bf16 tcgen05 path (included by joint_tc.cu).
+//
+//   z      = tanh(enc_proj[b,t,:] + pred_proj[b,u,:])        model/component/joint.py:57-67
+//   logits = z . W_out^T + b_out                             model/component/joint.py:68
+//   out    : lse, lp_blank, lp_label per lattice cell         log-softmax + gather of torchaudio rnnt_loss
+//                                                             (model/component/transducer.py:180-187)
+//
+// Tiles: 128 lattice cells = nu label columns x (128/nu) consecutive frames of one utterance,
+// nu in {4,2,1} (an utterance with W = U_b+1 columns is covered by W/4 groups of 4 columns and the
+// binary remainder).  TMEM lane r = 32*q + lane holds cell (t0 + (q/nu)*32 + lane, u0 + q%nu), so the
+// label of a cell is uniform across a warp and both gathered logits (blank, label) are one-column
+// tcgen05.ld's instead of per-element compares.
+//
+// One persistent CTA per SM, 512 threads, warp-specialised:
+//   warp 0      TMA: bf16 W_out k-blocks (two N-halves per k-block) into a smem ring
+//   warp 1      MMA issuer: tcgen05.mma M=128, N=Vp/2 (x2), K=16; fp32 accumulators in TMEM
+//   warp 2      TMEM allocator
+//   warp 3      TMA: slab ring - per k-block the nu pred rows and 128/nu enc rows (bf16, 128B swizzle)
+//   warps 4-7   epilogue: tcgen05.ld (thread = cell), online log-softmax in base 2, gathers, stores
+//   warps 8-15  A producers: tanh(e+p) -> bf16 -> K-major swizzled A tile (conflict-free LDS/STS)
+#pragma once
+#include "tc_common.cuh"
+
+namespace ctcvr {
+namespace tc {
+
+constexpr int F_A_STAGES = 3;
+constexpr int F_S_STAGES = 3;
+constexpr int F_SLAB_BYTES = 1024 + 128 * 128;   // [pred rows: 1 KB region][128 enc rows x 128 B]
+constexpr int F_MAX_W_STAGES = 4;
+
+struct FwdParams {
+  const float* bias;       // [V]
+  const float* bias_l2;    // [Vp] bias * log2(e), -inf beyond V
+  const int32_t* targets;  // [B,U1-1]
+  const int32_t* t_len;
+  const int32_t* u_len;
+  const int4* tiles;       // {b, u0, t0, nu}
+  const int* ntiles;
+  int B, T, U1, D, V, Vp, NH, blank, w_stages;
+  float* lse;
+  float* lp_blank;
+  float* lp_label;
+  long long* prof;
+};
+
+struct FwdSmem {
+  uint32_t a_base, w_base, w_bytes, s_base, bar_base;
+  float* bias_l2;
+  uint32_t* tmem_ptr;
+  __device__ __forceinline__ uint32_t a_stage(int i) const { return a_base + i * A_STAGE_BYTES; }
+  __device__ __forceinline__ uint32_t w_stage(int i) const { return w_base + i * w_bytes; }
+  __device__ __forceinline__ uint32_t s_stage(int i) const { return s_base + i * F_SLAB_BYTES; }
+  __device__ __forceinline__ uint32_t a_full(int i) const { return bar_base + i * 16; }
+  __device__ __forceinline__ uint32_t a_empty(int i) const { return bar_base + i * 16 + 8; }
+  __device__ __forceinline__ uint32_t s_full(int i) const { return bar_base + 64 + i * 16; }
+  __device__ __forceinline__ uint32_t s_empty(int i) const { return bar_base + 64 + i * 16 + 8; }
+  __device__ __forceinline__ uint32_t w_full(int i) const { return bar_base + 128 + i * 16; }
+  __device__ __forceinline__ uint32_t w_empty(int i) const { return bar_base + 128 + i * 16 + 8; }
+  __device__ __forceinline__ uint32_t tmem_full() const { return bar_base + 192; }
+  __device__ __forceinline__ uint32_t tmem_empty() const { return bar_base + 200; }
+};
+
+__host__ __device__ inline size_t fwd2_smem_bytes(int NH, int Vp, int w_stages) {
+  size_t s = 1024;
+  s += (size_t)F_A_STAGES * A_STAGE_BYTES;
+  s += (size_t)w_stages * NH * 128;
+  s = (s + 1023) / 1024 * 1024;
+  s += (size_t)F_S_STAGES * F_SLAB_BYTES;
+  s += (size_t)Vp * 4;
+  s += 256 + 16;
+  return s;
+}
+
+__device__ __forceinline__ void carve_fwd2(FwdSmem& L, uint8_t* raw, int NH, int Vp, int w_stages) {
+  const uint32_t base = smem_u32(raw);
+  uint32_t a = (base + 1023u) & ~1023u;
+  L.a_base = a; a += F_A_STAGES * A_STAGE_BYTES;
+  L.w_base = a; L.w_bytes = NH * 128; a += w_stages * NH * 128;
+  a = (a + 1023u) & ~1023u;
+  L.s_base = a; a += F_S_STAGES * F_SLAB_BYTES;
+  L.bias_l2 = reinterpret_cast<float*>(raw + (a - base)); a += Vp * 4;
+  a = (a + 15u) & ~15u;
+  L.bar_base = a; a += 256;
+  L.tmem_ptr = reinterpret_cast<uint32_t*>(raw + (a - base));
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_e,
+                  const __grid_constant__ CUtensorMap tmap_p, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  FwdSmem L;
+  carve_fwd2(L, smem_raw, p.NH, p.Vp, p.w_stages);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KB = p.D / BK;
+  const int ntiles = *p.ntiles;
+  const int WS = p.w_stages;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_e);
+    tma_prefetch_desc(&tmap_p);
+    for (int i = 0; i < F_A_STAGES; ++i) { mbar_init(L.a_full(i), PROD_THREADS); mbar_init(L.a_empty(i), 1); }
+    for (int i = 0; i < F_S_STAGES; ++i) { mbar_init(L.s_full(i), 1); mbar_init(L.s_empty(i), PROD_THREADS); }
+    for (int i = 0; i < F_MAX_W_STAGES; ++i) { mbar_init(L.w_full(i), 1); mbar_init(L.w_empty(i), 1); }
+    mbar_init(L.tmem_full(), 1);
+    mbar_init(L.tmem_empty(), 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(L.tmem_ptr), TMEM_COLS);
+  for (int i = tid; i < p.Vp; i += NTHREADS) L.bias_l2[i] = p.bias_l2[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *L.tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA: W_out k-blocks
+    if (lane == 0) {
+      Pipe wp;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+        for (int kb = 0; kb < KB; ++kb)
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(L.w_empty(wp.stage), wp.phase ^ 1u, 1);
+            mbar_arrive_expect_tx(L.w_full(wp.stage), (uint32_t)p.NH * 128u);
+            tma_load_2d(L.w_stage(wp.stage), &tmap_w, L.w_full(wp.stage), kb * BK, h * p.NH);
+            wp.advance(WS);
+          }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ TMA: enc / pred slabs
+    if (lane == 0) {
+      Pipe sp;
+      int prof_n = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int4 ti = p.tiles[tile];
+        const int nbox = 4 / ti.w;                       // 32-frame boxes: 128/nu frames
+        const int prow = ti.x * p.U1 + ti.y;
+        const int erow = ti.x * p.T + ti.z;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(L.s_empty(sp.stage), sp.phase ^ 1u, 2);
+          TC_PROF(0, kb);
+          const uint32_t st = L.s_stage(sp.stage);
+          mbar_arrive_expect_tx(L.s_full(sp.stage), 512u + (uint32_t)nbox * 4096u);
+          tma_load_2d(st, &tmap_p, L.s_full(sp.stage), kb * BK, prow);
+          for (int i = 0; i < nbox; ++i)
+            tma_load_2d(st + 1024 + i * 4096, &tmap_e, L.s_full(sp.stage), kb * BK, erow + 32 * i);
+          sp.advance(F_S_STAGES);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      Pipe ap, wp;
+      uint32_t tphase = 0;
+      int prof_n = 0;
+      const uint32_t idesc = make_idesc_bf16(BM, p.NH);
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        TC_PROF(1, 100);
+        mbar_wait(L.tmem_empty(), tphase ^ 1u, 3);
+        TC_PROF(1, 101);
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(L.a_full(ap.stage), ap.phase, 4);
+          TC_PROF(1, kb);
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(L.w_full(wp.stage), wp.phase, 5);
+            TC_PROF(1, 50 + kb * 2 + h);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < BK / 16; ++ks) {
+              const uint64_t ad = make_desc_sw128(L.a_stage(ap.stage) + ks * 32);
+              const uint64_t bd = make_desc_sw128(L.w_stage(wp.stage) + ks * 32);
+              umma_bf16(tmem_base + h * p.NH, ad, bd, idesc, (kb | ks) ? 1u : 0u);
+            }
+            umma_commit(L.w_empty(wp.stage));
+            wp.advance(WS);
+          }
+          umma_commit(L.a_empty(ap.stage));
+          ap.advance(F_A_STAGES);
+        }
+        umma_commit(L.tmem_full());
+        tphase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ epilogue: online log-softmax (base 2)
+    const int q = warp & 3;
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t tphase = 0;
+    int prof_n = 0;
+    const float bias_blank = __ldg(p.bias + p.blank);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int4 ti = p.tiles[tile];
+      pin(ti.x); pin(ti.y); pin(ti.z); pin(ti.w);
+      const int b = ti.x, nu = ti.w;
+      const int lognu = nu >> 1;                          // 4 -> 2, 2 -> 1, 1 -> 0
+      const int u = ti.y + (q & (nu - 1));
+      const int t = ti.z + ((q >> lognu) << 5) + lane;
+      int Tb = min(p.t_len[b], p.T), Ub = min(p.u_len[b], p.U1 - 1);
+      pin(Tb); pin(Ub);
+      const bool valid = t < Tb;
+      int lab = -1;
+      float bias_lab = 0.f;
+      if (u < Ub) { lab = p.targets[(size_t)b * (p.U1 - 1) + u]; bias_lab = __ldg(p.bias + lab); }
+      pin(lab);
+      mbar_wait(L.tmem_full(), tphase, 6);
+      if (tid == 128) TC_PROF(2, 1);
+      tc_fence_after();
+      const float xb = tmem_ld1(tq + p.blank);
+      const float xl = tmem_ld1(tq + (lab >= 0 ? lab : 0));
+      float m = kNegInf, s = 0.f;
+      float v[32];
+      tmem_ld32(tq, v);
+      for (int c0 = 0; c0 < p.Vp; c0 += 32) {
+        tmem_ld_wait();
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bj = *reinterpret_cast<const float4*>(L.bias_l2 + c0 + j);
+          y[j] = fmaf(v[j], LOG2E, bj.x);
+          y[j + 1] = fmaf(v[j + 1], LOG2E, bj.y);
+          y[j + 2] = fmaf(v[j + 2], LOG2E, bj.z);
+          y[j + 3] = fmaf(v[j + 3], LOG2E, bj.w);
+        }
+        if (c0 + 32 < p.Vp) tmem_ld32(tq + c0 + 32, v);     // next chunk in flight during the math below
+        float cm[4] = {kNegInf, kNegInf, kNegInf, kNegInf};
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) cm[e] = fmaxf(cm[e], y[j + e]);
+        const float nm = fmaxf(m, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[e] += ex2_fast(y[j + e] - nm);
+        s = s * ex2_fast(m - nm) + ((acc[0] + acc[1]) + (acc[2] + acc[3]));
+        m = nm;
+      }
+      tc_fence_before();
+      mbar_arrive(L.tmem_empty());
+      if (tid == 128) TC_PROF(2, 2);
+      if (valid) {
+        const size_t cell = ((size_t)b * p.T + t) * p.U1 + u;
+        const float l = (m + lg2_fast(s)) * LN2;
+        p.lse[cell] = l;
+        p.lp_blank[cell] = xb + bias_blank - l;
+        p.lp_label[cell] = (lab >= 0) ? xl + bias_lab - l : kNegInf;
+      }
+      tphase ^= 1u;
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ A producers
+    // thread (lr, c): 16-byte chunk c of rows lr, lr+32, lr+64, lr+96 (one per TMEM lane quarter)
+    const int pt = tid - 256;
+    const int c = pt & 7, lr = pt >> 3;
+    const uint32_t sw = (uint32_t)((c ^ (lr & 7)) << 4);
+    Pipe ap, sp;
+    int prof_n = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int nu = p.tiles[tile].w;
+      pin(nu);
+      const int lognu = nu >> 1;
+      uint32_t e_off[4], p_off[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ul = j & (nu - 1);
+        const int tloc = ((j >> lognu) << 5) + lr;
+        e_off[j] = 1024u + (uint32_t)tloc * 128u + sw;
+        p_off[j] = (uint32_t)ul * 128u + (uint32_t)((c ^ ul) << 4);
+      }
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(L.s_full(sp.stage), sp.phase, 7);
+        mbar_wait(L.a_empty(ap.stage), ap.phase ^ 1u, 8);
+        if (pt == 0) TC_PROF(3, kb);
+        const uint32_t sb = L.s_stage(sp.stage);
+        const uint32_t ab = L.a_stage(ap.stage) + (uint32_t)lr * 128u + sw;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 ev = lds128(sb + e_off[j]);
+          const uint4 pv = lds128(sb + p_off[j]);
+          sts128(ab + j * 4096, tanh_add_bf16x2(ev.x, pv.x), tanh_add_bf16x2(ev.y, pv.y),
+                 tanh_add_bf16x2(ev.z, pv.z), tanh_add_bf16x2(ev.w, pv.w));
+        }
+        fence_proxy_async();
+        mbar_arrive(L.a_full(ap.stage));
+        mbar_arrive(L.s_empty(sp.stage));
+        if (pt == 0) TC_PROF(3, 20 + kb);
+        ap.advance(F_A_STAGES);
+        sp.advance(F_S_STAGES);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// Tile table of the forward kernel: per utterance (W/4) groups of 4 label columns x 32-frame blocks, then a
+// 2-column group x 64-frame blocks if W & 2, then a 1-column group x 128-frame blocks if W & 1.
+__device__ __forceinline__ int fwd_tiles_of(int Tb, int W) {
+  if (Tb <= 0) return 0;
+  return (W >> 2) * ((Tb + 31) >> 5) + ((W & 2) ? ((Tb + 63) >> 6) : 0) + ((W & 1) ? ((Tb + 127) >> 7) : 0);
+}
+
+}  // namespace tc
+}  // namespace ctcvr

@@ -54,4 +54,4 @@ for r in range(4):
     ev=pr[r][pr[r]!=0]
     tags=(ev>>48); clk=(ev & 0xffffffffffff)-t0
     print(names[r], len(ev))
-    print(' '.join(f"{int(a)}:{int(c)}" for a,c in zip(tags[:90],clk[:90])))
+    print(' '.join(f"{int(a)}:{int(c)}" for a,c in zip(tags[:260],clk[:260])))
