@@ -30,6 +30,8 @@ constexpr int B_SLAB_BYTES = 2048 + 1024;      // 16 pred rows + 8 enc rows, 128
 constexpr int WORKERS = 384;
 
 struct BwdParams {
+  const __nv_bfloat16* w_t;  // tiled W_out   [KB][2][NH][64]     (prep_weights3_kernel)
+  const __nv_bfloat16* wt_t; // tiled W_out^T [MB][KBG][128][64]
   const float* bias;        // [V]
   const float* bias_l2;     // [Vp] bias*log2e, -inf beyond V
   const int32_t* targets;
@@ -44,8 +46,12 @@ struct BwdParams {
   const float* costs;
   const float* grad_costs;
   float clamp;
-  __nv_bfloat16* zt;        // [D][Rpad]
-  __nv_bfloat16* gt;        // [Vp][Rpad]
+  // spills, tiled per 128-row tile and pre-swizzled so that kernel 2 (and P4) fetch them with 1-D bulk copies:
+  //   zt [tile][MB][2][128 d][64 rows] : element (d, row rr) of a tile at box (d>>7, rr>>6), row d&127,
+  //                                      chunk ((rr&63)>>3) ^ (d&7), element rr&7
+  //   gt [tile][2][Vp][64 rows]        : element (v, rr) at half rr>>6, row v, chunk ((rr&63)>>3) ^ (v&7), element rr&7
+  __nv_bfloat16* zt;
+  __nv_bfloat16* gt;
   long Rpad;
   int scratch_tile;         // unused row tile (kept for layout compatibility)
   float* d_enc_part;        // [S][B,T,D]
@@ -117,19 +123,9 @@ __device__ __forceinline__ void carve_bwd2(Bwd2Smem& L, uint8_t* raw, int NH, in
   L.tmem_ptr = reinterpret_cast<uint32_t*>(raw + (a - base));
 }
 
-// tanh(a + b) on packed bf16 pairs: one packed add and one packed MUFU op per two elements.  The sum is rounded to
-// bf16 before the tanh (error <= 2^-9 |x| (1 - z^2) <= 9e-4, below the bf16 rounding of z itself).
-__device__ __forceinline__ uint32_t tanh_add_bf16x2_packed(uint32_t a, uint32_t b) {
-  uint32_t s, r;
-  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(s) : "r"(a), "r"(b));
-  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(r) : "r"(s));
-  return r;
-}
-
 __global__ void __launch_bounds__(NTHREADS, 1)
-joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_wt,
-                  const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_p,
-                  const __grid_constant__ CUtensorMap tmap_zt, const BwdParams p) {
+joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_p,
+                  const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   Bwd2Smem L;
   carve_bwd2(L, smem_raw, p.NH, p.Vp, p.D);
@@ -142,11 +138,8 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   const int tile_end = (int)(((long)ntiles * (blockIdx.x + 1)) / gridDim.x);
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_w);
-    tma_prefetch_desc(&tmap_wt);
     tma_prefetch_desc(&tmap_e);
     tma_prefetch_desc(&tmap_p);
-    tma_prefetch_desc(&tmap_zt);
     for (int i = 0; i < B_A_STAGES; ++i) { mbar_init(L.a_full(i), PROD_THREADS); mbar_init(L.a_empty(i), 1); }
     for (int i = 0; i < B_S_STAGES; ++i) { mbar_init(L.s_full(i), 1); mbar_init(L.s_empty(i), PROD_THREADS); }
     for (int i = 0; i < B_R1_STAGES; ++i) { mbar_init(L.r1_full(i), 1); mbar_init(L.r1_empty(i), 1); }
@@ -173,14 +166,15 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       int prof_n = 0;
       uint32_t ph = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const size_t row0 = (size_t)p.tiles[tile].w * BM;
+        const size_t rowtile = (size_t)p.tiles[tile].w;
         TC_PROF(0, 1);
         // the ring is drained here: the previous tile's dz_full was observed below
         for (int kb = 0; kb < KB; ++kb)
           for (int h = 0; h < 2; ++h) {
             mbar_wait(L.r1_empty(r1.stage), r1.phase ^ 1u, 11);
             mbar_arrive_expect_tx(L.r1_full(r1.stage), (uint32_t)p.NH * 128u);
-            tma_load_2d(L.r1_stage(r1.stage), &tmap_w, L.r1_full(r1.stage), kb * BK, h * p.NH);
+            bulk_load(L.r1_stage(r1.stage), p.w_t + (size_t)(kb * 2 + h) * p.NH * 64, (uint32_t)p.NH * 128u,
+                      L.r1_full(r1.stage));
             r1.advance(B_R1_STAGES);
           }
         TC_PROF(0, 2);
@@ -190,7 +184,7 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           for (int kb = 0; kb < KBG; ++kb) {
             mbar_wait(L.r3_empty(r3.stage), r3.phase ^ 1u, 13);
             mbar_arrive_expect_tx(L.r3_full(r3.stage), 16384u);
-            tma_load_2d(L.r3_stage(r3.stage), &tmap_wt, L.r3_full(r3.stage), kb * 64, mb * 128);
+            bulk_load(L.r3_stage(r3.stage), p.wt_t + (size_t)(mb * KBG + kb) * 8192, 16384u, L.r3_full(r3.stage));
             r3.advance(B_R3_STAGES);
           }
         TC_PROF(0, 4);
@@ -201,8 +195,7 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         TC_PROF(0, 6);
         for (int mb = 0; mb < MB; ++mb) {
           mbar_arrive_expect_tx(L.z_full(mb), 32768u);
-          tma_load_2d(L.z_box(2 * mb), &tmap_zt, L.z_full(mb), (int)row0, mb * 128);
-          tma_load_2d(L.z_box(2 * mb + 1), &tmap_zt, L.z_full(mb), (int)row0 + 64, mb * 128);
+          bulk_load(L.z_box(2 * mb), p.zt + ((rowtile * MB + mb) * 2) * 8192, 32768u, L.z_full(mb));
         }
         ph ^= 1u;
       }
@@ -335,7 +328,7 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       pin(ti.x); pin(ti.y); pin(ti.z); pin(ti.w);
       const RowMap g = tile_geometry<TILE_RECT>(p.t_len, p.u_len, p.T, p.U1, ti);
       if (g.b != cur_b || g.ubase != cur_ubase) { flush_pred(); cur_b = g.b; cur_ubase = g.ubase; }
-      const size_t row0 = (size_t)ti.w * BM;
+      const size_t rowtile = (size_t)ti.w;
 
       // ---------------- P1 (warps 8-15): A tile k-blocks + z^T spill
       if (producer) {
@@ -348,7 +341,9 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           const uint32_t sb = L.s_stage(sp.stage);
           const uint32_t ab = L.a_stage(ap.stage) + a_off;
           const uint4 pv = lds128(sb + p_off);
-          unsigned short* z = reinterpret_cast<unsigned short*>(p.zt) + (size_t)(kb * BK + pc * 8) * p.Rpad + row0 + lane;
+          // d = kb*64 + pc*8 + e -> box row (kb&1)*64 + pc*8 + e of d block kb>>1; tile row lane + 32j -> half j>>1
+          unsigned short* z = reinterpret_cast<unsigned short*>(p.zt) + ((rowtile * MB + (kb >> 1)) * 2) * 8192 +
+                              ((kb & 1) * 64 + pc * 8) * 64 + (lane & 7);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 ev = lds128(sb + e_off[j]);
@@ -358,10 +353,12 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             w[2] = tanh_add_bf16x2_packed(ev.z, pv.z);
             w[3] = tanh_add_bf16x2_packed(ev.w, pv.w);
             sts128(ab + j * 4096, w[0], w[1], w[2], w[3]);
+            const int chunk = (lane >> 3) + 4 * (j & 1);           // 8-row chunk of the 64-row half
+            unsigned short* zj = z + (j >> 1) * 8192;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              z[(size_t)(2 * e) * p.Rpad + 32 * j] = (unsigned short)(w[e] & 0xffffu);
-              z[(size_t)(2 * e + 1) * p.Rpad + 32 * j] = (unsigned short)(w[e] >> 16);
+              zj[(2 * e) * 64 + ((chunk ^ (2 * e)) << 3)] = (unsigned short)(w[e] & 0xffffu);
+              zj[(2 * e + 1) * 64 + ((chunk ^ (2 * e + 1)) << 3)] = (unsigned short)(w[e] >> 16);
             }
           }
           fence_proxy_async();
@@ -436,11 +433,13 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         for (int i = 0; i < 4; ++i)
           sts128(gb + (((ch0 + i) ^ (r & 7)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
         // g^T spill: gt[col][row0 + r] (lanes = consecutive rows -> 64 B per column)
-        unsigned short* gt = reinterpret_cast<unsigned short*>(p.gt) + (size_t)c0 * p.Rpad + row0 + r;
+        // g^T spill (tiled): column v of this row -> gt[tile][r>>6][v][chunk ((r&63)>>3) ^ (v&7)][r&7]
+        unsigned short* gt = reinterpret_cast<unsigned short*>(p.gt) + ((rowtile * 2 + (r >> 6)) * p.Vp + c0) * 64 + (r & 7);
+        const int gch = (r & 63) >> 3;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          gt[(size_t)(2 * j) * p.Rpad] = (unsigned short)(pk[j] & 0xffffu);
-          gt[(size_t)(2 * j + 1) * p.Rpad] = (unsigned short)(pk[j] >> 16);
+          gt[(2 * j) * 64 + ((gch ^ ((2 * j) & 7)) << 3)] = (unsigned short)(pk[j] & 0xffffu);
+          gt[(2 * j + 1) * 64 + ((gch ^ ((2 * j + 1) & 7)) << 3)] = (unsigned short)(pk[j] >> 16);
         }
       }
       named_barrier_sync(2, WORKERS);            // every generic entry of G / g^T is written
@@ -467,7 +466,8 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             const unsigned short h = __bfloat16_as_ushort(__float2bfloat16(val));
             const uint32_t a = L.g_kblock(col >> 6) + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4) + (col & 7) * 2;
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(h) : "memory");
-            reinterpret_cast<unsigned short*>(p.gt)[(size_t)col * p.Rpad + row0 + r] = h;
+            reinterpret_cast<unsigned short*>(p.gt)[((rowtile * 2 + (r >> 6)) * p.Vp + col) * 64 +
+                                                    ((((r & 63) >> 3) ^ (col & 7)) << 3) + (r & 7)] = h;
           };
           const float xbb = xb + __ldg(p.bias + p.blank);
           put(p.blank, entry(xbb, k_blank, (lab == p.blank) ? k_label : kNegInf));

@@ -12,7 +12,7 @@
 // tcgen05.ld's instead of per-element compares.
 //
 // One persistent CTA per SM, 512 threads, warp-specialised:
-//   warp 0      TMA: bf16 W_out k-blocks (two N-halves per k-block) into a smem ring
+//   warp 0      bulk copies: pre-tiled bf16 W_out k-blocks (two N-halves per k-block) into a smem ring
 //   warp 1      MMA issuer: tcgen05.mma M=128, N=Vp/2 (x2), K=16; fp32 accumulators in TMEM
 //   warp 2      TMEM allocator
 //   warp 3      TMA: slab ring - per k-block the nu pred rows and 128/nu enc rows (bf16, 128B swizzle)
@@ -30,6 +30,7 @@ constexpr int F_SLAB_BYTES = 1024 + 128 * 128;   // [pred rows: 1 KB region][128
 constexpr int F_MAX_W_STAGES = 4;
 
 struct FwdParams {
+  const __nv_bfloat16* w_t; // tiled W_out: [KB][2][NH][64] bf16, pre-swizzled (prep_weights3_kernel)
   const float* bias;       // [V]
   const float* bias_l2;    // [Vp] bias * log2(e), -inf beyond V
   const int32_t* targets;  // [B,U1-1]
@@ -86,8 +87,8 @@ __device__ __forceinline__ void carve_fwd2(FwdSmem& L, uint8_t* raw, int NH, int
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_e,
-                  const __grid_constant__ CUtensorMap tmap_p, const FwdParams p) {
+joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_p,
+                  const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   FwdSmem L;
   carve_fwd2(L, smem_raw, p.NH, p.Vp, p.w_stages);
@@ -97,7 +98,6 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   const int WS = p.w_stages;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_e);
     tma_prefetch_desc(&tmap_p);
     for (int i = 0; i < F_A_STAGES; ++i) { mbar_init(L.a_full(i), PROD_THREADS); mbar_init(L.a_empty(i), 1); }
@@ -123,7 +123,8 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           for (int h = 0; h < 2; ++h) {
             mbar_wait(L.w_empty(wp.stage), wp.phase ^ 1u, 1);
             mbar_arrive_expect_tx(L.w_full(wp.stage), (uint32_t)p.NH * 128u);
-            tma_load_2d(L.w_stage(wp.stage), &tmap_w, L.w_full(wp.stage), kb * BK, h * p.NH);
+            bulk_load(L.w_stage(wp.stage), p.w_t + (size_t)(kb * 2 + h) * p.NH * 64, (uint32_t)p.NH * 128u,
+                      L.w_full(wp.stage));
             wp.advance(WS);
           }
     }
@@ -284,8 +285,8 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         for (int j = 0; j < 4; ++j) {
           const uint4 ev = lds128(sb + e_off[j]);
           const uint4 pv = lds128(sb + p_off[j]);
-          sts128(ab + j * 4096, tanh_add_bf16x2(ev.x, pv.x), tanh_add_bf16x2(ev.y, pv.y),
-                 tanh_add_bf16x2(ev.z, pv.z), tanh_add_bf16x2(ev.w, pv.w));
+          sts128(ab + j * 4096, tanh_add_bf16x2_packed(ev.x, pv.x), tanh_add_bf16x2_packed(ev.y, pv.y),
+                 tanh_add_bf16x2_packed(ev.z, pv.z), tanh_add_bf16x2_packed(ev.w, pv.w));
         }
         fence_proxy_async();
         mbar_arrive(L.a_full(ap.stage));

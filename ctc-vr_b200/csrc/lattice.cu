@@ -12,6 +12,8 @@
 //
 // Algorithmic HBM bytes: 24 B per cell (2 log-probs read for alpha, again for beta, alpha and beta
 // written).  The kernel is bound by the T+U dependent diagonals, not by bandwidth.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ctcvr {
@@ -143,6 +145,167 @@ __global__ void __launch_bounds__(LAT_THREADS) rnnt_lattice_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fast variant (the whole utterance fits in shared memory four times: lp_blank, lp_label, alpha, beta).
+// Differences from the kernel above, all aimed at the per-diagonal latency (the kernel is a chain of T+U dependent
+// steps, nothing else matters):
+//   - base-2 domain: the staged log-probs are pre-multiplied by log2(e), so a step is max / sub / ex2 / add / lg2 / add
+//     with no scaling multiplies on the chain; alpha / beta are converted back when they are copied out
+//   - alpha / beta are written to shared memory during the sweep (conflict-free diagonal stores) and copied to global
+//     memory afterwards with coalesced row stores by all threads: the scattered per-diagonal global stores of the
+//     kernel above occupied the LSU for ~32 sectors per store
+//   - pointers advance by a constant per diagonal, predicates are selects (no divergent branches in the loop)
+constexpr int LAT2_THREADS = 256;
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// log2(2^a + 2^b); -inf safe without a branch: for a = b = -inf, m - m is NaN, so the difference is clamped first
+__device__ __forceinline__ float lae2(float a, float b) {
+  const float m = fmaxf(a, b), n = fminf(a, b);
+  const float d = (n == kNegInf) ? kNegInf : n - m;          // <= 0, -inf if the smaller operand is -inf
+  return m + lg2f(1.f + ex2f(d));
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(LAT2_THREADS) rnnt_lattice2_kernel(
+    const float* __restrict__ lp_blank, const float* __restrict__ lp_label, const int32_t* __restrict__ t_len,
+    const int32_t* __restrict__ u_len, float* __restrict__ alpha, float* __restrict__ beta,
+    float* __restrict__ costs, int T, int U1, int pitch) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x;
+  const int Tb = min(t_len[b], T), Ub = min(u_len[b], U1 - 1);
+  const size_t base = (size_t)b * T * U1;
+  if (Tb <= 0) { if (threadIdx.x == 0) costs[b] = 0.f; return; }
+  const int W = Ub + 1;
+  float* sb = sm;                               // lp_blank * log2e
+  float* sl = sm + (size_t)T * pitch;           // lp_label * log2e
+  float* sa = sm + (size_t)2 * T * pitch;       // alpha (base 2)
+  float* sc = sm + (size_t)3 * T * pitch;       // beta  (base 2)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = LAT2_THREADS >> 5;
+  {
+    // flat, 4-deep unrolled staging: the loads of four elements per array are in flight before the first store
+    const int n = Tb * U1;                      // rows are contiguous in global memory (row pitch U1)
+    const float* gb = lp_blank + base;
+    const float* gl = lp_label + base;
+    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * LAT2_THREADS) {
+      float xb[4], xl[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * LAT2_THREADS;
+        xb[k] = (i < n) ? __ldg(gb + i) : 0.f;
+        xl[k] = (i < n) ? __ldg(gl + i) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * LAT2_THREADS;
+        if (i < n) {
+          const int t = i / U1, u = i - t * U1;
+          sb[t * pitch + u] = xb[k] * kLog2e;
+          sl[t * pitch + u] = xl[k] * kLog2e;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int ndiag = Tb + Ub;
+  if (warp == 0) {
+    // ---------------- alpha(t,u) = LSE(alpha(t-1,u)+lpb(t-1,u), alpha(t,u-1)+lpl(t,u-1)),  t = d - u
+    float prev[NJ], nb[NJ], nl[NJ];
+    int ib[NJ], il[NJ], io[NJ];                 // smem indices at diagonal d: lpb[t-1][u], lpl[t][u-1], alpha[t][u]
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int u = lane + 32 * j;
+      prev[j] = kNegInf;
+      ib[j] = (-u - 1) * pitch + u;
+      il[j] = (-u) * pitch + u - 1;
+      io[j] = (-u) * pitch + u;
+    }
+    auto fetch = [&](int d) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int u = lane + 32 * j, t = d - u;
+        const bool in = (u <= Ub) && (t >= 0) && (t < Tb);
+        nb[j] = (in && t > 0) ? sb[ib[j] + d * pitch] : kNegInf;
+        nl[j] = (in && u > 0) ? sl[il[j] + d * pitch] : kNegInf;
+      }
+    };
+    fetch(0);
+    for (int d = 0; d < ndiag; ++d) {
+      float cb[NJ], cl[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { cb[j] = nb[j]; cl[j] = nl[j]; }
+      if (d + 1 < ndiag) fetch(d + 1);
+      float cur[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int u = lane + 32 * j, t = d - u;
+        const bool in = (u <= Ub) && (t >= 0) && (t < Tb);
+        float left = __shfl_up_sync(0xffffffffu, prev[j], 1);
+        const float wrap = __shfl_sync(0xffffffffu, prev[j > 0 ? j - 1 : 0], 31);
+        if (lane == 0) left = (j > 0) ? wrap : kNegInf;
+        float v = lae2(prev[j] + cb[j], left + cl[j]);
+        v = (d == 0 && u == 0) ? 0.f : v;
+        v = in ? v : kNegInf;
+        if (in) sa[io[j] + d * pitch] = v;
+        cur[j] = v;
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) prev[j] = cur[j];
+    }
+  } else if (warp == 1) {
+    // ---------------- beta(t,u) = LSE(beta(t+1,u)+lpb(t,u), beta(t,u+1)+lpl(t,u)),  beta(T-1,U) = lpb(T-1,U)
+    float prev[NJ], nb[NJ], nl[NJ];
+    int ix[NJ];                                 // smem index of cell (t,u) at diagonal d, minus d*pitch
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int u = lane + 32 * j;
+      prev[j] = kNegInf;
+      ix[j] = (-u) * pitch + u;
+    }
+    auto fetch = [&](int d) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int u = lane + 32 * j, t = d - u;
+        const bool in = (u <= Ub) && (t >= 0) && (t < Tb);
+        nb[j] = in ? sb[ix[j] + d * pitch] : kNegInf;
+        nl[j] = (in && u < Ub) ? sl[ix[j] + d * pitch] : kNegInf;
+      }
+    };
+    fetch(ndiag - 1);
+    for (int d = ndiag - 1; d >= 0; --d) {
+      float cb[NJ], cl[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { cb[j] = nb[j]; cl[j] = nl[j]; }
+      if (d > 0) fetch(d - 1);
+      float cur[NJ];
+#pragma unroll
+      for (int j = NJ - 1; j >= 0; --j) {
+        const int u = lane + 32 * j, t = d - u;
+        const bool in = (u <= Ub) && (t >= 0) && (t < Tb);
+        float right = __shfl_down_sync(0xffffffffu, prev[j], 1);
+        const float wrap = __shfl_sync(0xffffffffu, prev[(j + 1 < NJ) ? j + 1 : j], 0);
+        if (lane == 31) right = (j + 1 < NJ) ? wrap : kNegInf;
+        const float a = (t + 1 < Tb) ? prev[j] + cb[j] : kNegInf;
+        float v = lae2(a, right + cl[j]);
+        v = (t == Tb - 1 && u == Ub) ? cb[j] : v;
+        v = in ? v : kNegInf;
+        if (in) sc[ix[j] + d * pitch] = v;
+        cur[j] = v;
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) prev[j] = cur[j];
+    }
+    if (lane == 0) costs[b] = -prev[0] * kLn2;     // beta(0,0)
+  }
+  __syncthreads();
+  for (int t = warp; t < Tb; t += nwarp)
+    for (int u = lane; u < W; u += 32) {
+      alpha[base + (size_t)t * U1 + u] = sa[t * pitch + u] * kLn2;
+      beta[base + (size_t)t * U1 + u] = sc[t * pitch + u] * kLn2;
+    }
+}
+
 // Fallback for very long targets (U1 > 256): one CTA per utterance, block-wide diagonal sweep.
 __global__ void rnnt_lattice_generic_kernel(const float* __restrict__ lp_blank, const float* __restrict__ lp_label,
                                             const int32_t* __restrict__ t_len, const int32_t* __restrict__ u_len,
@@ -194,6 +357,17 @@ template <int NJ>
 static int launch_lattice(const float* lpb, const float* lpl, const int32_t* t_len, const int32_t* u_len,
                           float* alpha, float* beta, float* costs, int B, int T, int U1, cudaStream_t st) {
   int pitch = (U1 % 2 == 0) ? U1 : U1 + 1;       // pitch-1 odd => diagonal reads hit distinct banks
+  {
+    const size_t smem4 = (size_t)4 * T * pitch * sizeof(float);
+    const char* off = getenv("CTCVR_LATTICE_V1");
+    if (smem4 <= 220 * 1024 && !(off && off[0] == '1')) {
+      CTCVR_CHECK_CUDA(cudaFuncSetAttribute(rnnt_lattice2_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(220 * 1024)));
+      rnnt_lattice2_kernel<NJ><<<B, LAT2_THREADS, smem4, st>>>(lpb, lpl, t_len, u_len, alpha, beta, costs, T, U1, pitch);
+      CTCVR_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   size_t smem = (size_t)2 * T * pitch * sizeof(float);
   int use_smem = smem <= 200 * 1024;
   if (!use_smem) smem = 0;
