@@ -7,7 +7,8 @@ and no fallback: ops raise RuntimeError without the library or without a CUDA de
 from . import _lib  # noqa: F401
 from . import functional  # noqa: F401
 from .ctc import CTC, OnlineCTC  # noqa: F401
-from .decode import basic_greedy_search, greedy_batch, greedy_chunk  # noqa: F401
+from .decode import (BeamHypothesis, OnlineBeamState, basic_greedy_search, beam_chunk_online, greedy_batch,  # noqa: F401
+                     greedy_chunk, prefix_beam_search)
 from .functional import (ctc_greedy_search as ctc_greedy_hyps, ctc_loss_from_logits, fused_joint_rnnt_loss,  # noqa: F401
                          joint_logits, rnnt_loss)
 from .joint import TransducerJoint  # noqa: F401

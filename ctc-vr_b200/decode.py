@@ -150,3 +150,95 @@ def greedy_chunk(model, encoder_out_chunk: torch.Tensor, predictor_states: Optio
     hyps, h, c, last = greedy_batch(model, encoder_out_chunk, lens, n_steps, predictor_states[0],
                                     predictor_states[1], last)
     return hyps[0], [h, c], int(last.item())
+
+
+# ------------------------------------------------------------------------------------------------ A7
+class BeamHypothesis:
+    """model/online_rnnt_model.py:41-55."""
+
+    def __init__(self, tokens: List[int], log_prob: float, predictor_states):
+        self.tokens = tokens
+        self.log_prob = log_prob
+        self.predictor_states = predictor_states
+
+    def copy(self):
+        st = [s.clone() for s in self.predictor_states] if self.predictor_states is not None else None
+        return BeamHypothesis(list(self.tokens), self.log_prob, st)
+
+    def __lt__(self, other):
+        return self.log_prob < other.log_prob
+
+
+class OnlineBeamState:
+    """Device-resident beam of one stream, carried across chunks (the reference keeps a Python list of
+    BeamHypothesis on the module, model/online_rnnt_model.py:138-143)."""
+
+    def __init__(self, model, beam_size: int, n_steps: int, max_out: int = 4096):
+        self.w = _prepared(model).get()
+        self.beam, self.n_steps, self.max_out = int(beam_size), int(n_steps), int(max_out)
+        dev = next(model.joint.parameters()).device
+        with torch.cuda.device(dev):
+            nbytes = query("ctcvr_rnnt_beam_state_bytes", ctypes.byref(self.w), self.beam, self.n_steps, self.max_out)
+            self.buf = torch.zeros(int(nbytes), dtype=torch.uint8, device=dev)
+            call("ctcvr_rnnt_beam_reset", ptr(self.buf), ctypes.byref(self.w), self.beam, self.n_steps, self.max_out,
+                 stream())
+
+
+@torch.no_grad()
+def beam_chunk_online(model, encoder_out_chunk: torch.Tensor, state: Optional[OnlineBeamState], beam_size: int = 4,
+                      n_steps: int = 10) -> Tuple[List[BeamHypothesis], OnlineBeamState]:
+    """The search of OnlineRNNTModel._decode_chunk_beam_search (model/online_rnnt_model.py:425-522) for one
+    encoder chunk [1,Tc,H] (or [Tc,H]): one kernel launch per chunk, the beam stays on the device between
+    chunks.  Returns (hypotheses ordered as the reference's list, state)."""
+    if state is None:
+        state = OnlineBeamState(model, beam_size, n_steps)
+    w = _prepared(model).get()
+    blank = _blank_of(model)
+    x = encoder_out_chunk if encoder_out_chunk.dim() == 3 else encoder_out_chunk.unsqueeze(0)
+    ep = _enc_proj(model, x)[0].contiguous()
+    Tc = ep.shape[0]
+    dev = ep.device
+    beam, LH = state.beam, w.L * w.H
+    out_n = torch.zeros((1,), dtype=torch.int32, device=dev)
+    out_tok = torch.zeros((beam, state.max_out), dtype=torch.int32, device=dev)
+    out_len = torch.zeros((beam,), dtype=torch.int32, device=dev)
+    out_sc = torch.zeros((beam,), dtype=torch.float64, device=dev)
+    out_h = torch.zeros((beam, w.L, w.H), dtype=torch.float32, device=dev)
+    out_c = torch.zeros_like(out_h)
+    with torch.cuda.device(dev):
+        call("ctcvr_rnnt_beam_chunk", ctypes.byref(w), ptr(ep), Tc, ptr(state.buf), beam, state.n_steps, state.max_out,
+             blank, ptr(out_n), ptr(out_tok), ptr(out_len), ptr(out_sc), ptr(out_h), ptr(out_c), stream())
+    n = int(out_n.item())
+    lens, toks, sc = out_len.cpu(), out_tok.cpu(), out_sc.cpu()
+    hyps = [BeamHypothesis(toks[i, :int(lens[i])].tolist(), float(sc[i]),
+                           [out_h[i].unsqueeze(1).clone(), out_c[i].unsqueeze(1).clone()]) for i in range(n)]
+    return hyps, state
+
+
+# ------------------------------------------------------------------------------------------------ A8
+@torch.no_grad()
+def prefix_beam_search(model, encoder_out: torch.Tensor, ctc_logp: torch.Tensor, beam_size: int = 5,
+                       ctc_weight: float = 0.3, transducer_weight: float = 0.7) -> List[Tuple[List[int], float]]:
+    """wenet/transducer/search/prefix_beam_search.py:42-148 below the encoder call: encoder_out [T,H] (or
+    [1,T,H]), ctc_logp [T,V] = ctc.log_softmax(encoder_out).  Returns [(hyp tokens incl. the leading blank, score)]
+    best first."""
+    w = _prepared(model).get()
+    blank = _blank_of(model)
+    x = encoder_out if encoder_out.dim() == 3 else encoder_out.unsqueeze(0)
+    ep = _enc_proj(model, x)[0].contiguous()
+    T = ep.shape[0]
+    dev = ep.device
+    cl = ctc_logp.reshape(-1, ctc_logp.shape[-1]).detach().float().contiguous().to(dev)
+    beam = int(beam_size)
+    out_n = torch.zeros((1,), dtype=torch.int32, device=dev)
+    out_tok = torch.zeros((beam, T + 1), dtype=torch.int32, device=dev)
+    out_len = torch.zeros((beam,), dtype=torch.int32, device=dev)
+    out_sc = torch.zeros((beam,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = query("ctcvr_rnnt_prefix_beam_ws_bytes", ctypes.byref(w), beam, T)
+        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+        call("ctcvr_rnnt_prefix_beam", ctypes.byref(w), ptr(ep), ptr(cl), T, beam, blank, float(ctc_weight),
+             float(transducer_weight), ptr(out_n), ptr(out_tok), ptr(out_len), ptr(out_sc), ptr(ws), ws.numel(), stream())
+    n = int(out_n.item())
+    lens, toks, sc = out_len.cpu(), out_tok.cpu(), out_sc.cpu()
+    return [(toks[i, :int(lens[i])].tolist(), float(sc[i])) for i in range(n)]
