@@ -209,92 +209,143 @@ __global__ void __launch_bounds__(LAT2_THREADS) rnnt_lattice2_kernel(
   }
   __syncthreads();
   const int ndiag = Tb + Ub;
+  // Raw 32-bit shared addresses advanced by one row per diagonal: no generic->shared conversion, no index multiply and
+  // no divergent branch inside the dependent loop (loads of inactive cells read a safe address and are discarded).
+  // The NJ column groups of a lane are processed stage by stage so that their independent dependency chains interleave.
+  const uint32_t s_sb = (uint32_t)__cvta_generic_to_shared(sb), s_sl = (uint32_t)__cvta_generic_to_shared(sl);
+  const uint32_t s_sa = (uint32_t)__cvta_generic_to_shared(sa), s_sc = (uint32_t)__cvta_generic_to_shared(sc);
+  const uint32_t rowb = (uint32_t)pitch * 4u;
+  auto lds = [](uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; };
+  auto sts = [](uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); };
   if (warp == 0) {
     // ---------------- alpha(t,u) = LSE(alpha(t-1,u)+lpb(t-1,u), alpha(t,u-1)+lpl(t,u-1)),  t = d - u
     float prev[NJ], nb[NJ], nl[NJ];
-    int ib[NJ], il[NJ], io[NJ];                 // smem indices at diagonal d: lpb[t-1][u], lpl[t][u-1], alpha[t][u]
+    uint32_t ab[NJ], al[NJ], ao[NJ];            // addresses at diagonal d of lpb[t-1][u], lpl[t][u-1], alpha[t][u]
+    int tt[NJ];                                 // t = d - u
+    bool col[NJ];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int u = lane + 32 * j;
       prev[j] = kNegInf;
-      ib[j] = (-u - 1) * pitch + u;
-      il[j] = (-u) * pitch + u - 1;
-      io[j] = (-u) * pitch + u;
+      tt[j] = -u;
+      col[j] = u <= Ub;
+      ab[j] = s_sb + (uint32_t)((-u - 1) * pitch + u) * 4u;
+      al[j] = s_sl + (uint32_t)((-u) * pitch + u - 1) * 4u;
+      ao[j] = s_sa + (uint32_t)((-u) * pitch + u) * 4u;
     }
-    auto fetch = [&](int d) {
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const int u = lane + 32 * j, t = d - u;
-        const bool in = (u <= Ub) && (t >= 0) && (t < Tb);
-        nb[j] = (in && t > 0) ? sb[ib[j] + d * pitch] : kNegInf;
-        nl[j] = (in && u > 0) ? sl[il[j] + d * pitch] : kNegInf;
-      }
+    auto fetch = [&](int j, int t, uint32_t pb, uint32_t pl) {
+      const bool in = col[j] && (unsigned)t < (unsigned)Tb;
+      const bool okb = in && t > 0, okl = in && (lane + 32 * j) > 0;
+      const float xb = lds(okb ? pb : s_sb), xl = lds(okl ? pl : s_sl);
+      nb[j] = okb ? xb : kNegInf;
+      nl[j] = okl ? xl : kNegInf;
     };
-    fetch(0);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) fetch(j, tt[j], ab[j], al[j]);
     for (int d = 0; d < ndiag; ++d) {
       float cb[NJ], cl[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) { cb[j] = nb[j]; cl[j] = nl[j]; }
-      if (d + 1 < ndiag) fetch(d + 1);
-      float cur[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) fetch(j, tt[j] + 1, ab[j] + rowb, al[j] + rowb);     // next diagonal
+      float cur[NJ], left[NJ], wrap[NJ], xa[NJ], xb[NJ], mm[NJ], dd[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        const int u = lane + 32 * j, t = d - u;
-        const bool in = (u <= Ub) && (t >= 0) && (t < Tb);
-        float left = __shfl_up_sync(0xffffffffu, prev[j], 1);
-        const float wrap = __shfl_sync(0xffffffffu, prev[j > 0 ? j - 1 : 0], 31);
-        if (lane == 0) left = (j > 0) ? wrap : kNegInf;
-        float v = lae2(prev[j] + cb[j], left + cl[j]);
-        v = (d == 0 && u == 0) ? 0.f : v;
+        left[j] = __shfl_up_sync(0xffffffffu, prev[j], 1);
+        wrap[j] = __shfl_sync(0xffffffffu, prev[j > 0 ? j - 1 : 0], 31);
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (lane == 0) left[j] = (j > 0) ? wrap[j] : kNegInf;
+        xa[j] = prev[j] + cb[j];
+        xb[j] = left[j] + cl[j];
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        mm[j] = fmaxf(xa[j], xb[j]);
+        const float n = fminf(xa[j], xb[j]);
+        dd[j] = (n == kNegInf) ? kNegInf : n - mm[j];
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) dd[j] = ex2f(dd[j]);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) dd[j] = lg2f(1.f + dd[j]);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const bool in = col[j] && (unsigned)tt[j] < (unsigned)Tb;
+        float v = mm[j] + dd[j];
+        v = (d == 0 && j == 0 && lane == 0) ? 0.f : v;
         v = in ? v : kNegInf;
-        if (in) sa[io[j] + d * pitch] = v;
+        if (in) sts(ao[j], v);
         cur[j] = v;
       }
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) prev[j] = cur[j];
+      for (int j = 0; j < NJ; ++j) { prev[j] = cur[j]; tt[j] += 1; ab[j] += rowb; al[j] += rowb; ao[j] += rowb; }
     }
   } else if (warp == 1) {
     // ---------------- beta(t,u) = LSE(beta(t+1,u)+lpb(t,u), beta(t,u+1)+lpl(t,u)),  beta(T-1,U) = lpb(T-1,U)
     float prev[NJ], nb[NJ], nl[NJ];
-    int ix[NJ];                                 // smem index of cell (t,u) at diagonal d, minus d*pitch
+    uint32_t ax[NJ];                            // byte offset of cell (t,u) at diagonal d (same for lpb, lpl, beta)
+    int tt[NJ];
+    bool col[NJ];
+    const int d0 = ndiag - 1;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int u = lane + 32 * j;
       prev[j] = kNegInf;
-      ix[j] = (-u) * pitch + u;
+      tt[j] = d0 - u;
+      col[j] = u <= Ub;
+      ax[j] = (uint32_t)((d0 - u) * pitch + u) * 4u;
     }
-    auto fetch = [&](int d) {
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const int u = lane + 32 * j, t = d - u;
-        const bool in = (u <= Ub) && (t >= 0) && (t < Tb);
-        nb[j] = in ? sb[ix[j] + d * pitch] : kNegInf;
-        nl[j] = (in && u < Ub) ? sl[ix[j] + d * pitch] : kNegInf;
-      }
+    auto fetch = [&](int j, int t, uint32_t off) {
+      const bool in = col[j] && (unsigned)t < (unsigned)Tb;
+      const bool okl = in && (lane + 32 * j) < Ub;
+      const float xb = lds(s_sb + (in ? off : 0u)), xl = lds(s_sl + (okl ? off : 0u));
+      nb[j] = in ? xb : kNegInf;
+      nl[j] = okl ? xl : kNegInf;
     };
-    fetch(ndiag - 1);
-    for (int d = ndiag - 1; d >= 0; --d) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) fetch(j, tt[j], ax[j]);
+    for (int d = d0; d >= 0; --d) {
       float cb[NJ], cl[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) { cb[j] = nb[j]; cl[j] = nl[j]; }
-      if (d > 0) fetch(d - 1);
-      float cur[NJ];
 #pragma unroll
-      for (int j = NJ - 1; j >= 0; --j) {
-        const int u = lane + 32 * j, t = d - u;
-        const bool in = (u <= Ub) && (t >= 0) && (t < Tb);
-        float right = __shfl_down_sync(0xffffffffu, prev[j], 1);
-        const float wrap = __shfl_sync(0xffffffffu, prev[(j + 1 < NJ) ? j + 1 : j], 0);
-        if (lane == 31) right = (j + 1 < NJ) ? wrap : kNegInf;
-        const float a = (t + 1 < Tb) ? prev[j] + cb[j] : kNegInf;
-        float v = lae2(a, right + cl[j]);
-        v = (t == Tb - 1 && u == Ub) ? cb[j] : v;
+      for (int j = 0; j < NJ; ++j) fetch(j, tt[j] - 1, ax[j] - rowb);                    // next diagonal (d - 1)
+      float cur[NJ], right[NJ], wrap[NJ], xa[NJ], xb[NJ], mm[NJ], dd[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        right[j] = __shfl_down_sync(0xffffffffu, prev[j], 1);
+        wrap[j] = __shfl_sync(0xffffffffu, prev[(j + 1 < NJ) ? j + 1 : j], 0);
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (lane == 31) right[j] = (j + 1 < NJ) ? wrap[j] : kNegInf;
+        xa[j] = (tt[j] + 1 < Tb) ? prev[j] + cb[j] : kNegInf;
+        xb[j] = right[j] + cl[j];
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        mm[j] = fmaxf(xa[j], xb[j]);
+        const float n = fminf(xa[j], xb[j]);
+        dd[j] = (n == kNegInf) ? kNegInf : n - mm[j];
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) dd[j] = ex2f(dd[j]);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) dd[j] = lg2f(1.f + dd[j]);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int u = lane + 32 * j;
+        const bool in = col[j] && (unsigned)tt[j] < (unsigned)Tb;
+        float v = mm[j] + dd[j];
+        v = (tt[j] == Tb - 1 && u == Ub) ? cb[j] : v;
         v = in ? v : kNegInf;
-        if (in) sc[ix[j] + d * pitch] = v;
+        if (in) sts(s_sc + ax[j], v);
         cur[j] = v;
       }
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) prev[j] = cur[j];
+      for (int j = 0; j < NJ; ++j) { prev[j] = cur[j]; tt[j] -= 1; ax[j] -= rowb; }
     }
     if (lane == 0) costs[b] = -prev[0] * kLn2;     // beta(0,0)
   }
