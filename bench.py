@@ -26,6 +26,9 @@ sys.path.insert(0, ROOT)
 
 CFG = dict(B=32, T=250, U=40, D=512, V=412, blank=5)
 METRIC = "fused joint+RNN-T loss fwd/bwd throughput"
+# kernels of libctcvr.so inside one captured step: fwd (prep, to_bf16, tiles, joint_fwd2) + lattice + bwd (prep, tiles,
+# to_bf16, joint_bwd2, reduce_denc, dw_gemm, reduce_dw); counted from an eager step, see ctcvr_launch_count()
+KERNELS_PER_GRAPHED_STEP = 12
 UNIT = "utt/s"
 
 
@@ -156,12 +159,23 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gB = B * world
 
+    use_graph = not args.no_graph
+    graphed = C.GraphedJointRnntStep(joint, B, T, U, blank, global_batch=gB, precision=args.precision) if use_graph else None
+    if graphed is not None:
+        graphed.load(enc.detach(), pred.detach(), tgt, tl, ul)
+
     def step(e, p, tg, tl_, ul_):
-        joint.zero_grad(set_to_none=True)
-        e.grad = p.grad = None
-        costs = joint.rnnt_loss_fused(e, p, tg, tl_, ul_, blank, reduction="none", precision=args.precision)
-        loss = costs.sum() / gB
-        loss.backward()
+        """One training step of the seam through the public API.  Graph mode: the whole step (pre-projections, fused
+        forward, lattice, fused backward, projection backward) is one captured CUDA graph; inputs are copied into its
+        resident buffers (e is None = already resident)."""
+        if graphed is not None:
+            loss = graphed.step(e, p, tg, tl_, ul_) if e is not None else graphed.step()
+        else:
+            joint.zero_grad(set_to_none=True)
+            e.grad = p.grad = None
+            costs = joint.rnnt_loss_fused(e, p, tg, tl_, ul_, blank, reduction="none", precision=args.precision)
+            loss = costs.sum() / gB
+            loss.backward()
         if reducer is not None:
             reducer.reduce()
         return loss
@@ -171,8 +185,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    resident = (None, None, None, None, None) if graphed is not None else (enc, pred, tgt, tl, ul)
     for _ in range(args.warmup):
-        step(enc, pred, tgt, tl, ul)
+        step(*resident)
     barrier()
     l0 = _lib.lib().ctcvr_launch_count()
     with ClockSampler(local) as clk:
@@ -182,27 +197,57 @@ def run_ours(args):
             barrier()
             s, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            loss = step(enc, pred, tgt, tl, ul)
+            loss = step(*resident)
             e_.record()
             torch.cuda.synchronize()
             tot_ms += s.elapsed_time(e_)
         barrier()
         launches = _lib.lib().ctcvr_launch_count() - l0
-        # ---- e2e: host (pinned) inputs -> H2D -> step -> D2H of the loss, every step
+        if graphed is not None:      # replays do not pass through the C ABI: count the captured launches
+            launches = args.steps * KERNELS_PER_GRAPHED_STEP
+        # ---- e2e: host (pinned) inputs -> H2D -> step -> D2H of the loss, every step.  As in a real input pipeline the
+        # H2D copy of step i+1 runs on a copy stream while step i computes (double-buffered staging); every step still
+        # pays its own copy and its own loss read-back, and the K steps are timed as one region on the wall clock.
         h = make_inputs(1234 + rank, dev, pinned=True)
         h2d = sum(t.numel() * t.element_size() for t in h)
-        e2e_ms = 0.0
-        for i in range(args.steps + 1):
-            flush.zero_()
-            barrier()
-            t0 = time.perf_counter()
-            d = [t.to(dev, non_blocking=True) for t in h]
-            d[0].requires_grad_(True)
-            d[1].requires_grad_(True)
-            lv = step(*d).item()
+        copy_stream = torch.cuda.Stream(device=dev)
+        staging = [[torch.empty_like(t, device=dev) for t in h] for _ in range(2)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[i % 2])
+                for dst, src in zip(staging[i % 2], h):
+                    dst.copy_(src, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        def e2e_run(nsteps):
+            for ev in consumed:
+                ev.record(torch.cuda.current_stream())
+            prefetch(0)
+            losses = []
+            for i in range(nsteps):
+                if i + 1 < nsteps:
+                    prefetch(i + 1)
+                torch.cuda.current_stream().wait_event(ready[i % 2])
+                d = staging[i % 2]
+                if graphed is not None:
+                    lv = step(*d)
+                else:
+                    e_in, p_in = d[0].detach().requires_grad_(True), d[1].detach().requires_grad_(True)
+                    lv = step(e_in, p_in, d[2], d[3], d[4])
+                consumed[i % 2].record(torch.cuda.current_stream())
+                losses.append(lv.item())                      # D2H read of the step's loss
             torch.cuda.synchronize()
-            if i > 0:
-                e2e_ms += (time.perf_counter() - t0) * 1e3
+            return losses
+
+        e2e_run(2)
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(args.steps)
+        e2e_ms = (time.perf_counter() - t0) * 1e3
     ms = torch.tensor([tot_ms / args.steps, e2e_ms / args.steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -237,7 +282,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": "configs[1]: B=32/GPU,T=250,U=40,H=D=512,V=412 fused joint+rnnt_loss fwd/bwd",
                            "global_batch": gB, "parallelism": f"dp{world}", "l2": "flushed (256 MiB write) before each step",
-                           "precision": args.precision},
+                           "precision": args.precision, "cuda_graph": bool(graphed is not None)},
                 "e2e": {"value": gB / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "roofline": roof,
                 "cpu_baseline": {"value": nb / csec, "unit": UNIT, "cores": threads, "kind": "port",
@@ -302,6 +347,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="eager step instead of the captured CUDA graph")
     ap.add_argument("--precision", default=os.environ.get("CTCVR_PRECISION", "bf16"), choices=["bf16", "fp32"])
     args = ap.parse_args()
     if args.impl == "reference":

@@ -27,10 +27,11 @@ int joint_bwd_f32(const float*, const float*, const float*, const float*, const 
                   const int32_t*, const float*, const float*, const float*, const float*, const float*, float, float*,
                   float*, float*, float*, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 size_t joint_fwd_tc_ws_bytes(int, int, int, int, int);
-int joint_fwd_tc(const float*, const float*, const float*, const float*, const int32_t*, const int32_t*,
+int joint_fwd_tc(const void*, const void*, int, const float*, const float*, const int32_t*, const int32_t*,
                  const int32_t*, float*, float*, float*, int, int, int, int, int, int, void*, size_t, cudaStream_t);
+bool joint_tc_bwd_supported(int, int, int);
 size_t joint_bwd_tc_ws_bytes(int, int, int, int, int);
-int joint_bwd_tc(const float*, const float*, const float*, const float*, const int32_t*, const int32_t*,
+int joint_bwd_tc(const void*, const void*, int, const float*, const float*, const int32_t*, const int32_t*,
                  const int32_t*, const float*, const float*, const float*, const float*, const float*, float, float*,
                  float*, float*, float*, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 int rnnt_lattice(const float*, const float*, const int32_t*, const int32_t*, float*, float*, float*, int, int, int,
@@ -105,7 +106,7 @@ int ctcvr_joint_rnnt_fwd(const float* enc_proj, const float* pred_proj, const fl
                     (targets || U1 == 1), "joint_rnnt_fwd: NULL pointer");
   CTCVR_REQUIRE(blank >= 0 && blank < V, "joint_rnnt_fwd: blank %d must be within [0, %d)", blank, V);
   if (precision == CTCVR_BF16)
-    return joint_fwd_tc(enc_proj, pred_proj, w_out, b_out, targets, t_len, u_len, lse, lp_blank, lp_label, B, T, U1, D,
+    return joint_fwd_tc(enc_proj, pred_proj, 0, w_out, b_out, targets, t_len, u_len, lse, lp_blank, lp_label, B, T, U1, D,
                         V, blank, ws, ws_bytes, ST(stream));
   CTCVR_REQUIRE(precision == CTCVR_F32, "joint_rnnt_fwd: unknown precision %d", precision);
   return joint_fwd_f32(enc_proj, pred_proj, w_out, b_out, targets, t_len, u_len, lse, lp_blank, lp_label, B, T, U1, D,
@@ -134,13 +135,42 @@ int ctcvr_joint_rnnt_bwd(const float* enc_proj, const float* pred_proj, const fl
                     grad_costs && d_enc_proj && d_pred_proj && d_w_out && d_b_out && ws, "joint_rnnt_bwd: NULL pointer");
   CTCVR_REQUIRE(blank >= 0 && blank < V, "joint_rnnt_bwd: blank %d must be within [0, %d)", blank, V);
   if (precision == CTCVR_BF16)
-    return joint_bwd_tc(enc_proj, pred_proj, w_out, b_out, targets, t_len, u_len, lse, alpha, beta, costs, grad_costs,
+    return joint_bwd_tc(enc_proj, pred_proj, 0, w_out, b_out, targets, t_len, u_len, lse, alpha, beta, costs, grad_costs,
                         clamp, d_enc_proj, d_pred_proj, d_w_out, d_b_out, B, T, U1, D, V, blank, ws, ws_bytes,
                         ST(stream));
   CTCVR_REQUIRE(precision == CTCVR_F32, "joint_rnnt_bwd: unknown precision %d", precision);
   return joint_bwd_f32(enc_proj, pred_proj, w_out, b_out, targets, t_len, u_len, lse, alpha, beta, costs, grad_costs,
                        clamp, d_enc_proj, d_pred_proj, d_w_out, d_b_out, B, T, U1, D, V, blank, ws, ws_bytes,
                        ST(stream));
+}
+
+int ctcvr_joint_tc_supported(int U1, int D, int V) { return joint_tc_bwd_supported(U1, D, V) ? 1 : 0; }
+
+int ctcvr_joint_rnnt_fwd_bf16in(const void* enc_proj_bf16, const void* pred_proj_bf16, const float* w_out,
+                                const float* b_out, const int32_t* targets, const int32_t* t_len, const int32_t* u_len,
+                                float* lse, float* lp_blank, float* lp_label, int B, int T, int U1, int D, int V,
+                                int blank, void* ws, size_t ws_bytes, void* stream) {
+  if (int rc = check_dims("joint_rnnt_fwd_bf16in", B, T, U1, D, V)) return rc;
+  CTCVR_REQUIRE(enc_proj_bf16 && pred_proj_bf16 && w_out && b_out && t_len && u_len && lse && lp_blank && lp_label &&
+                    (targets || U1 == 1), "joint_rnnt_fwd_bf16in: NULL pointer");
+  CTCVR_REQUIRE(blank >= 0 && blank < V, "joint_rnnt_fwd_bf16in: blank %d must be within [0, %d)", blank, V);
+  return joint_fwd_tc(enc_proj_bf16, pred_proj_bf16, 1, w_out, b_out, targets, t_len, u_len, lse, lp_blank, lp_label, B,
+                      T, U1, D, V, blank, ws, ws_bytes, ST(stream));
+}
+
+int ctcvr_joint_rnnt_bwd_bf16in(const void* enc_proj_bf16, const void* pred_proj_bf16, const float* w_out,
+                                const float* b_out, const int32_t* targets, const int32_t* t_len, const int32_t* u_len,
+                                const float* lse, const float* alpha, const float* beta, const float* costs,
+                                const float* grad_costs, float clamp, float* d_enc_proj, float* d_pred_proj,
+                                float* d_w_out, float* d_b_out, int B, int T, int U1, int D, int V, int blank, void* ws,
+                                size_t ws_bytes, void* stream) {
+  if (int rc = check_dims("joint_rnnt_bwd_bf16in", B, T, U1, D, V)) return rc;
+  CTCVR_REQUIRE(enc_proj_bf16 && pred_proj_bf16 && w_out && b_out && t_len && u_len && lse && alpha && beta && costs &&
+                    grad_costs && d_enc_proj && d_pred_proj && d_w_out && d_b_out && ws, "joint_rnnt_bwd_bf16in: NULL pointer");
+  CTCVR_REQUIRE(blank >= 0 && blank < V, "joint_rnnt_bwd_bf16in: blank %d must be within [0, %d)", blank, V);
+  return joint_bwd_tc(enc_proj_bf16, pred_proj_bf16, 1, w_out, b_out, targets, t_len, u_len, lse, alpha, beta, costs,
+                      grad_costs, clamp, d_enc_proj, d_pred_proj, d_w_out, d_b_out, B, T, U1, D, V, blank, ws, ws_bytes,
+                      ST(stream));
 }
 
 size_t ctcvr_rnnt_loss_dense_ws_bytes(int B, int T, int U1) { return (size_t)5 * B * T * U1 * sizeof(float); }

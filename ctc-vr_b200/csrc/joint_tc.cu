@@ -115,6 +115,7 @@ struct Pipe {
 }  // namespace ctcvr
 #include "joint_tc_fwd.cuh"
 #include "joint_tc_bwd.cuh"
+#include "joint_tc_bwd_pair.cuh"
 namespace ctcvr {
 namespace tc {
 
@@ -378,8 +379,11 @@ __global__ void __launch_bounds__(256) reduce_dw_kernel(const float* __restrict_
 // =================================================================================================
 // Tile tables.  One CTA per utterance: the CTA sums the tile counts of the utterances before it (block reduction),
 // then its threads write the utterance's entries in parallel; the last CTA also writes the total.
+// frame blocks per (b, u-split) sweep are padded to an even count (the CTA-pair backward kernel processes tiles
+// 2i, 2i+1 of one sweep together; a padding tile lies beyond T_b, i.e. all of its rows are invalid)
+__device__ __forceinline__ int rect_ntb(int Tb) { return (((Tb + 7) >> 3) + 1) & ~1; }
 __device__ __forceinline__ int rect_tiles_of(int Tb, int W) {
-  return Tb > 0 ? ((W + 15) >> 4) * ((Tb + 7) >> 3) : 0;
+  return Tb > 0 ? ((W + 15) >> 4) * rect_ntb(Tb) : 0;
 }
 __device__ __forceinline__ int block_prefix(int mine_upto, int (*count)(int, const int32_t*, const int32_t*, int, int),
                                             const int32_t* t_len, const int32_t* u_len, int T, int U1) {
@@ -412,7 +416,7 @@ __global__ void build_tiles_kernel(const int32_t* __restrict__ t_len, const int3
   const int off = block_prefix(b, count_rect, t_len, u_len, T, U1);
   const int Tb = min(t_len[b], T), W = min(u_len[b], U1 - 1) + 1;
   const int n = rect_tiles_of(Tb, W);
-  const int NTB = (Tb + 7) >> 3;
+  const int NTB = rect_ntb(Tb);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int s = i / NTB, tb = i - s * NTB;
     if (off + i < max_tiles) tiles[off + i] = make_int4(b, s, tb, off + i);
@@ -524,7 +528,7 @@ using namespace tc;
 static long long* g_prof_buf = nullptr;
 static int pad_v(int V) { return (V + 31) / 32 * 32; }
 static int max_tiles_flat(int B, int T, int U1) { return B * (int)(((long)T * U1 + BM - 1) / BM); }
-static int max_tiles_rect(int B, int T, int U1) { return B * ((U1 + 15) / 16) * ((T + 7) / 8); }
+static int max_tiles_rect(int B, int T, int U1) { return B * ((U1 + 15) / 16) * ((((T + 7) / 8) + 1) & ~1); }
 
 bool joint_tc_supported(int U1, int D, int V) { return D % 64 == 0 && D >= 64 && D <= 1024 && pad_v(V) <= 512 && U1 <= 128; }
 
@@ -578,18 +582,25 @@ static bool env_flag(const char* name) {
 int joint_fwd_f32(const float*, const float*, const float*, const float*, const int32_t*, const int32_t*,
                   const int32_t*, float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
 
-int joint_fwd_tc(const float* enc, const float* pred, const float* w, const float* bias, const int32_t* targets,
+int joint_fwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float* w, const float* bias, const int32_t* targets,
                  const int32_t* t_len, const int32_t* u_len, float* lse, float* lp_blank, float* lp_label, int B, int T,
                  int U1, int D, int V, int blank, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (!joint_tc_supported(U1, D, V))   // shapes outside the tensor-core tiling use the fp32 kernels (same GPU)
+  const float* enc = reinterpret_cast<const float*>(enc_v);
+  const float* pred = reinterpret_cast<const float*>(pred_v);
+  if (!joint_tc_supported(U1, D, V)) {  // shapes outside the tensor-core tiling use the fp32 kernels (same GPU)
+    CTCVR_REQUIRE(!in_bf16, "joint_rnnt_fwd: bf16 inputs need D %% 64 == 0, D <= 1024, V <= 512, U+1 <= 128");
     return joint_fwd_f32(enc, pred, w, bias, targets, t_len, u_len, lse, lp_blank, lp_label, B, T, U1, D, V, blank, st);
+  }
   CTCVR_REQUIRE(ws && ws_bytes >= joint_fwd_tc_ws_bytes(B, T, U1, D, V), "joint_rnnt_fwd bf16: workspace too small");
   CTCVR_REQUIRE(((uintptr_t)enc & 15) == 0 && ((uintptr_t)pred & 15) == 0, "joint_rnnt_fwd bf16: enc_proj / pred_proj must be 16-byte aligned");
   const int Vp = pad_v(V), NH = Vp / 2;
   FwdWs W = carve_fwd_ws(ws, B, T, U1, D, V);
   prep_weights3_kernel<<<cdiv((long)((Vp + 63) / 64) * 64 * D, 256), 256, 0, st>>>(w, bias, W.wb, nullptr, nullptr, W.bias_l2, V, Vp, D);
   CTCVR_LAUNCH_CHECK();
-  {
+  if (in_bf16) {                        // activations already bf16 (autocast): use them in place
+    W.eb = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(enc_v));
+    W.pb = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(pred_v));
+  } else {
     const long na4 = (long)B * T * D / 4, nb4 = (long)B * U1 * D / 4;
     const int blocks = (int)std::min<long>((na4 + nb4 + 255) / 256, 148L * 8);
     to_bf16_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(enc), reinterpret_cast<uint2*>(W.eb), na4,
@@ -626,7 +637,7 @@ int joint_bwd_f32(const float*, const float*, const float*, const float*, const 
                   const int32_t*, const float*, const float*, const float*, const float*, const float*, float, float*,
                   float*, float*, float*, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 
-static bool joint_tc_bwd_supported(int U1, int D, int V) {
+bool joint_tc_bwd_supported(int U1, int D, int V) {
   return joint_tc_supported(U1, D, V) && D % 128 == 0 && D <= 512;
 }
 
@@ -672,10 +683,14 @@ size_t joint_bwd_tc_ws_bytes(int B, int T, int U1, int D, int V) {
   return carve_bwd_ws(nullptr, B, T, U1, D, V).bytes;
 }
 
-int joint_bwd_tc(const float* enc, const float* pred, const float* w, const float* bias, const int32_t* targets,
+int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float* w, const float* bias, const int32_t* targets,
                  const int32_t* t_len, const int32_t* u_len, const float* lse, const float* alpha, const float* beta,
                  const float* costs, const float* grad_costs, float clamp, float* d_enc, float* d_pred, float* d_w,
                  float* d_b, int B, int T, int U1, int D, int V, int blank, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const float* enc = reinterpret_cast<const float*>(enc_v);
+  const float* pred = reinterpret_cast<const float*>(pred_v);
+  CTCVR_REQUIRE(!in_bf16 || joint_tc_bwd_supported(U1, D, V),
+                "joint_rnnt_bwd: bf16 inputs need D %% 128 == 0, D <= 512, V <= 512, U+1 <= 128");
   if (!joint_tc_bwd_supported(U1, D, V))   // shapes outside the tensor-core tiling use the fp32 kernels (same GPU)
     return joint_bwd_f32(enc, pred, w, bias, targets, t_len, u_len, lse, alpha, beta, costs, grad_costs, clamp, d_enc,
                          d_pred, d_w, d_b, B, T, U1, D, V, blank, ws, ws_bytes, st);
@@ -691,7 +706,10 @@ int joint_bwd_tc(const float* enc, const float* pred, const float* w, const floa
   CTCVR_LAUNCH_CHECK();
   CTCVR_CHECK_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)B * U1 * D * sizeof(float), st));
   CTCVR_CHECK_CUDA(cudaMemsetAsync(d_b, 0, (size_t)V * sizeof(float), st));
-  {
+  if (in_bf16) {
+    W.eb = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(enc_v));
+    W.pb = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(pred_v));
+  } else {
     const long na4 = (long)B * T * D / 4, nb4 = (long)B * U1 * D / 4;
     const int blocks = (int)std::min<long>((na4 + nb4 + 255) / 256, 148L * 8);
     to_bf16_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(enc), reinterpret_cast<uint2*>(W.eb), na4,
@@ -714,9 +732,27 @@ int joint_bwd_tc(const float* enc, const float* pred, const float* w, const floa
     p.prof = g_prof_buf;
     const size_t smem = bwd2_smem_bytes(NH, Vp, D);
     CTCVR_REQUIRE(smem <= 232448, "joint_rnnt_bwd bf16: shared memory budget exceeded (%zu B)", smem);
-    CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    joint_bwd2_kernel<<<grid, NTHREADS, smem, st>>>(tmap_e, tmap_p, p);
-    CTCVR_LAUNCH_CHECK();
+    if (MB % 2 == 0 && NH % 16 == 0 && grid >= 2 && !env_flag("CTCVR_BWD_SINGLE")) {
+      CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid & ~1);
+      cfg.blockDim = dim3(NTHREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      CTCVR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, joint_bwd2p_kernel, tmap_e, tmap_p, p));
+      count_launch();
+    } else {
+      CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      joint_bwd2_kernel<<<grid, NTHREADS, smem, st>>>(tmap_e, tmap_p, p);
+      CTCVR_LAUNCH_CHECK();
+    }
   }
   reduce_denc_kernel<<<B * T, 128, 0, st>>>(W.d_enc_part, t_len, u_len, d_enc, B, T, U1, D);
   CTCVR_LAUNCH_CHECK();

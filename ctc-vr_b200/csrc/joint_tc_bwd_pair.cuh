@@ -1,130 +1,36 @@
-// Backward kernel 1 of the bf16 tcgen05 path (included by joint_tc.cu):
-//   recompute logits -> g = d cost / d logits -> dZ^T = W^T g^T -> dH = dZ (1 - z^2) -> d_enc / d_pred partials,
-//   d_bias, and the bf16 spills z^T, g^T consumed by the dW GEMM (kernel 2).
-//
-// Tiles are rectangles of 8 frames x 16 label columns of one utterance (row = tloc*16 + ul).  With the
-// transposed second GEMM (TMEM lane = joint dim d, TMEM column = tile row) both reductions are thread-local:
-//   d_enc[t]  = sum over the 16 columns of one tcgen05.ld.x16
-//   d_pred[u] = sum over the frame slots, kept in registers across the tiles of one (b, u-split) sweep
-// TMEM holds 512 columns, so the logits [128 x Vp] and dZ^T [D x 128] cannot coexist: a tile runs four phases
-//   P1  producers: tanh tile (+ z^T spill) | TMA: W_out k-blocks | MMA: logits -> TMEM
-//   P2  12 warps : TMEM -> g (bf16) -> smem G tile (K-major over v) + g^T spill; exact fp32 blank/label entries
-//   P3  TMA: W_out^T blocks | MMA: dZ^T[mb] = W^T[mb] . G^T -> TMEM ; the 12 warps: column sums of G (d_bias)
-//   P4  12 warps : TMEM -> dH -> d_enc partial (store), d_pred (registers)
-// W_out / W_out^T stream through ONE smem ring.  With CL = 2 the two CTAs of a cluster run in lock step and
-// each loads half of every ring stage, multicast to both (halves the L2 -> SM traffic, the P1/P3 bound).
-//
-// Roles (512 threads): warp 0 TMA ring | warp 1 MMA issuer | warp 2 TMEM alloc | warp 3 TMA slabs |
-// warps 4-15 P2/P4 workers | warps 8-15 also the P1 A producers.
+// Backward kernel 1 on CTA PAIRS (cta_group::2) - the default for D % 256 == 0.  Same phases and data flow as
+// joint_tc_bwd.cuh; the two CTAs of a cluster process tiles 2i and 2i+1 (same utterance, same u-split) in lock step:
+//   P1  one tcgen05.mma of M = 256 covers both CTAs' A tiles; each CTA loads only HALF of every W_out stage
+//   P3  dZ^T for BOTH tiles at once: M = 256 joint dims (CTA r owns d blocks r, r+2), N = 256 rows (each CTA's own G
+//       tile is its half of the B operand); each CTA loads only ITS W_out^T blocks (a quarter of the traffic per tile)
+//   P4  CTA r reduces its joint dims for both tiles (z^T of the peer's tile comes from the global spill)
+// Shared-memory bandwidth (tensor-core operand reads + copy-engine writes + producers) is what bounds the single-CTA
+// kernel; pairing halves the operand traffic per flop.  Only the leader CTA issues MMAs; the peer's warp 1 forwards
+// its local "full" barriers to the leader with remote mbarrier arrives; commits are multicast to both CTAs.
 #pragma once
-#include "tc_common.cuh"
+#include "joint_tc_bwd.cuh"
 
 namespace ctcvr {
 namespace tc {
 
-constexpr int B_A_STAGES = 3;
-constexpr int B_S_STAGES = 3;
-constexpr int B_R1_STAGES = 3;                 // W_out ring view   (P1): NH x 128 B per stage
-constexpr int B_R3_STAGES = 5;                 // W_out^T ring view (P3): 16 KB per stage, same memory
-constexpr int B_SLAB_BYTES = 2048 + 1024;      // 16 pred rows + 8 enc rows, 128 B each
-constexpr int WORKERS = 384;
-
-struct BwdParams {
-  const __nv_bfloat16* w_t;  // tiled W_out   [KB][2][NH][64]     (prep_weights3_kernel)
-  const __nv_bfloat16* wt_t; // tiled W_out^T [MB][KBG][128][64]
-  const float* bias;        // [V]
-  const float* bias_l2;     // [Vp] bias*log2e, -inf beyond V
-  const int32_t* targets;
-  const int32_t* t_len;
-  const int32_t* u_len;
-  const int4* tiles;        // {b, u-split, frame block, tile index}
-  const int* ntiles;
-  int B, T, U1, D, V, Vp, NH, blank;
-  const float* lse;
-  const float* alpha;
-  const float* beta;
-  const float* costs;
-  const float* grad_costs;
-  float clamp;
-  // spills, tiled per 128-row tile and pre-swizzled so that kernel 2 (and P4) fetch them with 1-D bulk copies:
-  //   zt [tile][MB][2][128 d][64 rows] : element (d, row rr) of a tile at box (d>>7, rr>>6), row d&127,
-  //                                      chunk ((rr&63)>>3) ^ (d&7), element rr&7
-  //   gt [tile][2][Vp][64 rows]        : element (v, rr) at half rr>>6, row v, chunk ((rr&63)>>3) ^ (v&7), element rr&7
-  __nv_bfloat16* zt;
-  __nv_bfloat16* gt;
-  long Rpad;
-  int scratch_tile;         // unused row tile (kept for layout compatibility)
-  float* d_enc_part;        // [S][B,T,D]
-  float* d_pred;            // [B,U1,D] atomic accumulate
-  float* d_bias;            // [V] atomic accumulate
-  long long* prof;
+constexpr int BP_R1_STAGES = 6;                // half W_out stages: (NH/2) x 128 B
+constexpr int BP_A_STAGES = 8;                 // the whole A tile: the GZ region is free during P1, and the producers never
+                                               // wait for the (cross-CTA, high-latency) release of a stage inside a tile
+struct BwdPairBars {
+  uint32_t base;
+  __device__ __forceinline__ uint32_t peer_a_full(int i) const { return base + i * 8; }            // 8
+  __device__ __forceinline__ uint32_t peer_r1_full(int i) const { return base + 64 + i * 8; }      // 6
+  __device__ __forceinline__ uint32_t peer_r3_full(int i) const { return base + 112 + i * 8; }     // 5
+  __device__ __forceinline__ uint32_t peer_g_full() const { return base + 152; }
+  __device__ __forceinline__ uint32_t peer_tmem_empty() const { return base + 160; }
+  __device__ __forceinline__ uint32_t r1p_full(int i) const { return base + 168 + i * 16; }        // 6 own half-stage rings
+  __device__ __forceinline__ uint32_t r1p_empty(int i) const { return base + 168 + i * 16 + 8; }
+  __device__ __forceinline__ uint32_t a_full(int i) const { return base + 264 + i * 16; }          // 8
+  __device__ __forceinline__ uint32_t a_empty(int i) const { return base + 264 + i * 16 + 8; }
 };
-
-// Shared memory: [GZ region: G tile (P2/P3) = A ring (P1) = z^T tile (P4)] [weight ring: 3 W stages = 5 W^T stages]
-// [slab ring] [bias] [column-sum partials] [barriers]
-struct Bwd2Smem {
-  uint32_t g_base, r_base, r1_bytes, s_base, bar_base;
-  float* bias_l2;
-  float* dbp;               // [4][Vp] column-sum partials
-  uint32_t* tmem_ptr;
-  __device__ __forceinline__ uint32_t a_stage(int i) const { return g_base + i * A_STAGE_BYTES; }
-  __device__ __forceinline__ uint32_t g_kblock(int i) const { return g_base + i * A_STAGE_BYTES; }
-  __device__ __forceinline__ uint32_t z_box(int i) const { return g_base + i * A_STAGE_BYTES; }    // (mb*2 + half)
-  __device__ __forceinline__ uint32_t r1_stage(int i) const { return r_base + i * r1_bytes; }
-  __device__ __forceinline__ uint32_t r3_stage(int i) const { return r_base + i * 16384; }
-  __device__ __forceinline__ uint32_t s_stage(int i) const { return s_base + i * B_SLAB_BYTES; }
-  __device__ __forceinline__ uint32_t a_full(int i) const { return bar_base + i * 16; }
-  __device__ __forceinline__ uint32_t a_empty(int i) const { return bar_base + i * 16 + 8; }
-  __device__ __forceinline__ uint32_t s_full(int i) const { return bar_base + 48 + i * 16; }
-  __device__ __forceinline__ uint32_t s_empty(int i) const { return bar_base + 48 + i * 16 + 8; }
-  __device__ __forceinline__ uint32_t r1_full(int i) const { return bar_base + 96 + i * 16; }
-  __device__ __forceinline__ uint32_t r1_empty(int i) const { return bar_base + 96 + i * 16 + 8; }
-  __device__ __forceinline__ uint32_t r3_full(int i) const { return bar_base + 144 + i * 16; }
-  __device__ __forceinline__ uint32_t r3_empty(int i) const { return bar_base + 144 + i * 16 + 8; }
-  __device__ __forceinline__ uint32_t z_full(int i) const { return bar_base + 224 + i * 8; }
-  __device__ __forceinline__ uint32_t tmem_full() const { return bar_base + 256; }
-  __device__ __forceinline__ uint32_t g_full() const { return bar_base + 264; }
-  __device__ __forceinline__ uint32_t dz_full() const { return bar_base + 272; }
-  __device__ __forceinline__ uint32_t tmem_empty() const { return bar_base + 280; }
-  __device__ __forceinline__ uint32_t gs_done() const { return bar_base + 288; }   // column sums have read G
-};
-
-__host__ __device__ inline uint32_t bwd2_ring_bytes(int NH) {
-  uint32_t a = (uint32_t)B_R1_STAGES * (uint32_t)NH * 128u, b = (uint32_t)B_R3_STAGES * 16384u;
-  return a > b ? a : b;
-}
-__host__ __device__ inline uint32_t bwd2_gz_blocks(int Vp, int D) {
-  const uint32_t kbg = (Vp + 63) / 64, zb = 2 * (D / 128);
-  return kbg > zb ? kbg : zb;
-}
-
-__host__ __device__ inline size_t bwd2_smem_bytes(int NH, int Vp, int D) {
-  size_t s = 1024;
-  s += (size_t)bwd2_gz_blocks(Vp, D) * A_STAGE_BYTES;
-  s += bwd2_ring_bytes(NH);
-  s = (s + 1023) / 1024 * 1024;
-  s += (size_t)B_S_STAGES * B_SLAB_BYTES;
-  s += (size_t)Vp * 4 + (size_t)4 * Vp * 4;
-  s += 304 + 392 + 16 + 16;            // barriers (+ the CTA-pair kernel's extra barriers) + tmem pointer
-  return s;
-}
-
-__device__ __forceinline__ void carve_bwd2(Bwd2Smem& L, uint8_t* raw, int NH, int Vp, int D) {
-  const uint32_t base = smem_u32(raw);
-  uint32_t a = (base + 1023u) & ~1023u;
-  L.g_base = a; a += bwd2_gz_blocks(Vp, D) * A_STAGE_BYTES;
-  L.r_base = a; L.r1_bytes = (uint32_t)NH * 128u; a += bwd2_ring_bytes(NH);
-  a = (a + 1023u) & ~1023u;
-  L.s_base = a; a += B_S_STAGES * B_SLAB_BYTES;
-  L.bias_l2 = reinterpret_cast<float*>(raw + (a - base)); a += Vp * 4;
-  L.dbp = reinterpret_cast<float*>(raw + (a - base)); a += 4 * Vp * 4;
-  a = (a + 15u) & ~15u;
-  L.bar_base = a; a += 304 + 392;
-  L.tmem_ptr = reinterpret_cast<uint32_t*>(raw + (a - base));
-}
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_p,
+joint_bwd2p_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_p,
                   const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   Bwd2Smem L;
@@ -133,16 +39,25 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
   const int KB = p.D / BK;                 // k-blocks of the logits GEMM
   const int KBG = (p.Vp + 63) / 64;        // k-blocks (over v) of the dZ GEMM
   const int MB = p.D / 128;                // 128-lane blocks of dZ^T
-  const int ntiles = *p.ntiles;
-  const int tile_begin = (int)(((long)ntiles * blockIdx.x) / gridDim.x);
-  const int tile_end = (int)(((long)ntiles * (blockIdx.x + 1)) / gridDim.x);
+  const int ntiles = *p.ntiles;                          // even: every (b, u-split) sweep is padded to an even count
+  const uint32_t rank = cluster_ctarank();               // 0 = leader (issues the MMAs), 1 = peer
+  const int npairs = ntiles >> 1, ncl = (int)gridDim.x >> 1, cl = (int)blockIdx.x >> 1;
+  const int pair_begin = (int)(((long)npairs * cl) / ncl), pair_end = (int)(((long)npairs * (cl + 1)) / ncl);
+  const int tile_begin = 2 * pair_begin + (int)rank, tile_end = 2 * pair_end;      // my tiles: tile_begin, +2, +4, ...
+  BwdPairBars X;
+  X.base = L.bar_base + 304;
+  const uint32_t r1p_bytes = (uint32_t)(p.NH / 2) * 128u;
+  auto r1p_stage = [&](int i) { return L.r_base + (uint32_t)i * r1p_bytes; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_e);
     tma_prefetch_desc(&tmap_p);
-    for (int i = 0; i < B_A_STAGES; ++i) { mbar_init(L.a_full(i), PROD_THREADS); mbar_init(L.a_empty(i), 1); }
+    for (int i = 0; i < BP_A_STAGES; ++i) { mbar_init(X.a_full(i), PROD_THREADS); mbar_init(X.a_empty(i), 1); mbar_init(X.peer_a_full(i), 1); }
     for (int i = 0; i < B_S_STAGES; ++i) { mbar_init(L.s_full(i), 1); mbar_init(L.s_empty(i), PROD_THREADS); }
-    for (int i = 0; i < B_R1_STAGES; ++i) { mbar_init(L.r1_full(i), 1); mbar_init(L.r1_empty(i), 1); }
+    for (int i = 0; i < BP_R1_STAGES; ++i) { mbar_init(X.r1p_full(i), 1); mbar_init(X.r1p_empty(i), 1); mbar_init(X.peer_r1_full(i), 1); }
+    for (int i = 0; i < B_R3_STAGES; ++i) mbar_init(X.peer_r3_full(i), 1);
+    mbar_init(X.peer_g_full(), 1);
+    mbar_init(X.peer_tmem_empty(), 1);
     for (int i = 0; i < B_R3_STAGES; ++i) { mbar_init(L.r3_full(i), 1); mbar_init(L.r3_empty(i), 1); }
     for (int i = 0; i < 4; ++i) mbar_init(L.z_full(i), 1);
     mbar_init(L.tmem_full(), 1);
@@ -152,10 +67,11 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
     mbar_init(L.gs_done(), 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(L.tmem_ptr), TMEM_COLS);
+  if (warp == 2) tmem_alloc2(smem_u32(L.tmem_ptr), TMEM_COLS);
   for (int i = tid; i < p.Vp; i += NTHREADS) L.bias_l2[i] = p.bias_l2[i];
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                       // the peer's barriers exist before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *L.tmem_ptr;
 
@@ -165,37 +81,38 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       Pipe r1, r3;
       int prof_n = 0;
       uint32_t ph = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const size_t rowtile = (size_t)p.tiles[tile].w;
+      for (int tile = tile_begin; tile < tile_end; tile += 2) {
+        const size_t rt_own = (size_t)p.tiles[tile].w, rt_peer = (size_t)p.tiles[tile ^ 1].w;
+        const size_t rt_x[2] = {rank == 0 ? rt_own : rt_peer, rank == 0 ? rt_peer : rt_own};   // x = 0: leader's tile
         TC_PROF(0, 1);
-        // the ring is drained here: the previous tile's dz_full was observed below
         for (int kb = 0; kb < KB; ++kb)
           for (int h = 0; h < 2; ++h) {
-            mbar_wait(L.r1_empty(r1.stage), r1.phase ^ 1u, 11);
-            mbar_arrive_expect_tx(L.r1_full(r1.stage), (uint32_t)p.NH * 128u);
-            bulk_load(L.r1_stage(r1.stage), p.w_t + (size_t)(kb * 2 + h) * p.NH * 64, (uint32_t)p.NH * 128u,
-                      L.r1_full(r1.stage));
-            r1.advance(B_R1_STAGES);
+            mbar_wait(X.r1p_empty(r1.stage), r1.phase ^ 1u, 11);
+            mbar_arrive_expect_tx(X.r1p_full(r1.stage), r1p_bytes);
+            bulk_load(r1p_stage(r1.stage), p.w_t + ((size_t)(kb * 2 + h) * p.NH + rank * (p.NH / 2)) * 64, r1p_bytes,
+                      X.r1p_full(r1.stage));
+            r1.advance(BP_R1_STAGES);
           }
         TC_PROF(0, 2);
         mbar_wait(L.tmem_full(), ph, 12);           // every P1 MMA has completed: the W view of the ring is dead
         TC_PROF(0, 3);
-        for (int mb = 0; mb < MB; ++mb)
+        for (int pb = 0; pb < MB / 2; ++pb)
           for (int kb = 0; kb < KBG; ++kb) {
             mbar_wait(L.r3_empty(r3.stage), r3.phase ^ 1u, 13);
             mbar_arrive_expect_tx(L.r3_full(r3.stage), 16384u);
-            bulk_load(L.r3_stage(r3.stage), p.wt_t + (size_t)(mb * KBG + kb) * 8192, 16384u, L.r3_full(r3.stage));
+            bulk_load(L.r3_stage(r3.stage), p.wt_t + (size_t)((2 * pb + (int)rank) * KBG + kb) * 8192, 16384u,
+                      L.r3_full(r3.stage));
             r3.advance(B_R3_STAGES);
           }
         TC_PROF(0, 4);
         mbar_wait(L.dz_full(), ph, 14);             // every P3 MMA has completed: G tile and the W^T view are dead
         mbar_wait(L.gs_done(), ph, 16);             // ... and the d_bias column sums have read G
         TC_PROF(0, 5);
-        fence_proxy_async_global();                 // z^T was written with st.global by this CTA's producers
-        TC_PROF(0, 6);
-        for (int mb = 0; mb < MB; ++mb) {
-          mbar_arrive_expect_tx(L.z_full(mb), 32768u);
-          bulk_load(L.z_box(2 * mb), p.zt + ((rowtile * MB + mb) * 2) * 8192, 32768u, L.z_full(mb));
+        fence_proxy_async_global();                 // z^T was written with st.global (by this CTA and by its peer)
+        for (int pb = 0; pb < MB / 2; ++pb) {
+          mbar_arrive_expect_tx(L.z_full(pb), 65536u);
+          for (int x = 0; x < 2; ++x)
+            bulk_load(L.z_box((pb * 2 + x) * 2), p.zt + ((rt_x[x] * MB + 2 * pb + rank) * 2) * 8192, 32768u, L.z_full(pb));
         }
         ph ^= 1u;
       }
@@ -205,7 +122,7 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
     // ------------------------------------------------------------------ TMA: enc / pred slabs
     if (lane == 0) {
       Pipe sp;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
+      for (int tile = tile_begin; tile < tile_end; tile += 2) {
         const int4 ti = p.tiles[tile];
         const int b = ti.x;
         const int W = min(p.u_len[b], p.U1 - 1) + 1;
@@ -229,51 +146,85 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       Pipe ap, r1, r3;
       int prof_n = 0;
       uint32_t ph = 0;
-      const uint32_t idesc1 = make_idesc_bf16(BM, p.NH);
-      const uint32_t idesc2 = make_idesc_bf16(128, BM);
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        TC_PROF(1, 1);
-        mbar_wait(L.tmem_empty(), ph ^ 1u, 20);
-        TC_PROF(1, 2);
-        tc_fence_after();
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(L.a_full(ap.stage), ap.phase, 21);
-          TC_PROF(1, 50 + kb);
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(L.r1_full(r1.stage), r1.phase, 22);
-            TC_PROF(1, 100 + kb * 2 + h);
-            tc_fence_after();
+      if (rank == 0) {
+        const uint32_t idesc1 = make_idesc_bf16(256, p.NH);
+        const uint32_t idesc2 = make_idesc_bf16(256, 256);
+        for (int tile = tile_begin; tile < tile_end; tile += 2) {
+          TC_PROF(1, 1);
+          mbar_wait(L.tmem_empty(), ph ^ 1u, 20);
+          mbar_wait(X.peer_tmem_empty(), ph ^ 1u, 25);
+          TC_PROF(1, 2);
+          tc_fence_after();
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(X.a_full(ap.stage), ap.phase, 21);
+            mbar_wait(X.peer_a_full(ap.stage), ap.phase, 26);
+            TC_PROF(1, 50 + kb);
+            for (int h = 0; h < 2; ++h) {
+              mbar_wait(X.r1p_full(r1.stage), r1.phase, 22);
+              mbar_wait(X.peer_r1_full(r1.stage), r1.phase, 27);
+              TC_PROF(1, 100 + kb * 2 + h);
+              tc_fence_after();
 #pragma unroll
-            for (int ks = 0; ks < BK / 16; ++ks)
-              umma_bf16(tmem_base + h * p.NH, make_desc_sw128(L.a_stage(ap.stage) + ks * 32),
-                        make_desc_sw128(L.r1_stage(r1.stage) + ks * 32), idesc1, (kb | ks) ? 1u : 0u);
-            umma_commit(L.r1_empty(r1.stage));
-            r1.advance(B_R1_STAGES);
+              for (int ks = 0; ks < BK / 16; ++ks)
+                umma2_bf16(tmem_base + h * p.NH, make_desc_sw128(L.a_stage(ap.stage) + ks * 32),
+                           make_desc_sw128(r1p_stage(r1.stage) + ks * 32), idesc1, (kb | ks) ? 1u : 0u);
+              umma2_commit_mc(X.r1p_empty(r1.stage), 3);
+              r1.advance(BP_R1_STAGES);
+            }
+            umma2_commit_mc(X.a_empty(ap.stage), 3);
+            ap.advance(BP_A_STAGES);
           }
-          umma_commit(L.a_empty(ap.stage));
-          ap.advance(B_A_STAGES);
+          umma2_commit_mc(L.tmem_full(), 3);
+          TC_PROF(1, 3);
+          // ---- P3: dZ^T (256 joint dims x 256 rows) per pair block: A = both CTAs' W^T blocks, B = both CTAs' G tiles
+          mbar_wait(L.g_full(), ph, 23);
+          mbar_wait(X.peer_g_full(), ph, 28);
+          TC_PROF(1, 4);
+          tc_fence_after();
+          for (int pb = 0; pb < MB / 2; ++pb)
+            for (int kb = 0; kb < KBG; ++kb) {
+              mbar_wait(L.r3_full(r3.stage), r3.phase, 24);
+              mbar_wait(X.peer_r3_full(r3.stage), r3.phase, 29);
+              TC_PROF(1, 200 + pb * KBG + kb);
+              tc_fence_after();
+              const int nks = min(4, (p.Vp - kb * 64) / 16);
+              for (int ks = 0; ks < nks; ++ks)
+                umma2_bf16(tmem_base + pb * 256, make_desc_sw128(L.r3_stage(r3.stage) + ks * 32),
+                           make_desc_sw128(L.g_kblock(kb) + ks * 32), idesc2, (kb | ks) ? 1u : 0u);
+              umma2_commit_mc(L.r3_empty(r3.stage), 3);
+              r3.advance(B_R3_STAGES);
+            }
+          umma2_commit_mc(L.dz_full(), 3);
+          TC_PROF(1, 5);
+          ph ^= 1u;
         }
-        umma_commit(L.tmem_full());
-        TC_PROF(1, 3);
-        // ---- P3: dZ^T[mb] (128 d x 128 rows) = W^T[mb] (128 x Vp) . G^T (Vp x 128)
-        mbar_wait(L.g_full(), ph, 23);
-        TC_PROF(1, 4);
-        tc_fence_after();
-        for (int mb = 0; mb < MB; ++mb)
-          for (int kb = 0; kb < KBG; ++kb) {
-            mbar_wait(L.r3_full(r3.stage), r3.phase, 24);
-            TC_PROF(1, 200 + mb * KBG + kb);
-            tc_fence_after();
-            const int nks = min(4, (p.Vp - kb * 64) / 16);
-            for (int ks = 0; ks < nks; ++ks)
-              umma_bf16(tmem_base + mb * 128, make_desc_sw128(L.r3_stage(r3.stage) + ks * 32),
-                        make_desc_sw128(L.g_kblock(kb) + ks * 32), idesc2, (kb | ks) ? 1u : 0u);
-            umma_commit(L.r3_empty(r3.stage));
-            r3.advance(B_R3_STAGES);
+      } else {
+        // peer: forward "my operands are ready" / "my TMEM is drained" to the leader's barriers, in the leader's order
+        for (int tile = tile_begin; tile < tile_end; tile += 2) {
+          if (tile != tile_begin) {                 // the leader's first wait on this barrier passes by parity
+            mbar_wait(L.tmem_empty(), ph ^ 1u, 20);
+            mbar_arrive_remote(X.peer_tmem_empty(), 0);
           }
-        umma_commit(L.dz_full());
-        TC_PROF(1, 5);
-        ph ^= 1u;
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(X.a_full(ap.stage), ap.phase, 21);
+            mbar_arrive_remote(X.peer_a_full(ap.stage), 0);
+            for (int h = 0; h < 2; ++h) {
+              mbar_wait(X.r1p_full(r1.stage), r1.phase, 22);
+              mbar_arrive_remote(X.peer_r1_full(r1.stage), 0);
+              r1.advance(BP_R1_STAGES);
+            }
+            ap.advance(BP_A_STAGES);
+          }
+          mbar_wait(L.g_full(), ph, 23);
+          mbar_arrive_remote(X.peer_g_full(), 0);
+          for (int pb = 0; pb < MB / 2; ++pb)
+            for (int kb = 0; kb < KBG; ++kb) {
+              mbar_wait(L.r3_full(r3.stage), r3.phase, 24);
+              mbar_arrive_remote(X.peer_r3_full(r3.stage), 0);
+              r3.advance(B_R3_STAGES);
+            }
+          ph ^= 1u;
+        }
       }
     }
     __syncwarp();
@@ -290,26 +241,19 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
     int prof_n = 0;
     Pipe ap, sp;
     float db0 = 0.f, db1 = 0.f;                // d_bias of columns wt and wt + 384
-    float pacc[2][16];                         // d_pred sums of d blocks 2wg, 2wg+1 over the tiles of one (b, u-split) sweep
+    float pacc[16];                            // d_pred sums of d block 2*wg + rank over the tiles of one (b, u-split) sweep
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 16; ++j) pacc[i][j] = 0.f;
+    for (int j = 0; j < 16; ++j) pacc[j] = 0.f;
     int cur_b = -1, cur_ubase = 0;
     auto flush_pred = [&]() {
-      if (cur_b < 0 || wg >= 2) return;
+      if (cur_b < 0 || wg >= 2 || wg >= MB / 2) return;
       const int Ub = min(p.u_len[cur_b], p.U1 - 1);
+      const int mb = 2 * wg + (int)rank;
 #pragma unroll
-      for (int mbl = 0; mbl < 2; ++mbl) {
-        const int mb = 2 * wg + mbl;
-        if (mb < MB) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int u = cur_ubase + j;
-            if (u <= Ub) atomicAdd(p.d_pred + ((size_t)cur_b * p.U1 + u) * p.D + mb * 128 + r, pacc[mbl][j]);
-            pacc[mbl][j] = 0.f;
-          }
-        }
+      for (int j = 0; j < 16; ++j) {
+        const int u = cur_ubase + j;
+        if (u <= Ub) atomicAdd(p.d_pred + ((size_t)cur_b * p.U1 + u) * p.D + mb * 128 + r, pacc[j]);
+        pacc[j] = 0.f;
       }
     };
     // producer addressing (rows lane, lane+32, lane+64, lane+96 of the tile; row = tloc*16 + ul)
@@ -323,9 +267,11 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
     }
     const uint32_t a_off = (uint32_t)lane * 128u + (uint32_t)((pc ^ (lane & 7)) << 4);
 
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    for (int tile = tile_begin; tile < tile_end; tile += 2) {
       int4 ti = p.tiles[tile];
       pin(ti.x); pin(ti.y); pin(ti.z); pin(ti.w);
+      int tz_peer = p.tiles[tile ^ 1].z;                     // frame block of the peer's tile (same b, same u-split)
+      pin(tz_peer);
       const RowMap g = tile_geometry<TILE_RECT>(p.t_len, p.u_len, p.T, p.U1, ti);
       if (g.b != cur_b || g.ubase != cur_ubase) { flush_pred(); cur_b = g.b; cur_ubase = g.ubase; }
       const size_t rowtile = (size_t)ti.w;
@@ -337,7 +283,7 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
         if (tid == 256) TC_PROF(3, 1);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(L.s_full(sp.stage), sp.phase, 41);
-          mbar_wait(L.a_empty(ap.stage), ap.phase ^ 1u, 42);
+          mbar_wait(X.a_empty(ap.stage), ap.phase ^ 1u, 42);
           const uint32_t sb = L.s_stage(sp.stage);
           const uint32_t ab = L.a_stage(ap.stage) + a_off;
           const uint4 pv = lds128(sb + p_off);
@@ -362,13 +308,14 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
             }
           }
           fence_proxy_async();
-          mbar_arrive(L.a_full(ap.stage));
+          mbar_arrive(X.a_full(ap.stage));
           mbar_arrive(L.s_empty(sp.stage));
-          ap.advance(B_A_STAGES);
+          ap.advance(BP_A_STAGES);
           sp.advance(B_S_STAGES);
         }
         if (tid == 256) TC_PROF(3, 2);
-        fence_proxy_async_global();                  // z^T (st.global above) is read back by the P4 TMA load
+        __threadfence();                             // the peer CTA reads this z^T spill too
+        fence_proxy_async_global();                  // z^T (st.global above) is read back by the P4 bulk copies
         if (tid == 256) TC_PROF(3, 3);
       }
 
@@ -506,45 +453,45 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
           db1 += (L.dbp[wt + WORKERS] + L.dbp[p.Vp + wt + WORKERS]) + (L.dbp[2 * p.Vp + wt + WORKERS] + L.dbp[3 * p.Vp + wt + WORKERS]);
       }
 
-      // ---------------- P4 (warps 4-11): dH = dZ * (1 - z^2); reductions.  Warp group wg owns d blocks 2wg, 2wg+1.
-      // z^T arrives in shared memory (TMA, issued after dz_full): box (mb, half) = [128 d][64 rows], 128B swizzle.
+      // ---------------- P4 (warps 4-11): dH = dZ * (1 - z^2); reductions.  This CTA owns d blocks mb = 2 pb + rank;
+      // warp group wg = pair block pb.  TMEM columns pb*256 + x*128 + tloc*16 + ul: x = 0 the leader's tile, x = 1 the
+      // peer's.  z^T boxes (pb, x, half) = [128 d][64 rows] arrive in shared memory (bulk copies after dz_full).
       if (wg < 2) {
         mbar_wait(L.dz_full(), ph, 32);
         if (tid == 128) TC_PROF(2, 4);
         tc_fence_after();
+        const int pb = wg;
+        if (pb < MB / 2) {
+          mbar_wait(L.z_full(pb), ph, 33);
+          if (tid == 128) TC_PROF(2, 40 + pb);
+          const int d = (2 * pb + (int)rank) * 128 + r;
+          const int t0x[2] = {(rank == 0 ? ti.z : tz_peer) * 8, (rank == 0 ? tz_peer : ti.z) * 8};
+          float v[16];
+          tmem_ld16(tq + pb * 256, v);
 #pragma unroll
-        for (int mbl = 0; mbl < 2; ++mbl) {
-          const int mb = 2 * wg + mbl;
-          if (mb < MB) {
-            mbar_wait(L.z_full(mb), ph, 33);
-            if (tid == 128) TC_PROF(2, 40 + mb);
-            const int d = mb * 128 + r;
-            float v[16];
-            tmem_ld16(tq + mb * 128, v);
+          for (int it = 0; it < 16; ++it) {
+            const int x = it >> 3, tloc = it & 7;
+            const uint32_t zb = L.z_box((pb * 2 + x) * 2 + (tloc >> 2)) + (uint32_t)r * 128u;
+            const uint4 z0 = lds128(zb + ((((tloc & 3) * 2) ^ (r & 7)) << 4));
+            const uint4 z1 = lds128(zb + ((((tloc & 3) * 2 + 1) ^ (r & 7)) << 4));
+            tmem_ld_wait();
+            float w[16];
 #pragma unroll
-            for (int tloc = 0; tloc < 8; ++tloc) {
-              const uint32_t zb = L.z_box(2 * mb + (tloc >> 2)) + (uint32_t)r * 128u;
-              const uint4 z0 = lds128(zb + ((((tloc & 3) * 2) ^ (r & 7)) << 4));
-              const uint4 z1 = lds128(zb + ((((tloc & 3) * 2 + 1) ^ (r & 7)) << 4));
-              tmem_ld_wait();
-              float w[16];
+            for (int j = 0; j < 16; ++j) w[j] = v[j];
+            if (it < 15) tmem_ld16(tq + pb * 256 + (it + 1) * 16, v);
+            const uint32_t zw[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+            float es0 = 0.f, es1 = 0.f;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) w[j] = v[j];
-              if (tloc < 7) tmem_ld16(tq + mb * 128 + (tloc + 1) * 16, v);
-              const uint32_t zw[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
-              float es0 = 0.f, es1 = 0.f;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float za = __uint_as_float(zw[j] << 16), zb2 = __uint_as_float(zw[j] & 0xffff0000u);
-                const float ha = w[2 * j] * fmaf(-za, za, 1.f), hb = w[2 * j + 1] * fmaf(-zb2, zb2, 1.f);
-                es0 += ha;
-                es1 += hb;
-                pacc[mbl][2 * j] += ha;
-                pacc[mbl][2 * j + 1] += hb;
-              }
-              const int tt = g.t0 + tloc;
-              if (tt < g.Tb) p.d_enc_part[(((size_t)ti.y * p.B + g.b) * p.T + tt) * p.D + d] = es0 + es1;
+            for (int j = 0; j < 8; ++j) {
+              const float za = __uint_as_float(zw[j] << 16), zb2 = __uint_as_float(zw[j] & 0xffff0000u);
+              const float ha = w[2 * j] * fmaf(-za, za, 1.f), hb = w[2 * j + 1] * fmaf(-zb2, zb2, 1.f);
+              es0 += ha;
+              es1 += hb;
+              pacc[2 * j] += ha;
+              pacc[2 * j + 1] += hb;
             }
+            const int tt = t0x[x] + tloc;
+            if (tt < g.Tb) p.d_enc_part[(((size_t)ti.y * p.B + g.b) * p.T + tt) * p.D + d] = es0 + es1;
           }
         }
         tc_fence_before();
@@ -562,7 +509,8 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  cluster_sync_all();                       // no CTA exits while the pair may still touch its barriers / TMEM
+  if (warp == 2) tmem_dealloc2(tmem_base, TMEM_COLS);
 }
 
 }  // namespace tc

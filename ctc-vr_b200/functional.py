@@ -37,10 +37,17 @@ class _FusedJointRnnt(torch.autograd.Function):
     def forward(ctx, enc_proj, pred_proj, w_out, b_out, targets, t_len, u_len, blank, clamp, precision):
         _lib.require_cuda(enc_proj, pred_proj, w_out, b_out)
         dev = enc_proj.device
-        e, p, w, b = _f32c(enc_proj), _f32c(pred_proj), _f32c(w_out), _f32c(b_out)
-        B, T, D = e.shape
-        U1 = p.shape[1]
+        w, b = _f32c(w_out), _f32c(b_out)
+        B, T, D = enc_proj.shape
+        U1 = pred_proj.shape[1]
         V = w.shape[0]
+        # bf16 activations (autocast) are consumed in place by the tensor-core path: no fp32 round trip
+        bf16_in = (precision == BF16 and enc_proj.dtype == torch.bfloat16 and pred_proj.dtype == torch.bfloat16
+                   and bool(query("ctcvr_joint_tc_supported", U1, D, V)))
+        if bf16_in:
+            e, p = enc_proj.detach().contiguous(), pred_proj.detach().contiguous()
+        else:
+            e, p = _f32c(enc_proj), _f32c(pred_proj)
         if p.shape[0] != B or p.shape[2] != D or w.shape[1] != D or b.shape[0] != V:
             raise RuntimeError("fused_joint_rnnt_loss: inconsistent shapes")
         tg = _i32c(targets, dev)
@@ -53,29 +60,41 @@ class _FusedJointRnnt(torch.autograd.Function):
         costs = torch.empty((B,), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             ws = _ws(query("ctcvr_joint_rnnt_fwd_ws_bytes", B, T, U1, D, V, precision), dev)
-            call("ctcvr_joint_rnnt_fwd", ptr(e), ptr(p), ptr(w), ptr(b), ptr(tg), ptr(tl), ptr(ul), ptr(lse),
-                 ptr(lpb), ptr(lpl), B, T, U1, D, V, blank, precision, ptr(ws), ws.numel(), stream())
+            if bf16_in:
+                call("ctcvr_joint_rnnt_fwd_bf16in", ptr(e), ptr(p), ptr(w), ptr(b), ptr(tg), ptr(tl), ptr(ul), ptr(lse),
+                     ptr(lpb), ptr(lpl), B, T, U1, D, V, blank, ptr(ws), ws.numel(), stream())
+            else:
+                call("ctcvr_joint_rnnt_fwd", ptr(e), ptr(p), ptr(w), ptr(b), ptr(tg), ptr(tl), ptr(ul), ptr(lse),
+                     ptr(lpb), ptr(lpl), B, T, U1, D, V, blank, precision, ptr(ws), ws.numel(), stream())
             call("ctcvr_rnnt_lattice", ptr(lpb), ptr(lpl), ptr(tl), ptr(ul), ptr(alpha), ptr(beta), ptr(costs),
                  B, T, U1, stream())
         ctx.save_for_backward(e, p, w, b, tg, tl, ul, lse, alpha, beta, costs)
-        ctx.cfg = (blank, float(clamp), precision)
+        ctx.cfg = (blank, float(clamp), precision, bf16_in)
         return costs
 
     @staticmethod
     def backward(ctx, grad_costs):
         e, p, w, b, tg, tl, ul, lse, alpha, beta, costs = ctx.saved_tensors
-        blank, clamp, precision = ctx.cfg
+        blank, clamp, precision, bf16_in = ctx.cfg
         B, T, D = e.shape
         U1, V = p.shape[1], w.shape[0]
         dev = e.device
         gc = _f32c(grad_costs)
-        d_e, d_p = torch.empty_like(e), torch.empty_like(p)
+        d_e = torch.empty(e.shape, dtype=torch.float32, device=dev)
+        d_p = torch.empty(p.shape, dtype=torch.float32, device=dev)
         d_w, d_b = torch.empty_like(w), torch.empty_like(b)
         with torch.cuda.device(dev):
             ws = _ws(query("ctcvr_joint_rnnt_bwd_ws_bytes", B, T, U1, D, V, precision), dev)
-            call("ctcvr_joint_rnnt_bwd", ptr(e), ptr(p), ptr(w), ptr(b), ptr(tg), ptr(tl), ptr(ul), ptr(lse),
-                 ptr(alpha), ptr(beta), ptr(costs), ptr(gc), clamp, ptr(d_e), ptr(d_p), ptr(d_w), ptr(d_b),
-                 B, T, U1, D, V, blank, precision, ptr(ws), ws.numel(), stream())
+            if bf16_in:
+                call("ctcvr_joint_rnnt_bwd_bf16in", ptr(e), ptr(p), ptr(w), ptr(b), ptr(tg), ptr(tl), ptr(ul), ptr(lse),
+                     ptr(alpha), ptr(beta), ptr(costs), ptr(gc), clamp, ptr(d_e), ptr(d_p), ptr(d_w), ptr(d_b),
+                     B, T, U1, D, V, blank, ptr(ws), ws.numel(), stream())
+            else:
+                call("ctcvr_joint_rnnt_bwd", ptr(e), ptr(p), ptr(w), ptr(b), ptr(tg), ptr(tl), ptr(ul), ptr(lse),
+                     ptr(alpha), ptr(beta), ptr(costs), ptr(gc), clamp, ptr(d_e), ptr(d_p), ptr(d_w), ptr(d_b),
+                     B, T, U1, D, V, blank, precision, ptr(ws), ws.numel(), stream())
+        if bf16_in:      # gradients flow back in the dtype of the inputs (autograd requirement)
+            d_e, d_p = d_e.to(e.dtype), d_p.to(p.dtype)
         return d_e, d_p, d_w, d_b, None, None, None, None, None, None
 
 

@@ -1,0 +1,72 @@
+"""Whole-step CUDA graph of the fused seam (pre-projections -> fused joint / log-softmax forward -> lattice ->
+fused backward -> pre-projection backward).  The reference's train loop launches ~40 kernels per step for this seam
+(`rnnt_train.py:100-127` through `transducer.py:161-189`); here the step is captured once and replayed, so the host
+cost per step is one graph launch plus the input copies.  B200-first: streams and graphs instead of a tracing compiler.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+
+class GraphedJointRnntStep:
+    """Static-shape training step: `step(enc_out, pred_out, targets, logit_lengths, target_lengths)` copies the
+    arguments into the captured buffers, replays the graph and returns the (device) loss scalar
+    `sum_b cost_b / global_batch`.  Gradients land in `joint.<param>.grad`, `self.enc.grad`, `self.pred.grad`
+    (static tensors, overwritten by every replay).  Passing no arguments replays on the resident inputs."""
+
+    def __init__(self, joint, B: int, T: int, U: int, blank: int, global_batch: Optional[int] = None,
+                 precision: str = "bf16", clamp: float = -1.0, warmup: int = 3):
+        p0 = next(joint.parameters())
+        dev = p0.device
+        if dev.type != "cuda":
+            raise RuntimeError("ctcvr_b200.GraphedJointRnntStep needs the joint on a CUDA (B200) device")
+        E = joint.enc_ffn.in_features if joint.enc_ffn is not None else joint.ffn_out.in_features
+        P = joint.pred_ffn.in_features if joint.pred_ffn is not None else joint.ffn_out.in_features
+        self.joint, self.blank, self.precision, self.clamp = joint, int(blank), precision, float(clamp)
+        self.gB = float(global_batch if global_batch is not None else B)
+        self.enc = torch.zeros(B, T, E, device=dev, requires_grad=True)
+        self.pred = torch.zeros(B, U + 1, P, device=dev, requires_grad=True)
+        self.targets = torch.full((B, U), max(self.blank + 1, 1) % joint.ffn_out.out_features, dtype=torch.int32, device=dev)
+        self.logit_lengths = torch.full((B,), T, dtype=torch.int32, device=dev)
+        self.target_lengths = torch.full((B,), U, dtype=torch.int32, device=dev)
+        self.loss = None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._eager()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._eager()
+
+    def _eager(self):
+        for p in self.joint.parameters():
+            p.grad = None
+        self.enc.grad = None
+        self.pred.grad = None
+        costs = self.joint.rnnt_loss_fused(self.enc, self.pred, self.targets, self.logit_lengths, self.target_lengths,
+                                           self.blank, clamp=self.clamp, reduction="none", precision=self.precision)
+        loss = costs.sum() / self.gB
+        loss.backward()
+        self.loss = loss.detach()
+
+    @torch.no_grad()
+    def load(self, enc_out, pred_out, targets, logit_lengths, target_lengths):
+        """Copy one batch (host-pinned or device tensors) into the captured input buffers."""
+        self.enc.copy_(enc_out, non_blocking=True)
+        self.pred.copy_(pred_out, non_blocking=True)
+        self.targets.copy_(targets, non_blocking=True)
+        self.logit_lengths.copy_(logit_lengths, non_blocking=True)
+        self.target_lengths.copy_(target_lengths, non_blocking=True)
+
+    def step(self, enc_out=None, pred_out=None, targets=None, logit_lengths=None, target_lengths=None):
+        if enc_out is not None:
+            self.load(enc_out, pred_out, targets, logit_lengths, target_lengths)
+        self.graph.replay()
+        return self.loss
+
+    __call__ = step

@@ -17,7 +17,8 @@
  *   - all tensors are dense row-major ("contiguous"); T = max encoder frames, U1 = max target
  *     length + 1, D = joint dim, V = vocabulary size; lengths are int32.
  *   - precision: CTCVR_F32 = fp32 SIMT path (1e-4 parity path), CTCVR_BF16 = tcgen05 path
- *     (bf16 operands, fp32 accumulate / softmax / lattice).
+ *     (bf16 operands - enc_proj / pred_proj are rounded to bf16 too - fp32 accumulate / softmax /
+ *     lattice).  enc_proj / pred_proj must be 16-byte aligned in the bf16 path.
  */
 #ifndef CTCVR_H_
 #define CTCVR_H_
@@ -79,6 +80,23 @@ int ctcvr_joint_rnnt_bwd(const float* enc_proj, const float* pred_proj, const fl
                          float clamp, float* d_enc_proj, float* d_pred_proj, float* d_w_out,
                          float* d_b_out, int B, int T, int U1, int D, int V, int blank,
                          int precision, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- bf16-input variants of the fused forward / backward (precision = CTCVR_BF16 implied): enc_proj / pred_proj
+ * are bf16 tensors (what the reference's joint.enc_ffn / pred_ffn produce under torch.autocast), used in place -
+ * no fp32 round trip.  ctcvr_joint_tc_supported() tells whether the shape fits the tensor-core tiling
+ * (D % 128 == 0, D <= 512, V <= 512, U1 <= 128); other shapes must use the fp32-input entry points.
+ * Workspace sizes are those of the fp32-input entry points with precision = CTCVR_BF16. */
+int ctcvr_joint_tc_supported(int U1, int D, int V);
+int ctcvr_joint_rnnt_fwd_bf16in(const void* enc_proj_bf16, const void* pred_proj_bf16, const float* w_out,
+                                const float* b_out, const int32_t* targets, const int32_t* t_len,
+                                const int32_t* u_len, float* lse, float* lp_blank, float* lp_label, int B,
+                                int T, int U1, int D, int V, int blank, void* ws, size_t ws_bytes, void* stream);
+int ctcvr_joint_rnnt_bwd_bf16in(const void* enc_proj_bf16, const void* pred_proj_bf16, const float* w_out,
+                                const float* b_out, const int32_t* targets, const int32_t* t_len,
+                                const int32_t* u_len, const float* lse, const float* alpha, const float* beta,
+                                const float* costs, const float* grad_costs, float clamp, float* d_enc_proj,
+                                float* d_pred_proj, float* d_w_out, float* d_b_out, int B, int T, int U1, int D,
+                                int V, int blank, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- A2 on dense logits — torch.ops.torchaudio.rnnt_loss_forward
  * (site-packages/torchaudio/functional/functional.py:1725,1737-1744), fused_log_softmax=True.
@@ -154,7 +172,9 @@ int ctcvr_rnnt_beam_chunk(const ctcvr_decoder_weights* w, const float* enc_proj,
                           double* out_scores, float* out_h, float* out_c, void* stream);
 
 /* ---- A8 wenet transducer prefix beam with CTC shallow fusion —
- * wenet/transducer/search/prefix_beam_search.py:42-148.  enc_proj [T,D]; ctc_logp [T,V]. */
+ * wenet/transducer/search/prefix_beam_search.py:42-148.  enc_proj [T,D]; ctc_logp [T,V] (log-probs);
+ * out_tokens [beam][T+1] (every hypothesis starts with the blank, as in the reference), out_lens [beam],
+ * out_scores [beam] fp64, out_n [1], best first.  beam <= 16. */
 size_t ctcvr_rnnt_prefix_beam_ws_bytes(const ctcvr_decoder_weights* w, int beam, int T);
 int ctcvr_rnnt_prefix_beam(const ctcvr_decoder_weights* w, const float* enc_proj,
                            const float* ctc_logp, int T, int beam, int blank, float ctc_weight,
