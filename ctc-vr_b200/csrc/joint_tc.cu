@@ -530,7 +530,8 @@ static int pad_v(int V) { return (V + 31) / 32 * 32; }
 static int max_tiles_flat(int B, int T, int U1) { return B * (int)(((long)T * U1 + BM - 1) / BM); }
 static int max_tiles_rect(int B, int T, int U1) { return B * ((U1 + 15) / 16) * ((((T + 7) / 8) + 1) & ~1); }
 
-bool joint_tc_supported(int U1, int D, int V) { return D % 64 == 0 && D >= 64 && D <= 1024 && pad_v(V) <= 512 && U1 <= 128; }
+// the forward keeps its A stages in the TMEM columns behind the accumulators: Vp + 96 <= 512
+bool joint_tc_supported(int U1, int D, int V) { return D % 64 == 0 && D >= 64 && D <= 1024 && pad_v(V) <= 416 && U1 <= 128; }
 
 static int max_tiles_fwd2(int B, int T, int U1) {
   return B * ((U1 >> 2) * ((T + 31) / 32) + (T + 63) / 64 + (T + 127) / 128);
@@ -627,7 +628,7 @@ int joint_fwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
   CTCVR_REQUIRE(smem <= 232448, "joint_rnnt_fwd bf16: shared memory budget exceeded (%zu B)", smem);
   CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(sm_count(), mt);
-  joint_fwd2_kernel<<<grid, NTHREADS, smem, st>>>(tmap_e, tmap_p, p);
+  joint_fwd2_kernel<<<grid, F_THREADS, smem, st>>>(tmap_e, tmap_p, p);
   CTCVR_LAUNCH_CHECK();
   return 0;
 }
@@ -732,7 +733,7 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
     p.prof = g_prof_buf;
     const size_t smem = bwd2_smem_bytes(NH, Vp, D);
     CTCVR_REQUIRE(smem <= 232448, "joint_rnnt_bwd bf16: shared memory budget exceeded (%zu B)", smem);
-    if (MB % 2 == 0 && NH % 16 == 0 && grid >= 2 && !env_flag("CTCVR_BWD_SINGLE")) {
+    if (MB % 2 == 0 && NH % 16 == 0 && grid >= 2 && env_flag("CTCVR_BWD_PAIR")) {
       CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(grid & ~1);

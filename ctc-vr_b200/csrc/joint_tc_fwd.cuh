@@ -13,21 +13,23 @@
 //
 // One persistent CTA per SM, 512 threads, warp-specialised:
 //   warp 0      bulk copies: pre-tiled bf16 W_out k-blocks (two N-halves per k-block) into a smem ring
-//   warp 1      MMA issuer: tcgen05.mma M=128, N=Vp/2 (x2), K=16; fp32 accumulators in TMEM
+//   warp 1      MMA issuer: tcgen05.mma M=128, N=Vp/2 (x2), K=16, A from TMEM, B from smem; fp32 accumulators in TMEM
 //   warp 2      TMEM allocator
 //   warp 3      TMA: slab ring - per k-block the nu pred rows and 128/nu enc rows (bf16, 128B swizzle)
 //   warps 4-7   epilogue: tcgen05.ld (thread = cell), online log-softmax in base 2, gathers, stores
-//   warps 8-15  A producers: tanh(e+p) -> bf16 -> K-major swizzled A tile (conflict-free LDS/STS)
+//   warps 8-15  A producers: tanh(e+p) -> packed bf16 -> tcgen05.st into the A stage of TENSOR MEMORY (TS-mode MMA):
+//               the A operand costs no shared-memory bandwidth, which is what bounds this kernel
 #pragma once
 #include "tc_common.cuh"
 
 namespace ctcvr {
 namespace tc {
 
-constexpr int F_A_STAGES = 3;
+constexpr int F_A_STAGES = 3;                    // A stages in TMEM: 32 columns each (64 k as bf16 pairs)
+constexpr int F_ACC_COLS = 416;                  // accumulator columns; the A stages follow (416 + 3*32 = 512)
 constexpr int F_S_STAGES = 3;
 constexpr int F_SLAB_BYTES = 1024 + 128 * 128;   // [pred rows: 1 KB region][128 enc rows x 128 B]
-constexpr int F_MAX_W_STAGES = 4;
+constexpr int F_MAX_W_STAGES = 6;
 
 struct FwdParams {
   const __nv_bfloat16* w_t; // tiled W_out: [KB][2][NH][64] bf16, pre-swizzled (prep_weights3_kernel)
@@ -48,6 +50,7 @@ struct FwdParams {
 struct FwdSmem {
   uint32_t a_base, w_base, w_bytes, s_base, bar_base;
   float* bias_l2;
+  float2* epi_x;            // [128] (max, sum) of epilogue group 1
   uint32_t* tmem_ptr;
   __device__ __forceinline__ uint32_t a_stage(int i) const { return a_base + i * A_STAGE_BYTES; }
   __device__ __forceinline__ uint32_t w_stage(int i) const { return w_base + i * w_bytes; }
@@ -58,17 +61,16 @@ struct FwdSmem {
   __device__ __forceinline__ uint32_t s_empty(int i) const { return bar_base + 64 + i * 16 + 8; }
   __device__ __forceinline__ uint32_t w_full(int i) const { return bar_base + 128 + i * 16; }
   __device__ __forceinline__ uint32_t w_empty(int i) const { return bar_base + 128 + i * 16 + 8; }
-  __device__ __forceinline__ uint32_t tmem_full() const { return bar_base + 192; }
-  __device__ __forceinline__ uint32_t tmem_empty() const { return bar_base + 200; }
+  __device__ __forceinline__ uint32_t tmem_full() const { return bar_base + 224; }
+  __device__ __forceinline__ uint32_t tmem_empty() const { return bar_base + 232; }
 };
 
 __host__ __device__ inline size_t fwd2_smem_bytes(int NH, int Vp, int w_stages) {
   size_t s = 1024;
-  s += (size_t)F_A_STAGES * A_STAGE_BYTES;
   s += (size_t)w_stages * NH * 128;
   s = (s + 1023) / 1024 * 1024;
   s += (size_t)F_S_STAGES * F_SLAB_BYTES;
-  s += (size_t)Vp * 4;
+  s += (size_t)Vp * 4 + 1024;
   s += 256 + 16;
   return s;
 }
@@ -76,17 +78,20 @@ __host__ __device__ inline size_t fwd2_smem_bytes(int NH, int Vp, int w_stages) 
 __device__ __forceinline__ void carve_fwd2(FwdSmem& L, uint8_t* raw, int NH, int Vp, int w_stages) {
   const uint32_t base = smem_u32(raw);
   uint32_t a = (base + 1023u) & ~1023u;
-  L.a_base = a; a += F_A_STAGES * A_STAGE_BYTES;
+  L.a_base = a;
   L.w_base = a; L.w_bytes = NH * 128; a += w_stages * NH * 128;
   a = (a + 1023u) & ~1023u;
   L.s_base = a; a += F_S_STAGES * F_SLAB_BYTES;
   L.bias_l2 = reinterpret_cast<float*>(raw + (a - base)); a += Vp * 4;
   a = (a + 15u) & ~15u;
+  L.epi_x = reinterpret_cast<float2*>(raw + (a - base)); a += 1024;
   L.bar_base = a; a += 256;
   L.tmem_ptr = reinterpret_cast<uint32_t*>(raw + (a - base));
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+constexpr int F_THREADS = 640;                   // 4 control + 8 epilogue + 8 producer warps
+
+__global__ void __launch_bounds__(F_THREADS, 1)
 joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_p,
                   const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -104,11 +109,11 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
     for (int i = 0; i < F_S_STAGES; ++i) { mbar_init(L.s_full(i), 1); mbar_init(L.s_empty(i), PROD_THREADS); }
     for (int i = 0; i < F_MAX_W_STAGES; ++i) { mbar_init(L.w_full(i), 1); mbar_init(L.w_empty(i), 1); }
     mbar_init(L.tmem_full(), 1);
-    mbar_init(L.tmem_empty(), 128);
+    mbar_init(L.tmem_empty(), 256);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(L.tmem_ptr), TMEM_COLS);
-  for (int i = tid; i < p.Vp; i += NTHREADS) L.bias_l2[i] = p.bias_l2[i];
+  for (int i = tid; i < p.Vp; i += F_THREADS) L.bias_l2[i] = p.bias_l2[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -173,9 +178,9 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
             tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < BK / 16; ++ks) {
-              const uint64_t ad = make_desc_sw128(L.a_stage(ap.stage) + ks * 32);
               const uint64_t bd = make_desc_sw128(L.w_stage(wp.stage) + ks * 32);
-              umma_bf16(tmem_base + h * p.NH, ad, bd, idesc, (kb | ks) ? 1u : 0u);
+              umma_bf16_ts(tmem_base + h * p.NH, tmem_base + F_ACC_COLS + ap.stage * 32 + ks * 8, bd, idesc,
+                           (kb | ks) ? 1u : 0u);
             }
             umma_commit(L.w_empty(wp.stage));
             wp.advance(WS);
@@ -188,13 +193,19 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       }
     }
     __syncwarp();
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 12) {
     // ------------------------------------------------------------------ epilogue: online log-softmax (base 2)
-    const int q = warp & 3;
+    // 8 warps: quarter q = TMEM lanes 32q..32q+31 (thread = cell), group eg = which half of the accumulator columns.
+    // The two groups keep their own (max, sum); group 1 hands its pair to group 0 through shared memory.
+    const int q = warp & 3, eg = (warp - 4) >> 2;
+    const int erow = q * 32 + lane;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t tphase = 0;
     int prof_n = 0;
     const float bias_blank = __ldg(p.bias + p.blank);
+    // column chunks of 16: group 0 takes [0, c_split), group 1 [c_split, Vp)
+    const int c_split = ((p.Vp / 16 + 1) / 2) * 16;
+    const int c_begin = eg == 0 ? 0 : c_split, c_end = eg == 0 ? c_split : p.Vp;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int4 ti = p.tiles[tile];
       pin(ti.x); pin(ti.y); pin(ti.z); pin(ti.w);
@@ -207,37 +218,37 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       const bool valid = t < Tb;
       int lab = -1;
       float bias_lab = 0.f;
-      if (u < Ub) { lab = p.targets[(size_t)b * (p.U1 - 1) + u]; bias_lab = __ldg(p.bias + lab); }
+      if (eg == 0 && u < Ub) { lab = p.targets[(size_t)b * (p.U1 - 1) + u]; bias_lab = __ldg(p.bias + lab); }
       pin(lab);
       mbar_wait(L.tmem_full(), tphase, 6);
       if (tid == 128) TC_PROF(2, 1);
       tc_fence_after();
-      const float xb = tmem_ld1(tq + p.blank);
-      const float xl = tmem_ld1(tq + (lab >= 0 ? lab : 0));
+      float xb = 0.f, xl = 0.f;
+      if (eg == 0) { xb = tmem_ld1(tq + p.blank); xl = tmem_ld1(tq + (lab >= 0 ? lab : 0)); }
       float m = kNegInf, s = 0.f;
-      float v[32];
-      tmem_ld32(tq, v);
-      for (int c0 = 0; c0 < p.Vp; c0 += 32) {
+      float v[16];
+      tmem_ld16(tq + c_begin, v);
+      for (int c0 = c_begin; c0 < c_end; c0 += 16) {
         tmem_ld_wait();
-        float y[32];
+        float y[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < 16; j += 4) {
           const float4 bj = *reinterpret_cast<const float4*>(L.bias_l2 + c0 + j);
           y[j] = fmaf(v[j], LOG2E, bj.x);
           y[j + 1] = fmaf(v[j + 1], LOG2E, bj.y);
           y[j + 2] = fmaf(v[j + 2], LOG2E, bj.z);
           y[j + 3] = fmaf(v[j + 3], LOG2E, bj.w);
         }
-        if (c0 + 32 < p.Vp) tmem_ld32(tq + c0 + 32, v);     // next chunk in flight during the math below
+        if (c0 + 16 < c_end) tmem_ld16(tq + c0 + 16, v);    // next chunk in flight during the math below
         float cm[4] = {kNegInf, kNegInf, kNegInf, kNegInf};
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
+        for (int j = 0; j < 16; j += 4)
 #pragma unroll
           for (int e = 0; e < 4; ++e) cm[e] = fmaxf(cm[e], y[j + e]);
         const float nm = fmaxf(m, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
+        for (int j = 0; j < 16; j += 4)
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc[e] += ex2_fast(y[j + e] - nm);
         s = s * ex2_fast(m - nm) + ((acc[0] + acc[1]) + (acc[2] + acc[3]));
@@ -246,52 +257,62 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       tc_fence_before();
       mbar_arrive(L.tmem_empty());
       if (tid == 128) TC_PROF(2, 2);
-      if (valid) {
-        const size_t cell = ((size_t)b * p.T + t) * p.U1 + u;
-        const float l = (m + lg2_fast(s)) * LN2;
-        p.lse[cell] = l;
-        p.lp_blank[cell] = xb + bias_blank - l;
-        p.lp_label[cell] = (lab >= 0) ? xl + bias_lab - l : kNegInf;
+      if (eg == 1) { L.epi_x[erow] = make_float2(m, s); }
+      named_barrier_sync(3, 256);                          // group 1's partials are visible
+      if (eg == 0) {
+        const float2 o = L.epi_x[erow];
+        const float nm = fmaxf(m, o.x);
+        s = s * ex2_fast(m - nm) + o.y * ex2_fast(o.x - nm);
+        m = nm;
+        if (valid) {
+          const size_t cell = ((size_t)b * p.T + t) * p.U1 + u;
+          const float l = (m + lg2_fast(s)) * LN2;
+          p.lse[cell] = l;
+          p.lp_blank[cell] = xb + bias_blank - l;
+          p.lp_label[cell] = (lab >= 0) ? xl + bias_lab - l : kNegInf;
+        }
       }
+      named_barrier_sync(3, 256);                          // partials consumed before the next tile overwrites them
       tphase ^= 1u;
     }
-  } else if (warp >= 8) {
-    // ------------------------------------------------------------------ A producers
-    // thread (lr, c): 16-byte chunk c of rows lr, lr+32, lr+64, lr+96 (one per TMEM lane quarter)
-    const int pt = tid - 256;
-    const int c = pt & 7, lr = pt >> 3;
-    const uint32_t sw = (uint32_t)((c ^ (lr & 7)) << 4);
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------------ A producers (A operand lives in TMEM)
+    // warp = (TMEM lane quarter q, k-half kh): thread = tile row 32q + lane, 32 of the 64 k of a k-block.
+    // tanh(e + p) for 32 k -> 16 packed bf16x2 -> one tcgen05.st into the A stage columns of the thread's own lane.
+    const int q = warp & 3, kh = (warp - 12) >> 2;
     Pipe ap, sp;
     int prof_n = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int nu = p.tiles[tile].w;
       pin(nu);
       const int lognu = nu >> 1;
-      uint32_t e_off[4], p_off[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int ul = j & (nu - 1);
-        const int tloc = ((j >> lognu) << 5) + lr;
-        e_off[j] = 1024u + (uint32_t)tloc * 128u + sw;
-        p_off[j] = (uint32_t)ul * 128u + (uint32_t)((c ^ ul) << 4);
-      }
+      const int ul = q & (nu - 1);
+      const int tloc = ((q >> lognu) << 5) + lane;
+      const uint32_t e_row = 1024u + (uint32_t)tloc * 128u, e_sw = (uint32_t)(tloc & 7);
+      const uint32_t p_row = (uint32_t)ul * 128u, p_sw = (uint32_t)ul;
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(L.s_full(sp.stage), sp.phase, 7);
         mbar_wait(L.a_empty(ap.stage), ap.phase ^ 1u, 8);
-        if (pt == 0) TC_PROF(3, kb);
+        if (tid == 384) TC_PROF(3, kb);
+        tc_fence_after();
         const uint32_t sb = L.s_stage(sp.stage);
-        const uint32_t ab = L.a_stage(ap.stage) + (uint32_t)lr * 128u + sw;
+        uint32_t w[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 ev = lds128(sb + e_off[j]);
-          const uint4 pv = lds128(sb + p_off[j]);
-          sts128(ab + j * 4096, tanh_add_bf16x2_packed(ev.x, pv.x), tanh_add_bf16x2_packed(ev.y, pv.y),
-                 tanh_add_bf16x2_packed(ev.z, pv.z), tanh_add_bf16x2_packed(ev.w, pv.w));
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const uint32_t c = (uint32_t)(kh * 4 + c4);
+          const uint4 ev = lds128(sb + e_row + ((c ^ e_sw) << 4));
+          const uint4 pv = lds128(sb + p_row + ((c ^ p_sw) << 4));
+          w[4 * c4 + 0] = tanh_add_bf16x2_packed(ev.x, pv.x);
+          w[4 * c4 + 1] = tanh_add_bf16x2_packed(ev.y, pv.y);
+          w[4 * c4 + 2] = tanh_add_bf16x2_packed(ev.z, pv.z);
+          w[4 * c4 + 3] = tanh_add_bf16x2_packed(ev.w, pv.w);
         }
-        fence_proxy_async();
+        tmem_st16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(F_ACC_COLS + ap.stage * 32 + kh * 16), w);
+        tmem_st_wait();
+        tc_fence_before();
         mbar_arrive(L.a_full(ap.stage));
         mbar_arrive(L.s_empty(sp.stage));
-        if (pt == 0) TC_PROF(3, 20 + kb);
+        if (tid == 384) TC_PROF(3, 20 + kb);
         ap.advance(F_A_STAGES);
         sp.advance(F_S_STAGES);
       }
