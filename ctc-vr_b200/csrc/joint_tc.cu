@@ -122,11 +122,11 @@ namespace tc {
 // d_enc[b,t,:] = sum over the u-splits of the partial sums (zero for padded frames)
 __global__ void reduce_denc_kernel(const float* __restrict__ part, const int32_t* __restrict__ t_len,
                                    const int32_t* __restrict__ u_len, float* __restrict__ d_enc, int B, int T, int U1,
-                                   int D) {
+                                   int D, int P) {
   const int bt = blockIdx.x;
   const int b = bt / T, t = bt - b * T;
   const int Tb = min(t_len[b], T), W = min(u_len[b], U1 - 1) + 1;
-  const int S = (W + 15) >> 4;
+  const int S = (W + P - 1) / P;
   const size_t row = ((size_t)b * T + t) * D, step = (size_t)B * T * D;
   for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -379,17 +379,11 @@ __global__ void __launch_bounds__(256) reduce_dw_kernel(const float* __restrict_
 // =================================================================================================
 // Tile tables.  One CTA per utterance: the CTA sums the tile counts of the utterances before it (block reduction),
 // then its threads write the utterance's entries in parallel; the last CTA also writes the total.
-// frame blocks per (b, u-split) sweep are padded to an even count (the CTA-pair backward kernel processes tiles
-// 2i, 2i+1 of one sweep together; a padding tile lies beyond T_b, i.e. all of its rows are invalid)
-__device__ __forceinline__ int rect_ntb(int Tb) { return (((Tb + 7) >> 3) + 1) & ~1; }
-__device__ __forceinline__ int rect_tiles_of(int Tb, int W) {
-  return Tb > 0 ? ((W + 15) >> 4) * rect_ntb(Tb) : 0;
-}
-__device__ __forceinline__ int block_prefix(int mine_upto, int (*count)(int, const int32_t*, const int32_t*, int, int),
-                                            const int32_t* t_len, const int32_t* u_len, int T, int U1) {
+template <class Count>
+__device__ __forceinline__ int block_prefix(int mine_upto, Count count) {
   __shared__ int s_part[32];
   int acc = 0;
-  for (int i = threadIdx.x; i < mine_upto; i += blockDim.x) acc += count(i, t_len, u_len, T, U1);
+  for (int i = threadIdx.x; i < mine_upto; i += blockDim.x) acc += count(i);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
@@ -399,24 +393,25 @@ __device__ __forceinline__ int block_prefix(int mine_upto, int (*count)(int, con
   __syncthreads();
   return tot;
 }
-__device__ int count_rect(int b, const int32_t* t_len, const int32_t* u_len, int T, int U1) {
-  return rect_tiles_of(min(t_len[b], T), min(u_len[b], U1 - 1) + 1);
-}
-__device__ int count_fwd(int b, const int32_t* t_len, const int32_t* u_len, int T, int U1) {
-  return fwd_tiles_of(min(t_len[b], T), min(u_len[b], U1 - 1) + 1);
-}
 
-// rect: tiles of 8 frames x 16 label columns, ordered (b, u-split, frame block) so that one CTA of the backward
-// kernel sweeps consecutive frame blocks of the same (b, u-split).  Entry = {b, u-split, frame block, tile index}.
+// Backward tiles: TT frames x P label columns (geom = P | TT << 8 | even << 16), ordered (b, u-split, frame block) so
+// that one CTA sweeps consecutive frame blocks of the same (b, u-split).  `even` pads every sweep to an even number of
+// frame blocks (the CTA-pair kernel processes tiles 2i, 2i+1 of one sweep together; a padding tile lies beyond T_b).
+// Entry = {b, u-split, frame block, tile index}.
 __global__ void build_tiles_kernel(const int32_t* __restrict__ t_len, const int32_t* __restrict__ u_len, int B, int T,
-                                   int U1, int rect, int4* __restrict__ tiles, int* __restrict__ ntiles,
+                                   int U1, int geom, int4* __restrict__ tiles, int* __restrict__ ntiles,
                                    int max_tiles) {
-  (void)rect;
+  const int P = geom & 0xff, TT = (geom >> 8) & 0xff, even = (geom >> 16) & 1;
+  auto ntb_of = [&](int Tb) { const int n = (Tb + TT - 1) / TT; return even ? ((n + 1) & ~1) : n; };
+  auto count = [&](int i) {
+    const int Tb = min(t_len[i], T), W = min(u_len[i], U1 - 1) + 1;
+    return Tb > 0 ? ((W + P - 1) / P) * ntb_of(Tb) : 0;
+  };
   const int b = blockIdx.x;
-  const int off = block_prefix(b, count_rect, t_len, u_len, T, U1);
-  const int Tb = min(t_len[b], T), W = min(u_len[b], U1 - 1) + 1;
-  const int n = rect_tiles_of(Tb, W);
-  const int NTB = rect_ntb(Tb);
+  const int off = block_prefix(b, count);
+  const int Tb = min(t_len[b], T);
+  const int n = count(b);
+  const int NTB = ntb_of(Tb);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int s = i / NTB, tb = i - s * NTB;
     if (off + i < max_tiles) tiles[off + i] = make_int4(b, s, tb, off + i);
@@ -469,7 +464,7 @@ __global__ void build_tiles_fwd_kernel(const int32_t* __restrict__ t_len, const 
                                        int T, int U1, int4* __restrict__ tiles, int* __restrict__ ntiles,
                                        int max_tiles) {
   const int b = blockIdx.x;
-  const int off = block_prefix(b, count_fwd, t_len, u_len, T, U1);
+  const int off = block_prefix(b, [&](int i) { return fwd_tiles_of(min(t_len[i], T), min(u_len[i], U1 - 1) + 1); });
   const int Tb = min(t_len[b], T), W = min(u_len[b], U1 - 1) + 1;
   const int n = fwd_tiles_of(Tb, W);
   const int nb32 = (Tb + 31) >> 5, n4 = (W >> 2) * nb32;
@@ -528,7 +523,18 @@ using namespace tc;
 static long long* g_prof_buf = nullptr;
 static int pad_v(int V) { return (V + 31) / 32 * 32; }
 static int max_tiles_flat(int B, int T, int U1) { return B * (int)(((long)T * U1 + BM - 1) / BM); }
-static int max_tiles_rect(int B, int T, int U1) { return B * ((U1 + 15) / 16) * ((((T + 7) / 8) + 1) & ~1); }
+// Backward tile geometry: P label columns x TT frames.  Pick the variant with fewer tile rows for this (T, U1);
+// the CTA-pair kernel (CTCVR_BWD_PAIR=1) is written for <16, 8> only.
+struct RectGeom { int P, TT, even; };
+static RectGeom pick_rect_geom(int T, int U1, bool pair) {
+  if (pair) return RectGeom{16, 8, 1};
+  auto tiles = [&](int P, int TT) { return (long)((U1 + P - 1) / P) * ((T + TT - 1) / TT); };
+  return tiles(21, 6) < tiles(16, 8) ? RectGeom{21, 6, 0} : RectGeom{16, 8, 0};
+}
+static int max_tiles_rect(int B, int T, int U1) {           // upper bound over both geometries and the even padding
+  const long a = (long)((U1 + 15) / 16) * ((((T + 7) / 8) + 1) & ~1), b = (long)((U1 + 20) / 21) * ((T + 5) / 6);
+  return B * (int)(a > b ? a : b);
+}
 
 // the forward keeps its A stages in the TMEM columns behind the accumulators: Vp + 96 <= 512
 bool joint_tc_supported(int U1, int D, int V) { return D % 64 == 0 && D >= 64 && D <= 1024 && pad_v(V) <= 416 && U1 <= 128; }
@@ -658,7 +664,7 @@ static BwdWs carve_bwd_ws(void* ws, int B, int T, int U1, int D, int V) {
   BwdWs w;
   w.mt = max_tiles_rect(B, T, U1);
   w.Rpad = (long)(w.mt + 1) * BM;           // + one scratch row tile for the dummy iterations of the lock-step loop
-  w.S_max = (U1 + 15) / 16;
+  w.S_max = (U1 + 15) / 16;               // >= the number of u-splits of either geometry
   const int MB = D / 128;
   w.KS = MB > 0 ? sm_count() / MB : 1;
   if (w.KS < 1) w.KS = 1;
@@ -703,7 +709,9 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
   prep_weights3_kernel<<<cdiv((long)KBG * 64 * D, 256), 256, 0, st>>>(w, bias, W.wb, W.wtb, W.bias_pad, W.bias_l2, V, Vp, D);
   CTCVR_LAUNCH_CHECK();
   const int mt = W.mt;
-  build_tiles_kernel<<<B, 128, 0, st>>>(t_len, u_len, B, T, U1, 1, W.tiles, W.ntiles, mt);
+  const bool pair = MB % 2 == 0 && NH % 16 == 0 && min(sm_count(), mt) >= 2 && env_flag("CTCVR_BWD_PAIR");
+  const RectGeom G = pick_rect_geom(T, U1, pair);
+  build_tiles_kernel<<<B, 128, 0, st>>>(t_len, u_len, B, T, U1, G.P | (G.TT << 8) | (G.even << 16), W.tiles, W.ntiles, mt);
   CTCVR_LAUNCH_CHECK();
   CTCVR_CHECK_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)B * U1 * D * sizeof(float), st));
   CTCVR_CHECK_CUDA(cudaMemsetAsync(d_b, 0, (size_t)V * sizeof(float), st));
@@ -720,8 +728,8 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
   {
     const int grid = min(sm_count(), mt);
     CUtensorMap tmap_e, tmap_p;
-    if (make_tmap_bf16_2d(&tmap_e, W.eb, (uint64_t)B * T, D, D, 8)) return 1;
-    if (make_tmap_bf16_2d(&tmap_p, W.pb, (uint64_t)B * U1, D, D, 16)) return 1;
+    if (make_tmap_bf16_2d(&tmap_e, W.eb, (uint64_t)B * T, D, D, G.TT)) return 1;
+    if (make_tmap_bf16_2d(&tmap_p, W.pb, (uint64_t)B * U1, D, D, G.P)) return 1;
     BwdParams p{};
     p.w_t = W.wb; p.wt_t = W.wtb;
     p.bias = bias; p.bias_l2 = W.bias_l2; p.targets = targets; p.t_len = t_len; p.u_len = u_len;
@@ -733,7 +741,7 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
     p.prof = g_prof_buf;
     const size_t smem = bwd2_smem_bytes(NH, Vp, D);
     CTCVR_REQUIRE(smem <= 232448, "joint_rnnt_bwd bf16: shared memory budget exceeded (%zu B)", smem);
-    if (MB % 2 == 0 && NH % 16 == 0 && grid >= 2 && env_flag("CTCVR_BWD_PAIR")) {
+    if (pair) {
       CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(grid & ~1);
@@ -749,13 +757,17 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
       cfg.numAttrs = 1;
       CTCVR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, joint_bwd2p_kernel, tmap_e, tmap_p, p));
       count_launch();
+    } else if (G.P == 21) {
+      CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd2_kernel<21, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      joint_bwd2_kernel<21, 6><<<grid, NTHREADS, smem, st>>>(tmap_e, tmap_p, p);
+      CTCVR_LAUNCH_CHECK();
     } else {
-      CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      joint_bwd2_kernel<<<grid, NTHREADS, smem, st>>>(tmap_e, tmap_p, p);
+      CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd2_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      joint_bwd2_kernel<16, 8><<<grid, NTHREADS, smem, st>>>(tmap_e, tmap_p, p);
       CTCVR_LAUNCH_CHECK();
     }
   }
-  reduce_denc_kernel<<<B * T, 128, 0, st>>>(W.d_enc_part, t_len, u_len, d_enc, B, T, U1, D);
+  reduce_denc_kernel<<<B * T, 128, 0, st>>>(W.d_enc_part, t_len, u_len, d_enc, B, T, U1, D, G.P);
   CTCVR_LAUNCH_CHECK();
   if (MB % 2 == 0 && NH % 16 == 0 && env_flag("CTCVR_DW_PAIR")) {
     const size_t smem = 1024 + (size_t)DW2_STAGES * (A_STAGE_BYTES + 2 * (size_t)(NH / 2) * 128) + 512;

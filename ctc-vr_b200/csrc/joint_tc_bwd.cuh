@@ -23,10 +23,41 @@ namespace ctcvr {
 namespace tc {
 
 constexpr int B_A_STAGES = 3;
-constexpr int B_S_STAGES = 3;
+constexpr int B_S_STAGES = 2;
 constexpr int B_R1_STAGES = 3;                 // W_out ring view   (P1): NH x 128 B per stage
 constexpr int B_R3_STAGES = 5;                 // W_out^T ring view (P3): 16 KB per stage, same memory
-constexpr int B_SLAB_BYTES = 2048 + 1024;      // 16 pred rows + 8 enc rows, 128 B each
+constexpr int B_SLAB_BYTES = 2048 + 1024;      // (CTA-pair kernel) 16 pred rows + 8 enc rows, 128 B each
+constexpr int B_SLAB_MAX = 4096;               // slab stage of the largest tile geometry: 24 pred rows (3 KB) + 8 enc rows
+
+// Tile geometry of the single-CTA kernel: TT frames x P label columns, row = tloc*P + ul (TT*P <= 128).
+//   <16, 8> : 128 rows, u-splits of <= 16 columns          <21, 6> : 126 rows, u-splits of <= 21 columns
+// The host picks the variant that wastes fewer rows for the batch's U (U+1 = 41 -> 2 x 21: 2.4% padding vs 14.6%).
+template <int P, int TT>
+struct BwdGeom {
+  int b, Tb, Ub, W, us, t0, ubase;
+  __device__ __forceinline__ void init(const int32_t* t_len, const int32_t* u_len, int T, int U1, int4 ti) {
+    b = ti.x;
+    Tb = min(t_len[b], T);
+    Ub = min(u_len[b], U1 - 1);
+    W = Ub + 1;
+    const int S = (W + P - 1) / P;
+    us = (W + S - 1) / S;
+    t0 = ti.z * TT;
+    ubase = ti.y * us;
+    pin(b); pin(Tb); pin(Ub); pin(W); pin(us); pin(t0); pin(ubase);
+  }
+  // tile row -> lattice cell; false for padding rows
+  __device__ __forceinline__ bool cell(int r, int& t, int& u, int& ul) const {
+    const int tloc = r / P;
+    ul = r - tloc * P;
+    t = t0 + tloc;
+    u = ubase + ul;
+    return tloc < TT && t < Tb && ul < us && u <= Ub;
+  }
+};
+template <int P>
+__host__ __device__ constexpr uint32_t bwd_pred_region() { return (uint32_t)((P * 128 + 1023) / 1024 * 1024); }
+
 constexpr int WORKERS = 384;
 
 struct BwdParams {
@@ -72,7 +103,7 @@ struct Bwd2Smem {
   __device__ __forceinline__ uint32_t z_box(int i) const { return g_base + i * A_STAGE_BYTES; }    // (mb*2 + half)
   __device__ __forceinline__ uint32_t r1_stage(int i) const { return r_base + i * r1_bytes; }
   __device__ __forceinline__ uint32_t r3_stage(int i) const { return r_base + i * 16384; }
-  __device__ __forceinline__ uint32_t s_stage(int i) const { return s_base + i * B_SLAB_BYTES; }
+  __device__ __forceinline__ uint32_t s_stage(int i) const { return s_base + i * B_SLAB_MAX; }
   __device__ __forceinline__ uint32_t a_full(int i) const { return bar_base + i * 16; }
   __device__ __forceinline__ uint32_t a_empty(int i) const { return bar_base + i * 16 + 8; }
   __device__ __forceinline__ uint32_t s_full(int i) const { return bar_base + 48 + i * 16; }
@@ -103,7 +134,7 @@ __host__ __device__ inline size_t bwd2_smem_bytes(int NH, int Vp, int D) {
   s += (size_t)bwd2_gz_blocks(Vp, D) * A_STAGE_BYTES;
   s += bwd2_ring_bytes(NH);
   s = (s + 1023) / 1024 * 1024;
-  s += (size_t)B_S_STAGES * B_SLAB_BYTES;
+  s += (size_t)B_S_STAGES * B_SLAB_MAX;
   s += (size_t)Vp * 4 + (size_t)4 * Vp * 4;
   s += 304 + 392 + 16 + 16;            // barriers (+ the CTA-pair kernel's extra barriers) + tmem pointer
   return s;
@@ -115,7 +146,7 @@ __device__ __forceinline__ void carve_bwd2(Bwd2Smem& L, uint8_t* raw, int NH, in
   L.g_base = a; a += bwd2_gz_blocks(Vp, D) * A_STAGE_BYTES;
   L.r_base = a; L.r1_bytes = (uint32_t)NH * 128u; a += bwd2_ring_bytes(NH);
   a = (a + 1023u) & ~1023u;
-  L.s_base = a; a += B_S_STAGES * B_SLAB_BYTES;
+  L.s_base = a; a += B_S_STAGES * B_SLAB_MAX;
   L.bias_l2 = reinterpret_cast<float*>(raw + (a - base)); a += Vp * 4;
   L.dbp = reinterpret_cast<float*>(raw + (a - base)); a += 4 * Vp * 4;
   a = (a + 15u) & ~15u;
@@ -123,6 +154,7 @@ __device__ __forceinline__ void carve_bwd2(Bwd2Smem& L, uint8_t* raw, int NH, in
   L.tmem_ptr = reinterpret_cast<uint32_t*>(raw + (a - base));
 }
 
+template <int P, int TT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_p,
                   const BwdParams p) {
@@ -209,15 +241,15 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
         const int4 ti = p.tiles[tile];
         const int b = ti.x;
         const int W = min(p.u_len[b], p.U1 - 1) + 1;
-        const int S = (W + 15) >> 4, us = (W + S - 1) / S;
+        const int S = (W + P - 1) / P, us = (W + S - 1) / S;
         const int prow = b * p.U1 + ti.y * us;
-        const int erow = b * p.T + ti.z * 8;
+        const int erow = b * p.T + ti.z * TT;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(L.s_empty(sp.stage), sp.phase ^ 1u, 15);
           const uint32_t st = L.s_stage(sp.stage);
-          mbar_arrive_expect_tx(L.s_full(sp.stage), (uint32_t)B_SLAB_BYTES);
+          mbar_arrive_expect_tx(L.s_full(sp.stage), (uint32_t)(P + TT) * 128u);
           tma_load_2d(st, &tmap_p, L.s_full(sp.stage), kb * BK, prow);
-          tma_load_2d(st + 2048, &tmap_e, L.s_full(sp.stage), kb * BK, erow);
+          tma_load_2d(st + bwd_pred_region<P>(), &tmap_e, L.s_full(sp.stage), kb * BK, erow);
           sp.advance(B_S_STAGES);
         }
       }
@@ -290,11 +322,11 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
     int prof_n = 0;
     Pipe ap, sp;
     float db0 = 0.f, db1 = 0.f;                // d_bias of columns wt and wt + 384
-    float pacc[2][16];                         // d_pred sums of d blocks 2wg, 2wg+1 over the tiles of one (b, u-split) sweep
+    float pacc[2][P];                          // d_pred sums of d blocks 2wg, 2wg+1 over the tiles of one (b, u-split) sweep
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) pacc[i][j] = 0.f;
+      for (int j = 0; j < P; ++j) pacc[i][j] = 0.f;
     int cur_b = -1, cur_ubase = 0;
     auto flush_pred = [&]() {
       if (cur_b < 0 || wg >= 2) return;
@@ -304,7 +336,7 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
         const int mb = 2 * wg + mbl;
         if (mb < MB) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < P; ++j) {
             const int u = cur_ubase + j;
             if (u <= Ub) atomicAdd(p.d_pred + ((size_t)cur_b * p.U1 + u) * p.D + mb * 128 + r, pacc[mbl][j]);
             pacc[mbl][j] = 0.f;
@@ -312,21 +344,22 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
         }
       }
     };
-    // producer addressing (rows lane, lane+32, lane+64, lane+96 of the tile; row = tloc*16 + ul)
-    const int ul_p = lane & 15;
-    const uint32_t p_off = (uint32_t)ul_p * 128u + (uint32_t)((pc ^ (ul_p & 7)) << 4);
-    uint32_t e_off[4];
+    // producer addressing: tile rows lane, lane+32, lane+64, lane+96 (row = tloc*P + ul); rows >= TT*P are padding
+    uint32_t e_off[4], p_off[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int tloc = (lane >> 4) + 2 * j;
-      e_off[j] = 2048u + (uint32_t)tloc * 128u + (uint32_t)((pc ^ tloc) << 4);
+      const int rr = lane + 32 * j;
+      const int tloc = min(rr / P, TT - 1), ul = rr % P;
+      e_off[j] = bwd_pred_region<P>() + (uint32_t)tloc * 128u + (uint32_t)((pc ^ (tloc & 7)) << 4);
+      p_off[j] = (uint32_t)ul * 128u + (uint32_t)((pc ^ (ul & 7)) << 4);
     }
     const uint32_t a_off = (uint32_t)lane * 128u + (uint32_t)((pc ^ (lane & 7)) << 4);
 
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       int4 ti = p.tiles[tile];
       pin(ti.x); pin(ti.y); pin(ti.z); pin(ti.w);
-      const RowMap g = tile_geometry<TILE_RECT>(p.t_len, p.u_len, p.T, p.U1, ti);
+      BwdGeom<P, TT> g;
+      g.init(p.t_len, p.u_len, p.T, p.U1, ti);
       if (g.b != cur_b || g.ubase != cur_ubase) { flush_pred(); cur_b = g.b; cur_ubase = g.ubase; }
       const size_t rowtile = (size_t)ti.w;
 
@@ -340,13 +373,13 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
           mbar_wait(L.a_empty(ap.stage), ap.phase ^ 1u, 42);
           const uint32_t sb = L.s_stage(sp.stage);
           const uint32_t ab = L.a_stage(ap.stage) + a_off;
-          const uint4 pv = lds128(sb + p_off);
           // d = kb*64 + pc*8 + e -> box row (kb&1)*64 + pc*8 + e of d block kb>>1; tile row lane + 32j -> half j>>1
           unsigned short* z = reinterpret_cast<unsigned short*>(p.zt) + ((rowtile * MB + (kb >> 1)) * 2) * 8192 +
                               ((kb & 1) * 64 + pc * 8) * 64 + (lane & 7);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 ev = lds128(sb + e_off[j]);
+            const uint4 pv = lds128(sb + p_off[j]);
             uint32_t w[4];
             w[0] = tanh_add_bf16x2_packed(ev.x, pv.x);
             w[1] = tanh_add_bf16x2_packed(ev.y, pv.y);
@@ -373,8 +406,8 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       }
 
       // ---------------- P2: g = d cost / d logits for row r, column chunks wg, wg+3, ...
-      int t, u;
-      const bool valid = row_cell<TILE_RECT>(g, ti, r, t, u);
+      int t, u, ul;
+      const bool valid = g.cell(r, t, u, ul);
       float k_all = kNegInf, k_blank = kNegInf, k_label = kNegInf, scale = 0.f;
       int lab = -1;
       if (valid) {
@@ -447,12 +480,12 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
         // exact (fp32, single rounding) blank and label entries of row r
         const float xb = tmem_ld1(tq + p.blank);
         float xl = 0.f;
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < P; ++i) {
           const int ui = g.ubase + i;
           int col = 0;
           if (ui < g.Ub) col = p.targets[(size_t)g.b * (p.U1 - 1) + ui];
           const float xi = tmem_ld1(tq + col);
-          if ((r & 15) == i) xl = xi;
+          if (ul == i) xl = xi;
         }
         tmem_ld_wait();
         if (valid) {
@@ -507,7 +540,9 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       }
 
       // ---------------- P4 (warps 4-11): dH = dZ * (1 - z^2); reductions.  Warp group wg owns d blocks 2wg, 2wg+1.
-      // z^T arrives in shared memory (TMA, issued after dz_full): box (mb, half) = [128 d][64 rows], 128B swizzle.
+      // z^T arrives in shared memory (bulk copy issued after dz_full): box (mb, half) = [128 d][64 rows], 128B swizzle.
+      // TMEM column c of a d block = tile row c = (frame slot c / P, label slot c % P): everything is static after
+      // unrolling, so any (P, TT) works with aligned 32-column loads.
       if (wg < 2) {
         mbar_wait(L.dz_full(), ph, 32);
         if (tid == 128) TC_PROF(2, 4);
@@ -519,31 +554,39 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
             mbar_wait(L.z_full(mb), ph, 33);
             if (tid == 128) TC_PROF(2, 40 + mb);
             const int d = mb * 128 + r;
-            float v[16];
-            tmem_ld16(tq + mb * 128, v);
+            float es[TT];
 #pragma unroll
-            for (int tloc = 0; tloc < 8; ++tloc) {
-              const uint32_t zb = L.z_box(2 * mb + (tloc >> 2)) + (uint32_t)r * 128u;
-              const uint4 z0 = lds128(zb + ((((tloc & 3) * 2) ^ (r & 7)) << 4));
-              const uint4 z1 = lds128(zb + ((((tloc & 3) * 2 + 1) ^ (r & 7)) << 4));
+            for (int i = 0; i < TT; ++i) es[i] = 0.f;
+            float v[32];
+            tmem_ld32(tq + mb * 128, v);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              const uint32_t zb = L.z_box(2 * mb + (ch >> 1)) + (uint32_t)r * 128u;
+              uint4 zc[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) zc[i] = lds128(zb + ((((ch & 1) * 4 + i) ^ (r & 7)) << 4));
               tmem_ld_wait();
-              float w[16];
+              float w[32];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) w[j] = v[j];
-              if (tloc < 7) tmem_ld16(tq + mb * 128 + (tloc + 1) * 16, v);
-              const uint32_t zw[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
-              float es0 = 0.f, es1 = 0.f;
+              for (int j = 0; j < 32; ++j) w[j] = v[j];
+              if (ch < 3) tmem_ld32(tq + mb * 128 + (ch + 1) * 32, v);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float za = __uint_as_float(zw[j] << 16), zb2 = __uint_as_float(zw[j] & 0xffff0000u);
-                const float ha = w[2 * j] * fmaf(-za, za, 1.f), hb = w[2 * j + 1] * fmaf(-zb2, zb2, 1.f);
-                es0 += ha;
-                es1 += hb;
-                pacc[mbl][2 * j] += ha;
-                pacc[mbl][2 * j + 1] += hb;
+              for (int j = 0; j < 32; ++j) {
+                const int c = ch * 32 + j;                     // tile row
+                if (c < TT * P) {
+                  const uint4 zq = zc[j >> 3];
+                  const uint32_t zw = ((j & 7) >> 1) == 0 ? zq.x : ((j & 7) >> 1) == 1 ? zq.y : ((j & 7) >> 1) == 2 ? zq.z : zq.w;
+                  const float z = (j & 1) ? __uint_as_float(zw & 0xffff0000u) : __uint_as_float(zw << 16);
+                  const float h = w[j] * fmaf(-z, z, 1.f);
+                  es[c / P] += h;
+                  pacc[mbl][c % P] += h;
+                }
               }
-              const int tt = g.t0 + tloc;
-              if (tt < g.Tb) p.d_enc_part[(((size_t)ti.y * p.B + g.b) * p.T + tt) * p.D + d] = es0 + es1;
+            }
+#pragma unroll
+            for (int i = 0; i < TT; ++i) {
+              const int tt = g.t0 + i;
+              if (tt < g.Tb) p.d_enc_part[(((size_t)ti.y * p.B + g.b) * p.T + tt) * p.D + d] = es[i];
             }
           }
         }
