@@ -235,6 +235,103 @@ dw_gemm_kernel(const __nv_bfloat16* __restrict__ zt, const __nv_bfloat16* __rest
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// Variant reading g as spilled row-major G tiles ([tile][2][KBG][64 rows][64 v], written by bulk stores from the
+// backward kernel's shared-memory G tile): the B operand is MN-major (label columns contiguous), N split at a
+// multiple of 64 columns (256 + the rest), one 1-D bulk load per operand and stage.
+__global__ void __launch_bounds__(DW_THREADS, 1)
+dw_gemm_mn_kernel(const __nv_bfloat16* __restrict__ zt, const __nv_bfloat16* __restrict__ gr,
+                  const int* __restrict__ ntiles_ptr, float* __restrict__ partials, int D, int Vp, int KBG, int KS) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  const uint32_t al = (base + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)KBG * 8192u;
+  const uint32_t stage_bytes = A_STAGE_BYTES + b_bytes;
+  const uint32_t bar = al + DW_STAGES * stage_bytes;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem_raw + (bar + 128 - base));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mb = blockIdx.x, ks = blockIdx.y;
+  const size_t MBD = (size_t)(D / 128);
+  const int kblocks = (*ntiles_ptr) * 2;
+  const int kb_begin = (int)(((long)kblocks * ks) / KS), kb_end = (int)(((long)kblocks * (ks + 1)) / KS);
+  auto full = [&](int i) { return bar + i * 16; };
+  auto empty = [&](int i) { return bar + i * 16 + 8; };
+  const uint32_t done = bar + DW_STAGES * 16;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < DW_STAGES; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_ptr), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      Pipe sp;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(empty(sp.stage), sp.phase ^ 1u, 50);
+        const uint32_t st = al + sp.stage * stage_bytes;
+        mbar_arrive_expect_tx(full(sp.stage), stage_bytes);
+        const size_t rt = (size_t)(kb >> 1), hh = (size_t)(kb & 1);
+        bulk_load(st, zt + ((rt * MBD + mb) * 2 + hh) * 8192, A_STAGE_BYTES, full(sp.stage));
+        bulk_load(st + A_STAGE_BYTES, gr + ((rt * 2 + hh) * (size_t)KBG) * 4096, b_bytes, full(sp.stage));
+        sp.advance(DW_STAGES);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      Pipe sp;
+      const int N0 = min(256, Vp), N1 = Vp - N0;
+      const uint32_t idesc0 = make_idesc_bf16_bmn(128, N0);
+      const uint32_t idesc1 = make_idesc_bf16_bmn(128, N1 > 0 ? N1 : 16);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(full(sp.stage), sp.phase, 51);
+        tc_fence_after();
+        const uint32_t st = al + sp.stage * stage_bytes;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint64_t ad = make_desc_sw128(st + k4 * 32);
+          const uint32_t acc = (kb > kb_begin || k4 > 0) ? 1u : 0u;
+          umma_bf16(tmem_base, ad, make_desc_mn_sw128(st + A_STAGE_BYTES + k4 * 2048, 8192u, 1024u), idesc0, acc);
+          if (N1 > 0)
+            umma_bf16(tmem_base + 256, ad, make_desc_mn_sw128(st + A_STAGE_BYTES + 4 * 8192 + k4 * 2048, 8192u, 1024u),
+                      idesc1, acc);
+        }
+        umma_commit(empty(sp.stage));
+        sp.advance(DW_STAGES);
+      }
+      umma_commit(done);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int d = mb * 128 + q * 32 + lane;
+    float* out = partials + ((size_t)ks * D + d) * Vp;
+    if (kb_end > kb_begin) {
+      mbar_wait(done, 0, 52);
+      tc_fence_after();
+      for (int c0 = 0; c0 < Vp; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        if (d < D) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+    } else if (d < D) {
+      for (int c0 = 0; c0 < Vp; c0 += 4) *reinterpret_cast<float4*>(out + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 // Same GEMM on CTA pairs (cta_group::2): the two CTAs of a cluster own d blocks 2i, 2i+1 of the same split-K range.
 // One tcgen05.mma covers M = 256 (both CTAs' z^T boxes) x N = NH; each CTA loads only HALF of every g^T box (its
 // N/2 rows), which halves the shared-memory traffic per flop - the bound of the single-CTA kernel above.
@@ -678,7 +775,7 @@ static BwdWs carve_bwd_ws(void* ws, int B, int T, int U1, int D, int V) {
   w.tiles = reinterpret_cast<int4*>(take((size_t)w.mt * 16));
   w.ntiles = reinterpret_cast<int*>(take(4));
   w.zt = reinterpret_cast<__nv_bfloat16*>(take((size_t)D * w.Rpad * 2));
-  w.gt = reinterpret_cast<__nv_bfloat16*>(take((size_t)Vp * w.Rpad * 2));
+  w.gt = reinterpret_cast<__nv_bfloat16*>(take((size_t)((Vp + 63) / 64) * 64 * w.Rpad * 2));
   w.d_enc_part = reinterpret_cast<float*>(take((size_t)w.S_max * B * T * D * 4));
   w.partials = reinterpret_cast<float*>(take((size_t)w.KS * D * Vp * 4));
   w.bytes = off;
@@ -711,6 +808,7 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
   const int mt = W.mt;
   const bool pair = MB % 2 == 0 && NH % 16 == 0 && min(sm_count(), mt) >= 2 && env_flag("CTCVR_BWD_PAIR");
   const RectGeom G = pick_rect_geom(T, U1, pair);
+  const bool g_rowmajor = !pair && !env_flag("CTCVR_GT_TRANSPOSED");
   build_tiles_kernel<<<B, 128, 0, st>>>(t_len, u_len, B, T, U1, G.P | (G.TT << 8) | (G.even << 16), W.tiles, W.ntiles, mt);
   CTCVR_LAUNCH_CHECK();
   CTCVR_CHECK_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)B * U1 * D * sizeof(float), st));
@@ -737,6 +835,7 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
     p.B = B; p.T = T; p.U1 = U1; p.D = D; p.V = V; p.Vp = Vp; p.NH = NH; p.blank = blank;
     p.lse = lse; p.alpha = alpha; p.beta = beta; p.costs = costs; p.grad_costs = grad_costs; p.clamp = clamp;
     p.zt = W.zt; p.gt = W.gt; p.Rpad = W.Rpad; p.scratch_tile = mt;
+    p.g_rowmajor = g_rowmajor ? 1 : 0;
     p.d_enc_part = W.d_enc_part; p.d_pred = d_pred; p.d_bias = d_b;
     p.prof = g_prof_buf;
     const size_t smem = bwd2_smem_bytes(NH, Vp, D);
@@ -769,7 +868,13 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
   }
   reduce_denc_kernel<<<B * T, 128, 0, st>>>(W.d_enc_part, t_len, u_len, d_enc, B, T, U1, D, G.P);
   CTCVR_LAUNCH_CHECK();
-  if (MB % 2 == 0 && NH % 16 == 0 && env_flag("CTCVR_DW_PAIR")) {
+  if (g_rowmajor) {
+    const size_t smem = 1024 + (size_t)DW_STAGES * (A_STAGE_BYTES + (size_t)KBG * 8192) + 256;
+    CTCVR_REQUIRE(smem <= 232448, "dW GEMM: shared memory budget exceeded (%zu B)", smem);
+    CTCVR_CHECK_CUDA(cudaFuncSetAttribute(dw_gemm_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dw_gemm_mn_kernel<<<dim3(MB, W.KS), DW_THREADS, smem, st>>>(W.zt, W.gt, W.ntiles, W.partials, D, Vp, KBG, W.KS);
+    CTCVR_LAUNCH_CHECK();
+  } else if (MB % 2 == 0 && NH % 16 == 0 && env_flag("CTCVR_DW_PAIR")) {
     const size_t smem = 1024 + (size_t)DW2_STAGES * (A_STAGE_BYTES + 2 * (size_t)(NH / 2) * 128) + 512;
     CTCVR_REQUIRE(smem <= 232448, "dW GEMM: shared memory budget exceeded (%zu B)", smem);
     CTCVR_CHECK_CUDA(cudaFuncSetAttribute(dw_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

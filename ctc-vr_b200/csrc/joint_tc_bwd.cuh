@@ -83,6 +83,7 @@ struct BwdParams {
   //   gt [tile][2][Vp][64 rows]        : element (v, rr) at half rr>>6, row v, chunk ((rr&63)>>3) ^ (v&7), element rr&7
   __nv_bfloat16* zt;
   __nv_bfloat16* gt;
+  int g_rowmajor;           // 1: g is spilled as the G tile itself, [tile][2][KBG][64 rows][64 v] (bulk stores from smem)
   long Rpad;
   int scratch_tile;         // unused row tile (kept for layout compatibility)
   float* d_enc_part;        // [S][B,T,D]
@@ -465,14 +466,15 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           sts128(gb + (((ch0 + i) ^ (r & 7)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-        // g^T spill: gt[col][row0 + r] (lanes = consecutive rows -> 64 B per column)
-        // g^T spill (tiled): column v of this row -> gt[tile][r>>6][v][chunk ((r&63)>>3) ^ (v&7)][r&7]
-        unsigned short* gt = reinterpret_cast<unsigned short*>(p.gt) + ((rowtile * 2 + (r >> 6)) * p.Vp + c0) * 64 + (r & 7);
-        const int gch = (r & 63) >> 3;
+        if (!p.g_rowmajor) {
+          // g^T spill (tiled): column v of this row -> gt[tile][r>>6][v][chunk ((r&63)>>3) ^ (v&7)][r&7]
+          unsigned short* gt = reinterpret_cast<unsigned short*>(p.gt) + ((rowtile * 2 + (r >> 6)) * p.Vp + c0) * 64 + (r & 7);
+          const int gch = (r & 63) >> 3;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          gt[(2 * j) * 64 + ((gch ^ ((2 * j) & 7)) << 3)] = (unsigned short)(pk[j] & 0xffffu);
-          gt[(2 * j + 1) * 64 + ((gch ^ ((2 * j + 1) & 7)) << 3)] = (unsigned short)(pk[j] >> 16);
+          for (int j = 0; j < 16; ++j) {
+            gt[(2 * j) * 64 + ((gch ^ ((2 * j) & 7)) << 3)] = (unsigned short)(pk[j] & 0xffffu);
+            gt[(2 * j + 1) * 64 + ((gch ^ ((2 * j + 1) & 7)) << 3)] = (unsigned short)(pk[j] >> 16);
+          }
         }
       }
       named_barrier_sync(2, WORKERS);            // every generic entry of G / g^T is written
@@ -499,8 +501,9 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
             const unsigned short h = __bfloat16_as_ushort(__float2bfloat16(val));
             const uint32_t a = L.g_kblock(col >> 6) + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4) + (col & 7) * 2;
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(h) : "memory");
-            reinterpret_cast<unsigned short*>(p.gt)[((rowtile * 2 + (r >> 6)) * p.Vp + col) * 64 +
-                                                    ((((r & 63) >> 3) ^ (col & 7)) << 3) + (r & 7)] = h;
+            if (!p.g_rowmajor)
+              reinterpret_cast<unsigned short*>(p.gt)[((rowtile * 2 + (r >> 6)) * p.Vp + col) * 64 +
+                                                      ((((r & 63) >> 3) ^ (col & 7)) << 3) + (r & 7)] = h;
           };
           const float xbb = xb + __ldg(p.bias + p.blank);
           put(p.blank, entry(xbb, k_blank, (lab == p.blank) ? k_label : kNegInf));
@@ -514,6 +517,16 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
 
       // ---------------- P3 (MMA busy): d_bias = column sums of the final G tile
       mbar_wait(L.g_full(), ph, 31);
+      if (p.g_rowmajor && wt == 0) {
+        // spill the finished G tile as it lies in shared memory: k-block i (64 label columns) -> two 8 KB boxes
+        // [64 rows][64 v] (rows 0-63 / 64-127), read back MN-major by the dW GEMM.  No per-thread stores.
+        __nv_bfloat16* gdst = p.gt + (rowtile * 2) * (size_t)KBG * 4096;
+        for (int i = 0; i < KBG; ++i) {
+          bulk_store(gdst + (size_t)i * 4096, L.g_kblock(i), 8192u);
+          bulk_store(gdst + (size_t)(KBG + i) * 4096, L.g_kblock(i) + 8192u, 8192u);
+        }
+        bulk_commit();
+      }
       {
         const int nchunk = p.Vp >> 3;
         if (wt < 4 * nchunk) {
@@ -533,7 +546,10 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
           *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
         named_barrier_sync(2, WORKERS);
-        if (wt == 0) mbar_arrive(L.gs_done());
+        if (wt == 0) {
+          if (p.g_rowmajor) bulk_wait_read<0>();      // the bulk stores have read G
+          mbar_arrive(L.gs_done());
+        }
         if (wt < p.Vp) db0 += (L.dbp[wt] + L.dbp[p.Vp + wt]) + (L.dbp[2 * p.Vp + wt] + L.dbp[3 * p.Vp + wt]);
         if (wt + WORKERS < p.Vp)
           db1 += (L.dbp[wt + WORKERS] + L.dbp[p.Vp + wt + WORKERS]) + (L.dbp[2 * p.Vp + wt + WORKERS] + L.dbp[3 * p.Vp + wt + WORKERS]);
