@@ -248,7 +248,7 @@ dw_gemm_mn_kernel(const __nv_bfloat16* __restrict__ zt, const __nv_bfloat16* __r
   const uint32_t stage_bytes = A_STAGE_BYTES + b_bytes;
   const uint32_t bar = al + DW_STAGES * stage_bytes;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem_raw + (bar + 128 - base));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int mb = blockIdx.x, ks = blockIdx.y;
   const size_t MBD = (size_t)(D / 128);
   const int kblocks = (*ntiles_ptr) * 2;
@@ -269,43 +269,45 @@ dw_gemm_mn_kernel(const __nv_bfloat16* __restrict__ zt, const __nv_bfloat16* __r
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      Pipe sp;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(empty(sp.stage), sp.phase ^ 1u, 50);
+    Pipe sp;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(empty(sp.stage), sp.phase ^ 1u, 50);
+      if (elect_one()) {
         const uint32_t st = al + sp.stage * stage_bytes;
         mbar_arrive_expect_tx(full(sp.stage), stage_bytes);
         const size_t rt = (size_t)(kb >> 1), hh = (size_t)(kb & 1);
         bulk_load(st, zt + ((rt * MBD + mb) * 2 + hh) * 8192, A_STAGE_BYTES, full(sp.stage));
         bulk_load(st + A_STAGE_BYTES, gr + ((rt * 2 + hh) * (size_t)KBG) * 4096, b_bytes, full(sp.stage));
-        sp.advance(DW_STAGES);
       }
+      __syncwarp();
+      sp.advance(DW_STAGES);
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      Pipe sp;
-      const int N0 = min(256, Vp), N1 = Vp - N0;
-      const uint32_t idesc0 = make_idesc_bf16_bmn(128, N0);
-      const uint32_t idesc1 = make_idesc_bf16_bmn(128, N1 > 0 ? N1 : 16);
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(full(sp.stage), sp.phase, 51);
-        tc_fence_after();
-        const uint32_t st = al + sp.stage * stage_bytes;
+    Pipe sp;
+    const int N0 = min(256, Vp), N1 = Vp - N0;
+    const uint32_t idesc0 = make_idesc_bf16_bmn(128, N0);
+    const uint32_t idesc1 = make_idesc_bf16_bmn(128, N1 > 0 ? N1 : 16);
+    const uint64_t a_desc0 = make_desc_sw128(al);
+    const uint64_t b_desc0 = make_desc_mn_sw128(al + A_STAGE_BYTES, 8192u, 1024u);
+    const uint32_t st_step = stage_bytes >> 4;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(full(sp.stage), sp.phase, 51);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t ad = a_desc0 + (uint64_t)(sp.stage * st_step);
+        const uint64_t bd = b_desc0 + (uint64_t)(sp.stage * st_step);
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
-          const uint64_t ad = make_desc_sw128(st + k4 * 32);
           const uint32_t acc = (kb > kb_begin || k4 > 0) ? 1u : 0u;
-          umma_bf16(tmem_base, ad, make_desc_mn_sw128(st + A_STAGE_BYTES + k4 * 2048, 8192u, 1024u), idesc0, acc);
-          if (N1 > 0)
-            umma_bf16(tmem_base + 256, ad, make_desc_mn_sw128(st + A_STAGE_BYTES + 4 * 8192 + k4 * 2048, 8192u, 1024u),
-                      idesc1, acc);
+          umma_bf16(tmem_base, ad + 2 * k4, bd + 128 * k4, idesc0, acc);
+          if (N1 > 0) umma_bf16(tmem_base + 256, ad + 2 * k4, bd + 2048 + 128 * k4, idesc1, acc);
         }
         umma_commit(empty(sp.stage));
-        sp.advance(DW_STAGES);
       }
-      umma_commit(done);
+      __syncwarp();
+      sp.advance(DW_STAGES);
     }
+    if (elect_one()) umma_commit(done);
     __syncwarp();
   } else if (warp >= 4) {
     const int q = warp & 3;
@@ -838,6 +840,7 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
     p.g_rowmajor = g_rowmajor ? 1 : 0;
     p.d_enc_part = W.d_enc_part; p.d_pred = d_pred; p.d_bias = d_b;
     p.prof = g_prof_buf;
+    { const char* e = getenv("CTCVR_DBG"); p.dbg = e ? atoi(e) : 0; }
     const size_t smem = bwd2_smem_bytes(NH, Vp, D);
     CTCVR_REQUIRE(smem <= 232448, "joint_rnnt_bwd bf16: shared memory budget exceeded (%zu B)", smem);
     if (pair) {

@@ -90,6 +90,7 @@ struct BwdParams {
   float* d_pred;            // [B,U1,D] atomic accumulate
   float* d_bias;            // [V] atomic accumulate
   long long* prof;
+  int dbg;                  // timing experiments only (CTCVR_DBG): 1 = no W^T copies in P3, 2 = no MMAs in P3
 };
 
 // Shared memory: [GZ region: G tile (P2/P3) = A ring (P1) = z^T tile (P4)] [weight ring: 3 W stages = 5 W^T stages]
@@ -162,7 +163,7 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   Bwd2Smem L;
   carve_bwd2(L, smem_raw, p.NH, p.Vp, p.D);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int KB = p.D / BK;                 // k-blocks of the logits GEMM
   const int KBG = (p.Vp + 63) / 64;        // k-blocks (over v) of the dZ GEMM
   const int MB = p.D / 128;                // 128-lane blocks of dZ^T
@@ -194,122 +195,144 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA: W_out (P1), W_out^T (P3), z^T tile (P4)
-    if (lane == 0) {
-      Pipe r1, r3;
-      int prof_n = 0;
-      uint32_t ph = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const size_t rowtile = (size_t)p.tiles[tile].w;
-        TC_PROF(0, 1);
-        // the ring is drained here: the previous tile's dz_full was observed below
-        for (int kb = 0; kb < KB; ++kb)
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(L.r1_empty(r1.stage), r1.phase ^ 1u, 11);
-            mbar_arrive_expect_tx(L.r1_full(r1.stage), (uint32_t)p.NH * 128u);
-            bulk_load(L.r1_stage(r1.stage), p.w_t + (size_t)(kb * 2 + h) * p.NH * 64, (uint32_t)p.NH * 128u,
-                      L.r1_full(r1.stage));
-            r1.advance(B_R1_STAGES);
-          }
-        TC_PROF(0, 2);
-        mbar_wait(L.tmem_full(), ph, 12);           // every P1 MMA has completed: the W view of the ring is dead
-        TC_PROF(0, 3);
-        for (int mb = 0; mb < MB; ++mb)
-          for (int kb = 0; kb < KBG; ++kb) {
-            mbar_wait(L.r3_empty(r3.stage), r3.phase ^ 1u, 13);
+    Pipe r1, r3;
+    int prof_n = 0;
+    uint32_t ph = 0;
+    const uint32_t r1_bytes = (uint32_t)p.NH * 128u;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const size_t rowtile = (size_t)p.tiles[tile].w;
+      if (lane == 0) TC_PROF(0, 1);
+      // the ring is drained here: the previous tile's dz_full was observed below
+      for (int i = 0; i < 2 * KB; ++i) {
+        mbar_wait(L.r1_empty(r1.stage), r1.phase ^ 1u, 11);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(L.r1_full(r1.stage), r1_bytes);
+          bulk_load(L.r1_stage(r1.stage), p.w_t + (size_t)i * p.NH * 64, r1_bytes, L.r1_full(r1.stage));
+        }
+        __syncwarp();
+        r1.advance(B_R1_STAGES);
+      }
+      if (lane == 0) TC_PROF(0, 2);
+      mbar_wait(L.tmem_full(), ph, 12);           // every P1 MMA has completed: the W view of the ring is dead
+      if (lane == 0) TC_PROF(0, 3);
+      for (int i = 0; i < MB * KBG; ++i) {
+        mbar_wait(L.r3_empty(r3.stage), r3.phase ^ 1u, 13);
+        if (elect_one()) {
+          if (p.dbg & 1) {
+            mbar_arrive(L.r3_full(r3.stage));
+          } else {
             mbar_arrive_expect_tx(L.r3_full(r3.stage), 16384u);
-            bulk_load(L.r3_stage(r3.stage), p.wt_t + (size_t)(mb * KBG + kb) * 8192, 16384u, L.r3_full(r3.stage));
-            r3.advance(B_R3_STAGES);
+            bulk_load(L.r3_stage(r3.stage), p.wt_t + (size_t)i * 8192, 16384u, L.r3_full(r3.stage));
           }
-        TC_PROF(0, 4);
-        mbar_wait(L.dz_full(), ph, 14);             // every P3 MMA has completed: G tile and the W^T view are dead
-        mbar_wait(L.gs_done(), ph, 16);             // ... and the d_bias column sums have read G
-        TC_PROF(0, 5);
-        fence_proxy_async_global();                 // z^T was written with st.global by this CTA's producers
-        TC_PROF(0, 6);
+        }
+        __syncwarp();
+        r3.advance(B_R3_STAGES);
+      }
+      if (lane == 0) TC_PROF(0, 4);
+      mbar_wait(L.dz_full(), ph, 14);             // every P3 MMA has completed: G tile and the W^T view are dead
+      mbar_wait(L.gs_done(), ph, 16);             // ... and the d_bias column sums have read G
+      if (lane == 0) TC_PROF(0, 5);
+      if (elect_one()) {
+        fence_proxy_async_global();               // z^T was written with st.global by this CTA's producers
         for (int mb = 0; mb < MB; ++mb) {
           mbar_arrive_expect_tx(L.z_full(mb), 32768u);
           bulk_load(L.z_box(2 * mb), p.zt + ((rowtile * MB + mb) * 2) * 8192, 32768u, L.z_full(mb));
         }
-        ph ^= 1u;
       }
+      __syncwarp();
+      ph ^= 1u;
     }
-    __syncwarp();
   } else if (warp == 3) {
     // ------------------------------------------------------------------ TMA: enc / pred slabs
-    if (lane == 0) {
-      Pipe sp;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const int4 ti = p.tiles[tile];
-        const int b = ti.x;
-        const int W = min(p.u_len[b], p.U1 - 1) + 1;
-        const int S = (W + P - 1) / P, us = (W + S - 1) / S;
-        const int prow = b * p.U1 + ti.y * us;
-        const int erow = b * p.T + ti.z * TT;
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(L.s_empty(sp.stage), sp.phase ^ 1u, 15);
+    Pipe sp;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int4 ti = p.tiles[tile];
+      const int b = ti.x;
+      const int W = min(p.u_len[b], p.U1 - 1) + 1;
+      const int S = (W + P - 1) / P, us = (W + S - 1) / S;
+      const int prow = b * p.U1 + ti.y * us;
+      const int erow = b * p.T + ti.z * TT;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(L.s_empty(sp.stage), sp.phase ^ 1u, 15);
+        if (elect_one()) {
           const uint32_t st = L.s_stage(sp.stage);
           mbar_arrive_expect_tx(L.s_full(sp.stage), (uint32_t)(P + TT) * 128u);
           tma_load_2d(st, &tmap_p, L.s_full(sp.stage), kb * BK, prow);
           tma_load_2d(st + bwd_pred_region<P>(), &tmap_e, L.s_full(sp.stage), kb * BK, erow);
-          sp.advance(B_S_STAGES);
         }
+        __syncwarp();
+        sp.advance(B_S_STAGES);
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      Pipe ap, r1, r3;
-      int prof_n = 0;
-      uint32_t ph = 0;
-      const uint32_t idesc1 = make_idesc_bf16(BM, p.NH);
-      const uint32_t idesc2 = make_idesc_bf16(128, BM);
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        TC_PROF(1, 1);
-        mbar_wait(L.tmem_empty(), ph ^ 1u, 20);
-        TC_PROF(1, 2);
-        tc_fence_after();
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(L.a_full(ap.stage), ap.phase, 21);
-          TC_PROF(1, 50 + kb);
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(L.r1_full(r1.stage), r1.phase, 22);
-            TC_PROF(1, 100 + kb * 2 + h);
-            tc_fence_after();
-#pragma unroll
-            for (int ks = 0; ks < BK / 16; ++ks)
-              umma_bf16(tmem_base + h * p.NH, make_desc_sw128(L.a_stage(ap.stage) + ks * 32),
-                        make_desc_sw128(L.r1_stage(r1.stage) + ks * 32), idesc1, (kb | ks) ? 1u : 0u);
+    // ------------------------------------------------------------------ MMA issuer (warp-wide loop, one elected lane issues)
+    Pipe ap, r1, r3;
+    int prof_n = 0;
+    uint32_t ph = 0;
+    const uint32_t idesc1 = make_idesc_bf16(BM, p.NH);
+    const uint32_t idesc2 = make_idesc_bf16(128, BM);
+    const uint64_t a_desc0 = make_desc_sw128(L.a_stage(0));       // + stage * 1024 (16 KB >> 4)
+    const uint64_t r1_desc0 = make_desc_sw128(L.r1_stage(0));     // + stage * NH * 8
+    const uint64_t r3_desc0 = make_desc_sw128(L.r3_stage(0));     // + stage * 1024
+    const uint64_t g_desc0 = make_desc_sw128(L.g_kblock(0));      // + kb * 1024
+    const uint32_t r1_step = (uint32_t)p.NH * 8u;
+    const int last_nks = (p.Vp - (KBG - 1) * 64) / 16;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      if (lane == 0) TC_PROF(1, 1);
+      mbar_wait(L.tmem_empty(), ph ^ 1u, 20);
+      if (lane == 0) TC_PROF(1, 2);
+      tc_fence_after();
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(L.a_full(ap.stage), ap.phase, 21);
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(L.r1_full(r1.stage), r1.phase, 22);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ad = a_desc0 + (uint64_t)(ap.stage * (A_STAGE_BYTES >> 4));
+            const uint64_t bd = r1_desc0 + (uint64_t)(r1.stage * r1_step);
+            const uint32_t d = tmem_base + h * p.NH;
+            umma_bf16(d, ad, bd, idesc1, kb ? 1u : 0u);
+            umma_bf16(d, ad + 2, bd + 2, idesc1, 1u);
+            umma_bf16(d, ad + 4, bd + 4, idesc1, 1u);
+            umma_bf16(d, ad + 6, bd + 6, idesc1, 1u);
             umma_commit(L.r1_empty(r1.stage));
-            r1.advance(B_R1_STAGES);
+            if (h == 1) umma_commit(L.a_empty(ap.stage));
           }
-          umma_commit(L.a_empty(ap.stage));
-          ap.advance(B_A_STAGES);
+          __syncwarp();
+          r1.advance(B_R1_STAGES);
         }
-        umma_commit(L.tmem_full());
-        TC_PROF(1, 3);
-        // ---- P3: dZ^T[mb] (128 d x 128 rows) = W^T[mb] (128 x Vp) . G^T (Vp x 128)
-        mbar_wait(L.g_full(), ph, 23);
-        TC_PROF(1, 4);
-        tc_fence_after();
-        for (int mb = 0; mb < MB; ++mb)
-          for (int kb = 0; kb < KBG; ++kb) {
-            mbar_wait(L.r3_full(r3.stage), r3.phase, 24);
-            TC_PROF(1, 200 + mb * KBG + kb);
-            tc_fence_after();
-            const int nks = min(4, (p.Vp - kb * 64) / 16);
-            for (int ks = 0; ks < nks; ++ks)
-              umma_bf16(tmem_base + mb * 128, make_desc_sw128(L.r3_stage(r3.stage) + ks * 32),
-                        make_desc_sw128(L.g_kblock(kb) + ks * 32), idesc2, (kb | ks) ? 1u : 0u);
-            umma_commit(L.r3_empty(r3.stage));
-            r3.advance(B_R3_STAGES);
-          }
-        umma_commit(L.dz_full());
-        TC_PROF(1, 5);
-        ph ^= 1u;
+        ap.advance(B_A_STAGES);
       }
+      if (elect_one()) umma_commit(L.tmem_full());
+      __syncwarp();
+      if (lane == 0) TC_PROF(1, 3);
+      // ---- P3: dZ^T[mb] (128 d x 128 rows) = W^T[mb] (128 x Vp) . G^T (Vp x 128)
+      mbar_wait(L.g_full(), ph, 23);
+      if (lane == 0) TC_PROF(1, 4);
+      tc_fence_after();
+      for (int mb = 0; mb < MB; ++mb)
+        for (int kb = 0; kb < KBG; ++kb) {
+          mbar_wait(L.r3_full(r3.stage), r3.phase, 24);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ad = r3_desc0 + (uint64_t)(r3.stage * 1024);
+            const uint64_t bd = g_desc0 + (uint64_t)(kb * 1024);
+            const uint32_t d = tmem_base + mb * 128;
+            const int nks = (p.dbg & 2) ? 0 : (kb == KBG - 1 ? last_nks : 4);
+            if (nks > 0) umma_bf16(d, ad, bd, idesc2, kb ? 1u : 0u);
+            if (nks > 1) umma_bf16(d, ad + 2, bd + 2, idesc2, 1u);
+            if (nks > 2) umma_bf16(d, ad + 4, bd + 4, idesc2, 1u);
+            if (nks > 3) umma_bf16(d, ad + 6, bd + 6, idesc2, 1u);
+            umma_commit(L.r3_empty(r3.stage));
+          }
+          __syncwarp();
+          r3.advance(B_R3_STAGES);
+        }
+      if (elect_one()) umma_commit(L.dz_full());
+      __syncwarp();
+      if (lane == 0) TC_PROF(1, 5);
+      ph ^= 1u;
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ workers (warps 4-15), producers (8-15)
     const int q = warp & 3;

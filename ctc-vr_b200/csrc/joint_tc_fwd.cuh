@@ -97,7 +97,7 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   FwdSmem L;
   carve_fwd2(L, smem_raw, p.NH, p.Vp, p.w_stages);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int KB = p.D / BK;
   const int ntiles = *p.ntiles;
   const int WS = p.w_stages;
@@ -120,79 +120,78 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
   const uint32_t tmem_base = *L.tmem_ptr;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA: W_out k-blocks
-    if (lane == 0) {
-      Pipe wp;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-        for (int kb = 0; kb < KB; ++kb)
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(L.w_empty(wp.stage), wp.phase ^ 1u, 1);
-            mbar_arrive_expect_tx(L.w_full(wp.stage), (uint32_t)p.NH * 128u);
-            bulk_load(L.w_stage(wp.stage), p.w_t + (size_t)(kb * 2 + h) * p.NH * 64, (uint32_t)p.NH * 128u,
-                      L.w_full(wp.stage));
-            wp.advance(WS);
-          }
-    }
-    __syncwarp();
+    // ------------------------------------------------------------------ TMA: W_out k-blocks (warp-wide loop, one lane issues)
+    Pipe wp;
+    const uint32_t w_bytes = (uint32_t)p.NH * 128u;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      for (int i = 0; i < 2 * KB; ++i) {
+        mbar_wait(L.w_empty(wp.stage), wp.phase ^ 1u, 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(L.w_full(wp.stage), w_bytes);
+          bulk_load(L.w_stage(wp.stage), p.w_t + (size_t)i * p.NH * 64, w_bytes, L.w_full(wp.stage));
+        }
+        __syncwarp();
+        wp.advance(WS);
+      }
   } else if (warp == 3) {
     // ------------------------------------------------------------------ TMA: enc / pred slabs
-    if (lane == 0) {
-      Pipe sp;
-      int prof_n = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int4 ti = p.tiles[tile];
-        const int nbox = 4 / ti.w;                       // 32-frame boxes: 128/nu frames
-        const int prow = ti.x * p.U1 + ti.y;
-        const int erow = ti.x * p.T + ti.z;
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(L.s_empty(sp.stage), sp.phase ^ 1u, 2);
-          TC_PROF(0, kb);
+    Pipe sp;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int4 ti = p.tiles[tile];
+      const int nbox = 4 / ti.w;                       // 32-frame boxes: 128/nu frames
+      const int prow = ti.x * p.U1 + ti.y;
+      const int erow = ti.x * p.T + ti.z;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(L.s_empty(sp.stage), sp.phase ^ 1u, 2);
+        if (elect_one()) {
           const uint32_t st = L.s_stage(sp.stage);
           mbar_arrive_expect_tx(L.s_full(sp.stage), 512u + (uint32_t)nbox * 4096u);
           tma_load_2d(st, &tmap_p, L.s_full(sp.stage), kb * BK, prow);
           for (int i = 0; i < nbox; ++i)
             tma_load_2d(st + 1024 + i * 4096, &tmap_e, L.s_full(sp.stage), kb * BK, erow + 32 * i);
-          sp.advance(F_S_STAGES);
         }
+        __syncwarp();
+        sp.advance(F_S_STAGES);
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      Pipe ap, wp;
-      uint32_t tphase = 0;
-      int prof_n = 0;
-      const uint32_t idesc = make_idesc_bf16(BM, p.NH);
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        TC_PROF(1, 100);
-        mbar_wait(L.tmem_empty(), tphase ^ 1u, 3);
-        TC_PROF(1, 101);
-        tc_fence_after();
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(L.a_full(ap.stage), ap.phase, 4);
-          TC_PROF(1, kb);
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(L.w_full(wp.stage), wp.phase, 5);
-            TC_PROF(1, 50 + kb * 2 + h);
-            tc_fence_after();
-#pragma unroll
-            for (int ks = 0; ks < BK / 16; ++ks) {
-              const uint64_t bd = make_desc_sw128(L.w_stage(wp.stage) + ks * 32);
-              umma_bf16_ts(tmem_base + h * p.NH, tmem_base + F_ACC_COLS + ap.stage * 32 + ks * 8, bd, idesc,
-                           (kb | ks) ? 1u : 0u);
-            }
+    // ------------------------------------------------------------------ MMA issuer (warp-wide loop, one lane issues)
+    Pipe ap, wp;
+    uint32_t tphase = 0;
+    int prof_n = 0;
+    const uint32_t idesc = make_idesc_bf16(BM, p.NH);
+    const uint64_t w_desc0 = make_desc_sw128(L.w_stage(0));
+    const uint32_t w_step = (uint32_t)p.NH * 8u;         // one ring stage, in 16-byte descriptor units
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      if (lane == 0) TC_PROF(1, 100);
+      mbar_wait(L.tmem_empty(), tphase ^ 1u, 3);
+      if (lane == 0) TC_PROF(1, 101);
+      tc_fence_after();
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(L.a_full(ap.stage), ap.phase, 4);
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(L.w_full(wp.stage), wp.phase, 5);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t bd = w_desc0 + (uint64_t)(wp.stage * w_step);
+            const uint32_t d = tmem_base + h * p.NH;
+            const uint32_t a = tmem_base + F_ACC_COLS + ap.stage * 32;
+            umma_bf16_ts(d, a, bd, idesc, kb ? 1u : 0u);
+            umma_bf16_ts(d, a + 8, bd + 2, idesc, 1u);
+            umma_bf16_ts(d, a + 16, bd + 4, idesc, 1u);
+            umma_bf16_ts(d, a + 24, bd + 6, idesc, 1u);
             umma_commit(L.w_empty(wp.stage));
-            wp.advance(WS);
+            if (h == 1) umma_commit(L.a_empty(ap.stage));
           }
-          umma_commit(L.a_empty(ap.stage));
-          ap.advance(F_A_STAGES);
+          __syncwarp();
+          wp.advance(WS);
         }
-        umma_commit(L.tmem_full());
-        tphase ^= 1u;
+        ap.advance(F_A_STAGES);
       }
+      if (elect_one()) umma_commit(L.tmem_full());
+      __syncwarp();
+      tphase ^= 1u;
     }
-    __syncwarp();
   } else if (warp >= 4 && warp < 12) {
     // ------------------------------------------------------------------ epilogue: online log-softmax (base 2)
     // 8 warps: quarter q = TMEM lanes 32q..32q+31 (thread = cell), group eg = which half of the accumulator columns.

@@ -328,6 +328,17 @@ __device__ __forceinline__ uint32_t tanh_add_bf16x2_packed(uint32_t a, uint32_t 
   return r;
 }
 
+// One lane of a converged warp.  Role warps run their loops warp-wide (loop state stays in uniform registers) and
+// guard the single-thread instructions (tcgen05.mma/commit, bulk copies) with this: a `lane == 0` branch around the
+// whole loop forces every descriptor through R2UR and wraps each UTCHMMA in an ELECT/BRA.U.ANY waterfall, which was
+// measured at 2x the MMA time per 4-MMA stage (tools/issue_bench.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\nselp.u32 %0, 1, 0, px;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+// Warp index as a value the compiler knows to be warp-uniform.
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ void named_barrier_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
