@@ -115,7 +115,6 @@ struct Pipe {
 }  // namespace ctcvr
 #include "joint_tc_fwd.cuh"
 #include "joint_tc_bwd.cuh"
-#include "joint_tc_bwd_pair.cuh"
 namespace ctcvr {
 namespace tc {
 
@@ -140,102 +139,12 @@ __global__ void reduce_denc_kernel(const float* __restrict__ part, const int32_t
 }
 
 // =================================================================================================
-// Backward kernel 2: dW^T[d][v] = sum_rows z^T[d][row] * g^T[v][row]  (plain TMA-fed tcgen05 GEMM, split-K)
+// Backward kernel 2: dW^T[d][v] = sum_rows z^T[d][row] * g[row][v]  (bulk-copy-fed tcgen05 GEMM, split-K)
 // =================================================================================================
 constexpr int DW_STAGES = 3;
 constexpr int DW_THREADS = 256;
 
-__global__ void __launch_bounds__(DW_THREADS, 1)
-dw_gemm_kernel(const __nv_bfloat16* __restrict__ zt, const __nv_bfloat16* __restrict__ gt,
-               const int* __restrict__ ntiles_ptr, float* __restrict__ partials, int D, int Vp, int NH, int KS) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = smem_u32(smem_raw);
-  const uint32_t al = (base + 1023u) & ~1023u;
-  const uint32_t stage_bytes = A_STAGE_BYTES + 2 * NH * 128;
-  const uint32_t bar = al + DW_STAGES * stage_bytes;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem_raw + (bar + 128 - base));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int mb = blockIdx.x, ks = blockIdx.y;
-  const size_t MBD = (size_t)(D / 128);
-  const int kblocks = (*ntiles_ptr) * 2;                      // 64-row k-blocks actually written by kernel 1
-  const int kb_begin = (int)(((long)kblocks * ks) / KS), kb_end = (int)(((long)kblocks * (ks + 1)) / KS);
-  auto full = [&](int i) { return bar + i * 16; };
-  auto empty = [&](int i) { return bar + i * 16 + 8; };
-  const uint32_t done = bar + DW_STAGES * 16;
-
-  if (warp == 0 && lane == 0) {
-    for (int i = 0; i < DW_STAGES; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
-    mbar_init(done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_ptr), TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      Pipe sp;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(empty(sp.stage), sp.phase ^ 1u, 50);
-        const uint32_t st = al + sp.stage * stage_bytes;
-        mbar_arrive_expect_tx(full(sp.stage), stage_bytes);
-        // k-block kb = rows 64*(kb&1).. of row tile kb>>1: one contiguous box of the tiled spills each
-        const size_t rt = (size_t)(kb >> 1), hh = (size_t)(kb & 1);
-        bulk_load(st, zt + ((rt * MBD + mb) * 2 + hh) * 8192, A_STAGE_BYTES, full(sp.stage));
-        bulk_load(st + A_STAGE_BYTES, gt + ((rt * 2 + hh) * Vp) * 64, (uint32_t)Vp * 128u, full(sp.stage));
-        sp.advance(DW_STAGES);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      Pipe sp;
-      const uint32_t idesc = make_idesc_bf16(128, NH);
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(full(sp.stage), sp.phase, 51);
-        tc_fence_after();
-        const uint32_t st = al + sp.stage * stage_bytes;
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            umma_bf16(tmem_base + h * NH, make_desc_sw128(st + k4 * 32),
-                      make_desc_sw128(st + A_STAGE_BYTES + h * NH * 128 + k4 * 32), idesc,
-                      (kb > kb_begin || k4 > 0) ? 1u : 0u);
-        umma_commit(empty(sp.stage));
-        sp.advance(DW_STAGES);
-      }
-      umma_commit(done);
-    }
-    __syncwarp();
-  } else if (warp >= 4) {
-    const int q = warp & 3;
-    const int d = mb * 128 + q * 32 + lane;
-    float* out = partials + ((size_t)ks * D + d) * Vp;
-    if (kb_end > kb_begin) {
-      mbar_wait(done, 0, 52);
-      tc_fence_after();
-      for (int c0 = 0; c0 < Vp; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-        tmem_ld_wait();
-        if (d < D) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-      }
-    } else if (d < D) {
-      for (int c0 = 0; c0 < Vp; c0 += 4) *reinterpret_cast<float4*>(out + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
-}
-
-// Variant reading g as spilled row-major G tiles ([tile][2][KBG][64 rows][64 v], written by bulk stores from the
+// g is read as spilled row-major G tiles ([tile][2][KBG][64 rows][64 v], written by bulk stores from the
 // backward kernel's shared-memory G tile): the B operand is MN-major (label columns contiguous), N split at a
 // multiple of 64 columns (256 + the rest), one 1-D bulk load per operand and stage.
 __global__ void __launch_bounds__(DW_THREADS, 1)
@@ -332,117 +241,6 @@ dw_gemm_mn_kernel(const __nv_bfloat16* __restrict__ zt, const __nv_bfloat16* __r
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
-}
-
-// Same GEMM on CTA pairs (cta_group::2): the two CTAs of a cluster own d blocks 2i, 2i+1 of the same split-K range.
-// One tcgen05.mma covers M = 256 (both CTAs' z^T boxes) x N = NH; each CTA loads only HALF of every g^T box (its
-// N/2 rows), which halves the shared-memory traffic per flop - the bound of the single-CTA kernel above.
-constexpr int DW2_STAGES = 5;
-
-__global__ void __launch_bounds__(DW_THREADS, 1)
-dw_gemm2_kernel(const __nv_bfloat16* __restrict__ zt, const __nv_bfloat16* __restrict__ gt,
-                const int* __restrict__ ntiles_ptr, float* __restrict__ partials, int D, int Vp, int NH, int KS) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = smem_u32(smem_raw);
-  const uint32_t al = (base + 1023u) & ~1023u;
-  const uint32_t bhalf = (uint32_t)(NH / 2) * 128u;                 // this CTA's rows of one N-half of a g^T box
-  const uint32_t stage_bytes = A_STAGE_BYTES + 2 * bhalf;
-  const uint32_t bar = al + DW2_STAGES * stage_bytes;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem_raw + (bar + 256 - base));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int mb = blockIdx.x, ks = blockIdx.y;
-  const uint32_t rank = cluster_ctarank();                          // == mb & 1
-  const size_t MBD = (size_t)(D / 128);
-  const int kblocks = (*ntiles_ptr) * 2;
-  const int kb_begin = (int)(((long)kblocks * ks) / KS), kb_end = (int)(((long)kblocks * (ks + 1)) / KS);
-  auto full = [&](int i) { return bar + i * 24; };                  // own loads landed
-  auto empty = [&](int i) { return bar + i * 24 + 8; };             // the pair's MMAs released the stage
-  auto peer_full = [&](int i) { return bar + i * 24 + 16; };        // (leader) the peer's loads landed
-  const uint32_t done = bar + DW2_STAGES * 24;
-
-  if (warp == 0 && lane == 0) {
-    for (int i = 0; i < DW2_STAGES; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); mbar_init(peer_full(i), 1); }
-    mbar_init(done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc2(smem_u32(tmem_ptr), TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      Pipe sp;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(empty(sp.stage), sp.phase ^ 1u, 60);
-        const uint32_t st = al + sp.stage * stage_bytes;
-        mbar_arrive_expect_tx(full(sp.stage), stage_bytes);
-        const size_t rt = (size_t)(kb >> 1), hh = (size_t)(kb & 1);
-        bulk_load(st, zt + ((rt * MBD + mb) * 2 + hh) * 8192, A_STAGE_BYTES, full(sp.stage));
-        const __nv_bfloat16* gbox = gt + ((rt * 2 + hh) * Vp) * 64;
-        bulk_load(st + A_STAGE_BYTES, gbox + (size_t)(rank * (NH / 2)) * 64, bhalf, full(sp.stage));
-        bulk_load(st + A_STAGE_BYTES + bhalf, gbox + (size_t)(NH + rank * (NH / 2)) * 64, bhalf, full(sp.stage));
-        sp.advance(DW2_STAGES);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      Pipe sp;
-      if (rank == 0) {
-        const uint32_t idesc = make_idesc_bf16(256, NH);
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(full(sp.stage), sp.phase, 61);
-          mbar_wait(peer_full(sp.stage), sp.phase, 62);
-          tc_fence_after();
-          const uint32_t st = al + sp.stage * stage_bytes;
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              umma2_bf16(tmem_base + h * NH, make_desc_sw128(st + k4 * 32),
-                         make_desc_sw128(st + A_STAGE_BYTES + h * bhalf + k4 * 32), idesc,
-                         (kb > kb_begin || k4 > 0) ? 1u : 0u);
-          umma2_commit_mc(empty(sp.stage), 3);
-          sp.advance(DW2_STAGES);
-        }
-        umma2_commit_mc(done, 3);
-      } else {
-        // peer: forward "my half of the stage has landed" to the leader's barrier
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(full(sp.stage), sp.phase, 63);
-          mbar_arrive_remote(peer_full(sp.stage), 0);
-          sp.advance(DW2_STAGES);
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp >= 4) {
-    const int q = warp & 3;
-    const int d = mb * 128 + q * 32 + lane;
-    float* out = partials + ((size_t)ks * D + d) * Vp;
-    if (kb_end > kb_begin) {
-      mbar_wait(done, 0, 64);
-      tc_fence_after();
-      for (int c0 = 0; c0 < Vp; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-        tmem_ld_wait();
-        if (d < D) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-      }
-    } else if (d < D) {
-      for (int c0 = 0; c0 < Vp; c0 += 4) *reinterpret_cast<float4*>(out + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 2) tmem_dealloc2(tmem_base, TMEM_COLS);
 }
 
 // d_w[v][d] = sum_ks partials[ks][d][v].  Block = 8 d x 32 v (warp = d row, lanes = consecutive v: coalesced
@@ -623,10 +421,9 @@ static long long* g_prof_buf = nullptr;
 static int pad_v(int V) { return (V + 31) / 32 * 32; }
 static int max_tiles_flat(int B, int T, int U1) { return B * (int)(((long)T * U1 + BM - 1) / BM); }
 // Backward tile geometry: P label columns x TT frames.  Pick the variant with fewer tile rows for this (T, U1);
-// the CTA-pair kernel (CTCVR_BWD_PAIR=1) is written for <16, 8> only.
+// `even` (pad the frame blocks of an utterance to an even count) is kept in the tile builder but unused.
 struct RectGeom { int P, TT, even; };
-static RectGeom pick_rect_geom(int T, int U1, bool pair) {
-  if (pair) return RectGeom{16, 8, 1};
+static RectGeom pick_rect_geom(int T, int U1) {
   auto tiles = [&](int P, int TT) { return (long)((U1 + P - 1) / P) * ((T + TT - 1) / TT); };
   return tiles(21, 6) < tiles(16, 8) ? RectGeom{21, 6, 0} : RectGeom{16, 8, 0};
 }
@@ -678,11 +475,6 @@ static int sm_count() {
     if (n <= 0) n = 148;
   }
   return n;
-}
-
-static bool env_flag(const char* name) {
-  const char* v = getenv(name);
-  return v && v[0] && v[0] != '0';
 }
 
 int joint_fwd_f32(const float*, const float*, const float*, const float*, const int32_t*, const int32_t*,
@@ -808,9 +600,7 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
   prep_weights3_kernel<<<cdiv((long)KBG * 64 * D, 256), 256, 0, st>>>(w, bias, W.wb, W.wtb, W.bias_pad, W.bias_l2, V, Vp, D);
   CTCVR_LAUNCH_CHECK();
   const int mt = W.mt;
-  const bool pair = MB % 2 == 0 && NH % 16 == 0 && min(sm_count(), mt) >= 2 && env_flag("CTCVR_BWD_PAIR");
-  const RectGeom G = pick_rect_geom(T, U1, pair);
-  const bool g_rowmajor = !pair && !env_flag("CTCVR_GT_TRANSPOSED");
+  const RectGeom G = pick_rect_geom(T, U1);
   build_tiles_kernel<<<B, 128, 0, st>>>(t_len, u_len, B, T, U1, G.P | (G.TT << 8) | (G.even << 16), W.tiles, W.ntiles, mt);
   CTCVR_LAUNCH_CHECK();
   CTCVR_CHECK_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)B * U1 * D * sizeof(float), st));
@@ -836,30 +626,12 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
     p.tiles = W.tiles; p.ntiles = W.ntiles;
     p.B = B; p.T = T; p.U1 = U1; p.D = D; p.V = V; p.Vp = Vp; p.NH = NH; p.blank = blank;
     p.lse = lse; p.alpha = alpha; p.beta = beta; p.costs = costs; p.grad_costs = grad_costs; p.clamp = clamp;
-    p.zt = W.zt; p.gt = W.gt; p.Rpad = W.Rpad; p.scratch_tile = mt;
-    p.g_rowmajor = g_rowmajor ? 1 : 0;
+    p.zt = W.zt; p.gt = W.gt; p.Rpad = W.Rpad;
     p.d_enc_part = W.d_enc_part; p.d_pred = d_pred; p.d_bias = d_b;
     p.prof = g_prof_buf;
-    { const char* e = getenv("CTCVR_DBG"); p.dbg = e ? atoi(e) : 0; }
     const size_t smem = bwd2_smem_bytes(NH, Vp, D);
     CTCVR_REQUIRE(smem <= 232448, "joint_rnnt_bwd bf16: shared memory budget exceeded (%zu B)", smem);
-    if (pair) {
-      CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(grid & ~1);
-      cfg.blockDim = dim3(NTHREADS);
-      cfg.dynamicSmemBytes = smem;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      CTCVR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, joint_bwd2p_kernel, tmap_e, tmap_p, p));
-      count_launch();
-    } else if (G.P == 21) {
+    if (G.P == 21) {
       CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd2_kernel<21, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       joint_bwd2_kernel<21, 6><<<grid, NTHREADS, smem, st>>>(tmap_e, tmap_p, p);
       CTCVR_LAUNCH_CHECK();
@@ -871,36 +643,11 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
   }
   reduce_denc_kernel<<<B * T, 128, 0, st>>>(W.d_enc_part, t_len, u_len, d_enc, B, T, U1, D, G.P);
   CTCVR_LAUNCH_CHECK();
-  if (g_rowmajor) {
+  {
     const size_t smem = 1024 + (size_t)DW_STAGES * (A_STAGE_BYTES + (size_t)KBG * 8192) + 256;
     CTCVR_REQUIRE(smem <= 232448, "dW GEMM: shared memory budget exceeded (%zu B)", smem);
     CTCVR_CHECK_CUDA(cudaFuncSetAttribute(dw_gemm_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dw_gemm_mn_kernel<<<dim3(MB, W.KS), DW_THREADS, smem, st>>>(W.zt, W.gt, W.ntiles, W.partials, D, Vp, KBG, W.KS);
-    CTCVR_LAUNCH_CHECK();
-  } else if (MB % 2 == 0 && NH % 16 == 0 && env_flag("CTCVR_DW_PAIR")) {
-    const size_t smem = 1024 + (size_t)DW2_STAGES * (A_STAGE_BYTES + 2 * (size_t)(NH / 2) * 128) + 512;
-    CTCVR_REQUIRE(smem <= 232448, "dW GEMM: shared memory budget exceeded (%zu B)", smem);
-    CTCVR_CHECK_CUDA(cudaFuncSetAttribute(dw_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(MB, W.KS);
-    cfg.blockDim = dim3(DW_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CTCVR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dw_gemm2_kernel, (const __nv_bfloat16*)W.zt, (const __nv_bfloat16*)W.gt,
-                                        (const int*)W.ntiles, W.partials, D, Vp, NH, W.KS));
-    count_launch();
-  } else {
-    size_t smem = 1024 + (size_t)DW_STAGES * (A_STAGE_BYTES + 2 * NH * 128) + 256;
-    CTCVR_REQUIRE(smem <= 232448, "dW GEMM: shared memory budget exceeded (%zu B)", smem);
-    CTCVR_CHECK_CUDA(cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dw_gemm_kernel<<<dim3(MB, W.KS), DW_THREADS, smem, st>>>(W.zt, W.gt, W.ntiles, W.partials, D, Vp, NH, W.KS);
     CTCVR_LAUNCH_CHECK();
   }
   reduce_dw_kernel<<<dim3(cdiv(D, 8), cdiv(Vp, 32)), 256, 0, st>>>(W.partials, d_w, D, V, Vp, W.KS);

@@ -23,10 +23,11 @@ namespace ctcvr {
 namespace tc {
 
 constexpr int B_A_STAGES = 3;
+constexpr int B_Z_STAGES = 3;                  // z^T staging (P1): GZ blocks 0..2, one 64-d k-block ([2 halves][64 d][64 rows]) each
+constexpr int B_ACC_COLS = 416;                // TMEM: logits [0, 416) | A stages 416 + 32*stage (P1) ; dZ^T [0, 512) (P3/P4)
 constexpr int B_S_STAGES = 2;
 constexpr int B_R1_STAGES = 3;                 // W_out ring view   (P1): NH x 128 B per stage
 constexpr int B_R3_STAGES = 5;                 // W_out^T ring view (P3): 16 KB per stage, same memory
-constexpr int B_SLAB_BYTES = 2048 + 1024;      // (CTA-pair kernel) 16 pred rows + 8 enc rows, 128 B each
 constexpr int B_SLAB_MAX = 4096;               // slab stage of the largest tile geometry: 24 pred rows (3 KB) + 8 enc rows
 
 // Tile geometry of the single-CTA kernel: TT frames x P label columns, row = tloc*P + ul (TT*P <= 128).
@@ -83,14 +84,11 @@ struct BwdParams {
   //   gt [tile][2][Vp][64 rows]        : element (v, rr) at half rr>>6, row v, chunk ((rr&63)>>3) ^ (v&7), element rr&7
   __nv_bfloat16* zt;
   __nv_bfloat16* gt;
-  int g_rowmajor;           // 1: g is spilled as the G tile itself, [tile][2][KBG][64 rows][64 v] (bulk stores from smem)
   long Rpad;
-  int scratch_tile;         // unused row tile (kept for layout compatibility)
   float* d_enc_part;        // [S][B,T,D]
   float* d_pred;            // [B,U1,D] atomic accumulate
   float* d_bias;            // [V] atomic accumulate
   long long* prof;
-  int dbg;                  // timing experiments only (CTCVR_DBG): 1 = no W^T copies in P3, 2 = no MMAs in P3
 };
 
 // Shared memory: [GZ region: G tile (P2/P3) = A ring (P1) = z^T tile (P4)] [weight ring: 3 W stages = 5 W^T stages]
@@ -100,8 +98,8 @@ struct Bwd2Smem {
   float* bias_l2;
   float* dbp;               // [4][Vp] column-sum partials
   uint32_t* tmem_ptr;
-  __device__ __forceinline__ uint32_t a_stage(int i) const { return g_base + i * A_STAGE_BYTES; }
   __device__ __forceinline__ uint32_t g_kblock(int i) const { return g_base + i * A_STAGE_BYTES; }
+  __device__ __forceinline__ uint32_t z_stage(int i) const { return g_base + i * A_STAGE_BYTES; }
   __device__ __forceinline__ uint32_t z_box(int i) const { return g_base + i * A_STAGE_BYTES; }    // (mb*2 + half)
   __device__ __forceinline__ uint32_t r1_stage(int i) const { return r_base + i * r1_bytes; }
   __device__ __forceinline__ uint32_t r3_stage(int i) const { return r_base + i * 16384; }
@@ -127,8 +125,9 @@ __host__ __device__ inline uint32_t bwd2_ring_bytes(int NH) {
   return a > b ? a : b;
 }
 __host__ __device__ inline uint32_t bwd2_gz_blocks(int Vp, int D) {
-  const uint32_t kbg = (Vp + 63) / 64, zb = 2 * (D / 128);
-  return kbg > zb ? kbg : zb;
+  const uint32_t kbg = (Vp + 63) / 64, zb = 2 * (D / 128), ring = B_Z_STAGES;
+  const uint32_t m = kbg > zb ? kbg : zb;
+  return m > ring ? m : ring;               // P1 view: z^T staging
 }
 
 __host__ __device__ inline size_t bwd2_smem_bytes(int NH, int Vp, int D) {
@@ -138,7 +137,7 @@ __host__ __device__ inline size_t bwd2_smem_bytes(int NH, int Vp, int D) {
   s = (s + 1023) / 1024 * 1024;
   s += (size_t)B_S_STAGES * B_SLAB_MAX;
   s += (size_t)Vp * 4 + (size_t)4 * Vp * 4;
-  s += 304 + 392 + 16 + 16;            // barriers (+ the CTA-pair kernel's extra barriers) + tmem pointer
+  s += 304 + 16 + 16;                  // barriers + tmem pointer
   return s;
 }
 
@@ -152,7 +151,7 @@ __device__ __forceinline__ void carve_bwd2(Bwd2Smem& L, uint8_t* raw, int NH, in
   L.bias_l2 = reinterpret_cast<float*>(raw + (a - base)); a += Vp * 4;
   L.dbp = reinterpret_cast<float*>(raw + (a - base)); a += 4 * Vp * 4;
   a = (a + 15u) & ~15u;
-  L.bar_base = a; a += 304 + 392;
+  L.bar_base = a; a += 304;
   L.tmem_ptr = reinterpret_cast<uint32_t*>(raw + (a - base));
 }
 
@@ -174,15 +173,15 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_e);
     tma_prefetch_desc(&tmap_p);
-    for (int i = 0; i < B_A_STAGES; ++i) { mbar_init(L.a_full(i), PROD_THREADS); mbar_init(L.a_empty(i), 1); }
-    for (int i = 0; i < B_S_STAGES; ++i) { mbar_init(L.s_full(i), 1); mbar_init(L.s_empty(i), PROD_THREADS); }
+    for (int i = 0; i < B_A_STAGES; ++i) { mbar_init(L.a_full(i), PROD_THREADS / 32); mbar_init(L.a_empty(i), 1); }
+    for (int i = 0; i < B_S_STAGES; ++i) { mbar_init(L.s_full(i), 1); mbar_init(L.s_empty(i), PROD_THREADS / 32); }
     for (int i = 0; i < B_R1_STAGES; ++i) { mbar_init(L.r1_full(i), 1); mbar_init(L.r1_empty(i), 1); }
     for (int i = 0; i < B_R3_STAGES; ++i) { mbar_init(L.r3_full(i), 1); mbar_init(L.r3_empty(i), 1); }
     for (int i = 0; i < 4; ++i) mbar_init(L.z_full(i), 1);
     mbar_init(L.tmem_full(), 1);
-    mbar_init(L.g_full(), WORKERS);
+    mbar_init(L.g_full(), WORKERS / 32);
     mbar_init(L.dz_full(), 1);
-    mbar_init(L.tmem_empty(), 256);
+    mbar_init(L.tmem_empty(), 8);
     mbar_init(L.gs_done(), 1);
     fence_barrier_init();
   }
@@ -205,6 +204,7 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       // the ring is drained here: the previous tile's dz_full was observed below
       for (int i = 0; i < 2 * KB; ++i) {
         mbar_wait(L.r1_empty(r1.stage), r1.phase ^ 1u, 11);
+        if (lane == 0) TC_PROF(0, 10 + i);
         if (elect_one()) {
           mbar_arrive_expect_tx(L.r1_full(r1.stage), r1_bytes);
           bulk_load(L.r1_stage(r1.stage), p.w_t + (size_t)i * p.NH * 64, r1_bytes, L.r1_full(r1.stage));
@@ -218,12 +218,8 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       for (int i = 0; i < MB * KBG; ++i) {
         mbar_wait(L.r3_empty(r3.stage), r3.phase ^ 1u, 13);
         if (elect_one()) {
-          if (p.dbg & 1) {
-            mbar_arrive(L.r3_full(r3.stage));
-          } else {
-            mbar_arrive_expect_tx(L.r3_full(r3.stage), 16384u);
-            bulk_load(L.r3_stage(r3.stage), p.wt_t + (size_t)i * 8192, 16384u, L.r3_full(r3.stage));
-          }
+          mbar_arrive_expect_tx(L.r3_full(r3.stage), 16384u);
+          bulk_load(L.r3_stage(r3.stage), p.wt_t + (size_t)i * 8192, 16384u, L.r3_full(r3.stage));
         }
         __syncwarp();
         r3.advance(B_R3_STAGES);
@@ -233,7 +229,6 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       mbar_wait(L.gs_done(), ph, 16);             // ... and the d_bias column sums have read G
       if (lane == 0) TC_PROF(0, 5);
       if (elect_one()) {
-        fence_proxy_async_global();               // z^T was written with st.global by this CTA's producers
         for (int mb = 0; mb < MB; ++mb) {
           mbar_arrive_expect_tx(L.z_full(mb), 32768u);
           bulk_load(L.z_box(2 * mb), p.zt + ((rowtile * MB + mb) * 2) * 8192, 32768u, L.z_full(mb));
@@ -271,7 +266,6 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
     uint32_t ph = 0;
     const uint32_t idesc1 = make_idesc_bf16(BM, p.NH);
     const uint32_t idesc2 = make_idesc_bf16(128, BM);
-    const uint64_t a_desc0 = make_desc_sw128(L.a_stage(0));       // + stage * 1024 (16 KB >> 4)
     const uint64_t r1_desc0 = make_desc_sw128(L.r1_stage(0));     // + stage * NH * 8
     const uint64_t r3_desc0 = make_desc_sw128(L.r3_stage(0));     // + stage * 1024
     const uint64_t g_desc0 = make_desc_sw128(L.g_kblock(0));      // + kb * 1024
@@ -284,17 +278,19 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       tc_fence_after();
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(L.a_full(ap.stage), ap.phase, 21);
+        if (lane == 0) TC_PROF(1, 50 + kb);
         for (int h = 0; h < 2; ++h) {
           mbar_wait(L.r1_full(r1.stage), r1.phase, 22);
+          if (lane == 0) TC_PROF(1, 100 + kb * 2 + h);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t ad = a_desc0 + (uint64_t)(ap.stage * (A_STAGE_BYTES >> 4));
+            const uint32_t a = tmem_base + B_ACC_COLS + ap.stage * 32;
             const uint64_t bd = r1_desc0 + (uint64_t)(r1.stage * r1_step);
             const uint32_t d = tmem_base + h * p.NH;
-            umma_bf16(d, ad, bd, idesc1, kb ? 1u : 0u);
-            umma_bf16(d, ad + 2, bd + 2, idesc1, 1u);
-            umma_bf16(d, ad + 4, bd + 4, idesc1, 1u);
-            umma_bf16(d, ad + 6, bd + 6, idesc1, 1u);
+            umma_bf16_ts(d, a, bd, idesc1, kb ? 1u : 0u);
+            umma_bf16_ts(d, a + 8, bd + 2, idesc1, 1u);
+            umma_bf16_ts(d, a + 16, bd + 4, idesc1, 1u);
+            umma_bf16_ts(d, a + 24, bd + 6, idesc1, 1u);
             umma_commit(L.r1_empty(r1.stage));
             if (h == 1) umma_commit(L.a_empty(ap.stage));
           }
@@ -318,7 +314,7 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
             const uint64_t ad = r3_desc0 + (uint64_t)(r3.stage * 1024);
             const uint64_t bd = g_desc0 + (uint64_t)(kb * 1024);
             const uint32_t d = tmem_base + mb * 128;
-            const int nks = (p.dbg & 2) ? 0 : (kb == KBG - 1 ? last_nks : 4);
+            const int nks = kb == KBG - 1 ? last_nks : 4;
             if (nks > 0) umma_bf16(d, ad, bd, idesc2, kb ? 1u : 0u);
             if (nks > 1) umma_bf16(d, ad + 2, bd + 2, idesc2, 1u);
             if (nks > 2) umma_bf16(d, ad + 4, bd + 4, idesc2, 1u);
@@ -341,10 +337,10 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
     const int r = q * 32 + lane;               // P2: tile row ; P4: lane of the d block
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool producer = warp >= 8;
-    const int pc = (warp - 8) & 7;             // producer: 16-byte chunk of the k-block handled by this warp
     uint32_t ph = 0;
     int prof_n = 0;
     Pipe ap, sp;
+    int zp = 0;
     float db0 = 0.f, db1 = 0.f;                // d_bias of columns wt and wt + 384
     float pacc[2][P];                          // d_pred sums of d blocks 2wg, 2wg+1 over the tiles of one (b, u-split) sweep
 #pragma unroll
@@ -368,16 +364,15 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
         }
       }
     };
-    // producer addressing: tile rows lane, lane+32, lane+64, lane+96 (row = tloc*P + ul); rows >= TT*P are padding
-    uint32_t e_off[4], p_off[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int rr = lane + 32 * j;
-      const int tloc = min(rr / P, TT - 1), ul = rr % P;
-      e_off[j] = bwd_pred_region<P>() + (uint32_t)tloc * 128u + (uint32_t)((pc ^ (tloc & 7)) << 4);
-      p_off[j] = (uint32_t)ul * 128u + (uint32_t)((pc ^ (ul & 7)) << 4);
-    }
-    const uint32_t a_off = (uint32_t)lane * 128u + (uint32_t)((pc ^ (lane & 7)) << 4);
+    // producer addressing (A operand lives in TMEM): thread = tile row r = 32q + lane (its own TMEM lane), k-half kh:
+    // 32 of the 64 k of a k-block -> 16 packed bf16x2 -> one tcgen05.st ; rows >= TT*P are padding
+    const int kh = (warp - 8) >> 2;
+    const int p_tloc = min(r / P, TT - 1), p_ul = r % P;
+    const uint32_t e_row = bwd_pred_region<P>() + (uint32_t)p_tloc * 128u, e_sw = (uint32_t)(p_tloc & 7);
+    const uint32_t p_row = (uint32_t)p_ul * 128u, p_sw = (uint32_t)(p_ul & 7);
+    // z^T staging of the same values: row kh*32 + d of the 64-d k-block, half r>>6, 16-byte chunk ((r&63)>>3) ^ (d&7)
+    const uint32_t z_off = (uint32_t)(r >> 6) * 8192u + (uint32_t)(kh * 32) * 128u + (uint32_t)(r & 7) * 2u;
+    const uint32_t z_chunk = (uint32_t)((r & 63) >> 3);
 
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       int4 ti = p.tiles[tile];
@@ -387,46 +382,59 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       if (g.b != cur_b || g.ubase != cur_ubase) { flush_pred(); cur_b = g.b; cur_ubase = g.ubase; }
       const size_t rowtile = (size_t)ti.w;
 
-      // ---------------- P1 (warps 8-15): A tile k-blocks + z^T spill
+      // ---------------- P1 (warps 8-15): A k-blocks into TMEM + z^T spill (staged in shared memory, bulk-stored)
       if (producer) {
-        // the A ring overlays the z^T tile of the previous iteration: wait until its readers (P4) are done
+        // the staging blocks overlay the z^T tile of the previous iteration, the A columns its dZ^T accumulator:
+        // wait until its readers (P4) are done
         mbar_wait(L.tmem_empty(), ph ^ 1u, 40);
         if (tid == 256) TC_PROF(3, 1);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(L.s_full(sp.stage), sp.phase, 41);
           mbar_wait(L.a_empty(ap.stage), ap.phase ^ 1u, 42);
+          tc_fence_after();
           const uint32_t sb = L.s_stage(sp.stage);
-          const uint32_t ab = L.a_stage(ap.stage) + a_off;
-          // d = kb*64 + pc*8 + e -> box row (kb&1)*64 + pc*8 + e of d block kb>>1; tile row lane + 32j -> half j>>1
-          unsigned short* z = reinterpret_cast<unsigned short*>(p.zt) + ((rowtile * MB + (kb >> 1)) * 2) * 8192 +
-                              ((kb & 1) * 64 + pc * 8) * 64 + (lane & 7);
+          uint4 ev[4], pv[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 ev = lds128(sb + e_off[j]);
-            const uint4 pv = lds128(sb + p_off[j]);
-            uint32_t w[4];
-            w[0] = tanh_add_bf16x2_packed(ev.x, pv.x);
-            w[1] = tanh_add_bf16x2_packed(ev.y, pv.y);
-            w[2] = tanh_add_bf16x2_packed(ev.z, pv.z);
-            w[3] = tanh_add_bf16x2_packed(ev.w, pv.w);
-            sts128(ab + j * 4096, w[0], w[1], w[2], w[3]);
-            const int chunk = (lane >> 3) + 4 * (j & 1);           // 8-row chunk of the 64-row half
-            unsigned short* zj = z + (j >> 1) * 8192;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              zj[(2 * e) * 64 + ((chunk ^ (2 * e)) << 3)] = (unsigned short)(w[e] & 0xffffu);
-              zj[(2 * e + 1) * 64 + ((chunk ^ (2 * e + 1)) << 3)] = (unsigned short)(w[e] >> 16);
-            }
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const uint32_t c = (uint32_t)(kh * 4 + c4);
+            ev[c4] = lds128(sb + e_row + ((c ^ e_sw) << 4));
+            pv[c4] = lds128(sb + p_row + ((c ^ p_sw) << 4));
           }
+          uint32_t w[16];
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            w[4 * c4 + 0] = tanh_add_bf16x2_packed(ev[c4].x, pv[c4].x);
+            w[4 * c4 + 1] = tanh_add_bf16x2_packed(ev[c4].y, pv[c4].y);
+            w[4 * c4 + 2] = tanh_add_bf16x2_packed(ev[c4].z, pv[c4].z);
+            w[4 * c4 + 3] = tanh_add_bf16x2_packed(ev[c4].w, pv[c4].w);
+          }
+          tmem_st16(tq + (uint32_t)(B_ACC_COLS + ap.stage * 32 + kh * 16), w);
+          const uint32_t zs = L.z_stage(zp) + z_off;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            // w[i] holds d = 2i, 2i+1 of this thread's 32
+            sts16(zs + (2 * i) * 128 + ((z_chunk ^ (uint32_t)((2 * i) & 7)) << 4), w[i] & 0xffffu);
+            sts16(zs + (2 * i + 1) * 128 + ((z_chunk ^ (uint32_t)((2 * i + 1) & 7)) << 4), w[i] >> 16);
+          }
+          tmem_st_wait();
+          tc_fence_before();
           fence_proxy_async();
-          mbar_arrive(L.a_full(ap.stage));
-          mbar_arrive(L.s_empty(sp.stage));
+          warp_arrive(L.a_full(ap.stage));
+          warp_arrive(L.s_empty(sp.stage));
+          named_barrier_sync(4, PROD_THREADS);        // the staged k-block is complete (and fenced) in shared memory
+          if (tid == 256) {
+            __nv_bfloat16* zdst = p.zt + ((rowtile * MB + (kb >> 1)) * 2) * 8192 + (kb & 1) * 4096;
+            bulk_store(zdst, L.z_stage(zp), 8192u);
+            bulk_store(zdst + 8192, L.z_stage(zp) + 8192u, 8192u);
+            bulk_commit();
+            bulk_wait_read<1>();                      // the k-block staged before this one has left shared memory
+          }
+          zp = (zp + 1 == B_Z_STAGES) ? 0 : zp + 1;
           ap.advance(B_A_STAGES);
           sp.advance(B_S_STAGES);
         }
+        if (tid == 256) bulk_wait_all<0>();           // z^T is in global memory before P4's bulk loads (ordered via g_full)
         if (tid == 256) TC_PROF(3, 2);
-        fence_proxy_async_global();                  // z^T (st.global above) is read back by the P4 TMA load
-        if (tid == 256) TC_PROF(3, 3);
       }
 
       // ---------------- P2: g = d cost / d logits for row r, column chunks wg, wg+3, ...
@@ -451,6 +459,7 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       const float kr = (valid && fast) ? fmaf(k_all, LOG2E, lg2_fast(scale)) : kNegInf;
       if (tid == 128) TC_PROF(2, 1);
       mbar_wait(L.tmem_full(), ph, 30);
+      named_barrier_sync(5, WORKERS);            // the z^T staging blocks (overlaid by G) have been stored
       if (tid == 128) TC_PROF(2, 2);
       tc_fence_after();
       for (int c0 = wg * 32; c0 < p.Vp; c0 += 96) {
@@ -489,18 +498,8 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           sts128(gb + (((ch0 + i) ^ (r & 7)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-        if (!p.g_rowmajor) {
-          // g^T spill (tiled): column v of this row -> gt[tile][r>>6][v][chunk ((r&63)>>3) ^ (v&7)][r&7]
-          unsigned short* gt = reinterpret_cast<unsigned short*>(p.gt) + ((rowtile * 2 + (r >> 6)) * p.Vp + c0) * 64 + (r & 7);
-          const int gch = (r & 63) >> 3;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            gt[(2 * j) * 64 + ((gch ^ ((2 * j) & 7)) << 3)] = (unsigned short)(pk[j] & 0xffffu);
-            gt[(2 * j + 1) * 64 + ((gch ^ ((2 * j + 1) & 7)) << 3)] = (unsigned short)(pk[j] >> 16);
-          }
-        }
       }
-      named_barrier_sync(2, WORKERS);            // every generic entry of G / g^T is written
+      named_barrier_sync(2, WORKERS);            // every generic entry of G is written
       if (wg == 0) {
         // exact (fp32, single rounding) blank and label entries of row r
         const float xb = tmem_ld1(tq + p.blank);
@@ -524,9 +523,6 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
             const unsigned short h = __bfloat16_as_ushort(__float2bfloat16(val));
             const uint32_t a = L.g_kblock(col >> 6) + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4) + (col & 7) * 2;
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(h) : "memory");
-            if (!p.g_rowmajor)
-              reinterpret_cast<unsigned short*>(p.gt)[((rowtile * 2 + (r >> 6)) * p.Vp + col) * 64 +
-                                                      ((((r & 63) >> 3) ^ (col & 7)) << 3) + (r & 7)] = h;
           };
           const float xbb = xb + __ldg(p.bias + p.blank);
           put(p.blank, entry(xbb, k_blank, (lab == p.blank) ? k_label : kNegInf));
@@ -535,12 +531,12 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       }
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(L.g_full());
+      warp_arrive(L.g_full());
       if (tid == 128) TC_PROF(2, 3);
 
       // ---------------- P3 (MMA busy): d_bias = column sums of the final G tile
       mbar_wait(L.g_full(), ph, 31);
-      if (p.g_rowmajor && wt == 0) {
+      if (wt == 0) {
         // spill the finished G tile as it lies in shared memory: k-block i (64 label columns) -> two 8 KB boxes
         // [64 rows][64 v] (rows 0-63 / 64-127), read back MN-major by the dW GEMM.  No per-thread stores.
         __nv_bfloat16* gdst = p.gt + (rowtile * 2) * (size_t)KBG * 4096;
@@ -570,7 +566,7 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
         }
         named_barrier_sync(2, WORKERS);
         if (wt == 0) {
-          if (p.g_rowmajor) bulk_wait_read<0>();      // the bulk stores have read G
+          bulk_wait_read<0>();                        // the bulk stores have read G
           mbar_arrive(L.gs_done());
         }
         if (wt < p.Vp) db0 += (L.dbp[wt] + L.dbp[p.Vp + wt]) + (L.dbp[2 * p.Vp + wt] + L.dbp[3 * p.Vp + wt]);
@@ -630,7 +626,7 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
           }
         }
         tc_fence_before();
-        mbar_arrive(L.tmem_empty());
+        warp_arrive(L.tmem_empty());
         if (tid == 128) TC_PROF(2, 5);
       }
       ph ^= 1u;

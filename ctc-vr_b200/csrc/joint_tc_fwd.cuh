@@ -105,11 +105,11 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_e);
     tma_prefetch_desc(&tmap_p);
-    for (int i = 0; i < F_A_STAGES; ++i) { mbar_init(L.a_full(i), PROD_THREADS); mbar_init(L.a_empty(i), 1); }
-    for (int i = 0; i < F_S_STAGES; ++i) { mbar_init(L.s_full(i), 1); mbar_init(L.s_empty(i), PROD_THREADS); }
+    for (int i = 0; i < F_A_STAGES; ++i) { mbar_init(L.a_full(i), PROD_THREADS / 32); mbar_init(L.a_empty(i), 1); }
+    for (int i = 0; i < F_S_STAGES; ++i) { mbar_init(L.s_full(i), 1); mbar_init(L.s_empty(i), PROD_THREADS / 32); }
     for (int i = 0; i < F_MAX_W_STAGES; ++i) { mbar_init(L.w_full(i), 1); mbar_init(L.w_empty(i), 1); }
     mbar_init(L.tmem_full(), 1);
-    mbar_init(L.tmem_empty(), 256);
+    mbar_init(L.tmem_empty(), 8);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(L.tmem_ptr), TMEM_COLS);
@@ -254,7 +254,7 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
         m = nm;
       }
       tc_fence_before();
-      mbar_arrive(L.tmem_empty());
+      warp_arrive(L.tmem_empty());
       if (tid == 128) TC_PROF(2, 2);
       if (eg == 1) { L.epi_x[erow] = make_float2(m, s); }
       named_barrier_sync(3, 256);                          // group 1's partials are visible
@@ -309,8 +309,8 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
         tmem_st16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(F_ACC_COLS + ap.stage * 32 + kh * 16), w);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(L.a_full(ap.stage));
-        mbar_arrive(L.s_empty(sp.stage));
+        warp_arrive(L.a_full(ap.stage));
+        warp_arrive(L.s_empty(sp.stage));
         if (tid == 384) TC_PROF(3, 20 + kb);
         ap.advance(F_A_STAGES);
         sp.advance(F_S_STAGES);
