@@ -38,7 +38,7 @@ constexpr int PROF_CAP = 2048;
 // timeline probe for CTA 0 (one lane per role); compiled in always, active only when p.prof != nullptr
 #define TC_PROF(role, tag)                                                                         \
   do {                                                                                             \
-    if (p.prof != nullptr && blockIdx.x == 0) {                                                    \
+    if (p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {                                                   \
       int _n = prof_n++;                                                                           \
       if (_n < PROF_CAP) p.prof[(role)*PROF_CAP + _n] = ((long long)(tag) << 48) | (clock64() & 0xffffffffffffLL); \
     }                                                                                              \
@@ -139,35 +139,73 @@ __global__ void reduce_denc_kernel(const float* __restrict__ part, const int32_t
 }
 
 // =================================================================================================
-// Backward kernel 2: dW^T[d][v] = sum_rows z^T[d][row] * g[row][v]  (bulk-copy-fed tcgen05 GEMM, split-K)
+// Backward kernel 2: dW^T[d][v] = sum_rows z^T[d][row] * g[row][v]  (tcgen05 GEMM, split-K over the row tiles).
+// g is read as the row-major G tiles spilled by kernel 1 ([tile][2][KBG][64 rows][64 v], one 1-D bulk copy per 64-row
+// stage): the B operand is MN-major (label columns contiguous), N split at a multiple of 64 columns (256 + the rest).
+// z^T is RECOMPUTED instead of spilled by kernel 1 and read back: z = tanh(enc + pred) costs one MUFU op per element
+// (512 cycles per 64-row stage per SM, under the 832 cycles of the stage's MMAs), whereas a z^T spill is
+// D x rows x 2 B = 352 MB at cfg2, written once and read once from HBM.  The A operand lives in TMEM (TS mode):
+// lane = d, one 32-bit column per pair of rows.  Producer thread = (d, 32 rows of the stage); it holds the TT enc and
+// P pred values of its d for the current row tile in registers, read from a TMA-staged slab once per 128 rows.
+// TMEM: accumulators [0, Vp) | A stages 416.. (3 x 32 columns).
 // =================================================================================================
 constexpr int DW_STAGES = 3;
-constexpr int DW_THREADS = 256;
+constexpr int DWR_THREADS = 384;
+constexpr int DWR_A_STAGES = 3;
+constexpr int DWR_ACC_COLS = 416;
 
-// g is read as spilled row-major G tiles ([tile][2][KBG][64 rows][64 v], written by bulk stores from the
-// backward kernel's shared-memory G tile): the B operand is MN-major (label columns contiguous), N split at a
-// multiple of 64 columns (256 + the rest), one 1-D bulk load per operand and stage.
-__global__ void __launch_bounds__(DW_THREADS, 1)
-dw_gemm_mn_kernel(const __nv_bfloat16* __restrict__ zt, const __nv_bfloat16* __restrict__ gr,
+// rows R0 .. R0+31 of a tile: 16 packed (row 2c, row 2c+1) pairs of tanh(e[tloc] + p[ul]), row = tloc*P + ul
+template <int P, int TT, int R0>
+__device__ __forceinline__ void dwr_rows(const uint32_t (&e)[TT], const uint32_t (&pr)[P], uint32_t (&w)[16]) {
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const int r0 = R0 + 2 * c, r1 = r0 + 1;
+    const int tl0 = (r0 / P < TT) ? r0 / P : TT - 1, tl1 = (r1 / P < TT) ? r1 / P : TT - 1;
+    const int u0 = r0 % P, u1 = r1 % P;
+    const uint32_t ep = __byte_perm(e[tl0], e[tl1], 0x5410);
+    const uint32_t pp = __byte_perm(pr[u0], pr[u1], 0x5410);
+    w[c] = tanh_add_bf16x2_packed(ep, pp);
+  }
+}
+
+constexpr int DWR_S_STAGES = 3;
+template <int P>
+__host__ __device__ constexpr uint32_t dwr_slab_bytes() {          // [d half][pred region | enc region], 1 KB aligned (SW128)
+  return 2u * (bwd_pred_region<P>() + 1024u);
+}
+
+template <int P, int TT>
+__global__ void __launch_bounds__(DWR_THREADS, 1)
+dw_gemm_rz_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_p,
+                  const __nv_bfloat16* __restrict__ gr, const int4* __restrict__ tile_rows,
                   const int* __restrict__ ntiles_ptr, float* __restrict__ partials, int D, int Vp, int KBG, int KS) {
+  static_assert(TT <= 8, "enc region is one 1 KB swizzle atom");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   const uint32_t al = (base + 1023u) & ~1023u;
-  const uint32_t b_bytes = (uint32_t)KBG * 8192u;
-  const uint32_t stage_bytes = A_STAGE_BYTES + b_bytes;
-  const uint32_t bar = al + DW_STAGES * stage_bytes;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem_raw + (bar + 128 - base));
+  const uint32_t b_bytes = (uint32_t)KBG * 8192u;          // one 64-row half of a G tile: [KBG][64 rows][64 v]
+  const uint32_t slab = al + DW_STAGES * b_bytes;          // DWR_S_STAGES slabs of enc / pred rows (one per row tile)
+  const uint32_t bar = slab + DWR_S_STAGES * dwr_slab_bytes<P>();
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem_raw + (bar + 192 - base));
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int mb = blockIdx.x, ks = blockIdx.y;
-  const size_t MBD = (size_t)(D / 128);
-  const int kblocks = (*ntiles_ptr) * 2;
+  const int kblocks = (*ntiles_ptr) * 2;                   // 64-row k-blocks written by kernel 1
   const int kb_begin = (int)(((long)kblocks * ks) / KS), kb_end = (int)(((long)kblocks * (ks + 1)) / KS);
+  const int rt_begin = kb_begin >> 1, rt_end = (kb_end + 1) >> 1;
   auto full = [&](int i) { return bar + i * 16; };
   auto empty = [&](int i) { return bar + i * 16 + 8; };
-  const uint32_t done = bar + DW_STAGES * 16;
+  auto a_full = [&](int i) { return bar + 48 + i * 16; };
+  auto a_empty = [&](int i) { return bar + 48 + i * 16 + 8; };
+  auto s_full = [&](int i) { return bar + 96 + i * 16; };
+  auto s_empty = [&](int i) { return bar + 96 + i * 16 + 8; };
+  const uint32_t done = bar + 144;
 
   if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_e);
+    tma_prefetch_desc(&tmap_p);
     for (int i = 0; i < DW_STAGES; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+    for (int i = 0; i < DWR_A_STAGES; ++i) { mbar_init(a_full(i), 8); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < DWR_S_STAGES; ++i) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 8); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -178,64 +216,128 @@ dw_gemm_mn_kernel(const __nv_bfloat16* __restrict__ zt, const __nv_bfloat16* __r
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
+    // ---- G loader: one 1-D bulk copy per stage
     Pipe sp;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(empty(sp.stage), sp.phase ^ 1u, 50);
       if (elect_one()) {
-        const uint32_t st = al + sp.stage * stage_bytes;
-        mbar_arrive_expect_tx(full(sp.stage), stage_bytes);
-        const size_t rt = (size_t)(kb >> 1), hh = (size_t)(kb & 1);
-        bulk_load(st, zt + ((rt * MBD + mb) * 2 + hh) * 8192, A_STAGE_BYTES, full(sp.stage));
-        bulk_load(st + A_STAGE_BYTES, gr + ((rt * 2 + hh) * (size_t)KBG) * 4096, b_bytes, full(sp.stage));
+        mbar_arrive_expect_tx(full(sp.stage), b_bytes);
+        bulk_load(al + sp.stage * b_bytes, gr + (size_t)kb * KBG * 4096, b_bytes, full(sp.stage));
       }
       __syncwarp();
       sp.advance(DW_STAGES);
     }
+  } else if (warp == 3) {
+    // ---- slab loader: the P pred rows and TT enc rows of each row tile, this CTA's 128 d as two 64-wide boxes
+    Pipe ss;
+    for (int rt = rt_begin; rt < rt_end; ++rt) {
+      mbar_wait(s_empty(ss.stage), ss.phase ^ 1u, 55);
+      if (elect_one()) {
+        const int4 tr = __ldg(tile_rows + rt);             // {first enc row, first pred row, ..}
+        const uint32_t st = slab + ss.stage * dwr_slab_bytes<P>();
+        mbar_arrive_expect_tx(s_full(ss.stage), 2u * (uint32_t)(P + TT) * 128u);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t sh = st + h * (bwd_pred_region<P>() + 1024u);
+          tma_load_2d(sh, &tmap_p, s_full(ss.stage), mb * 128 + h * 64, tr.y);
+          tma_load_2d(sh + bwd_pred_region<P>(), &tmap_e, s_full(ss.stage), mb * 128 + h * 64, tr.x);
+        }
+      }
+      __syncwarp();
+      ss.advance(DWR_S_STAGES);
+    }
   } else if (warp == 1) {
-    Pipe sp;
+    // ---- MMA issuer: D[128 d][Vp] += z^T (TMEM) . G (MN-major B, N split 256 + rest)
+    Pipe sp, ap;
     const int N0 = min(256, Vp), N1 = Vp - N0;
     const uint32_t idesc0 = make_idesc_bf16_bmn(128, N0);
     const uint32_t idesc1 = make_idesc_bf16_bmn(128, N1 > 0 ? N1 : 16);
-    const uint64_t a_desc0 = make_desc_sw128(al);
-    const uint64_t b_desc0 = make_desc_mn_sw128(al + A_STAGE_BYTES, 8192u, 1024u);
-    const uint32_t st_step = stage_bytes >> 4;
+    const uint64_t b_desc0 = make_desc_mn_sw128(al, 8192u, 1024u);
+    const uint32_t st_step = b_bytes >> 4;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(a_full(ap.stage), ap.phase, 53);
       mbar_wait(full(sp.stage), sp.phase, 51);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t ad = a_desc0 + (uint64_t)(sp.stage * st_step);
+        const uint32_t a = tmem_base + DWR_ACC_COLS + ap.stage * 32;
         const uint64_t bd = b_desc0 + (uint64_t)(sp.stage * st_step);
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
           const uint32_t acc = (kb > kb_begin || k4 > 0) ? 1u : 0u;
-          umma_bf16(tmem_base, ad + 2 * k4, bd + 128 * k4, idesc0, acc);
-          if (N1 > 0) umma_bf16(tmem_base + 256, ad + 2 * k4, bd + 2048 + 128 * k4, idesc1, acc);
+          umma_bf16_ts(tmem_base, a + 8 * k4, bd + 128 * k4, idesc0, acc);
+          if (N1 > 0) umma_bf16_ts(tmem_base + 256, a + 8 * k4, bd + 2048 + 128 * k4, idesc1, acc);
         }
         umma_commit(empty(sp.stage));
+        umma_commit(a_empty(ap.stage));
       }
       __syncwarp();
       sp.advance(DW_STAGES);
+      ap.advance(DWR_A_STAGES);
     }
     if (elect_one()) umma_commit(done);
     __syncwarp();
   } else if (warp >= 4) {
-    const int q = warp & 3;
-    const int d = mb * 128 + q * 32 + lane;
-    float* out = partials + ((size_t)ks * D + d) * Vp;
-    if (kb_end > kb_begin) {
-      mbar_wait(done, 0, 52);
-      tc_fence_after();
-      for (int c0 = 0; c0 < Vp; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-        tmem_ld_wait();
-        if (d < D) {
+    // ---- producers: warp = (d quarter q, row half rh of the 64-row stage); lane = d
+    const int q = warp & 3, rh = (warp - 4) >> 2;
+    const int dl = q * 32 + lane;                          // d within the CTA's 128
+    const int d = mb * 128 + dl;
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+    // slab addressing: box half dl>>6, 16-byte chunk ((dl&63)>>3) ^ (row & 7), element dl&7
+    const uint32_t s_off = (uint32_t)(dl >> 6) * (bwd_pred_region<P>() + 1024u) + (uint32_t)(dl & 7) * 2u;
+    const uint32_t s_chunk = (uint32_t)((dl & 63) >> 3);
+    Pipe ap, ss;
+    for (int rt = rt_begin; rt < rt_end; ++rt) {
+      uint32_t e[TT], pr[P];
+      mbar_wait(s_full(ss.stage), ss.phase, 56);
+      {
+        const uint32_t st = slab + ss.stage * dwr_slab_bytes<P>() + s_off;
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+          unsigned short v;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(st + i * 128 + ((s_chunk ^ (uint32_t)(i & 7)) << 4)));
+          pr[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < TT; ++i) {
+          unsigned short v;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(st + bwd_pred_region<P>() + i * 128 + ((s_chunk ^ (uint32_t)(i & 7)) << 4)));
+          e[i] = v;
+        }
+      }
+      warp_arrive(s_empty(ss.stage));
+      ss.advance(DWR_S_STAGES);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int kb = rt * 2 + hh;
+        if (kb < kb_begin || kb >= kb_end) continue;
+        uint32_t w[16];
+        if (hh == 0) { if (rh == 0) dwr_rows<P, TT, 0>(e, pr, w); else dwr_rows<P, TT, 32>(e, pr, w); }
+        else         { if (rh == 0) dwr_rows<P, TT, 64>(e, pr, w); else dwr_rows<P, TT, 96>(e, pr, w); }
+        mbar_wait(a_empty(ap.stage), ap.phase ^ 1u, 54);
+        tc_fence_after();
+        tmem_st16(tq + (uint32_t)(DWR_ACC_COLS + ap.stage * 32 + rh * 16), w);
+        tmem_st_wait();
+        tc_fence_before();
+        warp_arrive(a_full(ap.stage));
+        ap.advance(DWR_A_STAGES);
+      }
+    }
+    // ---- epilogue (warps 4-7): accumulators -> split-K partials
+    if (rh == 0) {
+      float* out = partials + ((size_t)ks * D + d) * Vp;
+      if (kb_end > kb_begin) {
+        mbar_wait(done, 0, 52);
+        tc_fence_after();
+        for (int c0 = 0; c0 < Vp; c0 += 32) {
+          float v[32];
+          tmem_ld32(tq + c0, v);
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
+      } else {
+        for (int c0 = 0; c0 < Vp; c0 += 4) *reinterpret_cast<float4*>(out + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    } else if (d < D) {
-      for (int c0 = 0; c0 < Vp; c0 += 4) *reinterpret_cast<float4*>(out + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   tc_fence_before();
@@ -296,8 +398,8 @@ __device__ __forceinline__ int block_prefix(int mine_upto, Count count) {
 // frame blocks (the CTA-pair kernel processes tiles 2i, 2i+1 of one sweep together; a padding tile lies beyond T_b).
 // Entry = {b, u-split, frame block, tile index}.
 __global__ void build_tiles_kernel(const int32_t* __restrict__ t_len, const int32_t* __restrict__ u_len, int B, int T,
-                                   int U1, int geom, int4* __restrict__ tiles, int* __restrict__ ntiles,
-                                   int max_tiles) {
+                                   int U1, int geom, int4* __restrict__ tiles, int4* __restrict__ tile_rows,
+                                   int* __restrict__ ntiles, int max_tiles) {
   const int P = geom & 0xff, TT = (geom >> 8) & 0xff, even = (geom >> 16) & 1;
   auto ntb_of = [&](int Tb) { const int n = (Tb + TT - 1) / TT; return even ? ((n + 1) & ~1) : n; };
   auto count = [&](int i) {
@@ -311,7 +413,15 @@ __global__ void build_tiles_kernel(const int32_t* __restrict__ t_len, const int3
   const int NTB = ntb_of(Tb);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int s = i / NTB, tb = i - s * NTB;
-    if (off + i < max_tiles) tiles[off + i] = make_int4(b, s, tb, off + i);
+    if (off + i < max_tiles) {
+      tiles[off + i] = make_int4(b, s, tb, off + i);
+      if (tile_rows) {
+        // first enc / pred row of the tile and how many rows may be read past them (kernel 2 recomputes z from these)
+        const int W = min(u_len[b], U1 - 1) + 1, S = (W + P - 1) / P, us = (W + S - 1) / S;
+        const int t0 = tb * TT, ub = s * us;
+        tile_rows[off + i] = make_int4(b * T + min(t0, T - 1), b * U1 + min(ub, U1 - 1), max(T - 1 - t0, 0), max(U1 - 1 - ub, 0));
+      }
+    }
   }
   if (b == B - 1 && threadIdx.x == 0) *ntiles = min(off + n, max_tiles);
 }
@@ -542,7 +652,7 @@ bool joint_tc_bwd_supported(int U1, int D, int V) {
 struct BwdWs {
   __nv_bfloat16 *wb, *wtb, *zt, *gt, *eb, *pb;
   float *bias_pad, *bias_l2, *d_enc_part, *partials;
-  int4* tiles;
+  int4 *tiles, *tile_rows;
   int* ntiles;
   long Rpad;
   int KS, S_max, mt;
@@ -567,8 +677,9 @@ static BwdWs carve_bwd_ws(void* ws, int B, int T, int U1, int D, int V) {
   w.bias_pad = reinterpret_cast<float*>(take((size_t)Vp * 4));
   w.bias_l2 = reinterpret_cast<float*>(take((size_t)Vp * 4));
   w.tiles = reinterpret_cast<int4*>(take((size_t)w.mt * 16));
+  w.tile_rows = reinterpret_cast<int4*>(take((size_t)w.mt * 16));
   w.ntiles = reinterpret_cast<int*>(take(4));
-  w.zt = reinterpret_cast<__nv_bfloat16*>(take((size_t)D * w.Rpad * 2));
+  w.zt = reinterpret_cast<__nv_bfloat16*>(take((size_t)D * BM * 2 * sm_count()));   // per-CTA z^T tile scratch (stays in L2)
   w.gt = reinterpret_cast<__nv_bfloat16*>(take((size_t)((Vp + 63) / 64) * 64 * w.Rpad * 2));
   w.d_enc_part = reinterpret_cast<float*>(take((size_t)w.S_max * B * T * D * 4));
   w.partials = reinterpret_cast<float*>(take((size_t)w.KS * D * Vp * 4));
@@ -601,7 +712,7 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
   CTCVR_LAUNCH_CHECK();
   const int mt = W.mt;
   const RectGeom G = pick_rect_geom(T, U1);
-  build_tiles_kernel<<<B, 128, 0, st>>>(t_len, u_len, B, T, U1, G.P | (G.TT << 8) | (G.even << 16), W.tiles, W.ntiles, mt);
+  build_tiles_kernel<<<B, 128, 0, st>>>(t_len, u_len, B, T, U1, G.P | (G.TT << 8) | (G.even << 16), W.tiles, W.tile_rows, W.ntiles, mt);
   CTCVR_LAUNCH_CHECK();
   CTCVR_CHECK_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)B * U1 * D * sizeof(float), st));
   CTCVR_CHECK_CUDA(cudaMemsetAsync(d_b, 0, (size_t)V * sizeof(float), st));
@@ -644,10 +755,22 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
   reduce_denc_kernel<<<B * T, 128, 0, st>>>(W.d_enc_part, t_len, u_len, d_enc, B, T, U1, D, G.P);
   CTCVR_LAUNCH_CHECK();
   {
-    const size_t smem = 1024 + (size_t)DW_STAGES * (A_STAGE_BYTES + (size_t)KBG * 8192) + 256;
-    CTCVR_REQUIRE(smem <= 232448, "dW GEMM: shared memory budget exceeded (%zu B)", smem);
-    CTCVR_CHECK_CUDA(cudaFuncSetAttribute(dw_gemm_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dw_gemm_mn_kernel<<<dim3(MB, W.KS), DW_THREADS, smem, st>>>(W.zt, W.gt, W.ntiles, W.partials, D, Vp, KBG, W.KS);
+    CUtensorMap tmap_e, tmap_p;          // the same 64-wide SW128 boxes as kernel 1: TT enc rows / P pred rows
+    if (make_tmap_bf16_2d(&tmap_e, W.eb, (uint64_t)B * T, D, D, G.TT)) return 1;
+    if (make_tmap_bf16_2d(&tmap_p, W.pb, (uint64_t)B * U1, D, D, G.P)) return 1;
+    if (G.P == 21) {
+      const size_t smem = 1024 + (size_t)DW_STAGES * ((size_t)KBG * 8192) + DWR_S_STAGES * dwr_slab_bytes<21>() + 256;
+      CTCVR_REQUIRE(smem <= 232448, "dW GEMM: shared memory budget exceeded (%zu B)", smem);
+      CTCVR_CHECK_CUDA(cudaFuncSetAttribute(dw_gemm_rz_kernel<21, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dw_gemm_rz_kernel<21, 6><<<dim3(MB, W.KS), DWR_THREADS, smem, st>>>(tmap_e, tmap_p, W.gt, W.tile_rows, W.ntiles,
+                                                                         W.partials, D, Vp, KBG, W.KS);
+    } else {
+      const size_t smem = 1024 + (size_t)DW_STAGES * ((size_t)KBG * 8192) + DWR_S_STAGES * dwr_slab_bytes<16>() + 256;
+      CTCVR_REQUIRE(smem <= 232448, "dW GEMM: shared memory budget exceeded (%zu B)", smem);
+      CTCVR_CHECK_CUDA(cudaFuncSetAttribute(dw_gemm_rz_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dw_gemm_rz_kernel<16, 8><<<dim3(MB, W.KS), DWR_THREADS, smem, st>>>(tmap_e, tmap_p, W.gt, W.tile_rows, W.ntiles,
+                                                                         W.partials, D, Vp, KBG, W.KS);
+    }
     CTCVR_LAUNCH_CHECK();
   }
   reduce_dw_kernel<<<dim3(cdiv(D, 8), cdiv(Vp, 32)), 256, 0, st>>>(W.partials, d_w, D, V, Vp, W.KS);

@@ -78,10 +78,10 @@ struct BwdParams {
   const float* costs;
   const float* grad_costs;
   float clamp;
-  // spills, tiled per 128-row tile and pre-swizzled so that kernel 2 (and P4) fetch them with 1-D bulk copies:
-  //   zt [tile][MB][2][128 d][64 rows] : element (d, row rr) of a tile at box (d>>7, rr>>6), row d&127,
-  //                                      chunk ((rr&63)>>3) ^ (d&7), element rr&7
-  //   gt [tile][2][Vp][64 rows]        : element (v, rr) at half rr>>6, row v, chunk ((rr&63)>>3) ^ (v&7), element rr&7
+  // zt [CTA][MB][2][128 d][64 rows] : z^T of the CTA's current tile, pre-swizzled boxes for P4's 1-D bulk loads (element
+  //                                   (d, row rr) at box (d>>7, rr>>6), row d&127, chunk ((rr&63)>>3) ^ (d&7), element
+  //                                   rr&7).  Reused every tile, so it lives in L2; kernel 2 recomputes z instead.
+  // gt [tile][2][KBG][64 rows][64 v] : the G tile as it lies in shared memory (bulk stores), read MN-major by kernel 2
   __nv_bfloat16* zt;
   __nv_bfloat16* gt;
   long Rpad;
@@ -199,7 +199,6 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
     uint32_t ph = 0;
     const uint32_t r1_bytes = (uint32_t)p.NH * 128u;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
-      const size_t rowtile = (size_t)p.tiles[tile].w;
       if (lane == 0) TC_PROF(0, 1);
       // the ring is drained here: the previous tile's dz_full was observed below
       for (int i = 0; i < 2 * KB; ++i) {
@@ -231,7 +230,7 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       if (elect_one()) {
         for (int mb = 0; mb < MB; ++mb) {
           mbar_arrive_expect_tx(L.z_full(mb), 32768u);
-          bulk_load(L.z_box(2 * mb), p.zt + ((rowtile * MB + mb) * 2) * 8192, 32768u, L.z_full(mb));
+          bulk_load(L.z_box(2 * mb), p.zt + (((size_t)blockIdx.x * MB + mb) * 2) * 8192, 32768u, L.z_full(mb));
         }
       }
       __syncwarp();
@@ -423,7 +422,7 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
           warp_arrive(L.s_empty(sp.stage));
           named_barrier_sync(4, PROD_THREADS);        // the staged k-block is complete (and fenced) in shared memory
           if (tid == 256) {
-            __nv_bfloat16* zdst = p.zt + ((rowtile * MB + (kb >> 1)) * 2) * 8192 + (kb & 1) * 4096;
+            __nv_bfloat16* zdst = p.zt + (((size_t)blockIdx.x * MB + (kb >> 1)) * 2) * 8192 + (kb & 1) * 4096;
             bulk_store(zdst, L.z_stage(zp), 8192u);
             bulk_store(zdst + 8192, L.z_stage(zp) + 8192u, 8192u);
             bulk_commit();

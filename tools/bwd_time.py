@@ -2,6 +2,8 @@
 import sys, os, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctcvr_b200 as C
+import ctcvr_b200._lib as _L
+if os.environ.get('CTCVR_LIB'): _L.LIB_PATH = os.environ['CTCVR_LIB']   # experiment builds (tools/exp_build.sh)
 from ctcvr_b200._lib import call, ptr, query, stream
 torch.manual_seed(0)
 B,T,U1,D,V,blank=32,250,41,512,412,5
@@ -26,4 +28,4 @@ ts=[]
 for _ in range(10):
     flush.zero_(); a=torch.cuda.Event(enable_timing=True); c=torch.cuda.Event(enable_timing=True)
     a.record(); runb(); c.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(c)*1e3)
-ts.sort(); print("CTCVR_DBG=%s bwd total us: median %.1f min %.1f" % (os.environ.get("CTCVR_DBG","0"), ts[len(ts)//2], ts[0]))
+ts.sort(); print("%s bwd total us: median %.1f min %.1f" % (os.environ.get("CTCVR_LIB","default"), ts[len(ts)//2], ts[0]))
