@@ -15,7 +15,7 @@
 // each loads half of every ring stage, multicast to both (halves the L2 -> SM traffic, the P1/P3 bound).
 //
 // Roles (512 threads): warp 0 TMA ring | warp 1 MMA issuer | warp 2 TMEM alloc | warp 3 TMA slabs |
-// warps 4-15 P2/P4 workers | warps 8-15 also the P1 A producers.
+// warps 4-15: P1 A producers, P2 workers, (4-11) P4 workers.
 #pragma once
 #include "tc_common.cuh"
 
@@ -23,7 +23,8 @@ namespace ctcvr {
 namespace tc {
 
 constexpr int B_A_STAGES = 3;
-constexpr int B_Z_STAGES = 3;                  // z^T staging (P1): GZ blocks 0..2, one 64-d k-block ([2 halves][64 d][64 rows]) each
+constexpr int B_Z_STAGES = 3;                  // z^T staging (P1): 3 warp groups x 3 buffers x 8 KB in the GZ region, one
+                                               // (k-block, k-half) slot ([2 row halves][32 d][64 rows]) each
 constexpr int B_ACC_COLS = 416;                // TMEM: logits [0, 416) | A stages 416 + 32*stage (P1) ; dZ^T [0, 512) (P3/P4)
 constexpr int B_S_STAGES = 2;
 constexpr int B_R1_STAGES = 3;                 // W_out ring view   (P1): NH x 128 B per stage
@@ -99,7 +100,7 @@ struct Bwd2Smem {
   float* dbp;               // [4][Vp] column-sum partials
   uint32_t* tmem_ptr;
   __device__ __forceinline__ uint32_t g_kblock(int i) const { return g_base + i * A_STAGE_BYTES; }
-  __device__ __forceinline__ uint32_t z_stage(int i) const { return g_base + i * A_STAGE_BYTES; }
+  __device__ __forceinline__ uint32_t z_stage(int grp, int i) const { return g_base + (uint32_t)(grp * B_Z_STAGES + i) * 8192u; }
   __device__ __forceinline__ uint32_t z_box(int i) const { return g_base + i * A_STAGE_BYTES; }    // (mb*2 + half)
   __device__ __forceinline__ uint32_t r1_stage(int i) const { return r_base + i * r1_bytes; }
   __device__ __forceinline__ uint32_t r3_stage(int i) const { return r_base + i * 16384; }
@@ -125,7 +126,7 @@ __host__ __device__ inline uint32_t bwd2_ring_bytes(int NH) {
   return a > b ? a : b;
 }
 __host__ __device__ inline uint32_t bwd2_gz_blocks(int Vp, int D) {
-  const uint32_t kbg = (Vp + 63) / 64, zb = 2 * (D / 128), ring = B_Z_STAGES;
+  const uint32_t kbg = (Vp + 63) / 64, zb = 2 * (D / 128), ring = (3 * B_Z_STAGES * 8192 + A_STAGE_BYTES - 1) / A_STAGE_BYTES;
   const uint32_t m = kbg > zb ? kbg : zb;
   return m > ring ? m : ring;               // P1 view: z^T staging
 }
@@ -173,8 +174,8 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_e);
     tma_prefetch_desc(&tmap_p);
-    for (int i = 0; i < B_A_STAGES; ++i) { mbar_init(L.a_full(i), PROD_THREADS / 32); mbar_init(L.a_empty(i), 1); }
-    for (int i = 0; i < B_S_STAGES; ++i) { mbar_init(L.s_full(i), 1); mbar_init(L.s_empty(i), PROD_THREADS / 32); }
+    for (int i = 0; i < B_A_STAGES; ++i) { mbar_init(L.a_full(i), 8); mbar_init(L.a_empty(i), 1); }
+    for (int i = 0; i < B_S_STAGES; ++i) { mbar_init(L.s_full(i), 1); mbar_init(L.s_empty(i), 8); }
     for (int i = 0; i < B_R1_STAGES; ++i) { mbar_init(L.r1_full(i), 1); mbar_init(L.r1_empty(i), 1); }
     for (int i = 0; i < B_R3_STAGES; ++i) { mbar_init(L.r3_full(i), 1); mbar_init(L.r3_empty(i), 1); }
     for (int i = 0; i < 4; ++i) mbar_init(L.z_full(i), 1);
@@ -329,16 +330,14 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       ph ^= 1u;
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ workers (warps 4-15), producers (8-15)
+    // ------------------------------------------------------------------ workers (warps 4-15): P1 producers, P2, P4
     const int q = warp & 3;
     const int wg = (warp - 4) >> 2;            // 0..2
     const int wt = tid - 128;                  // 0..383
     const int r = q * 32 + lane;               // P2: tile row ; P4: lane of the d block
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
-    const bool producer = warp >= 8;
     uint32_t ph = 0;
     int prof_n = 0;
-    Pipe ap, sp;
     int zp = 0;
     float db0 = 0.f, db1 = 0.f;                // d_bias of columns wt and wt + 384
     float pacc[2][P];                          // d_pred sums of d blocks 2wg, 2wg+1 over the tiles of one (b, u-split) sweep
@@ -363,15 +362,17 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
         }
       }
     };
-    // producer addressing (A operand lives in TMEM): thread = tile row r = 32q + lane (its own TMEM lane), k-half kh:
-    // 32 of the 64 k of a k-block -> 16 packed bf16x2 -> one tcgen05.st ; rows >= TT*P are padding
-    const int kh = (warp - 8) >> 2;
+    // producer addressing (A operand lives in TMEM): thread = tile row r = 32q + lane (its own TMEM lane).  All 12
+    // worker warps produce: a k-block is two slots (k-half kh: 32 of its 64 k -> 16 packed bf16x2 -> one tcgen05.st);
+    // warp group wg takes the slots s = 2 kb + kh with s % 3 == wg.  rows >= TT*P are padding
     const int p_tloc = min(r / P, TT - 1), p_ul = r % P;
     const uint32_t e_row = bwd_pred_region<P>() + (uint32_t)p_tloc * 128u, e_sw = (uint32_t)(p_tloc & 7);
     const uint32_t p_row = (uint32_t)p_ul * 128u, p_sw = (uint32_t)(p_ul & 7);
-    // z^T staging of the same values: row kh*32 + d of the 64-d k-block, half r>>6, 16-byte chunk ((r&63)>>3) ^ (d&7)
-    const uint32_t z_off = (uint32_t)(r >> 6) * 8192u + (uint32_t)(kh * 32) * 128u + (uint32_t)(r & 7) * 2u;
+    // z^T staging of the same values (one 8 KB buffer per slot: [2 row halves][32 d][64 rows]): row d of the slot,
+    // half r>>6, 16-byte chunk ((r&63)>>3) ^ (d&7), element r&7
+    const uint32_t z_off = (uint32_t)(r >> 6) * 4096u + (uint32_t)(r & 7) * 2u;
     const uint32_t z_chunk = (uint32_t)((r & 63) >> 3);
+    uint32_t kb_base = 0;                       // k-blocks produced before this tile (ring stages follow it)
 
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       int4 ti = p.tiles[tile];
@@ -381,17 +382,21 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       if (g.b != cur_b || g.ubase != cur_ubase) { flush_pred(); cur_b = g.b; cur_ubase = g.ubase; }
       const size_t rowtile = (size_t)ti.w;
 
-      // ---------------- P1 (warps 8-15): A k-blocks into TMEM + z^T spill (staged in shared memory, bulk-stored)
-      if (producer) {
+      // ---------------- P1: A k-blocks into TMEM + z^T spill (staged in shared memory, bulk-stored)
+      {
         // the staging blocks overlay the z^T tile of the previous iteration, the A columns its dZ^T accumulator:
         // wait until its readers (P4) are done
         mbar_wait(L.tmem_empty(), ph ^ 1u, 40);
-        if (tid == 256) TC_PROF(3, 1);
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(L.s_full(sp.stage), sp.phase, 41);
-          mbar_wait(L.a_empty(ap.stage), ap.phase ^ 1u, 42);
+        if (tid == 128) TC_PROF(3, 1);
+        for (int s = wg; s < 2 * KB; s += 3) {
+          const int kb = s >> 1, kh = s & 1;
+          const uint32_t kbc = kb_base + (uint32_t)kb;
+          const uint32_t a_stg = kbc % B_A_STAGES, a_ph = (kbc / B_A_STAGES) & 1u;
+          const uint32_t s_stg = kbc % B_S_STAGES, s_ph = (kbc / B_S_STAGES) & 1u;
+          mbar_wait(L.s_full(s_stg), s_ph, 41);
+          mbar_wait(L.a_empty(a_stg), a_ph ^ 1u, 42);
           tc_fence_after();
-          const uint32_t sb = L.s_stage(sp.stage);
+          const uint32_t sb = L.s_stage(s_stg);
           uint4 ev[4], pv[4];
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
@@ -407,8 +412,9 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
             w[4 * c4 + 2] = tanh_add_bf16x2_packed(ev[c4].z, pv[c4].z);
             w[4 * c4 + 3] = tanh_add_bf16x2_packed(ev[c4].w, pv[c4].w);
           }
-          tmem_st16(tq + (uint32_t)(B_ACC_COLS + ap.stage * 32 + kh * 16), w);
-          const uint32_t zs = L.z_stage(zp) + z_off;
+          tmem_st16(tq + (uint32_t)(B_ACC_COLS + a_stg * 32 + kh * 16), w);
+          const uint32_t zbuf = L.z_stage(wg, zp);
+          const uint32_t zs = zbuf + z_off;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             // w[i] holds d = 2i, 2i+1 of this thread's 32
@@ -418,22 +424,22 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
           tmem_st_wait();
           tc_fence_before();
           fence_proxy_async();
-          warp_arrive(L.a_full(ap.stage));
-          warp_arrive(L.s_empty(sp.stage));
-          named_barrier_sync(4, PROD_THREADS);        // the staged k-block is complete (and fenced) in shared memory
-          if (tid == 256) {
-            __nv_bfloat16* zdst = p.zt + (((size_t)blockIdx.x * MB + (kb >> 1)) * 2) * 8192 + (kb & 1) * 4096;
-            bulk_store(zdst, L.z_stage(zp), 8192u);
-            bulk_store(zdst + 8192, L.z_stage(zp) + 8192u, 8192u);
+          warp_arrive(L.a_full(a_stg));
+          warp_arrive(L.s_empty(s_stg));
+          named_barrier_sync(4 + wg, 128);            // the group's staged slot is complete (and fenced) in shared memory
+          if (q == 0 && lane == 0) {
+            // box (kb>>1, half hh): rows (kb&1)*64 + kh*32 .. +31 of 128 B
+            __nv_bfloat16* zdst = p.zt + (((size_t)blockIdx.x * MB + (kb >> 1)) * 2) * 8192 + ((kb & 1) * 64 + kh * 32) * 64;
+            bulk_store(zdst, zbuf, 4096u);
+            bulk_store(zdst + 8192, zbuf + 4096u, 4096u);
             bulk_commit();
-            bulk_wait_read<1>();                      // the k-block staged before this one has left shared memory
+            bulk_wait_read<1>();                      // the slot staged before this one has left shared memory
           }
           zp = (zp + 1 == B_Z_STAGES) ? 0 : zp + 1;
-          ap.advance(B_A_STAGES);
-          sp.advance(B_S_STAGES);
         }
-        if (tid == 256) bulk_wait_all<0>();           // z^T is in global memory before P4's bulk loads (ordered via g_full)
-        if (tid == 256) TC_PROF(3, 2);
+        kb_base += (uint32_t)KB;
+        if (q == 0 && lane == 0) bulk_wait_all<0>();  // z^T is in global memory before P4's bulk loads (ordered via g_full)
+        if (tid == 128) TC_PROF(3, 2);
       }
 
       // ---------------- P2: g = d cost / d logits for row r, column chunks wg, wg+3, ...
@@ -458,7 +464,7 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       const float kr = (valid && fast) ? fmaf(k_all, LOG2E, lg2_fast(scale)) : kNegInf;
       if (tid == 128) TC_PROF(2, 1);
       mbar_wait(L.tmem_full(), ph, 30);
-      named_barrier_sync(5, WORKERS);            // the z^T staging blocks (overlaid by G) have been stored
+      named_barrier_sync(7, WORKERS);            // the z^T staging blocks (overlaid by G) have been stored
       if (tid == 128) TC_PROF(2, 2);
       tc_fence_after();
       for (int c0 = wg * 32; c0 < p.Vp; c0 += 96) {
