@@ -28,7 +28,7 @@ CFG = dict(B=32, T=250, U=40, D=512, V=412, blank=5)
 METRIC = "fused joint+RNN-T loss fwd/bwd throughput"
 # kernels of libctcvr.so inside one captured step: fwd (prep, to_bf16, tiles, joint_fwd2) + lattice + bwd (prep, tiles,
 # to_bf16, joint_bwd2, reduce_denc, dw_gemm, reduce_dw); counted from an eager step, see ctcvr_launch_count()
-KERNELS_PER_GRAPHED_STEP = 12
+KERNELS_PER_GRAPHED_STEP = 10
 UNIT = "utt/s"
 
 

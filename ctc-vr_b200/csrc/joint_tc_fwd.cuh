@@ -26,6 +26,11 @@ namespace ctcvr {
 namespace tc {
 
 constexpr int F_A_STAGES = 3;                    // A stages in TMEM: 32 columns each (64 k as bf16 pairs)
+constexpr int F_EPI_GROUPS = 4;                  // epilogue column groups (4 warps each): more warps hide the TMEM-load and
+                                                 // MUFU latencies of the softmax sweep, the phase no MMA overlaps
+constexpr int F_EPI_WARPS = 4 * F_EPI_GROUPS;
+constexpr int F_PROD_WARP0 = 4 + F_EPI_WARPS;    // first producer warp
+constexpr int F_THREADS = (F_PROD_WARP0 + 8) * 32;   // 4 control + epilogue + 8 producer warps
 constexpr int F_ACC_COLS = 416;                  // accumulator columns; the A stages follow (416 + 3*32 = 512)
 constexpr int F_S_STAGES = 3;
 constexpr int F_SLAB_BYTES = 1024 + 128 * 128;   // [pred rows: 1 KB region][128 enc rows x 128 B]
@@ -50,7 +55,7 @@ struct FwdParams {
 struct FwdSmem {
   uint32_t a_base, w_base, w_bytes, s_base, bar_base;
   float* bias_l2;
-  float2* epi_x;            // [128] (max, sum) of epilogue group 1
+  float2* epi_x;            // [groups - 1][128] (max, sum) of epilogue groups 1..
   uint32_t* tmem_ptr;
   __device__ __forceinline__ uint32_t a_stage(int i) const { return a_base + i * A_STAGE_BYTES; }
   __device__ __forceinline__ uint32_t w_stage(int i) const { return w_base + i * w_bytes; }
@@ -70,7 +75,7 @@ __host__ __device__ inline size_t fwd2_smem_bytes(int NH, int Vp, int w_stages) 
   s += (size_t)w_stages * NH * 128;
   s = (s + 1023) / 1024 * 1024;
   s += (size_t)F_S_STAGES * F_SLAB_BYTES;
-  s += (size_t)Vp * 4 + 1024;
+  s += (size_t)Vp * 4 + 1024 * (F_EPI_GROUPS - 1);
   s += 256 + 16;
   return s;
 }
@@ -84,12 +89,11 @@ __device__ __forceinline__ void carve_fwd2(FwdSmem& L, uint8_t* raw, int NH, int
   L.s_base = a; a += F_S_STAGES * F_SLAB_BYTES;
   L.bias_l2 = reinterpret_cast<float*>(raw + (a - base)); a += Vp * 4;
   a = (a + 15u) & ~15u;
-  L.epi_x = reinterpret_cast<float2*>(raw + (a - base)); a += 1024;
+  L.epi_x = reinterpret_cast<float2*>(raw + (a - base)); a += 1024 * (F_EPI_GROUPS - 1);
   L.bar_base = a; a += 256;
   L.tmem_ptr = reinterpret_cast<uint32_t*>(raw + (a - base));
 }
 
-constexpr int F_THREADS = 640;                   // 4 control + 8 epilogue + 8 producer warps
 
 __global__ void __launch_bounds__(F_THREADS, 1)
 joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_p,
@@ -109,7 +113,7 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
     for (int i = 0; i < F_S_STAGES; ++i) { mbar_init(L.s_full(i), 1); mbar_init(L.s_empty(i), PROD_THREADS / 32); }
     for (int i = 0; i < F_MAX_W_STAGES; ++i) { mbar_init(L.w_full(i), 1); mbar_init(L.w_empty(i), 1); }
     mbar_init(L.tmem_full(), 1);
-    mbar_init(L.tmem_empty(), 8);
+    mbar_init(L.tmem_empty(), F_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(L.tmem_ptr), TMEM_COLS);
@@ -192,19 +196,19 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       __syncwarp();
       tphase ^= 1u;
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= 4 && warp < F_PROD_WARP0) {
     // ------------------------------------------------------------------ epilogue: online log-softmax (base 2)
-    // 8 warps: quarter q = TMEM lanes 32q..32q+31 (thread = cell), group eg = which half of the accumulator columns.
-    // The two groups keep their own (max, sum); group 1 hands its pair to group 0 through shared memory.
+    // quarter q = TMEM lanes 32q..32q+31 (thread = cell), group eg = which slice of the accumulator columns.
+    // The groups keep their own (max, sum); groups 1.. hand their pairs to group 0 through shared memory.
     const int q = warp & 3, eg = (warp - 4) >> 2;
     const int erow = q * 32 + lane;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t tphase = 0;
     int prof_n = 0;
     const float bias_blank = __ldg(p.bias + p.blank);
-    // column chunks of 16: group 0 takes [0, c_split), group 1 [c_split, Vp)
-    const int c_split = ((p.Vp / 16 + 1) / 2) * 16;
-    const int c_begin = eg == 0 ? 0 : c_split, c_end = eg == 0 ? c_split : p.Vp;
+    // column chunks of 16, dealt to the groups in contiguous runs
+    const int nch = p.Vp / 16;
+    const int c_begin = (nch * eg / F_EPI_GROUPS) * 16, c_end = (nch * (eg + 1) / F_EPI_GROUPS) * 16;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int4 ti = p.tiles[tile];
       pin(ti.x); pin(ti.y); pin(ti.z); pin(ti.w);
@@ -226,7 +230,7 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       if (eg == 0) { xb = tmem_ld1(tq + p.blank); xl = tmem_ld1(tq + (lab >= 0 ? lab : 0)); }
       float m = kNegInf, s = 0.f;
       float v[16];
-      tmem_ld16(tq + c_begin, v);
+      if (c_begin < c_end) tmem_ld16(tq + c_begin, v);
       for (int c0 = c_begin; c0 < c_end; c0 += 16) {
         tmem_ld_wait();
         float y[16];
@@ -256,13 +260,16 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       tc_fence_before();
       warp_arrive(L.tmem_empty());
       if (tid == 128) TC_PROF(2, 2);
-      if (eg == 1) { L.epi_x[erow] = make_float2(m, s); }
-      named_barrier_sync(3, 256);                          // group 1's partials are visible
+      if (eg > 0) { L.epi_x[(eg - 1) * 128 + erow] = make_float2(m, s); }
+      named_barrier_sync(3, F_EPI_WARPS * 32);             // the other groups' partials are visible
       if (eg == 0) {
-        const float2 o = L.epi_x[erow];
-        const float nm = fmaxf(m, o.x);
-        s = s * ex2_fast(m - nm) + o.y * ex2_fast(o.x - nm);
-        m = nm;
+#pragma unroll
+        for (int gi = 0; gi < F_EPI_GROUPS - 1; ++gi) {
+          const float2 o = L.epi_x[gi * 128 + erow];
+          const float nm = fmaxf(m, o.x);
+          s = s * ex2_fast(m - nm) + o.y * ex2_fast(o.x - nm);
+          m = nm;
+        }
         if (valid) {
           const size_t cell = ((size_t)b * p.T + t) * p.U1 + u;
           const float l = (m + lg2_fast(s)) * LN2;
@@ -271,14 +278,14 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
           p.lp_label[cell] = (lab >= 0) ? xl + bias_lab - l : kNegInf;
         }
       }
-      named_barrier_sync(3, 256);                          // partials consumed before the next tile overwrites them
+      named_barrier_sync(3, F_EPI_WARPS * 32);             // partials consumed before the next tile overwrites them
       tphase ^= 1u;
     }
-  } else if (warp >= 12) {
+  } else if (warp >= F_PROD_WARP0) {
     // ------------------------------------------------------------------ A producers (A operand lives in TMEM)
     // warp = (TMEM lane quarter q, k-half kh): thread = tile row 32q + lane, 32 of the 64 k of a k-block.
     // tanh(e + p) for 32 k -> 16 packed bf16x2 -> one tcgen05.st into the A stage columns of the thread's own lane.
-    const int q = warp & 3, kh = (warp - 12) >> 2;
+    const int q = warp & 3, kh = (warp - F_PROD_WARP0) >> 2;
     Pipe ap, sp;
     int prof_n = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -292,7 +299,7 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(L.s_full(sp.stage), sp.phase, 7);
         mbar_wait(L.a_empty(ap.stage), ap.phase ^ 1u, 8);
-        if (tid == 384) TC_PROF(3, kb);
+        if (tid == F_PROD_WARP0 * 32) TC_PROF(3, kb);
         tc_fence_after();
         const uint32_t sb = L.s_stage(sp.stage);
         uint32_t w[16];
@@ -311,7 +318,7 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
         tc_fence_before();
         warp_arrive(L.a_full(ap.stage));
         warp_arrive(L.s_empty(sp.stage));
-        if (tid == 384) TC_PROF(3, 20 + kb);
+        if (tid == F_PROD_WARP0 * 32) TC_PROF(3, 20 + kb);
         ap.advance(F_A_STAGES);
         sp.advance(F_S_STAGES);
       }
