@@ -467,41 +467,47 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       named_barrier_sync(7, WORKERS);            // the z^T staging blocks (overlaid by G) have been stored
       if (tid == 128) TC_PROF(2, 2);
       tc_fence_after();
-      for (int c0 = wg * 32; c0 < p.Vp; c0 += 96) {
-        float v[32];
-        tmem_ld32(tq + c0, v);
+      // 16-column pieces (two per 32-column chunk wg, wg+3, ..); the next piece's TMEM load is in flight during the math
+      const int npieces = 2 * ((p.Vp / 32 - wg + 2) / 3);
+      auto piece_col = [&](int i) { return wg * 32 + (i >> 1) * 96 + (i & 1) * 16; };
+      float v[16];
+      if (npieces > 0) tmem_ld16(tq + piece_col(0), v);
+      for (int pi = 0; pi < npieces; ++pi) {
+        const int c0 = piece_col(pi);
         tmem_ld_wait();
-        uint32_t pk[16];
+        float y[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bj = *reinterpret_cast<const float4*>(L.bias_l2 + c0 + j);
+          y[j] = fmaf(v[j], LOG2E, bj.x);
+          y[j + 1] = fmaf(v[j + 1], LOG2E, bj.y);
+          y[j + 2] = fmaf(v[j + 2], LOG2E, bj.z);
+          y[j + 3] = fmaf(v[j + 3], LOG2E, bj.w);
+        }
+        if (pi + 1 < npieces) tmem_ld16(tq + piece_col(pi + 1), v);
+        uint32_t pk[8];
         if (fast) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bj = *reinterpret_cast<const float4*>(L.bias_l2 + c0 + j);
-            const float g0 = ex2_fast(fmaf(v[j], LOG2E, bj.x) + kr);
-            const float g1 = ex2_fast(fmaf(v[j + 1], LOG2E, bj.y) + kr);
-            const float g2 = ex2_fast(fmaf(v[j + 2], LOG2E, bj.z) + kr);
-            const float g3 = ex2_fast(fmaf(v[j + 3], LOG2E, bj.w) + kr);
-            pk[j >> 1] = pack_bf16(g0, g1);
-            pk[(j >> 1) + 1] = pack_bf16(g2, g3);
-          }
+          for (int j = 0; j < 16; j += 2) pk[j >> 1] = pack_bf16(ex2_fast(y[j] + kr), ex2_fast(y[j + 1] + kr));
         } else {
           const float ka2 = k_all * LOG2E;
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
+          for (int j = 0; j < 16; j += 2) {
             float gg[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              float gv = ex2_fast(fmaf(v[j + e], LOG2E, L.bias_l2[c0 + j + e]) + ka2);
+              float gv = ex2_fast(y[j + e] + ka2);
               if (p.clamp > 0.f) gv = fminf(gv, p.clamp);
               gg[e] = valid ? gv * scale : 0.f;
             }
             pk[j >> 1] = pack_bf16(gg[0], gg[1]);
           }
         }
-        // G tile: k-block c0/64, row r, 16-byte chunks (c0%64)/8 .. +3, 128B swizzle
+        // G tile: k-block c0/64, row r, 16-byte chunks (c0%64)/8, +1, 128B swizzle
         const uint32_t gb = L.g_kblock(c0 >> 6) + r * 128;
         const int ch0 = (c0 & 63) >> 3;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 2; ++i)
           sts128(gb + (((ch0 + i) ^ (r & 7)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
       }
       named_barrier_sync(2, WORKERS);            // every generic entry of G is written
