@@ -1,21 +1,26 @@
 // Backward kernel 1 of the bf16 tcgen05 path (included by joint_tc.cu):
 //   recompute logits -> g = d cost / d logits -> dZ^T = W^T g^T -> dH = dZ (1 - z^2) -> d_enc / d_pred partials,
-//   d_bias, and the bf16 spills z^T, g^T consumed by the dW GEMM (kernel 2).
+//   d_bias, and the bf16 spill of the G tiles consumed by the dW GEMM (kernel 2, which recomputes z).
+//   (model/component/joint.py:57-68 + torchaudio rnnt_loss backward, model/component/transducer.py:180-187)
 //
-// Tiles are rectangles of 8 frames x 16 label columns of one utterance (row = tloc*16 + ul).  With the
-// transposed second GEMM (TMEM lane = joint dim d, TMEM column = tile row) both reductions are thread-local:
-//   d_enc[t]  = sum over the 16 columns of one tcgen05.ld.x16
+// Tiles are rectangles of TT frames x P label columns of one utterance (row = tloc*P + ul; <21,6> or <16,8>).
+// With the transposed second GEMM (TMEM lane = joint dim d, TMEM column = tile row) both reductions are
+// thread-local:
+//   d_enc[t]  = sum over the P columns of a frame
 //   d_pred[u] = sum over the frame slots, kept in registers across the tiles of one (b, u-split) sweep
 // TMEM holds 512 columns, so the logits [128 x Vp] and dZ^T [D x 128] cannot coexist: a tile runs four phases
-//   P1  producers: tanh tile (+ z^T spill) | TMA: W_out k-blocks | MMA: logits -> TMEM
-//   P2  12 warps : TMEM -> g (bf16) -> smem G tile (K-major over v) + g^T spill; exact fp32 blank/label entries
-//   P3  TMA: W_out^T blocks | MMA: dZ^T[mb] = W^T[mb] . G^T -> TMEM ; the 12 warps: column sums of G (d_bias)
-//   P4  12 warps : TMEM -> dH -> d_enc partial (store), d_pred (registers)
-// W_out / W_out^T stream through ONE smem ring.  With CL = 2 the two CTAs of a cluster run in lock step and
-// each loads half of every ring stage, multicast to both (halves the L2 -> SM traffic, the P1/P3 bound).
+//   P1  12 warps : tanh k-half slots -> A operand in TMEM (tcgen05.st) + z^T staged in smem and bulk-stored to the
+//                  CTA's zt scratch | bulk copies: W_out k-blocks | MMA (TS): logits -> TMEM
+//   P2  12 warps : TMEM -> g (bf16) -> smem G tile (K-major over v); exact fp32 blank/label entries
+//   P3  bulk copies: W_out^T blocks | MMA (SS): dZ^T[mb] = W^T[mb] . G^T -> TMEM ; one thread bulk-stores the G tile,
+//                  the 12 warps sum its columns (d_bias)
+//   P4  8 warps  : z^T boxes bulk-loaded back | TMEM -> dH -> d_enc partial (store), d_pred (registers)
+// W_out / W_out^T stream through ONE smem ring (3 x NH*128 B in P1, 5 x 16 KB in P3); the 128 KB "GZ" region is the
+// z^T staging (P1), the G tile (P2/P3) and the z^T boxes (P4) in turn.
 //
-// Roles (512 threads): warp 0 TMA ring | warp 1 MMA issuer | warp 2 TMEM alloc | warp 3 TMA slabs |
-// warps 4-15: P1 A producers, P2 workers, (4-11) P4 workers.
+// Roles (512 threads): warp 0 bulk-copy ring | warp 1 MMA issuer | warp 2 TMEM alloc | warp 3 TMA slabs |
+// warps 4-15: P1 A producers, P2 workers, (4-11) P4 workers.  Role loops run warp-wide with elect.sync around
+// the single-thread instructions (tc_common.cuh: elect_one).
 #pragma once
 #include "tc_common.cuh"
 

@@ -11,13 +11,14 @@
 // label of a cell is uniform across a warp and both gathered logits (blank, label) are one-column
 // tcgen05.ld's instead of per-element compares.
 //
-// One persistent CTA per SM, 512 threads, warp-specialised:
+// One persistent CTA per SM, 896 threads, warp-specialised (role loops run warp-wide, elect.sync around the
+// single-thread instructions):
 //   warp 0      bulk copies: pre-tiled bf16 W_out k-blocks (two N-halves per k-block) into a smem ring
 //   warp 1      MMA issuer: tcgen05.mma M=128, N=Vp/2 (x2), K=16, A from TMEM, B from smem; fp32 accumulators in TMEM
 //   warp 2      TMEM allocator
 //   warp 3      TMA: slab ring - per k-block the nu pred rows and 128/nu enc rows (bf16, 128B swizzle)
-//   warps 4-7   epilogue: tcgen05.ld (thread = cell), online log-softmax in base 2, gathers, stores
-//   warps 8-15  A producers: tanh(e+p) -> packed bf16 -> tcgen05.st into the A stage of TENSOR MEMORY (TS-mode MMA):
+//   warps 4-19  epilogue: tcgen05.ld (thread = cell, 4 column groups), online log-softmax in base 2, gathers, stores
+//   warps 20-27 A producers: tanh(e+p) -> packed bf16 -> tcgen05.st into the A stage of TENSOR MEMORY (TS-mode MMA):
 //               the A operand costs no shared-memory bandwidth, which is what bounds this kernel
 #pragma once
 #include "tc_common.cuh"
