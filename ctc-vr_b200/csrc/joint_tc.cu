@@ -118,11 +118,22 @@ struct Pipe {
 namespace ctcvr {
 namespace tc {
 
-// d_enc[b,t,:] = sum over the u-splits of the partial sums (zero for padded frames)
+// d_enc[b,t,:] = sum over the u-splits of the partial sums (zero for padded frames).  OUT_BF16 (bf16-input entry
+// point): d_enc is written as bf16 and blocks B*T.. convert the fp32 d_pred accumulator to bf16 as well.
+template <bool OUT_BF16>
 __global__ void reduce_denc_kernel(const float* __restrict__ part, const int32_t* __restrict__ t_len,
-                                   const int32_t* __restrict__ u_len, float* __restrict__ d_enc, int B, int T, int U1,
-                                   int D, int P) {
+                                   const int32_t* __restrict__ u_len, void* __restrict__ d_enc_out, int B, int T, int U1,
+                                   int D, int P, const float* __restrict__ d_pred_acc, void* __restrict__ d_pred_out) {
   const int bt = blockIdx.x;
+  if (bt >= B * T) {                      // d_pred rows (OUT_BF16 only)
+    const size_t row = (size_t)(bt - B * T) * D;
+    for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {
+      const float4 x = *reinterpret_cast<const float4*>(d_pred_acc + row + d);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d_pred_out) + row + d) =
+          make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+    }
+    return;
+  }
   const int b = bt / T, t = bt - b * T;
   const int Tb = min(t_len[b], T), W = min(u_len[b], U1 - 1) + 1;
   const int S = (W + P - 1) / P;
@@ -134,7 +145,10 @@ __global__ void reduce_denc_kernel(const float* __restrict__ part, const int32_t
         const float4 x = __ldg(reinterpret_cast<const float4*>(part + (size_t)i * step + row + d));
         s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
       }
-    *reinterpret_cast<float4*>(d_enc + row + d) = s;
+    if (OUT_BF16)
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d_enc_out) + row + d) = make_uint2(pack_bf16(s.x, s.y), pack_bf16(s.z, s.w));
+    else
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(d_enc_out) + row + d) = s;
   }
 }
 
@@ -397,16 +411,15 @@ __device__ __forceinline__ int block_prefix(int mine_upto, Count count) {
 // that one CTA sweeps consecutive frame blocks of the same (b, u-split).  `even` pads every sweep to an even number of
 // frame blocks (the CTA-pair kernel processes tiles 2i, 2i+1 of one sweep together; a padding tile lies beyond T_b).
 // Entry = {b, u-split, frame block, tile index}.
-__global__ void build_tiles_kernel(const int32_t* __restrict__ t_len, const int32_t* __restrict__ u_len, int B, int T,
-                                   int U1, int geom, int4* __restrict__ tiles, int4* __restrict__ tile_rows,
-                                   int* __restrict__ ntiles, int max_tiles) {
+__device__ void build_tiles_block(int b, const int32_t* __restrict__ t_len, const int32_t* __restrict__ u_len, int B, int T,
+                                  int U1, int geom, int4* __restrict__ tiles, int4* __restrict__ tile_rows,
+                                  int* __restrict__ ntiles, int max_tiles) {
   const int P = geom & 0xff, TT = (geom >> 8) & 0xff, even = (geom >> 16) & 1;
   auto ntb_of = [&](int Tb) { const int n = (Tb + TT - 1) / TT; return even ? ((n + 1) & ~1) : n; };
   auto count = [&](int i) {
     const int Tb = min(t_len[i], T), W = min(u_len[i], U1 - 1) + 1;
     return Tb > 0 ? ((W + P - 1) / P) * ntb_of(Tb) : 0;
   };
-  const int b = blockIdx.x;
   const int off = block_prefix(b, count);
   const int Tb = min(t_len[b], T);
   const int n = count(b);
@@ -428,10 +441,9 @@ __global__ void build_tiles_kernel(const int32_t* __restrict__ t_len, const int3
 
 // fp32 -> bf16 copies of the activations (n4 float4 groups each); the bf16 path rounds enc_proj / pred_proj
 // to bf16 (under autocast they already are bf16 values, so this is lossless there).
-__global__ void to_bf16_kernel(const float4* __restrict__ a, uint2* __restrict__ ab, long na4,
-                               const float4* __restrict__ b, uint2* __restrict__ bb, long nb4) {
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < na4 + nb4; i += stride) {
+__device__ void to_bf16_part(long first_i, long stride, const float4* __restrict__ a, uint2* __restrict__ ab, long na4,
+                             const float4* __restrict__ b, uint2* __restrict__ bb, long nb4) {
+  for (long i = first_i; i < na4 + nb4; i += stride) {
     const bool first = i < na4;
     const float4 v = first ? __ldg(a + i) : __ldg(b + (i - na4));
     const uint2 o = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
@@ -443,11 +455,10 @@ __global__ void to_bf16_kernel(const float4* __restrict__ a, uint2* __restrict__
 //   w_t  [KB][2][NH][64]   stage (kb,h): rows v' = v - h*NH, k' = k - 64 kb; chunk (k'>>3) stored at (k'>>3) ^ (v'&7)
 //   wt_t [MB][KBG][128][64] stage (mb,kb): rows d' = d - 128 mb, v' = v - 64 kb; chunk (v'>>3) at (v'>>3) ^ (d'&7)
 // plus bias_pad / bias_l2.  One thread per (v, d) of the zero-padded [KBG*64][D] weight.
-__global__ void prep_weights3_kernel(const float* __restrict__ w, const float* __restrict__ bias,
-                                     __nv_bfloat16* __restrict__ w_t, __nv_bfloat16* __restrict__ wt_t,
-                                     float* __restrict__ bias_pad, float* __restrict__ bias_l2, int V, int Vp, int D) {
+__device__ void prep_weights3_part(int i, const float* __restrict__ w, const float* __restrict__ bias,
+                                   __nv_bfloat16* __restrict__ w_t, __nv_bfloat16* __restrict__ wt_t,
+                                   float* __restrict__ bias_pad, float* __restrict__ bias_l2, int V, int Vp, int D) {
   const int KBG = (Vp + 63) / 64, NH = Vp / 2;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < KBG * 64 * D) {
     const int v = i / D, d = i - v * D;
     const __nv_bfloat16 x = __float2bfloat16((v < V) ? w[(size_t)v * D + d] : 0.f);
@@ -467,10 +478,9 @@ __global__ void prep_weights3_kernel(const float* __restrict__ w, const float* _
 }
 
 // Forward tile table (see joint_tc_fwd.cuh): entry = {b, u0, t0, nu}.
-__global__ void build_tiles_fwd_kernel(const int32_t* __restrict__ t_len, const int32_t* __restrict__ u_len, int B,
-                                       int T, int U1, int4* __restrict__ tiles, int* __restrict__ ntiles,
-                                       int max_tiles) {
-  const int b = blockIdx.x;
+__device__ void build_tiles_fwd_block(int b, const int32_t* __restrict__ t_len, const int32_t* __restrict__ u_len, int B,
+                                      int T, int U1, int4* __restrict__ tiles, int* __restrict__ ntiles,
+                                      int max_tiles) {
   const int off = block_prefix(b, [&](int i) { return fwd_tiles_of(min(t_len[i], T), min(u_len[i], U1 - 1) + 1); });
   const int Tb = min(t_len[b], T), W = min(u_len[b], U1 - 1) + 1;
   const int n = fwd_tiles_of(Tb, W);
@@ -484,6 +494,32 @@ __global__ void build_tiles_fwd_kernel(const int32_t* __restrict__ t_len, const 
     if (off + i < max_tiles) tiles[off + i] = e;
   }
   if (b == B - 1 && threadIdx.x == 0) *ntiles = min(off + n, max_tiles);
+}
+
+// One launch for everything the joint kernels need prepared: tiled weights (blocks [0, nW)), the tile table (blocks
+// [nW, nW + B): geom = 0 builds the forward table), and grid-stride zero fills / fp32 -> bf16 activation copies on the
+// remaining blocks.  Graph nodes are not free (~3 us each): this replaces up to five of them.
+struct PrepArgs {
+  const float* w; const float* bias; __nv_bfloat16* w_t; __nv_bfloat16* wt_t; float* bias_pad; float* bias_l2;
+  int V, Vp, D, nW;
+  const int32_t* t_len; const int32_t* u_len; int B, T, U1, geom, max_tiles;
+  int4* tiles; int4* tile_rows; int* ntiles;
+  float* zero0; long n0; float* zero1; long n1;
+  const float4* a; uint2* ab; long na4; const float4* b4; uint2* bb; long nb4;
+};
+__global__ void __launch_bounds__(256) prep_kernel(const PrepArgs q) {
+  const int blk = blockIdx.x;
+  if (blk < q.nW) {
+    prep_weights3_part(blk * 256 + threadIdx.x, q.w, q.bias, q.w_t, q.wt_t, q.bias_pad, q.bias_l2, q.V, q.Vp, q.D);
+  } else if (blk < q.nW + q.B) {
+    if (q.geom) build_tiles_block(blk - q.nW, q.t_len, q.u_len, q.B, q.T, q.U1, q.geom, q.tiles, q.tile_rows, q.ntiles, q.max_tiles);
+    else build_tiles_fwd_block(blk - q.nW, q.t_len, q.u_len, q.B, q.T, q.U1, q.tiles, q.ntiles, q.max_tiles);
+  } else {
+    const long nb = gridDim.x - q.nW - q.B, first = (long)(blk - q.nW - q.B) * 256 + threadIdx.x, stride = nb * 256;
+    for (long i = first; i < q.n0; i += stride) q.zero0[i] = 0.f;
+    for (long i = first; i < q.n1; i += stride) q.zero1[i] = 0.f;
+    if (q.na4 + q.nb4 > 0) to_bf16_part(first, stride, q.a, q.ab, q.na4, q.b4, q.bb, q.nb4);
+  }
 }
 
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
@@ -603,21 +639,25 @@ int joint_fwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
   CTCVR_REQUIRE(((uintptr_t)enc & 15) == 0 && ((uintptr_t)pred & 15) == 0, "joint_rnnt_fwd bf16: enc_proj / pred_proj must be 16-byte aligned");
   const int Vp = pad_v(V), NH = Vp / 2;
   FwdWs W = carve_fwd_ws(ws, B, T, U1, D, V);
-  prep_weights3_kernel<<<cdiv((long)((Vp + 63) / 64) * 64 * D, 256), 256, 0, st>>>(w, bias, W.wb, nullptr, nullptr, W.bias_l2, V, Vp, D);
-  CTCVR_LAUNCH_CHECK();
-  if (in_bf16) {                        // activations already bf16 (autocast): use them in place
-    W.eb = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(enc_v));
-    W.pb = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(pred_v));
-  } else {
-    const long na4 = (long)B * T * D / 4, nb4 = (long)B * U1 * D / 4;
-    const int blocks = (int)std::min<long>((na4 + nb4 + 255) / 256, 148L * 8);
-    to_bf16_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(enc), reinterpret_cast<uint2*>(W.eb), na4,
-                                           reinterpret_cast<const float4*>(pred), reinterpret_cast<uint2*>(W.pb), nb4);
+  const int mt = max_tiles_fwd2(B, T, U1);
+  {
+    PrepArgs q{};
+    q.w = w; q.bias = bias; q.w_t = W.wb; q.bias_l2 = W.bias_l2; q.V = V; q.Vp = Vp; q.D = D;
+    q.nW = cdiv((long)((Vp + 63) / 64) * 64 * D, 256);
+    q.t_len = t_len; q.u_len = u_len; q.B = B; q.T = T; q.U1 = U1; q.geom = 0; q.max_tiles = mt;
+    q.tiles = W.tiles; q.ntiles = W.ntiles;
+    int extra = 0;
+    if (in_bf16) {                      // activations already bf16 (autocast): use them in place
+      W.eb = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(enc_v));
+      W.pb = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(pred_v));
+    } else {
+      q.a = reinterpret_cast<const float4*>(enc); q.ab = reinterpret_cast<uint2*>(W.eb); q.na4 = (long)B * T * D / 4;
+      q.b4 = reinterpret_cast<const float4*>(pred); q.bb = reinterpret_cast<uint2*>(W.pb); q.nb4 = (long)B * U1 * D / 4;
+      extra = (int)std::min<long>((q.na4 + q.nb4 + 255) / 256, 148L * 8);
+    }
+    prep_kernel<<<q.nW + B + extra, 256, 0, st>>>(q);
     CTCVR_LAUNCH_CHECK();
   }
-  const int mt = max_tiles_fwd2(B, T, U1);
-  build_tiles_fwd_kernel<<<B, 128, 0, st>>>(t_len, u_len, B, T, U1, W.tiles, W.ntiles, mt);
-  CTCVR_LAUNCH_CHECK();
   CUtensorMap tmap_e, tmap_p;
   if (make_tmap_bf16_2d(&tmap_e, W.eb, (uint64_t)B * T, D, D, 32)) return 1;
   if (make_tmap_bf16_2d(&tmap_p, W.pb, (uint64_t)B * U1, D, D, 4)) return 1;
@@ -651,7 +691,7 @@ bool joint_tc_bwd_supported(int U1, int D, int V) {
 
 struct BwdWs {
   __nv_bfloat16 *wb, *wtb, *zt, *gt, *eb, *pb;
-  float *bias_pad, *bias_l2, *d_enc_part, *partials;
+  float *bias_pad, *bias_l2, *d_enc_part, *partials, *d_pred_acc;
   int4 *tiles, *tile_rows;
   int* ntiles;
   long Rpad;
@@ -683,6 +723,7 @@ static BwdWs carve_bwd_ws(void* ws, int B, int T, int U1, int D, int V) {
   w.gt = reinterpret_cast<__nv_bfloat16*>(take((size_t)((Vp + 63) / 64) * 64 * w.Rpad * 2));
   w.d_enc_part = reinterpret_cast<float*>(take((size_t)w.S_max * B * T * D * 4));
   w.partials = reinterpret_cast<float*>(take((size_t)w.KS * D * Vp * 4));
+  w.d_pred_acc = reinterpret_cast<float*>(take((size_t)B * U1 * D * 4));
   w.bytes = off;
   return w;
 }
@@ -708,22 +749,26 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
   const int Vp = pad_v(V), NH = Vp / 2, MB = D / 128;
   BwdWs W = carve_bwd_ws(ws, B, T, U1, D, V);
   const int KBG = (Vp + 63) / 64;
-  prep_weights3_kernel<<<cdiv((long)KBG * 64 * D, 256), 256, 0, st>>>(w, bias, W.wb, W.wtb, W.bias_pad, W.bias_l2, V, Vp, D);
-  CTCVR_LAUNCH_CHECK();
   const int mt = W.mt;
   const RectGeom G = pick_rect_geom(T, U1);
-  build_tiles_kernel<<<B, 128, 0, st>>>(t_len, u_len, B, T, U1, G.P | (G.TT << 8) | (G.even << 16), W.tiles, W.tile_rows, W.ntiles, mt);
-  CTCVR_LAUNCH_CHECK();
-  CTCVR_CHECK_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)B * U1 * D * sizeof(float), st));
-  CTCVR_CHECK_CUDA(cudaMemsetAsync(d_b, 0, (size_t)V * sizeof(float), st));
-  if (in_bf16) {
-    W.eb = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(enc_v));
-    W.pb = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(pred_v));
-  } else {
-    const long na4 = (long)B * T * D / 4, nb4 = (long)B * U1 * D / 4;
-    const int blocks = (int)std::min<long>((na4 + nb4 + 255) / 256, 148L * 8);
-    to_bf16_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(enc), reinterpret_cast<uint2*>(W.eb), na4,
-                                           reinterpret_cast<const float4*>(pred), reinterpret_cast<uint2*>(W.pb), nb4);
+  // bf16 inputs -> bf16 gradients: d_pred is accumulated in fp32 in the workspace and converted by the d_enc reduction
+  float* d_pred_acc = in_bf16 ? W.d_pred_acc : d_pred;
+  {
+    PrepArgs q{};
+    q.w = w; q.bias = bias; q.w_t = W.wb; q.wt_t = W.wtb; q.bias_pad = W.bias_pad; q.bias_l2 = W.bias_l2;
+    q.V = V; q.Vp = Vp; q.D = D; q.nW = cdiv((long)KBG * 64 * D, 256);
+    q.t_len = t_len; q.u_len = u_len; q.B = B; q.T = T; q.U1 = U1; q.geom = G.P | (G.TT << 8) | (G.even << 16);
+    q.max_tiles = mt; q.tiles = W.tiles; q.tile_rows = W.tile_rows; q.ntiles = W.ntiles;
+    q.zero0 = d_pred_acc; q.n0 = (long)B * U1 * D; q.zero1 = d_b; q.n1 = V;
+    if (in_bf16) {
+      W.eb = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(enc_v));
+      W.pb = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(pred_v));
+    } else {
+      q.a = reinterpret_cast<const float4*>(enc); q.ab = reinterpret_cast<uint2*>(W.eb); q.na4 = (long)B * T * D / 4;
+      q.b4 = reinterpret_cast<const float4*>(pred); q.bb = reinterpret_cast<uint2*>(W.pb); q.nb4 = (long)B * U1 * D / 4;
+    }
+    const int extra = (int)std::min<long>((q.n0 + q.na4 * 4 + q.nb4 * 4 + 1023) / 1024, 148L * 8);
+    prep_kernel<<<q.nW + B + extra, 256, 0, st>>>(q);
     CTCVR_LAUNCH_CHECK();
   }
   {
@@ -738,7 +783,7 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
     p.B = B; p.T = T; p.U1 = U1; p.D = D; p.V = V; p.Vp = Vp; p.NH = NH; p.blank = blank;
     p.lse = lse; p.alpha = alpha; p.beta = beta; p.costs = costs; p.grad_costs = grad_costs; p.clamp = clamp;
     p.zt = W.zt; p.gt = W.gt; p.Rpad = W.Rpad;
-    p.d_enc_part = W.d_enc_part; p.d_pred = d_pred; p.d_bias = d_b;
+    p.d_enc_part = W.d_enc_part; p.d_pred = d_pred_acc; p.d_bias = d_b;
     p.prof = g_prof_buf;
     const size_t smem = bwd2_smem_bytes(NH, Vp, D);
     CTCVR_REQUIRE(smem <= 232448, "joint_rnnt_bwd bf16: shared memory budget exceeded (%zu B)", smem);
@@ -752,7 +797,10 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
       CTCVR_LAUNCH_CHECK();
     }
   }
-  reduce_denc_kernel<<<B * T, 128, 0, st>>>(W.d_enc_part, t_len, u_len, d_enc, B, T, U1, D, G.P);
+  if (in_bf16)
+    reduce_denc_kernel<true><<<B * T + B * U1, 128, 0, st>>>(W.d_enc_part, t_len, u_len, d_enc, B, T, U1, D, G.P, d_pred_acc, d_pred);
+  else
+    reduce_denc_kernel<false><<<B * T, 128, 0, st>>>(W.d_enc_part, t_len, u_len, d_enc, B, T, U1, D, G.P, nullptr, nullptr);
   CTCVR_LAUNCH_CHECK();
   {
     CUtensorMap tmap_e, tmap_p;          // the same 64-wide SW128 boxes as kernel 1: TT enc rows / P pred rows

@@ -80,8 +80,10 @@ class _FusedJointRnnt(torch.autograd.Function):
         U1, V = p.shape[1], w.shape[0]
         dev = e.device
         gc = _f32c(grad_costs)
-        d_e = torch.empty(e.shape, dtype=torch.float32, device=dev)
-        d_p = torch.empty(p.shape, dtype=torch.float32, device=dev)
+        # bf16-input entry point: gradients come back in bf16 (the dtype autograd expects for bf16 inputs)
+        gdt = torch.bfloat16 if bf16_in else torch.float32
+        d_e = torch.empty(e.shape, dtype=gdt, device=dev)
+        d_p = torch.empty(p.shape, dtype=gdt, device=dev)
         d_w, d_b = torch.empty_like(w), torch.empty_like(b)
         with torch.cuda.device(dev):
             ws = _ws(query("ctcvr_joint_rnnt_bwd_ws_bytes", B, T, U1, D, V, precision), dev)
@@ -93,8 +95,6 @@ class _FusedJointRnnt(torch.autograd.Function):
                 call("ctcvr_joint_rnnt_bwd", ptr(e), ptr(p), ptr(w), ptr(b), ptr(tg), ptr(tl), ptr(ul), ptr(lse),
                      ptr(alpha), ptr(beta), ptr(costs), ptr(gc), clamp, ptr(d_e), ptr(d_p), ptr(d_w), ptr(d_b),
                      B, T, U1, D, V, blank, precision, ptr(ws), ws.numel(), stream())
-        if bf16_in:      # gradients flow back in the dtype of the inputs (autograd requirement)
-            d_e, d_p = d_e.to(e.dtype), d_p.to(p.dtype)
         return d_e, d_p, d_w, d_b, None, None, None, None, None, None
 
 

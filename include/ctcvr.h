@@ -83,7 +83,8 @@ int ctcvr_joint_rnnt_bwd(const float* enc_proj, const float* pred_proj, const fl
 
 /* ---- bf16-input variants of the fused forward / backward (precision = CTCVR_BF16 implied): enc_proj / pred_proj
  * are bf16 tensors (what the reference's joint.enc_ffn / pred_ffn produce under torch.autocast), used in place -
- * no fp32 round trip.  ctcvr_joint_tc_supported() tells whether the shape fits the tensor-core tiling
+ * no fp32 round trip - and the backward returns d_enc_proj / d_pred_proj as bf16 tensors of the same shapes (autograd
+ * hands gradients back in the dtype of the inputs); d_w_out / d_b_out stay fp32.  ctcvr_joint_tc_supported() tells whether the shape fits the tensor-core tiling
  * (D % 128 == 0, D <= 512, V <= 512, U1 <= 128); other shapes must use the fp32-input entry points.
  * Workspace sizes are those of the fp32-input entry points with precision = CTCVR_BF16. */
 int ctcvr_joint_tc_supported(int U1, int D, int V);
@@ -94,8 +95,8 @@ int ctcvr_joint_rnnt_fwd_bf16in(const void* enc_proj_bf16, const void* pred_proj
 int ctcvr_joint_rnnt_bwd_bf16in(const void* enc_proj_bf16, const void* pred_proj_bf16, const float* w_out,
                                 const float* b_out, const int32_t* targets, const int32_t* t_len,
                                 const int32_t* u_len, const float* lse, const float* alpha, const float* beta,
-                                const float* costs, const float* grad_costs, float clamp, float* d_enc_proj,
-                                float* d_pred_proj, float* d_w_out, float* d_b_out, int B, int T, int U1, int D,
+                                const float* costs, const float* grad_costs, float clamp, void* d_enc_proj_bf16,
+                                void* d_pred_proj_bf16, float* d_w_out, float* d_b_out, int B, int T, int U1, int D,
                                 int V, int blank, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- A2 on dense logits — torch.ops.torchaudio.rnnt_loss_forward
