@@ -164,15 +164,16 @@ __global__ void reduce_denc_kernel(const float* __restrict__ part, const int32_t
 // TMEM: accumulators [0, Vp) | A stages 416.. (3 x 32 columns).
 // =================================================================================================
 constexpr int DW_STAGES = 3;
-constexpr int DWR_THREADS = 384;
+constexpr int DWR_ROW_PARTS = 4;                 // producer warps per d quarter: each takes 64 / parts rows of a stage
+constexpr int DWR_THREADS = (4 + 4 * DWR_ROW_PARTS) * 32;
 constexpr int DWR_A_STAGES = 3;
 constexpr int DWR_ACC_COLS = 416;
 
-// rows R0 .. R0+31 of a tile: 16 packed (row 2c, row 2c+1) pairs of tanh(e[tloc] + p[ul]), row = tloc*P + ul
-template <int P, int TT, int R0>
-__device__ __forceinline__ void dwr_rows(const uint32_t (&e)[TT], const uint32_t (&pr)[P], uint32_t (&w)[16]) {
+// rows R0 .. R0+2*NP-1 of a tile: NP packed (row 2c, row 2c+1) pairs of tanh(e[tloc] + p[ul]), row = tloc*P + ul
+template <int P, int TT, int R0, int NP>
+__device__ __forceinline__ void dwr_rows(const uint32_t (&e)[TT], const uint32_t (&pr)[P], uint32_t (&w)[NP]) {
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
+  for (int c = 0; c < NP; ++c) {
     const int r0 = R0 + 2 * c, r1 = r0 + 1;
     const int tl0 = (r0 / P < TT) ? r0 / P : TT - 1, tl1 = (r1 / P < TT) ? r1 / P : TT - 1;
     const int u0 = r0 % P, u1 = r1 % P;
@@ -218,8 +219,8 @@ dw_gemm_rz_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
     tma_prefetch_desc(&tmap_e);
     tma_prefetch_desc(&tmap_p);
     for (int i = 0; i < DW_STAGES; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
-    for (int i = 0; i < DWR_A_STAGES; ++i) { mbar_init(a_full(i), 8); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < DWR_S_STAGES; ++i) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 8); }
+    for (int i = 0; i < DWR_A_STAGES; ++i) { mbar_init(a_full(i), 4 * DWR_ROW_PARTS); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < DWR_S_STAGES; ++i) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 4 * DWR_ROW_PARTS); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -291,8 +292,8 @@ dw_gemm_rz_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
     if (elect_one()) umma_commit(done);
     __syncwarp();
   } else if (warp >= 4) {
-    // ---- producers: warp = (d quarter q, row half rh of the 64-row stage); lane = d
-    const int q = warp & 3, rh = (warp - 4) >> 2;
+    // ---- producers: warp = (d quarter q, row part rh of the 64-row stage); lane = d
+    const int q = warp & 3, rh = (warp - 4) >> 2;          // rh < DWR_ROW_PARTS (2 or 4)
     const int dl = q * 32 + lane;                          // d within the CTA's 128
     const int d = mb * 128 + dl;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -324,12 +325,21 @@ dw_gemm_rz_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       for (int hh = 0; hh < 2; ++hh) {
         const int kb = rt * 2 + hh;
         if (kb < kb_begin || kb >= kb_end) continue;
-        uint32_t w[16];
-        if (hh == 0) { if (rh == 0) dwr_rows<P, TT, 0>(e, pr, w); else dwr_rows<P, TT, 32>(e, pr, w); }
-        else         { if (rh == 0) dwr_rows<P, TT, 64>(e, pr, w); else dwr_rows<P, TT, 96>(e, pr, w); }
+        constexpr int NP = 32 / DWR_ROW_PARTS;           // row pairs (= TMEM columns) per producer warp and stage
+        uint32_t w[NP];
+        // rows hh*64 + rh*2*NP ..: one instantiation per (hh, rh) so that every (tloc, ul) is a compile-time constant
+        auto rows = [&](auto HH) {
+          constexpr int R = decltype(HH)::value * 64;
+          if (rh == 0) dwr_rows<P, TT, R, NP>(e, pr, w);
+          else if (rh == 1) dwr_rows<P, TT, R + 2 * NP, NP>(e, pr, w);
+          else if (rh == 2) dwr_rows<P, TT, R + 4 * NP, NP>(e, pr, w);
+          else dwr_rows<P, TT, R + 6 * NP, NP>(e, pr, w);
+        };
+        if (hh == 0) rows(std::integral_constant<int, 0>{}); else rows(std::integral_constant<int, 1>{});
         mbar_wait(a_empty(ap.stage), ap.phase ^ 1u, 54);
         tc_fence_after();
-        tmem_st16(tq + (uint32_t)(DWR_ACC_COLS + ap.stage * 32 + rh * 16), w);
+        if constexpr (NP == 16) tmem_st16(tq + (uint32_t)(DWR_ACC_COLS + ap.stage * 32 + rh * NP), w);
+        else tmem_st8(tq + (uint32_t)(DWR_ACC_COLS + ap.stage * 32 + rh * NP), w);
         tmem_st_wait();
         tc_fence_before();
         warp_arrive(a_full(ap.stage));
