@@ -276,7 +276,7 @@ def run_ours(args):
         ach_bwd = flops_bwd / (kern["bwd_ms"] * 1e-3) / 1e12
         ach_fwd = flops_fwd / (kern["fwd_ms"] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "joint_rnnt_bwd (dominant)", "achieved": ach_bwd,
-                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach_bwd / pk["tf_sust"], "traffic": None,
+                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach_bwd / pk["tf_sust"], "traffic": _ncu_traffic(),
                 "peak_source": pk["src"] + " bf16 sustained",
                 "step_frac": (6.0 * M * D * V / (ms_step * 1e-3) / 1e12) / pk["tf_sust"],
                 "fwd": {"achieved": ach_fwd, "frac": ach_fwd / pk["tf_sust"], "ms": kern["fwd_ms"]},
@@ -304,6 +304,17 @@ def run_ours(args):
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line))
+
+
+def _ncu_traffic():
+    """DRAM bytes (read + write) of the backward entry point's two tensor-core kernels per call, from the committed
+    `ncu --set full` capture of this round (profiles/r1_v5_traffic.json); None when the file is absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_v5_traffic.json")
+    try:
+        k = json.load(open(path))["kernels"]
+        return float(sum(k[n]["dram_read_bytes"] + k[n]["dram_write_bytes"] for n in ("joint_bwd2_kernel", "dw_gemm_rz_kernel")))
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def time_kernels(C, joint, enc, pred, tgt, tl, ul, blank, precision, flush, reps=5):
