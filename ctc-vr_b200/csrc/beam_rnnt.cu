@@ -451,6 +451,8 @@ __global__ void __launch_bounds__(BM_THREADS, 1) rnnt_prefix_beam_kernel(
   __shared__ int sh_tok[NB];
   __shared__ unsigned long long sh_hash[BM_BEAM_MAX];
   __shared__ int sh_nb, sh_sel[BM_BEAM_MAX], sh_nsel;
+  __shared__ unsigned long long sh_ch[BM_BEAM_MAX * BM_BEAM_MAX];      // merge keys of the frame's candidates
+  __shared__ int sh_cl[BM_BEAM_MAX * BM_BEAM_MAX], sh_cf[BM_BEAM_MAX * BM_BEAM_MAX];
 
   // initial beam: [blank], score 0, zero state
   if (tid == 0) { b_score(0)[0] = 0.0; b_len(0)[0] = 1; b_tok(0)[0] = blank; sh_nb = 1; sh_hash[0] = bm_hash(1469598103934665603ULL, blank); }
@@ -512,30 +514,49 @@ __global__ void __launch_bounds__(BM_THREADS, 1) rnnt_prefix_beam_kernel(
       const int j = c_src[c];
       return (pos < b_len(buf)[j]) ? b_tok(buf)[(size_t)j * ML + pos] : c_tok[c];
     };
+    // The order-dependent part (candidate i merges into the FIRST surviving equal candidate q < i) runs on one warp;
+    // its search over q is lane-parallel on shared-memory keys (hash, length, survivor flag) and only hash matches
+    // are verified token by token.
+    for (int i = tid; i < nc; i += BM_THREADS) {
+      const int c = cidx(i);
+      sh_ch[i] = c_hash[c];
+      sh_cl[i] = c_len[c];
+      sh_cf[i] = i;
+    }
+    __syncthreads();
     if (warp == 0) {
       for (int i = 1; i < nc; ++i) {
         const int c = cidx(i);
+        const unsigned long long hi = sh_ch[i];
+        const int li = sh_cl[i];
         int target = -1;
-        for (int q = 0; q < i && target < 0; ++q) {
-          const int o = cidx(q);
-          if (c_first[o] != o) continue;                                  // o itself was merged away
-          if (c_hash[o] == c_hash[c] && c_len[o] == c_len[c]) {
+        for (int q0 = 0; q0 < i && target < 0; q0 += 32) {
+          const int q = q0 + lane;
+          const bool cand = q < i && sh_cf[q] == q && sh_ch[q] == hi && sh_cl[q] == li;
+          unsigned m = __ballot_sync(0xffffffffu, cand);
+          while (m && target < 0) {
+            const int qq = q0 + __ffs(m) - 1;
+            m &= m - 1;
+            const int o = cidx(qq);
             bool same = true;
-            for (int pos = lane; pos < c_len[c]; pos += 32) same &= (tok_at(o, pos) == tok_at(c, pos));
-            if (__all_sync(0xffffffffu, same)) target = o;
+            for (int pos = lane; pos < li; pos += 32) same &= (tok_at(o, pos) == tok_at(c, pos));
+            if (__all_sync(0xffffffffu, same)) target = qq;
           }
         }
         if (target >= 0 && lane == 0) {
-          const double a = c_score[target], bb = c_score[c];
+          const int o = cidx(target);
+          const double a = c_score[o], bb = c_score[c];
           double r;
           if (a == -INFINITY && bb == -INFINITY) r = -INFINITY;
-          else { const double m = fmax(a, bb); r = m + log(exp(a - m) + exp(bb - m)); }
-          c_score[target] = r;
-          c_first[c] = target;
+          else { const double m2 = fmax(a, bb); r = m2 + log(exp(a - m2) + exp(bb - m2)); }
+          c_score[o] = r;
+          sh_cf[i] = target;
         }
         __syncwarp();
       }
     }
+    __syncthreads();
+    for (int i = tid; i < nc; i += BM_THREADS) c_first[cidx(i)] = cidx(sh_cf[i]);
     __syncthreads();
     // ---- stable sort (score desc, candidate order asc) of the fused list, keep `beam`
     for (int i = tid; i < nc; i += BM_THREADS) {
