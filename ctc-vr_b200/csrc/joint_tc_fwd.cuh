@@ -250,12 +250,14 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
 #pragma unroll
           for (int e = 0; e < 4; ++e) cm[e] = fmaxf(cm[e], y[j + e]);
         const float nm = fmaxf(m, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
+        // a group whose columns so far are all padding (bias -inf) has nm = -inf: subtract 0 instead (every term is 0)
+        const float nz = (nm == kNegInf) ? 0.f : nm;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) acc[e] += ex2_fast(y[j + e] - nm);
-        s = s * ex2_fast(m - nm) + ((acc[0] + acc[1]) + (acc[2] + acc[3]));
+          for (int e = 0; e < 4; ++e) acc[e] += ex2_fast(y[j + e] - nz);
+        s = s * ex2_fast(m - nz) + ((acc[0] + acc[1]) + (acc[2] + acc[3]));
         m = nm;
       }
       tc_fence_before();
@@ -268,7 +270,8 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
         for (int gi = 0; gi < F_EPI_GROUPS - 1; ++gi) {
           const float2 o = L.epi_x[gi * 128 + erow];
           const float nm = fmaxf(m, o.x);
-          s = s * ex2_fast(m - nm) + o.y * ex2_fast(o.x - nm);
+          const float nz = (nm == kNegInf) ? 0.f : nm;
+          s = s * ex2_fast(m - nz) + o.y * ex2_fast(o.x - nz);
           m = nm;
         }
         if (valid) {

@@ -9,6 +9,36 @@ from torch import nn
 from . import functional as CF
 
 
+class _Bf16Linear(torch.autograd.Function):
+    """`F.linear` for the two pre-projections of the bf16 path: bf16 operands, fp32 accumulation (what
+    `torch.autocast` gives), but the backward writes fp32 gradients straight from the library GEMMs
+    (`torch.mm(..., out_dtype=float32)`) and takes the bias gradient as a ones-row GEMM - three GEMMs instead of
+    autocast's two GEMMs + a column-sum reduction + three cast kernels per layer and step."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        xb = x.reshape(-1, x.shape[-1]).to(torch.bfloat16)
+        wb = weight.to(torch.bfloat16)
+        y = torch.addmm(bias.to(torch.bfloat16), xb, wb.t())
+        ctx.save_for_backward(xb, wb)
+        ctx.x_shape, ctx.x_dtype, ctx.w_dtype = x.shape, x.dtype, weight.dtype
+        return y.reshape(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, wb = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1]).to(torch.bfloat16)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.mm(dy2, wb, out_dtype=torch.float32).reshape(ctx.x_shape).to(ctx.x_dtype)
+        if ctx.needs_input_grad[1]:
+            dw = torch.mm(dy2.t(), xb, out_dtype=torch.float32).to(ctx.w_dtype)
+        if ctx.needs_input_grad[2]:
+            ones = torch.ones(1, dy2.shape[0], dtype=torch.bfloat16, device=dy2.device)
+            db = torch.mm(ones, dy2, out_dtype=torch.float32).reshape(-1).to(ctx.w_dtype)
+        return dx, dw, db
+
+
 class TransducerJoint(nn.Module):
     def __init__(self, vocab_size: int, enc_output_size: int, pred_output_size: int, join_dim: int,
                  prejoin_linear: bool = True, postjoin_linear: bool = False, joint_mode: str = "add",
@@ -69,8 +99,11 @@ class TransducerJoint(nn.Module):
             raise RuntimeError("rnnt_loss_fused: only joint_mode='add', activation='tanh', postjoin_linear=False")
         if precision in ("bf16", CF.BF16) and enc_out.is_cuda:
             # bf16 path: the two pre-projections are plain library GEMMs; run them on the tensor cores too
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                e, p = self.project(enc_out, pred_out, pre_project)
+            if pre_project and self.prejoin_linear and self.enc_ffn is not None and self.pred_ffn is not None:
+                e = _Bf16Linear.apply(enc_out, self.enc_ffn.weight, self.enc_ffn.bias)
+                p = _Bf16Linear.apply(pred_out, self.pred_ffn.weight, self.pred_ffn.bias)
+            else:
+                e, p = enc_out, pred_out
         else:
             e, p = self.project(enc_out, pred_out, pre_project)
         return CF.fused_joint_rnnt_loss(e, p, self.ffn_out.weight, self.ffn_out.bias, targets, logit_lengths,
