@@ -160,8 +160,7 @@ def run_ours(args):
     gB = B * world
 
     use_graph = not args.no_graph
-    graphed = (C.GraphedJointRnntStep(joint, B, T, U, blank, global_batch=gB, precision=args.precision, reducer=reducer)
-               if use_graph else None)
+    graphed = C.GraphedJointRnntStep(joint, B, T, U, blank, global_batch=gB, precision=args.precision) if use_graph else None
     if graphed is not None:
         graphed.load(enc.detach(), pred.detach(), tgt, tl, ul)
 
@@ -177,7 +176,7 @@ def run_ours(args):
             costs = joint.rnnt_loss_fused(e, p, tg, tl_, ul_, blank, reduction="none", precision=args.precision)
             loss = costs.sum() / gB
             loss.backward()
-        if reducer is not None and graphed is None:      # graph mode: the all-reduce is a node of the captured graph
+        if reducer is not None:
             reducer.reduce()
         return loss
 

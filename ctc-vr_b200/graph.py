@@ -15,11 +15,11 @@ class GraphedJointRnntStep:
     arguments into the captured buffers, replays the graph and returns the (device) loss scalar
     `sum_b cost_b / global_batch`.  Gradients land in `joint.<param>.grad`, `self.enc.grad`, `self.pred.grad`
     (static tensors, overwritten by every replay).  Passing no arguments replays on the resident inputs.
-    With `reducer` (a `dist.GradAllReducer` over the joint's parameters) the NCCL gradient all-reduce of the
-    data-parallel step is captured in the same graph, right behind the backward kernels."""
+    The data-parallel gradient all-reduce stays outside the graph (capturing the NCCL collective in it hung on the
+    2-GPU box of this round); call `dist.GradAllReducer.reduce()` after `step()`."""
 
     def __init__(self, joint, B: int, T: int, U: int, blank: int, global_batch: Optional[int] = None,
-                 precision: str = "bf16", clamp: float = -1.0, warmup: int = 3, reducer=None):
+                 precision: str = "bf16", clamp: float = -1.0, warmup: int = 3):
         p0 = next(joint.parameters())
         dev = p0.device
         if dev.type != "cuda":
@@ -27,7 +27,6 @@ class GraphedJointRnntStep:
         E = joint.enc_ffn.in_features if joint.enc_ffn is not None else joint.ffn_out.in_features
         P = joint.pred_ffn.in_features if joint.pred_ffn is not None else joint.ffn_out.in_features
         self.joint, self.blank, self.precision, self.clamp = joint, int(blank), precision, float(clamp)
-        self.reducer = reducer        # dist.GradAllReducer: the data-parallel gradient all-reduce becomes a node of the graph
         self.gB = float(global_batch if global_batch is not None else B)
         self.enc = torch.zeros(B, T, E, device=dev, requires_grad=True)
         self.pred = torch.zeros(B, U + 1, P, device=dev, requires_grad=True)
@@ -55,8 +54,6 @@ class GraphedJointRnntStep:
                                            self.blank, clamp=self.clamp, reduction="none", precision=self.precision)
         loss = costs.sum() / self.gB
         loss.backward()
-        if self.reducer is not None:
-            self.reducer.reduce()
         self.loss = loss.detach()
 
     @torch.no_grad()
