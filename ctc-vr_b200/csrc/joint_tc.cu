@@ -560,9 +560,27 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
+// Mapped pinned host word written by a kernel whose bounded mbarrier wait timed out (a protocol bug or a wedged
+// copy): read WITHOUT a host synchronisation at the next tensor-core entry-point call, which then fails loudly.
+static unsigned int* tc_error_host_word(unsigned int** dev_ptr) {
+  static unsigned int* h = nullptr;
+  static unsigned int* d = nullptr;
+  if (!h) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h), sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess) { h = nullptr; cudaGetLastError(); }
+    else { *h = 0u; if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0) != cudaSuccess) { d = nullptr; cudaGetLastError(); } }
+  }
+  if (dev_ptr) *dev_ptr = d;
+  return h;
+}
 static int check_tc_error(const char* where) {
-  // asynchronous: reads the flag left by a PREVIOUS launch (no host sync on the hot path)
-  (void)where;
+  unsigned int* h = tc_error_host_word(nullptr);
+  if (h && *reinterpret_cast<volatile unsigned int*>(h) != 0u) {
+    const unsigned int code = *h;
+    *h = 0u;
+    set_error("%s: an earlier tcgen05 kernel gave up on a bounded mbarrier wait (flag 0x%08x: site %u, CTA %u); "
+              "the results of that call are invalid", where, code, (code >> 16) & 0x7fffu, code & 0xffffu);
+    return 1;
+  }
   return 0;
 }
 
@@ -645,6 +663,7 @@ int joint_fwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
     CTCVR_REQUIRE(!in_bf16, "joint_rnnt_fwd: bf16 inputs need D %% 64 == 0, D <= 1024, V <= 512, U+1 <= 128");
     return joint_fwd_f32(enc, pred, w, bias, targets, t_len, u_len, lse, lp_blank, lp_label, B, T, U1, D, V, blank, st);
   }
+  if (check_tc_error("joint_rnnt_fwd")) return 1;
   CTCVR_REQUIRE(ws && ws_bytes >= joint_fwd_tc_ws_bytes(B, T, U1, D, V), "joint_rnnt_fwd bf16: workspace too small");
   CTCVR_REQUIRE(((uintptr_t)enc & 15) == 0 && ((uintptr_t)pred & 15) == 0, "joint_rnnt_fwd bf16: enc_proj / pred_proj must be 16-byte aligned");
   const int Vp = pad_v(V), NH = Vp / 2;
@@ -678,6 +697,7 @@ int joint_fwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
   p.B = B; p.T = T; p.U1 = U1; p.D = D; p.V = V; p.Vp = Vp; p.NH = NH; p.blank = blank;
   p.lse = lse; p.lp_blank = lp_blank; p.lp_label = lp_label;
   p.prof = g_prof_buf;
+  tc_error_host_word(&p.err_host);
   int ws_n = F_MAX_W_STAGES;
   while (ws_n > 2 && fwd2_smem_bytes(NH, Vp, ws_n) > 232448) --ws_n;
   p.w_stages = ws_n;
@@ -754,6 +774,7 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
   if (!joint_tc_bwd_supported(U1, D, V))   // shapes outside the tensor-core tiling use the fp32 kernels (same GPU)
     return joint_bwd_f32(enc, pred, w, bias, targets, t_len, u_len, lse, alpha, beta, costs, grad_costs, clamp, d_enc,
                          d_pred, d_w, d_b, B, T, U1, D, V, blank, ws, ws_bytes, st);
+  if (check_tc_error("joint_rnnt_bwd")) return 1;
   CTCVR_REQUIRE(ws && ws_bytes >= joint_bwd_tc_ws_bytes(B, T, U1, D, V), "joint_rnnt_bwd bf16: workspace too small");
   CTCVR_REQUIRE(((uintptr_t)enc & 15) == 0 && ((uintptr_t)pred & 15) == 0, "joint_rnnt_bwd bf16: enc_proj / pred_proj must be 16-byte aligned");
   const int Vp = pad_v(V), NH = Vp / 2, MB = D / 128;
@@ -795,6 +816,7 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
     p.zt = W.zt; p.gt = W.gt; p.Rpad = W.Rpad;
     p.d_enc_part = W.d_enc_part; p.d_pred = d_pred_acc; p.d_bias = d_b;
     p.prof = g_prof_buf;
+    tc_error_host_word(&p.err_host);
     const size_t smem = bwd2_smem_bytes(NH, Vp, D);
     CTCVR_REQUIRE(smem <= 232448, "joint_rnnt_bwd bf16: shared memory budget exceeded (%zu B)", smem);
     if (G.P == 21) {

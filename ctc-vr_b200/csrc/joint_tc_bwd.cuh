@@ -95,6 +95,7 @@ struct BwdParams {
   float* d_pred;            // [B,U1,D] atomic accumulate
   float* d_bias;            // [V] atomic accumulate
   long long* prof;
+  unsigned int* err_host;   // mapped host word for bounded-wait time-outs (tc_common.cuh)
 };
 
 // Shared memory: [GZ region: G tile (P2/P3) = A ring (P1) = z^T tile (P4)] [weight ring: 3 W stages = 5 W^T stages]
@@ -177,6 +178,7 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
   const int tile_end = (int)(((long)ntiles * (blockIdx.x + 1)) / gridDim.x);
 
   if (warp == 0 && lane == 0) {
+    g_tc_error_host = p.err_host;
     tma_prefetch_desc(&tmap_e);
     tma_prefetch_desc(&tmap_p);
     for (int i = 0; i < B_A_STAGES; ++i) { mbar_init(L.a_full(i), 8); mbar_init(L.a_empty(i), 1); }

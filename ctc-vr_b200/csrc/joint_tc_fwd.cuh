@@ -51,6 +51,7 @@ struct FwdParams {
   float* lp_blank;
   float* lp_label;
   long long* prof;
+  unsigned int* err_host;   // mapped host word for bounded-wait time-outs (tc_common.cuh)
 };
 
 struct FwdSmem {
@@ -108,6 +109,7 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
   const int WS = p.w_stages;
 
   if (warp == 0 && lane == 0) {
+    g_tc_error_host = p.err_host;
     tma_prefetch_desc(&tmap_e);
     tma_prefetch_desc(&tmap_p);
     for (int i = 0; i < F_A_STAGES; ++i) { mbar_init(L.a_full(i), PROD_THREADS / 32); mbar_init(L.a_empty(i), 1); }

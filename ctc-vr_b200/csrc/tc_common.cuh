@@ -18,6 +18,9 @@ namespace tc {
 // Every mbarrier wait is bounded: a protocol bug must not hang the GPU.  On timeout the kernel
 // records where, and all later waits return immediately; the host reads the flag after the call.
 __device__ unsigned int g_tc_error = 0;
+// mapped pinned host word (set by every tcgen05 kernel from its parameters): the host reads it without a
+// synchronisation at the next entry-point call and fails that call loudly
+__device__ unsigned int* g_tc_error_host = nullptr;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -55,7 +58,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // memory: the error flag is only consulted / written after ~2^20 failed probes (each probe already
 // suspends the warp in hardware for a while), so a protocol bug degrades into a slow, flagged exit.
 __device__ __noinline__ bool mbar_timeout(uint32_t site) {
-  atomicCAS(&g_tc_error, 0u, 0x80000000u | (site << 16) | (blockIdx.x & 0xffffu));
+  const unsigned int code = 0x80000000u | (site << 16) | (blockIdx.x & 0xffffu);
+  atomicCAS(&g_tc_error, 0u, code);
+  unsigned int* h = g_tc_error_host;
+  if (h != nullptr) { *reinterpret_cast<volatile unsigned int*>(h) = code; __threadfence_system(); }
   return true;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t site) {
