@@ -357,6 +357,158 @@ __global__ void __launch_bounds__(LAT2_THREADS) rnnt_lattice2_kernel(
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// v3: the same wavefront with the boundary handling moved out of the dependent loop.  The dependent chain of a
+// diagonal is one warp's instruction stream (v2: ~70 instructions = 340 cycles per diagonal, mostly predicates, selects
+// and address math).  Here the staged log-prob arrays are PADDED with a large negative sentinel (-1e30, never -inf:
+// no NaN from inf - inf, no special cases) - `pad` rows before and after the utterance, one column before, the
+// columns beyond U_b - so every lane runs the plain recurrence on every diagonal: cells outside the lattice compute
+// sentinel-sized values into padding rows of the alpha/beta arrays and never reach a real cell with a weight above
+// 2^-1e30.  Initial conditions are data: lpb[-1][0] = 0 with alpha(-1,0) = 0, and beta(T_b, U_b) = 0.
+// Lanes of columns beyond U_b mirror column U_b's addresses and are forced to the sentinel (one select), their
+// stores are predicated off by a loop-invariant predicate.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr float kLatNeg = -1.0e30f;
+
+template <int NJ>
+__global__ void __launch_bounds__(LAT2_THREADS) rnnt_lattice3_kernel(
+    const float* __restrict__ lp_blank, const float* __restrict__ lp_label, const int32_t* __restrict__ t_len,
+    const int32_t* __restrict__ u_len, float* __restrict__ alpha, float* __restrict__ beta,
+    float* __restrict__ costs, int T, int U1, int pitch, int pad) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x;
+  const int Tb = min(t_len[b], T), Ub = min(u_len[b], U1 - 1);
+  const size_t base = (size_t)b * T * U1;
+  if (Tb <= 0) { if (threadIdx.x == 0) costs[b] = 0.f; return; }
+  const int W = Ub + 1;
+  const int R = T + 2 * pad;                    // rows per array; element (t, u) at (t + pad) * pitch + u + 1
+  float* sb = sm;                               // lp_blank * log2e
+  float* sl = sm + (size_t)R * pitch;           // lp_label * log2e
+  float* sa = sm + (size_t)2 * R * pitch;       // alpha (base 2)
+  float* sc = sm + (size_t)3 * R * pitch;       // beta  (base 2)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = LAT2_THREADS >> 5;
+  // sentinel fill of the rows the sweeps can touch ([-pad, Tb + pad)), then the utterance's log-probs
+  {
+    const int nfill = (Tb + 2 * pad) * pitch;
+    for (int i = threadIdx.x; i < nfill; i += LAT2_THREADS) { sb[i] = kLatNeg; sl[i] = kLatNeg; }
+  }
+  __syncthreads();
+  {
+    const int n = Tb * U1;                      // rows are contiguous in global memory (row pitch U1)
+    const float* gb = lp_blank + base;
+    const float* gl = lp_label + base;
+    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * LAT2_THREADS) {
+      float xb[4], xl[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * LAT2_THREADS;
+        xb[k] = (i < n) ? __ldg(gb + i) : 0.f;
+        xl[k] = (i < n) ? __ldg(gl + i) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * LAT2_THREADS;
+        if (i < n) {
+          const int t = i / U1, u = i - t * U1;
+          if (u <= Ub) sb[(t + pad) * pitch + u + 1] = fmaxf(xb[k] * kLog2e, kLatNeg);
+          if (u < Ub) sl[(t + pad) * pitch + u + 1] = fmaxf(xl[k] * kLog2e, kLatNeg);     // no label leaves column U_b
+        }
+      }
+    }
+    if (threadIdx.x == 0) sb[(pad - 1) * pitch + 1] = 0.f;        // lpb[-1][0] = 0: alpha(0,0) = alpha(-1,0) + 0 = 0
+  }
+  __syncthreads();
+  const int ndiag = Tb + Ub;
+  const uint32_t s_sb = (uint32_t)__cvta_generic_to_shared(sb), s_sl = (uint32_t)__cvta_generic_to_shared(sl);
+  const uint32_t s_sa = (uint32_t)__cvta_generic_to_shared(sa), s_sc = (uint32_t)__cvta_generic_to_shared(sc);
+  const uint32_t rowb = (uint32_t)pitch * 4u;
+  auto lds = [](uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; };
+  auto sts = [](uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); };
+  auto lse2 = [](float a, float c) {            // log2(2^a + 2^c) for finite operands
+    const float m = fmaxf(a, c), n = fminf(a, c);
+    return m + lg2f(1.f + ex2f(n - m));
+  };
+  if (warp == 0) {
+    // ---------------- alpha(t,u) = LSE(alpha(t-1,u)+lpb(t-1,u), alpha(t,u-1)+lpl(t,u-1)),  t = d - u
+    float prev[NJ], nb[NJ], nl[NJ];
+    uint32_t a0[NJ];                            // byte offset of element (t, u) at the current diagonal
+    bool col[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int u = lane + 32 * j, uc = min(u, Ub);
+      col[j] = u <= Ub;
+      prev[j] = (u == 0) ? 0.f : kLatNeg;       // alpha(-1, 0) = 0
+      a0[j] = (uint32_t)((0 - uc + pad) * pitch + uc + 1) * 4u;
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { nb[j] = lds(s_sb + a0[j] - rowb); nl[j] = lds(s_sl + a0[j] - 4u); }
+    for (int d = 0; d < ndiag; ++d) {
+      float cb[NJ], cl[NJ], left[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { cb[j] = nb[j]; cl[j] = nl[j]; }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { nb[j] = lds(s_sb + a0[j]); nl[j] = lds(s_sl + a0[j] + rowb - 4u); }   // next diagonal
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        left[j] = __shfl_up_sync(0xffffffffu, prev[j], 1);
+        if (j > 0) { const float w = __shfl_sync(0xffffffffu, prev[j - 1], 31); if (lane == 0) left[j] = w; }
+        else if (lane == 0) left[j] = kLatNeg;
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        float v = lse2(prev[j] + cb[j], left[j] + cl[j]);
+        v = col[j] ? v : kLatNeg;
+        if (col[j]) sts(s_sa + a0[j], v);
+        prev[j] = v;
+        a0[j] += rowb;
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- beta(t,u) = LSE(beta(t+1,u)+lpb(t,u), beta(t,u+1)+lpl(t,u)),  beta(T_b, U_b) = 0
+    float prev[NJ], nb[NJ], nl[NJ];
+    uint32_t a0[NJ];
+    bool col[NJ];
+    const int d0 = ndiag - 1;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int u = lane + 32 * j, uc = min(u, Ub);
+      col[j] = u <= Ub;
+      prev[j] = (u == Ub) ? 0.f : kLatNeg;
+      a0[j] = (uint32_t)((d0 - uc + pad) * pitch + uc + 1) * 4u;
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { nb[j] = lds(s_sb + a0[j]); nl[j] = lds(s_sl + a0[j]); }
+    for (int d = d0; d >= 0; --d) {
+      float cb[NJ], cl[NJ], right[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { cb[j] = nb[j]; cl[j] = nl[j]; }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { nb[j] = lds(s_sb + a0[j] - rowb); nl[j] = lds(s_sl + a0[j] - rowb); }   // diagonal d - 1
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        right[j] = __shfl_down_sync(0xffffffffu, prev[j], 1);
+        if (j + 1 < NJ) { const float w = __shfl_sync(0xffffffffu, prev[j + 1], 0); if (lane == 31) right[j] = w; }
+        else if (lane == 31) right[j] = kLatNeg;
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        float v = lse2(prev[j] + cb[j], right[j] + cl[j]);
+        v = col[j] ? v : kLatNeg;
+        if (col[j]) sts(s_sc + a0[j], v);
+        prev[j] = v;
+        a0[j] -= rowb;
+      }
+    }
+    if (lane == 0) costs[b] = -prev[0] * kLn2;     // beta(0,0)
+  }
+  __syncthreads();
+  for (int t = warp; t < Tb; t += nwarp)
+    for (int u = lane; u < W; u += 32) {
+      alpha[base + (size_t)t * U1 + u] = sa[(t + pad) * pitch + u + 1] * kLn2;
+      beta[base + (size_t)t * U1 + u] = sc[(t + pad) * pitch + u + 1] * kLn2;
+    }
+}
+
 // Fallback for very long targets (U1 > 256): one CTA per utterance, block-wide diagonal sweep.
 __global__ void rnnt_lattice_generic_kernel(const float* __restrict__ lp_blank, const float* __restrict__ lp_label,
                                             const int32_t* __restrict__ t_len, const int32_t* __restrict__ u_len,
@@ -407,6 +559,19 @@ __global__ void rnnt_lattice_generic_kernel(const float* __restrict__ lp_blank, 
 template <int NJ>
 static int launch_lattice(const float* lpb, const float* lpl, const int32_t* t_len, const int32_t* u_len,
                           float* alpha, float* beta, float* costs, int B, int T, int U1, cudaStream_t st) {
+  {
+    // v3: padded arrays ([T + 2 pad][U1 + 1 rounded up to even]); CTCVR_LATTICE_V2=1 selects the previous kernel
+    const int pad3 = U1, pitch3 = (U1 + 2) & ~1;
+    const size_t smem3 = (size_t)4 * (T + 2 * pad3) * pitch3 * sizeof(float);
+    const char* v2 = getenv("CTCVR_LATTICE_V2");
+    if (smem3 <= 227 * 1024 && !(v2 && v2[0] == '1')) {
+      CTCVR_CHECK_CUDA(cudaFuncSetAttribute(rnnt_lattice3_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(227 * 1024)));
+      rnnt_lattice3_kernel<NJ><<<B, LAT2_THREADS, smem3, st>>>(lpb, lpl, t_len, u_len, alpha, beta, costs, T, U1, pitch3, pad3);
+      CTCVR_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   int pitch = (U1 % 2 == 0) ? U1 : U1 + 1;       // pitch-1 odd => diagonal reads hit distinct banks
   {
     const size_t smem4 = (size_t)4 * T * pitch * sizeof(float);
