@@ -370,8 +370,9 @@ __global__ void __launch_bounds__(LAT2_THREADS) rnnt_lattice2_kernel(
 // ---------------------------------------------------------------------------------------------------------------
 constexpr float kLatNeg = -1.0e30f;
 
+constexpr int LAT3_THREADS = 1024;               // 2 warps sweep, all 32 stage the log-probs / copy alpha, beta out
 template <int NJ>
-__global__ void __launch_bounds__(LAT2_THREADS) rnnt_lattice3_kernel(
+__global__ void __launch_bounds__(LAT3_THREADS) rnnt_lattice3_kernel(
     const float* __restrict__ lp_blank, const float* __restrict__ lp_label, const int32_t* __restrict__ t_len,
     const int32_t* __restrict__ u_len, float* __restrict__ alpha, float* __restrict__ beta,
     float* __restrict__ costs, int T, int U1, int pitch, int pad) {
@@ -386,28 +387,28 @@ __global__ void __launch_bounds__(LAT2_THREADS) rnnt_lattice3_kernel(
   float* sl = sm + (size_t)R * pitch;           // lp_label * log2e
   float* sa = sm + (size_t)2 * R * pitch;       // alpha (base 2)
   float* sc = sm + (size_t)3 * R * pitch;       // beta  (base 2)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = LAT2_THREADS >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = LAT3_THREADS >> 5;
   // sentinel fill of the rows the sweeps can touch ([-pad, Tb + pad)), then the utterance's log-probs
   {
     const int nfill = (Tb + 2 * pad) * pitch;
-    for (int i = threadIdx.x; i < nfill; i += LAT2_THREADS) { sb[i] = kLatNeg; sl[i] = kLatNeg; }
+    for (int i = threadIdx.x; i < nfill; i += LAT3_THREADS) { sb[i] = kLatNeg; sl[i] = kLatNeg; }
   }
   __syncthreads();
   {
     const int n = Tb * U1;                      // rows are contiguous in global memory (row pitch U1)
     const float* gb = lp_blank + base;
     const float* gl = lp_label + base;
-    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * LAT2_THREADS) {
+    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * LAT3_THREADS) {
       float xb[4], xl[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int i = i0 + k * LAT2_THREADS;
+        const int i = i0 + k * LAT3_THREADS;
         xb[k] = (i < n) ? __ldg(gb + i) : 0.f;
         xl[k] = (i < n) ? __ldg(gl + i) : 0.f;
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int i = i0 + k * LAT2_THREADS;
+        const int i = i0 + k * LAT3_THREADS;
         if (i < n) {
           const int t = i / U1, u = i - t * U1;
           if (u <= Ub) sb[(t + pad) * pitch + u + 1] = fmaxf(xb[k] * kLog2e, kLatNeg);
@@ -422,6 +423,10 @@ __global__ void __launch_bounds__(LAT2_THREADS) rnnt_lattice3_kernel(
   const uint32_t s_sb = (uint32_t)__cvta_generic_to_shared(sb), s_sl = (uint32_t)__cvta_generic_to_shared(sl);
   const uint32_t s_sa = (uint32_t)__cvta_generic_to_shared(sa), s_sc = (uint32_t)__cvta_generic_to_shared(sc);
   const uint32_t rowb = (uint32_t)pitch * 4u;
+  // opaque to the optimiser: otherwise the shared-window base (S2UR SR_CgaCtaId ...) and the row pitch (LDC) are
+  // re-materialised inside the dependent loop
+  uint32_t k_sb = s_sb, k_sl = s_sl, k_sa = s_sa, k_sc = s_sc, k_row = rowb;
+  asm volatile("" : "+r"(k_sb), "+r"(k_sl), "+r"(k_sa), "+r"(k_sc), "+r"(k_row));
   auto lds = [](uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; };
   auto sts = [](uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); };
   auto lse2 = [](float a, float c) {            // log2(2^a + 2^c) for finite operands
@@ -441,13 +446,13 @@ __global__ void __launch_bounds__(LAT2_THREADS) rnnt_lattice3_kernel(
       a0[j] = (uint32_t)((0 - uc + pad) * pitch + uc + 1) * 4u;
     }
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) { nb[j] = lds(s_sb + a0[j] - rowb); nl[j] = lds(s_sl + a0[j] - 4u); }
+    for (int j = 0; j < NJ; ++j) { nb[j] = lds(k_sb + a0[j] - k_row); nl[j] = lds(k_sl + a0[j] - 4u); }
     for (int d = 0; d < ndiag; ++d) {
       float cb[NJ], cl[NJ], left[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) { cb[j] = nb[j]; cl[j] = nl[j]; }
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) { nb[j] = lds(s_sb + a0[j]); nl[j] = lds(s_sl + a0[j] + rowb - 4u); }   // next diagonal
+      for (int j = 0; j < NJ; ++j) { nb[j] = lds(k_sb + a0[j]); nl[j] = lds(k_sl + a0[j] + k_row - 4u); }   // next diagonal
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         left[j] = __shfl_up_sync(0xffffffffu, prev[j], 1);
@@ -458,9 +463,9 @@ __global__ void __launch_bounds__(LAT2_THREADS) rnnt_lattice3_kernel(
       for (int j = 0; j < NJ; ++j) {
         float v = lse2(prev[j] + cb[j], left[j] + cl[j]);
         v = col[j] ? v : kLatNeg;
-        if (col[j]) sts(s_sa + a0[j], v);
+        if (col[j]) sts(k_sa + a0[j], v);
         prev[j] = v;
-        a0[j] += rowb;
+        a0[j] += k_row;
       }
     }
   } else if (warp == 1) {
@@ -477,13 +482,13 @@ __global__ void __launch_bounds__(LAT2_THREADS) rnnt_lattice3_kernel(
       a0[j] = (uint32_t)((d0 - uc + pad) * pitch + uc + 1) * 4u;
     }
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) { nb[j] = lds(s_sb + a0[j]); nl[j] = lds(s_sl + a0[j]); }
+    for (int j = 0; j < NJ; ++j) { nb[j] = lds(k_sb + a0[j]); nl[j] = lds(k_sl + a0[j]); }
     for (int d = d0; d >= 0; --d) {
       float cb[NJ], cl[NJ], right[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) { cb[j] = nb[j]; cl[j] = nl[j]; }
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) { nb[j] = lds(s_sb + a0[j] - rowb); nl[j] = lds(s_sl + a0[j] - rowb); }   // diagonal d - 1
+      for (int j = 0; j < NJ; ++j) { nb[j] = lds(k_sb + a0[j] - k_row); nl[j] = lds(k_sl + a0[j] - k_row); }   // diagonal d - 1
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         right[j] = __shfl_down_sync(0xffffffffu, prev[j], 1);
@@ -494,9 +499,9 @@ __global__ void __launch_bounds__(LAT2_THREADS) rnnt_lattice3_kernel(
       for (int j = 0; j < NJ; ++j) {
         float v = lse2(prev[j] + cb[j], right[j] + cl[j]);
         v = col[j] ? v : kLatNeg;
-        if (col[j]) sts(s_sc + a0[j], v);
+        if (col[j]) sts(k_sc + a0[j], v);
         prev[j] = v;
-        a0[j] -= rowb;
+        a0[j] -= k_row;
       }
     }
     if (lane == 0) costs[b] = -prev[0] * kLn2;     // beta(0,0)
@@ -567,7 +572,7 @@ static int launch_lattice(const float* lpb, const float* lpl, const int32_t* t_l
     if (smem3 <= 227 * 1024 && !(v2 && v2[0] == '1')) {
       CTCVR_CHECK_CUDA(cudaFuncSetAttribute(rnnt_lattice3_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(227 * 1024)));
-      rnnt_lattice3_kernel<NJ><<<B, LAT2_THREADS, smem3, st>>>(lpb, lpl, t_len, u_len, alpha, beta, costs, T, U1, pitch3, pad3);
+      rnnt_lattice3_kernel<NJ><<<B, LAT3_THREADS, smem3, st>>>(lpb, lpl, t_len, u_len, alpha, beta, costs, T, U1, pitch3, pad3);
       CTCVR_LAUNCH_CHECK();
       return 0;
     }
