@@ -5,6 +5,8 @@
 //     wenet/transformer/search.py:107-122
 // Algorithmic HBM bytes of the loss: read log-probs once (fwd gather is a subset), write the gradient
 // once, alpha scratch written+read: B*T*(2*V + 2*S)*4 B.  The kernel is bound by its T dependent steps.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ctcvr {
@@ -172,9 +174,217 @@ __global__ void ctc_loss_kernel(const float* __restrict__ lp, const int64_t* __r
   for (size_t i = (size_t)Tb * V + s; i < (size_t)T * V; i += nthr) gb[i] = 0.f;
 }
 
+// ---------------------------------------------------------------- CTC loss, split form (default)
+// The kernel above keeps everything of a time step on one CTA's critical path (6 block barriers, a dependent global
+// load and the V-wide gradient row per step: 2.9 us per step at T = 500).  Split form:
+//   kernel A (one CTA per utterance): the log-probs the DP needs, lp[t][label(s)], are gathered into shared memory
+//     once (T x S floats, -1e30 sentinel instead of -inf so the recurrences have no special cases);
+//     alpha (warps 0..) and beta (the next warps) then sweep concurrently, one named barrier per step each, and store
+//     alpha / beta [T][Sp] to the workspace together with the same-label chains of the extended label sequence;
+//   kernel B (one warp per (b, t) row, fully parallel): per-label log-sum of alpha + beta, then the gradient row.
+constexpr float kCtcNeg = -1.0e30f;
+constexpr float kCtcLog2e = 1.4426950408889634f, kCtcLn2 = 0.6931471805599453f;
+__device__ __forceinline__ float ctc_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ctc_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// log(e^a + e^b + e^c) for finite operands.  Natural-log domain on purpose: the log-probs are added exactly (a base-2
+// DP would round lp * log2e, an error proportional to |lp|, at every step); the base change multiplies the small
+// differences a - m (exact by Sterbenz for the terms that matter), never the large magnitudes.
+__device__ __forceinline__ float ctc_lse3(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  const float e = ctc_ex2((a - m) * kCtcLog2e) + ctc_ex2((b - m) * kCtcLog2e) + ctc_ex2((c - m) * kCtcLog2e);
+  return fmaf(ctc_lg2(e), kCtcLn2, m);
+}
+
+struct CtcWs {
+  float* alpha;   // [B][T][Sp]
+  float* beta;    // [B][T][Sp]
+  int* meta;      // [B][3][Sp]: label of state s | next state with the same label (-1) | 1 if s is the first of its label
+  int* flags;     // [B] 1: no valid alignment (nll = inf) or empty input -> zero gradient
+};
+static CtcWs carve_ctc_ws(void* ws, int B, int T, int Sp) {
+  CtcWs w;
+  w.alpha = reinterpret_cast<float*>(ws);
+  w.beta = w.alpha + (size_t)B * T * Sp;
+  w.meta = reinterpret_cast<int*>(w.beta + (size_t)B * T * Sp);
+  w.flags = w.meta + (size_t)B * 3 * Sp;
+  return w;
+}
+
+__global__ void ctc_alpha_beta_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targets,
+                                      const int32_t* __restrict__ in_lens, const int32_t* __restrict__ tgt_lens,
+                                      float* __restrict__ nll_out, float* __restrict__ alpha_ws,
+                                      float* __restrict__ beta_ws, int* __restrict__ meta, int* __restrict__ flags,
+                                      int T, int V, int Umax, int Sp, int blank, int zero_infinity) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const int Tb = min(in_lens[b], T), Ub = tgt_lens[b];
+  const int S = 2 * Ub + 1;
+  float* sel = sm;                               // [Tb][S]  lp[t][label(s)]
+  float* ca = sel + (size_t)T * S;               // [2][Sp + 4] alpha exchange, two guard cells on each side
+  float* cb = ca + 2 * (Sp + 4);                 // [2][Sp + 4] beta exchange
+  int* slot = reinterpret_cast<int*>(cb + 2 * (Sp + 4));   // [V] label -> first state carrying it
+  int* lab_s = slot + V;                         // [Sp]
+  int* nxt = lab_s + Sp;                         // [Sp]
+  const float* lpb = lp + (size_t)b * T * V;
+  const int grp = tid / Sp, s = tid - grp * Sp;  // group 0: alpha, group 1: beta
+  int* mb = meta + (size_t)b * 3 * Sp;
+
+  for (int i = tid; i < Sp; i += nthr) {
+    int l = blank;
+    if (i < S && (i & 1)) l = (int)targets[(size_t)b * Umax + (i >> 1)];
+    lab_s[i] = l;
+    nxt[i] = -1;
+  }
+  for (int v = tid; v < V; v += nthr) slot[v] = -1;
+  __syncthreads();
+  if (tid == 0) {
+    for (int q = 1; q < S; q += 2) {
+      const int l = lab_s[q];
+      if (slot[l] < 0) slot[l] = q;
+      else { int pp = slot[l]; while (nxt[pp] >= 0) pp = nxt[pp]; nxt[pp] = q; }
+    }
+  }
+  // gather: every thread, fully parallel loads
+  for (int i = tid; i < Tb * S; i += nthr) {
+    const int t = i / S, q = i - t * S;
+    sel[i] = fmaxf(lpb[(size_t)t * V + lab_s[q]], kCtcNeg);
+  }
+  for (int i = tid; i < 2 * (Sp + 4); i += nthr) { ca[i] = kCtcNeg; cb[i] = kCtcNeg; }
+  __syncthreads();
+  for (int i = tid; i < Sp; i += nthr) {
+    mb[i] = lab_s[i];
+    mb[Sp + i] = nxt[i];
+    mb[2 * Sp + i] = (i < S && (i & 1) && slot[lab_s[i]] == i) ? 1 : 0;
+  }
+  if (Tb == 0) {
+    if (tid == 0) {
+      const bool inf = Ub != 0;
+      nll_out[b] = inf ? (zero_infinity ? 0.f : INFINITY) : 0.f;
+      flags[b] = 1;
+    }
+    return;
+  }
+  const int lab = lab_s[s];
+  float* ga = alpha_ws + (size_t)b * T * Sp;
+  float* gbt = beta_ws + (size_t)b * T * Sp;
+  if (grp == 0) {
+    // ---- alpha_t(s) = lse(alpha_{t-1}(s), alpha_{t-1}(s-1), [alpha_{t-1}(s-2)]) + lp_t(label(s))
+    const bool skip = (s < S && (s & 1) && s >= 2) && (lab != lab_s[s - 2]);
+    const bool live = s < S;
+    float v = (live && s < 2) ? sel[s] : kCtcNeg;
+    int buf = 0;
+    ca[buf * (Sp + 4) + 2 + s] = v;
+    ga[s] = v;
+    asm volatile("bar.sync 1, %0;" ::"r"(Sp));
+    for (int t = 1; t < Tb; ++t) {
+      const float* c = ca + buf * (Sp + 4) + 2 + s;
+      const float x = live ? sel[t * S + s] : kCtcNeg;
+      v = ctc_lse3(c[0], c[-1], skip ? c[-2] : kCtcNeg) + x;
+      v = live ? fmaxf(v, kCtcNeg) : kCtcNeg;
+      buf ^= 1;
+      ca[buf * (Sp + 4) + 2 + s] = v;
+      ga[(size_t)t * Sp + s] = v;
+      asm volatile("bar.sync 1, %0;" ::"r"(Sp));
+    }
+    if (s == 0) {
+      const float* c = ca + buf * (Sp + 4) + 2;
+      const float a1 = c[S - 1], a2 = (S > 1) ? c[S - 2] : kCtcNeg;
+      const float ll = ctc_lse3(a1, a2, kCtcNeg);
+      const bool inf = ll < -1.0e29f;
+      nll_out[b] = inf ? (zero_infinity ? 0.f : INFINITY) : -ll;
+      flags[b] = inf ? 1 : 0;
+    }
+  } else if (grp == 1) {
+    // ---- beta_t(s) = lse(beta_{t+1}(s), beta_{t+1}(s+1), [beta_{t+1}(s+2)]) + lp_t(label(s))
+    const bool skip = (s < S && (s & 1) && s + 2 < S) && (lab != lab_s[s + 2]);
+    const bool live = s < S;
+    float v = (live && s >= S - 2) ? sel[(Tb - 1) * S + s] : kCtcNeg;
+    int buf = 0;
+    cb[buf * (Sp + 4) + 2 + s] = v;
+    gbt[(size_t)(Tb - 1) * Sp + s] = v;
+    asm volatile("bar.sync 2, %0;" ::"r"(Sp));
+    for (int t = Tb - 2; t >= 0; --t) {
+      const float* c = cb + buf * (Sp + 4) + 2 + s;
+      const float x = live ? sel[t * S + s] : kCtcNeg;
+      v = ctc_lse3(c[0], c[1], skip ? c[2] : kCtcNeg) + x;
+      v = live ? fmaxf(v, kCtcNeg) : kCtcNeg;
+      buf ^= 1;
+      cb[buf * (Sp + 4) + 2 + s] = v;
+      gbt[(size_t)t * Sp + s] = v;
+      asm volatile("bar.sync 2, %0;" ::"r"(Sp));
+    }
+  }
+}
+
+constexpr int CTC_GRAD_ROWS = 8;     // rows per CTA (4 warps x 2)
+__global__ void __launch_bounds__(128) ctc_grad_kernel(const float* __restrict__ lp, const int32_t* __restrict__ in_lens,
+                                                       const int32_t* __restrict__ tgt_lens,
+                                                       const float* __restrict__ grad_scale, const float* __restrict__ nll,
+                                                       const float* __restrict__ alpha_ws, const float* __restrict__ beta_ws,
+                                                       const int* __restrict__ meta, const int* __restrict__ flags,
+                                                       float* __restrict__ grad, int T, int V, int Sp, int blank) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Tb = min(in_lens[b], T), S = 2 * tgt_lens[b] + 1;
+  int* mlab = reinterpret_cast<int*>(sm);        // [3][Sp]
+  float* abw = sm + 3 * Sp + warp * Sp;          // [4][Sp] alpha + beta of the warp's row
+  float* acc = sm + 7 * Sp + warp * V;           // [4][V] per-label log-sum
+  const int* mb = meta + (size_t)b * 3 * Sp;
+  for (int i = threadIdx.x; i < 3 * Sp; i += 128) mlab[i] = mb[i];
+  __syncthreads();
+  const bool dead = flags[b] != 0;
+  const float scale = grad_scale ? grad_scale[b] : 1.f;
+  const float nllb = nll[b];
+  for (int r = warp; r < CTC_GRAD_ROWS; r += 4) {
+    const int t = blockIdx.x * CTC_GRAD_ROWS + r;
+    if (t >= T) break;
+    float* grow = grad + ((size_t)b * T + t) * V;
+    if (t >= Tb || dead) {
+      for (int v = lane; v < V; v += 32) grow[v] = 0.f;
+      continue;
+    }
+    const float* ar = alpha_ws + ((size_t)b * T + t) * Sp;
+    const float* br = beta_ws + ((size_t)b * T + t) * Sp;
+    float bm = kCtcNeg;
+    for (int q = lane; q < Sp; q += 32) {
+      const float x = (q < S) ? ar[q] + br[q] : kCtcNeg;
+      abw[q] = x;
+      if (!(q & 1)) bm = fmaxf(bm, x);
+    }
+    for (int v = lane; v < V; v += 32) acc[v] = kCtcNeg;
+    __syncwarp();
+    // blank: log-sum over the even states
+    bm = warp_max(bm);
+    float be = 0.f;
+    for (int q = 2 * lane; q < S; q += 64) be += ctc_ex2((abw[q] - bm) * kCtcLog2e);
+    be = warp_sum(be);
+    const float lc_blank = fmaf(ctc_lg2(be), kCtcLn2, bm);
+    // labels: the first state of every label sums its chain
+    for (int q = 1 + 2 * lane; q < S; q += 64) {
+      if (mlab[2 * Sp + q]) {
+        float m = abw[q];
+        for (int k = mlab[Sp + q]; k >= 0; k = mlab[Sp + k]) m = fmaxf(m, abw[k]);
+        float e = 0.f;
+        for (int k = q; k >= 0; k = mlab[Sp + k]) e += ctc_ex2((abw[k] - m) * kCtcLog2e);
+        acc[mlab[q]] = fmaf(ctc_lg2(e), kCtcLn2, m);
+      }
+    }
+    __syncwarp();
+    const float* lrow = lp + ((size_t)b * T + t) * V;
+    for (int v = lane; v < V; v += 32) {
+      const float l = lrow[v];
+      float g = expf(l);
+      const float c = (v == blank) ? lc_blank : acc[v];
+      if (c > -1.0e29f) g -= expf(c - l + nllb);
+      grow[v] = g * scale;
+    }
+    __syncwarp();
+  }
+}
+
 size_t ctc_loss_ws_bytes(int B, int T, int Umax) {
   int Sp = (2 * Umax + 1 + 31) / 32 * 32;
-  return (size_t)B * T * Sp * sizeof(float) + 256;
+  return ((size_t)2 * B * T * Sp + (size_t)3 * B * Sp + B) * sizeof(float) + 256;
 }
 
 int ctc_loss(const float* lp, const int64_t* targets, const int32_t* in_lens, const int32_t* tgt_lens,
@@ -183,6 +393,27 @@ int ctc_loss(const float* lp, const int64_t* targets, const int32_t* in_lens, co
   int Sp = (2 * Umax + 1 + 31) / 32 * 32;
   CTCVR_REQUIRE(Sp <= 1024, "ctc_loss: target length %d too long (2U+1 must be <= 1024)", Umax);
   CTCVR_REQUIRE(ws_bytes >= ctc_loss_ws_bytes(B, T, Umax), "ctc_loss: workspace too small");
+  const int Smax = 2 * Umax + 1;
+  // split form when the gathered log-probs of one utterance fit in shared memory
+  const size_t smemA = ((size_t)T * Smax + 4 * (Sp + 4)) * sizeof(float) + (size_t)(V + 2 * Sp) * sizeof(int);
+  const char* v1 = getenv("CTCVR_CTC_V1");
+  if (smemA <= 220 * 1024 && 2 * Sp <= 1024 && !(v1 && v1[0] == '1')) {
+    CtcWs W = carve_ctc_ws(ws, B, T, Sp);
+    const int threads = 2 * Sp < 256 ? 256 : 2 * Sp;
+    CTCVR_CHECK_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    ctc_alpha_beta_kernel<<<B, threads, smemA, st>>>(lp, targets, in_lens, tgt_lens, nll, W.alpha, W.beta, W.meta, W.flags,
+                                                     T, V, Umax, Sp, blank, zero_infinity);
+    CTCVR_LAUNCH_CHECK();
+    if (grad) {
+      const size_t smemB = ((size_t)7 * Sp + (size_t)4 * V) * sizeof(float);
+      CTCVR_REQUIRE(smemB <= 200 * 1024, "ctc_loss: vocabulary %d too large", V);
+      CTCVR_CHECK_CUDA(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+      ctc_grad_kernel<<<dim3(cdiv(T, CTC_GRAD_ROWS), B), 128, smemB, st>>>(lp, in_lens, tgt_lens, grad_scale, nll, W.alpha, W.beta,
+                                                                            W.meta, W.flags, grad, T, V, Sp, blank);
+      CTCVR_LAUNCH_CHECK();
+    }
+    return 0;
+  }
   int threads = Sp < 64 ? 64 : Sp;
   size_t smem = (size_t)(3 * Sp + 32) * sizeof(float) + (size_t)(V + Sp) * sizeof(int);
   CTCVR_REQUIRE(smem <= 200 * 1024, "ctc_loss: vocabulary %d too large", V);
