@@ -308,8 +308,8 @@ def run_ours(args):
 
 def _ncu_traffic():
     """DRAM bytes (read + write) of the backward entry point's two tensor-core kernels per call, from the committed
-    `ncu --set full` capture of this round (profiles/r1_v5_traffic.json); None when the file is absent."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_v5_traffic.json")
+    `ncu --set full` capture of this round (profiles/r1_v6_traffic.json); None when the file is absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_v6_traffic.json")
     try:
         k = json.load(open(path))["kernels"]
         return float(sum(k[n]["dram_read_bytes"] + k[n]["dram_write_bytes"] for n in ("joint_bwd2_kernel", "dw_gemm_rz_kernel")))
