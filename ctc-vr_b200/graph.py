@@ -34,6 +34,7 @@ class GraphedJointRnntStep:
         self.logit_lengths = torch.full((B,), T, dtype=torch.int32, device=dev)
         self.target_lengths = torch.full((B,), U, dtype=torch.int32, device=dev)
         self.loss = None
+        self._seed = torch.full((B,), 1.0 / self.gB, dtype=torch.float32, device=dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -52,9 +53,10 @@ class GraphedJointRnntStep:
         self.pred.grad = None
         costs = self.joint.rnnt_loss_fused(self.enc, self.pred, self.targets, self.logit_lengths, self.target_lengths,
                                            self.blank, clamp=self.clamp, reduction="none", precision=self.precision)
-        loss = costs.sum() / self.gB
-        loss.backward()
-        self.loss = loss.detach()
+        # loss = sum_b cost_b / global_batch: the constant d loss / d cost_b vector seeds the backward directly (no
+        # sum / div / fill / mul / expand kernels of the scalar-loss autograd chain), the value is one dot product
+        torch.autograd.backward(costs, grad_tensors=self._seed)
+        self.loss = torch.dot(costs.detach(), self._seed)
 
     @torch.no_grad()
     def load(self, enc_out, pred_out, targets, logit_lengths, target_lengths):
