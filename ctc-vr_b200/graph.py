@@ -45,6 +45,10 @@ class GraphedJointRnntStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._eager()
+        # the gradient tensors this graph writes: step() re-points `.grad` at them, so several graphed steps over the same
+        # parameters (e.g. one per input staging buffer of a double-buffered loader) can be replayed in turn
+        self._param_grads = [(p, p.grad) for p in self.joint.parameters()]
+        self._loss_buf = self.loss
 
     def _eager(self):
         for p in self.joint.parameters():
@@ -71,6 +75,14 @@ class GraphedJointRnntStep:
         if enc_out is not None:
             self.load(enc_out, pred_out, targets, logit_lengths, target_lengths)
         self.graph.replay()
+        for p, g in self._param_grads:
+            p.grad = g
+        self.loss = self._loss_buf
         return self.loss
+
+    def input_buffers(self):
+        """The captured input tensors [enc, pred, targets, logit_lengths, target_lengths]: a loader may copy the next
+        batch straight into them (e.g. H2D on a copy stream) once the previous replay of THIS graph has finished."""
+        return [self.enc, self.pred, self.targets, self.logit_lengths, self.target_lengths]
 
     __call__ = step
