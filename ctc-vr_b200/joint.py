@@ -9,6 +9,18 @@ from torch import nn
 from . import functional as CF
 
 
+_ONES = {}
+
+
+def _ones_row(n: int, device) -> torch.Tensor:
+    """[1, n] bf16 ones, cached per (n, device): the bias gradient of a pre-projection is ones @ dy."""
+    key = (n, str(device))
+    t = _ONES.get(key)
+    if t is None:
+        t = _ONES[key] = torch.ones(1, n, dtype=torch.bfloat16, device=device)
+    return t
+
+
 class _Bf16Linear(torch.autograd.Function):
     """`F.linear` for the two pre-projections of the bf16 path: bf16 operands, fp32 accumulation (what
     `torch.autocast` gives), but the backward writes fp32 gradients straight from the library GEMMs
@@ -34,8 +46,7 @@ class _Bf16Linear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = torch.mm(dy2.t(), xb, out_dtype=torch.float32).to(ctx.w_dtype)
         if ctx.needs_input_grad[2]:
-            ones = torch.ones(1, dy2.shape[0], dtype=torch.bfloat16, device=dy2.device)
-            db = torch.mm(ones, dy2, out_dtype=torch.float32).reshape(-1).to(ctx.w_dtype)
+            db = torch.mm(_ones_row(dy2.shape[0], dy2.device), dy2, out_dtype=torch.float32).reshape(-1).to(ctx.w_dtype)
         return dx, dw, db
 
 
