@@ -375,10 +375,8 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
     const int p_tloc = min(r / P, TT - 1), p_ul = r % P;
     const uint32_t e_row = bwd_pred_region<P>() + (uint32_t)p_tloc * 128u, e_sw = (uint32_t)(p_tloc & 7);
     const uint32_t p_row = (uint32_t)p_ul * 128u, p_sw = (uint32_t)(p_ul & 7);
-    // z^T staging of the same values (one 8 KB buffer per slot: [2 row halves][32 d][64 rows]): row d of the slot,
-    // half r>>6, 16-byte chunk ((r&63)>>3) ^ (d&7), element r&7
-    const uint32_t z_off = (uint32_t)(r >> 6) * 4096u + (uint32_t)(r & 7) * 2u;
-    const uint32_t z_chunk = (uint32_t)((r & 63) >> 3);
+    // z^T staging (one 8 KB buffer per slot: [2 row halves][32 d][64 rows]): row d of the slot, half r>>6, 16-byte
+    // chunk ((r&63)>>3) ^ (d&7), element r&7 - written by stmatrix.trans from the A stage in TMEM (see P1)
     uint32_t kb_base = 0;                       // k-blocks produced before this tile (ring stages follow it)
 
     for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -419,16 +417,27 @@ joint_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
             w[4 * c4 + 2] = tanh_add_bf16x2_packed(ev[c4].z, pv[c4].z);
             w[4 * c4 + 3] = tanh_add_bf16x2_packed(ev[c4].w, pv[c4].w);
           }
-          tmem_st16(tq + (uint32_t)(B_ACC_COLS + a_stg * 32 + kh * 16), w);
-          const uint32_t zbuf = L.z_stage(wg, zp);
-          const uint32_t zs = zbuf + z_off;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            // w[i] holds d = 2i, 2i+1 of this thread's 32
-            sts16(zs + (2 * i) * 128 + ((z_chunk ^ (uint32_t)((2 * i) & 7)) << 4), w[i] & 0xffffu);
-            sts16(zs + (2 * i + 1) * 128 + ((z_chunk ^ (uint32_t)((2 * i + 1) & 7)) << 4), w[i] >> 16);
-          }
+          const uint32_t acol = (uint32_t)(B_ACC_COLS + a_stg * 32 + kh * 16);
+          tmem_st16(tq + acol, w);
           tmem_st_wait();
+          // z^T staging straight from the A stage: read the quarter's 32 lanes x 16 columns back in fragment layout
+          // (two 16-lane halves) and let stmatrix.trans write the 8x8 tiles transposed - row d of the box gets the
+          // 16-byte chunk of 8 consecutive tile rows, the same bytes the per-element stores produced
+          const uint32_t zbuf = L.z_stage(wg, zp);
+          {
+            uint32_t f0[8], f1[8];
+            tmem_ld_16x128b_x4(tq + acol, f0);
+            tmem_ld_16x128b_x4(tq + (16u << 16) + acol, f1);
+            tmem_ld_wait();
+            const uint32_t m = (uint32_t)lane >> 3, j = (uint32_t)lane & 7u;
+            const uint32_t zrow = zbuf + (uint32_t)(q >> 1) * 4096u + ((m >> 1) * 8u + j) * 128u;
+            const uint32_t ch = (uint32_t)(q & 1) * 4u + (m & 1u);                 // + 2 for the second half
+            // call c: column groups 2c, 2c+1 -> staging rows 16c + (m>>1)*8 + j
+            stmatrix_x4_trans(zrow + ((ch ^ j) << 4), f0[0], f0[1], f0[2], f0[3]);
+            stmatrix_x4_trans(zrow + 2048u + ((ch ^ j) << 4), f0[4], f0[5], f0[6], f0[7]);
+            stmatrix_x4_trans(zrow + (((ch + 2u) ^ j) << 4), f1[0], f1[1], f1[2], f1[3]);
+            stmatrix_x4_trans(zrow + 2048u + (((ch + 2u) ^ j) << 4), f1[4], f1[5], f1[6], f1[7]);
+          }
           tc_fence_before();
           fence_proxy_async();
           warp_arrive(L.a_full(a_stg));

@@ -181,6 +181,20 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+// 16 lanes x 16 columns in the MMA-fragment layout: thread t receives, for column group cg = 0..3,
+// r[2cg] = (lane t/4, column 4cg + t%4) and r[2cg+1] = (lane 8 + t/4, same column)  (tools/tmem_shape_probe.cu).
+// With bf16 pairs in the columns this is exactly the operand layout of stmatrix (8x8 b16 tiles).
+__device__ __forceinline__ void tmem_ld_16x128b_x4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x128b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+// four 8x8 b16 tiles stored TRANSPOSED: threads 8m..8m+7 supply the shared addresses of the 8 rows (16 bytes each) of
+// tile m; row j of the stored tile = column j of the fragment held in r[m]
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t row_addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(row_addr), "r"(r0), "r"(r1),
+               "r"(r2), "r"(r3) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // one column: thread i of the warp receives TMEM lane (lane_base + i), column col

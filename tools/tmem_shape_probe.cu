@@ -40,19 +40,27 @@ __global__ void __launch_bounds__(128, 1) k(int* out) {
     asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(tmem));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     out[lane * 8 + 3] = (int)a0; out[lane * 8 + 4] = (int)a1; out[lane * 8 + 5] = (int)a2; out[lane * 8 + 6] = (int)a3;
+    // 16x128b.x4 from lane 16 of the quarter: 8 registers
+    uint32_t b[8];
+    asm volatile("tcgen05.ld.sync.aligned.16x128b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]) : "r"(tmem + (16u << 16)));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int i = 0; i < 8; ++i) out[256 + lane * 8 + i] = (int)b[i];
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32) : "memory");
 }
 int main() {
-  int* out; cudaMalloc(&out, 32 * 8 * 4); cudaMemset(out, 0xff, 32 * 8 * 4);
+  int* out; cudaMalloc(&out, 2 * 32 * 8 * 4); cudaMemset(out, 0xff, 2 * 32 * 8 * 4);
   k<<<1, 128>>>(out);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("err %s\n", cudaGetErrorString(e)); return 1; }
-  int h[256]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+  int h[512]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
   printf("value = lane*100 + column.  thread : 16x64b.x1 | 16x128b.x1 (2 regs) | 16x256b.x1 (4 regs)\n");
   for (int t = 0; t < 32; ++t)
     printf("t%02d : %5d | %5d %5d | %5d %5d %5d %5d\n", t, h[t * 8], h[t * 8 + 1], h[t * 8 + 2], h[t * 8 + 3], h[t * 8 + 4], h[t * 8 + 5], h[t * 8 + 6]);
+  printf("16x128b.x4 at lane offset 16 (8 regs)\n");
+  for (int t = 0; t < 32; t += 1) { printf("t%02d :", t); for (int i = 0; i < 8; ++i) printf(" %5d", h[256 + t * 8 + i]); printf("\n"); }
   return 0;
 }
