@@ -58,6 +58,7 @@ __global__ void ctc_loss_kernel(const float* __restrict__ lp, const int64_t* __r
 
   int lab = blank;
   if (s < S && (s & 1)) lab = (int)targets[(size_t)b * Umax + (s >> 1)];
+  if ((unsigned)lab >= (unsigned)V) lab = blank;    // out-of-range label (undefined in the reference): no stray index
   bool skip_ok = false;             // may take the s-2 transition
   if (s < S && (s & 1) && s >= 2) skip_ok = (lab != (int)targets[(size_t)b * Umax + (s >> 1) - 1]);
 
@@ -69,6 +70,7 @@ __global__ void ctc_loss_kernel(const float* __restrict__ lp, const int64_t* __r
     slot[blank] = 0;                // all even states: handled by a block reduction, leader 0
     for (int q = 1; q < S; q += 2) {
       int l = (int)targets[(size_t)b * Umax + (q >> 1)];
+      if ((unsigned)l >= (unsigned)V) continue;     // out-of-range label: not tracked (its state keeps lab = blank)
       if (slot[l] < 0) slot[l] = q;
       else { int p = slot[l]; while (nxt[p] >= 0) p = nxt[p]; nxt[p] = q; }
     }
@@ -232,6 +234,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lp, const int64_
   for (int i = tid; i < Sp; i += nthr) {
     int l = blank;
     if (i < S && (i & 1)) l = (int)targets[(size_t)b * Umax + (i >> 1)];
+    if ((unsigned)l >= (unsigned)V) l = blank;      // out-of-range label (undefined in the reference): no stray index
     lab_s[i] = l;
     nxt[i] = -1;
   }
