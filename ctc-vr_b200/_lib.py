@@ -32,10 +32,10 @@ _SIGS = {
     "ctcvr_joint_rnnt_fwd": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, Z, P]),
     "ctcvr_rnnt_lattice": (I, [P, P, P, P, P, P, P, I, I, I, P]),
     "ctcvr_joint_rnnt_bwd_ws_bytes": (Z, [I, I, I, I, I, I]),
-    "ctcvr_joint_rnnt_bwd": (I, [P] * 12 + [F] + [P] * 4 + [I] * 7 + [P, Z, P]),
+    "ctcvr_joint_rnnt_bwd": (I, [P] * 14 + [F] + [P] * 4 + [I] * 7 + [P, Z, P]),
     "ctcvr_joint_tc_supported": (I, [I, I, I]),
     "ctcvr_joint_rnnt_fwd_bf16in": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P, Z, P]),
-    "ctcvr_joint_rnnt_bwd_bf16in": (I, [P] * 12 + [F] + [P] * 4 + [I] * 6 + [P, Z, P]),
+    "ctcvr_joint_rnnt_bwd_bf16in": (I, [P] * 14 + [F] + [P] * 4 + [I] * 6 + [P, Z, P]),
     "ctcvr_rnnt_loss_dense_ws_bytes": (Z, [I, I, I]),
     "ctcvr_rnnt_loss_dense": (I, [P, P, P, P, P, P, I, I, I, I, I, F, P, Z, P]),
     "ctcvr_log_softmax": (I, [P, P, c_long, I, P]),

@@ -720,7 +720,7 @@ bool joint_tc_bwd_supported(int U1, int D, int V) {
 }
 
 struct BwdWs {
-  __nv_bfloat16 *wb, *wtb, *zt, *gt, *eb, *pb;
+  __nv_bfloat16 *wb, *wtb, *gt, *eb, *pb;
   float *bias_pad, *bias_l2, *d_enc_part, *partials, *d_pred_acc;
   int4 *tiles, *tile_rows;
   int* ntiles;
@@ -749,7 +749,6 @@ static BwdWs carve_bwd_ws(void* ws, int B, int T, int U1, int D, int V) {
   w.tiles = reinterpret_cast<int4*>(take((size_t)w.mt * 16));
   w.tile_rows = reinterpret_cast<int4*>(take((size_t)w.mt * 16));
   w.ntiles = reinterpret_cast<int*>(take(4));
-  w.zt = reinterpret_cast<__nv_bfloat16*>(take((size_t)D * BM * 2 * sm_count()));   // per-CTA z^T tile scratch (stays in L2)
   w.gt = reinterpret_cast<__nv_bfloat16*>(take((size_t)((Vp + 63) / 64) * 64 * w.Rpad * 2));
   w.d_enc_part = reinterpret_cast<float*>(take((size_t)w.S_max * B * T * D * 4));
   w.partials = reinterpret_cast<float*>(take((size_t)w.KS * D * Vp * 4));
@@ -764,7 +763,8 @@ size_t joint_bwd_tc_ws_bytes(int B, int T, int U1, int D, int V) {
 }
 
 int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float* w, const float* bias, const int32_t* targets,
-                 const int32_t* t_len, const int32_t* u_len, const float* lse, const float* alpha, const float* beta,
+                 const int32_t* t_len, const int32_t* u_len, const float* lse, const float* lp_blank, const float* lp_label,
+                 const float* alpha, const float* beta,
                  const float* costs, const float* grad_costs, float clamp, float* d_enc, float* d_pred, float* d_w,
                  float* d_b, int B, int T, int U1, int D, int V, int blank, void* ws, size_t ws_bytes, cudaStream_t st) {
   const float* enc = reinterpret_cast<const float*>(enc_v);
@@ -809,23 +809,25 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
     if (make_tmap_bf16_2d(&tmap_p, W.pb, (uint64_t)B * U1, D, D, G.P)) return 1;
     BwdParams p{};
     p.w_t = W.wb; p.wt_t = W.wtb;
-    p.bias = bias; p.bias_l2 = W.bias_l2; p.targets = targets; p.t_len = t_len; p.u_len = u_len;
+    p.bias_l2 = W.bias_l2; p.targets = targets; p.t_len = t_len; p.u_len = u_len;
     p.tiles = W.tiles; p.ntiles = W.ntiles;
     p.B = B; p.T = T; p.U1 = U1; p.D = D; p.V = V; p.Vp = Vp; p.NH = NH; p.blank = blank;
-    p.lse = lse; p.alpha = alpha; p.beta = beta; p.costs = costs; p.grad_costs = grad_costs; p.clamp = clamp;
-    p.zt = W.zt; p.gt = W.gt; p.Rpad = W.Rpad;
+    p.r1_stages = bwd3_r1_stages(NH, Vp);
+    p.lse = lse; p.lp_blank = lp_blank; p.lp_label = lp_label;
+    p.alpha = alpha; p.beta = beta; p.costs = costs; p.grad_costs = grad_costs; p.clamp = clamp;
+    p.gt = W.gt;
     p.d_enc_part = W.d_enc_part; p.d_pred = d_pred_acc; p.d_bias = d_b;
     p.prof = g_prof_buf;
     tc_error_host_word(&p.err_host);
-    const size_t smem = bwd2_smem_bytes(NH, Vp, D);
-    CTCVR_REQUIRE(smem <= 232448, "joint_rnnt_bwd bf16: shared memory budget exceeded (%zu B)", smem);
+    const size_t smem = bwd3_smem_bytes(NH, Vp, D);
+    CTCVR_REQUIRE(smem <= 232448 && p.r1_stages >= 2, "joint_rnnt_bwd bf16: shared memory budget exceeded (%zu B)", smem);
     if (G.P == 21) {
-      CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd2_kernel<21, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      joint_bwd2_kernel<21, 6><<<grid, NTHREADS, smem, st>>>(tmap_e, tmap_p, p);
+      CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd3_kernel<21, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      joint_bwd3_kernel<21, 6><<<grid, NTHREADS, smem, st>>>(tmap_e, tmap_p, p);
       CTCVR_LAUNCH_CHECK();
     } else {
-      CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd2_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      joint_bwd2_kernel<16, 8><<<grid, NTHREADS, smem, st>>>(tmap_e, tmap_p, p);
+      CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd3_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      joint_bwd3_kernel<16, 8><<<grid, NTHREADS, smem, st>>>(tmap_e, tmap_p, p);
       CTCVR_LAUNCH_CHECK();
     }
   }

@@ -68,13 +68,13 @@ class _FusedJointRnnt(torch.autograd.Function):
                      ptr(lpb), ptr(lpl), B, T, U1, D, V, blank, precision, ptr(ws), ws.numel(), stream())
             call("ctcvr_rnnt_lattice", ptr(lpb), ptr(lpl), ptr(tl), ptr(ul), ptr(alpha), ptr(beta), ptr(costs),
                  B, T, U1, stream())
-        ctx.save_for_backward(e, p, w, b, tg, tl, ul, lse, alpha, beta, costs)
+        ctx.save_for_backward(e, p, w, b, tg, tl, ul, lse, lpb, lpl, alpha, beta, costs)
         ctx.cfg = (blank, float(clamp), precision, bf16_in)
         return costs
 
     @staticmethod
     def backward(ctx, grad_costs):
-        e, p, w, b, tg, tl, ul, lse, alpha, beta, costs = ctx.saved_tensors
+        e, p, w, b, tg, tl, ul, lse, lpb, lpl, alpha, beta, costs = ctx.saved_tensors
         blank, clamp, precision, bf16_in = ctx.cfg
         B, T, D = e.shape
         U1, V = p.shape[1], w.shape[0]
@@ -89,11 +89,11 @@ class _FusedJointRnnt(torch.autograd.Function):
             ws = _ws(query("ctcvr_joint_rnnt_bwd_ws_bytes", B, T, U1, D, V, precision), dev)
             if bf16_in:
                 call("ctcvr_joint_rnnt_bwd_bf16in", ptr(e), ptr(p), ptr(w), ptr(b), ptr(tg), ptr(tl), ptr(ul), ptr(lse),
-                     ptr(alpha), ptr(beta), ptr(costs), ptr(gc), clamp, ptr(d_e), ptr(d_p), ptr(d_w), ptr(d_b),
+                     ptr(lpb), ptr(lpl), ptr(alpha), ptr(beta), ptr(costs), ptr(gc), clamp, ptr(d_e), ptr(d_p), ptr(d_w), ptr(d_b),
                      B, T, U1, D, V, blank, ptr(ws), ws.numel(), stream())
             else:
                 call("ctcvr_joint_rnnt_bwd", ptr(e), ptr(p), ptr(w), ptr(b), ptr(tg), ptr(tl), ptr(ul), ptr(lse),
-                     ptr(alpha), ptr(beta), ptr(costs), ptr(gc), clamp, ptr(d_e), ptr(d_p), ptr(d_w), ptr(d_b),
+                     ptr(lpb), ptr(lpl), ptr(alpha), ptr(beta), ptr(costs), ptr(gc), clamp, ptr(d_e), ptr(d_p), ptr(d_w), ptr(d_b),
                      B, T, U1, D, V, blank, precision, ptr(ws), ws.numel(), stream())
         return d_e, d_p, d_w, d_b, None, None, None, None, None, None
 

@@ -75,7 +75,8 @@ int ctcvr_rnnt_lattice(const float* lp_blank, const float* lp_label, const int32
 size_t ctcvr_joint_rnnt_bwd_ws_bytes(int B, int T, int U1, int D, int V, int precision);
 int ctcvr_joint_rnnt_bwd(const float* enc_proj, const float* pred_proj, const float* w_out,
                          const float* b_out, const int32_t* targets, const int32_t* t_len,
-                         const int32_t* u_len, const float* lse, const float* alpha,
+                         const int32_t* u_len, const float* lse, const float* lp_blank,
+                         const float* lp_label, const float* alpha,
                          const float* beta, const float* costs, const float* grad_costs,
                          float clamp, float* d_enc_proj, float* d_pred_proj, float* d_w_out,
                          float* d_b_out, int B, int T, int U1, int D, int V, int blank,
@@ -94,7 +95,8 @@ int ctcvr_joint_rnnt_fwd_bf16in(const void* enc_proj_bf16, const void* pred_proj
                                 int T, int U1, int D, int V, int blank, void* ws, size_t ws_bytes, void* stream);
 int ctcvr_joint_rnnt_bwd_bf16in(const void* enc_proj_bf16, const void* pred_proj_bf16, const float* w_out,
                                 const float* b_out, const int32_t* targets, const int32_t* t_len,
-                                const int32_t* u_len, const float* lse, const float* alpha, const float* beta,
+                                const int32_t* u_len, const float* lse, const float* lp_blank,
+                                const float* lp_label, const float* alpha, const float* beta,
                                 const float* costs, const float* grad_costs, float clamp, void* d_enc_proj_bf16,
                                 void* d_pred_proj_bf16, float* d_w_out, float* d_b_out, int B, int T, int U1, int D,
                                 int V, int blank, void* ws, size_t ws_bytes, void* stream);

@@ -21,7 +21,7 @@ gc=torch.full((B,),1.0/B,device=dev)
 d_e=torch.empty_like(e); d_p=torch.empty_like(p); d_w=torch.empty_like(w); d_b=torch.empty_like(b)
 wsb=torch.empty(query("ctcvr_joint_rnnt_bwd_ws_bytes",B,T,U1,D,V,1),dtype=torch.uint8,device=dev)
 def runb():
-    call("ctcvr_joint_rnnt_bwd",ptr(e),ptr(p),ptr(w),ptr(b),ptr(tgt),ptr(tl),ptr(ul),ptr(lse),ptr(al),ptr(be),ptr(costs),ptr(gc),-1.0,ptr(d_e),ptr(d_p),ptr(d_w),ptr(d_b),B,T,U1,D,V,blank,1,ptr(wsb),wsb.numel(),stream())
+    call("ctcvr_joint_rnnt_bwd",ptr(e),ptr(p),ptr(w),ptr(b),ptr(tgt),ptr(tl),ptr(ul),ptr(lse),ptr(lpb),ptr(lpl),ptr(al),ptr(be),ptr(costs),ptr(gc),-1.0,ptr(d_e),ptr(d_p),ptr(d_w),ptr(d_b),B,T,U1,D,V,blank,1,ptr(wsb),wsb.numel(),stream())
 flush=torch.empty(256<<20,dtype=torch.uint8,device=dev)
 for _ in range(3): runb()
 ts=[]
