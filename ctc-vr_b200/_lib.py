@@ -27,6 +27,7 @@ _SIGS = {
     "ctcvr_launch_count": (ctypes.c_ulonglong, []),
     "ctcvr_debug_tc_error": (ctypes.c_uint, []),
     "ctcvr_debug_set_prof": (None, [P]),
+    "ctcvr_debug_set_mode": (None, [I]),
     "ctcvr_joint_logits": (I, [P, P, P, P, P, I, I, I, I, I, P]),
     "ctcvr_joint_rnnt_fwd_ws_bytes": (Z, [I, I, I, I, I, I]),
     "ctcvr_joint_rnnt_fwd": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, Z, P]),

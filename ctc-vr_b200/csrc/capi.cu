@@ -59,6 +59,7 @@ int ctc_prefix_beam(const float*, const int32_t*, int, int, int, int, int, int32
 
 unsigned int tc_error_flag();
 void tc_set_prof(void*);
+void tc_set_mode(int);
 
 static int check_dims(const char* op, int B, int T, int U1, int D, int V) {
   CTCVR_REQUIRE(B > 0 && T > 0 && U1 > 0 && D > 0 && V > 0, "%s: bad dims B=%d T=%d U1=%d D=%d V=%d", op, B, T, U1, D, V);
@@ -85,6 +86,7 @@ const char* ctcvr_last_error(void) { return g_err; }
 int ctcvr_version(void) { return 100; }
 unsigned int ctcvr_debug_tc_error(void) { return tc_error_flag(); }
 void ctcvr_debug_set_prof(void* buf) { tc_set_prof(buf); }
+void ctcvr_debug_set_mode(int single_cta) { tc_set_mode(single_cta); }
 unsigned long long ctcvr_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int ctcvr_joint_logits(const float* enc_proj, const float* pred_proj, const float* w_out, const float* b_out,

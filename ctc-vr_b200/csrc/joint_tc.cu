@@ -114,6 +114,7 @@ struct Pipe {
 }  // namespace tc
 }  // namespace ctcvr
 #include "joint_tc_fwd.cuh"
+#include "joint_tc_fwd_pair.cuh"
 #include "joint_tc_bwd.cuh"
 namespace ctcvr {
 namespace tc {
@@ -490,17 +491,17 @@ __device__ void prep_weights3_part(int i, const float* __restrict__ w, const flo
 // Forward tile table (see joint_tc_fwd.cuh): entry = {b, u0, t0, nu}.
 __device__ void build_tiles_fwd_block(int b, const int32_t* __restrict__ t_len, const int32_t* __restrict__ u_len, int B,
                                       int T, int U1, int4* __restrict__ tiles, int* __restrict__ ntiles,
-                                      int max_tiles) {
-  const int off = block_prefix(b, [&](int i) { return fwd_tiles_of(min(t_len[i], T), min(u_len[i], U1 - 1) + 1); });
-  const int Tb = min(t_len[b], T), W = min(u_len[b], U1 - 1) + 1;
-  const int n = fwd_tiles_of(Tb, W);
+                                      int max_tiles, int pair) {
+  const int off = block_prefix(b, [&](int i) { return fwd_tiles_of(min(t_len[i], T), max(min(u_len[i], U1 - 1), 0) + 1, pair); });
+  const int Tb = min(t_len[b], T), W = max(min(u_len[b], U1 - 1), 0) + 1;
+  const int n = fwd_tiles_of(Tb, W, pair);
   const int nb32 = (Tb + 31) >> 5, n4 = (W >> 2) * nb32;
   const int n2 = (W & 2) ? ((Tb + 63) >> 6) : 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     int4 e;
     if (i < n4) { const int g = i / nb32; e = make_int4(b, 4 * g, 32 * (i - g * nb32), 4); }
     else if (i < n4 + n2) e = make_int4(b, (W >> 2) * 4, 64 * (i - n4), 2);
-    else e = make_int4(b, W - 1, 128 * (i - n4 - n2), 1);
+    else e = make_int4(b, W - 1, (pair ? 64 : 128) * (i - n4 - n2), 1);
     if (off + i < max_tiles) tiles[off + i] = e;
   }
   if (b == B - 1 && threadIdx.x == 0) *ntiles = min(off + n, max_tiles);
@@ -512,7 +513,7 @@ __device__ void build_tiles_fwd_block(int b, const int32_t* __restrict__ t_len, 
 struct PrepArgs {
   const float* w; const float* bias; __nv_bfloat16* w_t; __nv_bfloat16* wt_t; float* bias_pad; float* bias_l2;
   int V, Vp, D, nW;
-  const int32_t* t_len; const int32_t* u_len; int B, T, U1, geom, max_tiles;
+  const int32_t* t_len; const int32_t* u_len; int B, T, U1, geom, max_tiles, fwd_pair;
   int4* tiles; int4* tile_rows; int* ntiles;
   float* zero0; long n0; float* zero1; long n1;
   const float4* a; uint2* ab; long na4; const float4* b4; uint2* bb; long nb4;
@@ -523,7 +524,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs q) {
     prep_weights3_part(blk * 256 + threadIdx.x, q.w, q.bias, q.w_t, q.wt_t, q.bias_pad, q.bias_l2, q.V, q.Vp, q.D);
   } else if (blk < q.nW + q.B) {
     if (q.geom) build_tiles_block(blk - q.nW, q.t_len, q.u_len, q.B, q.T, q.U1, q.geom, q.tiles, q.tile_rows, q.ntiles, q.max_tiles);
-    else build_tiles_fwd_block(blk - q.nW, q.t_len, q.u_len, q.B, q.T, q.U1, q.tiles, q.ntiles, q.max_tiles);
+    else build_tiles_fwd_block(blk - q.nW, q.t_len, q.u_len, q.B, q.T, q.U1, q.tiles, q.ntiles, q.max_tiles, q.fwd_pair);
   } else {
     const long nb = gridDim.x - q.nW - q.B, first = (long)(blk - q.nW - q.B) * 256 + threadIdx.x, stride = nb * 256;
     for (long i = first; i < q.n0; i += stride) q.zero0[i] = 0.f;
@@ -533,7 +534,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs q) {
 }
 
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
-                      uint32_t box_rows) {
+                      uint32_t box_rows, bool swizzle) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* sym = nullptr;
@@ -550,8 +551,8 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu box_rows=%u)", (int)r,
               (unsigned long long)rows, (unsigned long long)cols, box_rows);
@@ -592,6 +593,7 @@ static int check_tc_error(const char* where) {
 using namespace tc;
 
 static long long* g_prof_buf = nullptr;
+static int g_force_single_cta = 0;      // dev switch (ctcvr_debug_set_mode): run the single-CTA kernels
 static int pad_v(int V) { return (V + 31) / 32 * 32; }
 static int max_tiles_flat(int B, int T, int U1) { return B * (int)(((long)T * U1 + BM - 1) / BM); }
 // Backward tile geometry: P label columns x TT frames.  Pick the variant with fewer tile rows for this (T, U1);
@@ -610,7 +612,7 @@ static int max_tiles_rect(int B, int T, int U1) {           // upper bound over 
 bool joint_tc_supported(int U1, int D, int V) { return D % 64 == 0 && D >= 64 && D <= 1024 && pad_v(V) <= 416 && U1 <= 128; }
 
 static int max_tiles_fwd2(int B, int T, int U1) {
-  return B * ((U1 >> 2) * ((T + 31) / 32) + (T + 63) / 64 + (T + 127) / 128);
+  return B * ((U1 >> 2) * ((T + 31) / 32) + (T + 63) / 64 + (T + 63) / 64);
 }
 
 struct FwdWs {
@@ -669,8 +671,10 @@ int joint_fwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
   const int Vp = pad_v(V), NH = Vp / 2;
   FwdWs W = carve_fwd_ws(ws, B, T, U1, D, V);
   const int mt = max_tiles_fwd2(B, T, U1);
+  const bool use_pair = fwdp_smem_bytes(NH, D) <= 232448 && sm_count() >= 2 && !g_force_single_cta;
   {
     PrepArgs q{};
+    q.fwd_pair = use_pair ? 1 : 0;
     q.w = w; q.bias = bias; q.w_t = W.wb; q.bias_l2 = W.bias_l2; q.V = V; q.Vp = Vp; q.D = D;
     q.nW = cdiv((long)((Vp + 63) / 64) * 64 * D, 256);
     q.t_len = t_len; q.u_len = u_len; q.B = B; q.T = T; q.U1 = U1; q.geom = 0; q.max_tiles = mt;
@@ -686,6 +690,26 @@ int joint_fwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
     }
     prep_kernel<<<q.nW + B + extra, 256, 0, st>>>(q);
     CTCVR_LAUNCH_CHECK();
+  }
+  if (use_pair) {
+    // CTA-pair kernel: W_out resident in shared memory, double-buffered accumulators (joint_tc_fwd_pair.cuh)
+    CUtensorMap tmap_e, tmap_p;
+    if (make_tmap_bf16_2d(&tmap_e, W.eb, (uint64_t)B * T, D, D, 32)) return 1;
+    if (make_tmap_bf16_2d(&tmap_p, W.pb, (uint64_t)B * U1, D, D, 2, /*swizzle=*/false)) return 1;
+    FwdPairParams q{};
+    q.w_t = W.wb;
+    q.bias = bias; q.bias_l2 = W.bias_l2; q.targets = targets; q.t_len = t_len; q.u_len = u_len;
+    q.tiles = W.tiles; q.ntiles = W.ntiles;
+    q.B = B; q.T = T; q.U1 = U1; q.D = D; q.V = V; q.Vp = Vp; q.NH = NH; q.blank = blank;
+    q.lse = lse; q.lp_blank = lp_blank; q.lp_label = lp_label;
+    q.prof = g_prof_buf;
+    tc_error_host_word(&q.err_host);
+    const size_t smem = fwdp_smem_bytes(NH, D);
+    CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::max(2, std::min(sm_count() & ~1, 2 * mt));
+    joint_fwd3_kernel<<<grid, FP_THREADS, smem, st>>>(tmap_e, tmap_p, q);
+    CTCVR_LAUNCH_CHECK();
+    return 0;
   }
   CUtensorMap tmap_e, tmap_p;
   if (make_tmap_bf16_2d(&tmap_e, W.eb, (uint64_t)B * T, D, D, 32)) return 1;
@@ -861,6 +885,7 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
 }
 
 void tc_set_prof(void* buf) { g_prof_buf = reinterpret_cast<long long*>(buf); }
+void tc_set_mode(int single_cta) { g_force_single_cta = single_cta; }
 
 unsigned int tc_error_flag() {
   unsigned int v = 0;

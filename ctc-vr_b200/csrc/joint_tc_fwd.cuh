@@ -337,10 +337,12 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
 }
 
 // Tile table of the forward kernel: per utterance (W/4) groups of 4 label columns x 32-frame blocks, then a
-// 2-column group x 64-frame blocks if W & 2, then a 1-column group x 128-frame blocks if W & 1.
-__device__ __forceinline__ int fwd_tiles_of(int Tb, int W) {
+// 2-column group x 64-frame blocks if W & 2, then a 1-column group x 128-frame blocks if W & 1 (64-frame blocks for
+// the CTA-pair kernel, joint_tc_fwd_pair.cuh).
+__device__ __forceinline__ int fwd_tiles_of(int Tb, int W, int pair) {
   if (Tb <= 0) return 0;
-  return (W >> 2) * ((Tb + 31) >> 5) + ((W & 2) ? ((Tb + 63) >> 6) : 0) + ((W & 1) ? ((Tb + 127) >> 7) : 0);
+  const int n1 = pair ? ((Tb + 63) >> 6) : ((Tb + 127) >> 7);
+  return (W >> 2) * ((Tb + 31) >> 5) + ((W & 2) ? ((Tb + 63) >> 6) : 0) + ((W & 1) ? n1 : 0);
 }
 
 }  // namespace tc

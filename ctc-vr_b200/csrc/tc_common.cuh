@@ -131,6 +131,77 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 
 
+// ---- cta_group::2 (CTA pair).  The pair kernels use M = 128: 64 rows per CTA at the full tensor rate (N/4 cycles per
+// K = 16 step, tools/pair_probe.cu).  D of CTA r: row m (0..63) -> TMEM lane m for columns n < N/2 and lane m + 64 for
+// n >= N/2 (column n - N/2): a 64 x N fp32 accumulator takes 128 lanes x N/2 columns - half the columns of the M = 256
+// and single-CTA forms, which is what lets two accumulators (or logits and dZ^T) coexist in 512 columns.
+// A from tensor memory (TS form): row m of the CTA's 64 rows must be present in lane m AND lane m + 64.
+// B: N split, rows [0, N/2) in the leader's shared memory, [N/2, N) in the peer's, at the same offset.
+// Only the leader (cluster rank 0) issues MMAs and commits; commits are multicast to both CTAs.
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all previously issued MMAs of this thread completed) on the barrier at this offset in every CTA of mask
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask) : "memory");
+}
+// arrive on the mbarrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// Same without release semantics (no cluster-scope fence in front of the arrive, which costs ~1 k cycles per call): for
+// hand-offs whose payload is tensor memory, already complete (tcgen05.wait::st / ::ld) and fenced
+// (tcgen05.fence::before_thread_sync) when the CTA-local barrier that precedes this forward was signalled.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t bar, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// one arrival per warp on the LEADER's barrier (local arrive on rank 0, remote arrive from rank 1)
+__device__ __forceinline__ void warp_arrive_leader(uint32_t bar, uint32_t rank) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    if (rank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0);
+  }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // 32 lanes x 32 columns of fp32: thread i of the warp receives TMEM lane (lane_base + i), columns col..col+31.
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -301,9 +372,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 2-D bf16 row-major tensor [rows][cols] (cols contiguous, row pitch `pitch_elems`), box [box_rows][64 cols],
-// 128-byte swizzle, zero fill out of bounds.
+// 128-byte swizzle (or none), zero fill out of bounds.
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
-                      uint32_t box_rows);
+                      uint32_t box_rows, bool swizzle = true);
 // 2-D fp32 row-major tensor, box [box_rows][32 cols] (= 128 B), 128-byte swizzle, zero fill out of bounds.
 int make_tmap_f32_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                      uint32_t box_rows);
