@@ -593,7 +593,9 @@ static int check_tc_error(const char* where) {
 using namespace tc;
 
 static long long* g_prof_buf = nullptr;
-static int g_force_single_cta = 0;      // dev switch (ctcvr_debug_set_mode): run the single-CTA kernels
+// dev switch (ctcvr_debug_set_mode(0)): run the experimental CTA-pair forward kernel (joint_tc_fwd_pair.cuh).  It is
+// correct (tools/fwd_pair_check.py) but at 200 us against 148 us it is not the default: see DESIGN.md section 5.
+static int g_force_single_cta = 1;
 static int pad_v(int V) { return (V + 31) / 32 * 32; }
 static int max_tiles_flat(int B, int T, int U1) { return B * (int)(((long)T * U1 + BM - 1) / BM); }
 // Backward tile geometry: P label columns x TT frames.  Pick the variant with fewer tile rows for this (T, U1);
@@ -693,11 +695,8 @@ int joint_fwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
   }
   if (use_pair) {
     // CTA-pair kernel: W_out resident in shared memory, double-buffered accumulators (joint_tc_fwd_pair.cuh)
-    CUtensorMap tmap_e, tmap_p;
-    if (make_tmap_bf16_2d(&tmap_e, W.eb, (uint64_t)B * T, D, D, 32)) return 1;
-    if (make_tmap_bf16_2d(&tmap_p, W.pb, (uint64_t)B * U1, D, D, 2, /*swizzle=*/false)) return 1;
     FwdPairParams q{};
-    q.w_t = W.wb;
+    q.w_t = W.wb; q.eb = W.eb; q.pb = W.pb;
     q.bias = bias; q.bias_l2 = W.bias_l2; q.targets = targets; q.t_len = t_len; q.u_len = u_len;
     q.tiles = W.tiles; q.ntiles = W.ntiles;
     q.B = B; q.T = T; q.U1 = U1; q.D = D; q.V = V; q.Vp = Vp; q.NH = NH; q.blank = blank;
@@ -707,7 +706,7 @@ int joint_fwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
     const size_t smem = fwdp_smem_bytes(NH, D);
     CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::max(2, std::min(sm_count() & ~1, 2 * mt));
-    joint_fwd3_kernel<<<grid, FP_THREADS, smem, st>>>(tmap_e, tmap_p, q);
+    joint_fwd3_kernel<<<grid, FP_THREADS, smem, st>>>(q);
     CTCVR_LAUNCH_CHECK();
     return 0;
   }

@@ -13,20 +13,23 @@
 // accumulators fit, and the epilogue of tile i runs under the MMAs of tile i+1.
 // W_out stays RESIDENT in shared memory (each CTA holds the 104 rows per N-half that the pair MMA reads from it, all of
 // K): no weight streaming at all - the copy engine and L2 carry nothing in steady state, and shared memory only serves
-// the tensor core's B reads and the small enc / pred slabs (per k-block 32 enc rows and 2 pred rows per CTA, TMA ring).
+// the tensor core's B reads.  The producers read their enc / pred rows straight from global memory (L2) into registers.
 //
 // Tiles as in joint_tc_fwd.cuh: 128 cells = nu label columns x 128/nu frames, row R = 32 q' + lane, cell
 // (t0 + (q' / nu) * 32 + lane, u0 + q' % nu); CTA r of the pair owns q' = 2r, 2r+1 (rows 64r .. 64r+63).  A one-column
-// tile (nu = 1) spans 64 frames only (CTA r: frames 32r .., its second quarter idle) so that every CTA needs exactly one
-// 32-row enc box per k-block.
+// tile (nu = 1) spans 64 frames only (CTA r: frames 32r .., its second quarter idle).
 // TMEM lane l of a CTA: row l & 63, column half l >> 6 (logits v = h*NH + (l >> 6)*NH/2 + j at column h*NH/2 + j).
 //
-// Roles (640 threads): warp 0 W_out load (once) | warp 1 MMA issuer (leader CTA) | warp 2 TMEM alloc | warp 3 TMA slabs |
-// warps 4-11 epilogue (TMEM quarter q = warp & 3, column group eg) | warps 12-19 A producers (quarter q, k-half kh):
+// Roles (640 threads): warp 0 W_out load (once) | warp 1 MMA issuer (leader CTA) | warp 2 TMEM alloc |
+// warps 4-11 epilogue (TMEM quarter q = warp & 3, column group eg) | warps 12-19 A producers (quarter q, j):
 // tanh(e+p) -> packed bf16 -> tcgen05.st into the A stage; lanes l and l + 64 hold the same row (the pair MMA needs the
-// A rows in both lane halves), so quarters q and q^2 produce the same values.
+// A rows in both lane halves): the two quarters split the k range and swap their halves through shared memory.
 #pragma once
 #include "tc_common.cuh"
+
+#ifndef CTCVR_EXP
+#define CTCVR_EXP 0        // tools/exp_build.sh: timing experiments that drop a piece of the kernel (results invalid)
+#endif
 
 namespace ctcvr {
 namespace tc {
@@ -38,10 +41,15 @@ constexpr int FP_PROD_WARP0 = 4 + FP_EPI_WARPS;
 constexpr int FP_PROD_WARPS = 8;
 constexpr int FP_THREADS = (FP_PROD_WARP0 + FP_PROD_WARPS) * 32;
 constexpr int FP_A_COL = 416;                    // A stages behind the two accumulators (2 * NH <= 416)
-constexpr int FP_S_STAGES = 3;                   // slab ring: [32 enc rows x 128 B, 128B swizzle] + [2 pred rows x 128 B]
+#ifndef FP_POLY_MASK
+#define FP_POLY_MASK 0x0                         // which of every 4 softmax exponentials run on the FMA pipe (ex2_poly)
+#endif
+constexpr int FP_PF = 3;    static_assert(FP_PF == 3, "the producer's slot dispatch is written for 3");                         // k-blocks of enc / pred operands in flight per producer thread (registers)
 
 struct FwdPairParams {
   const __nv_bfloat16* w_t; // tiled W_out: [KB][2][NH][64] bf16, pre-swizzled (prep_weights3_part)
+  const __nv_bfloat16* eb;  // bf16 enc_proj [B*T][D]
+  const __nv_bfloat16* pb;  // bf16 pred_proj [B*U1][D]
   const float* bias;        // [V]
   const float* bias_l2;     // [Vp] bias * log2(e), -inf beyond V
   const int32_t* targets;   // [B,U1-1]
@@ -58,7 +66,7 @@ struct FwdPairParams {
 };
 
 struct FwdPairSmem {
-  uint32_t w_base, e_base, p_base, bar_base;
+  uint32_t w_base, x_base, bar_base;
   float* bias_r;            // [2 lane halves][NH] bias_l2 in TMEM column order
   float2* epi_x;            // [2*groups - 1][64] (max, sum) partials of the other (lane half, group) threads of a row
   float* gx;                // [2][64] gathered blank / label logits
@@ -69,16 +77,12 @@ struct FwdPairSmem {
   __device__ __forceinline__ uint32_t acc_empty(int i) const { return bar_base + 48 + i * 16 + 8; }
   __device__ __forceinline__ uint32_t w_full() const { return bar_base + 80; }
   __device__ __forceinline__ uint32_t w_ready() const { return bar_base + 88; }
-  __device__ __forceinline__ uint32_t s_full(int i) const { return bar_base + 96 + i * 16; }
-  __device__ __forceinline__ uint32_t s_empty(int i) const { return bar_base + 96 + i * 16 + 8; }
-  __device__ __forceinline__ uint32_t e_stage(int i) const { return e_base + i * 4096; }
-  __device__ __forceinline__ uint32_t p_stage(int i) const { return p_base + i * 256; }
 };
 
 __host__ __device__ inline size_t fwdp_smem_bytes(int NH, int D) {
   size_t s = 0;                                                // the dynamic shared memory is declared 1024-byte aligned
   s += (size_t)(D / BK) * 2 * (NH / 2) * 128;                  // resident W half
-  s += (size_t)FP_S_STAGES * (4096 + 256);
+  s += (size_t)FP_PROD_WARPS * 1024;                           // producer exchange slots
   s += (size_t)2 * NH * 4;
   s += (size_t)(2 * FP_EPI_GROUPS - 1) * 64 * 8 + 2 * 64 * 4;
   s += 16 + 144 + 16;
@@ -86,8 +90,7 @@ __host__ __device__ inline size_t fwdp_smem_bytes(int NH, int D) {
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FP_THREADS, 1)
-joint_fwd3_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_p,
-                  const FwdPairParams p) {
+joint_fwd3_kernel(const FwdPairParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   FwdPairSmem L;
   const int NH = p.NH, NQ = NH >> 1, KB = p.D / BK;
@@ -95,8 +98,7 @@ joint_fwd3_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
     const uint32_t base = smem_u32(smem_raw);
     uint32_t a = base;                    // 1024-byte aligned (W blocks are multiples of 1 KB: NQ % 8 == 0)
     L.w_base = a; a += (uint32_t)KB * 2u * (uint32_t)NQ * 128u;
-    L.e_base = a; a += FP_S_STAGES * 4096;
-    L.p_base = a; a += FP_S_STAGES * 256;
+    L.x_base = a; a += FP_PROD_WARPS * 1024;
     L.bias_r = reinterpret_cast<float*>(smem_raw + (a - base)); a += 2 * NH * 4;
     L.epi_x = reinterpret_cast<float2*>(smem_raw + (a - base)); a += (2 * FP_EPI_GROUPS - 1) * 64 * 8;
     L.gx = reinterpret_cast<float*>(smem_raw + (a - base)); a += 2 * 64 * 4;
@@ -118,9 +120,6 @@ joint_fwd3_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
     for (int i = 0; i < 2; ++i) { mbar_init(L.acc_full(i), 1); mbar_init(L.acc_empty(i), FP_EPI_WARPS + fwd); }
     mbar_init(L.w_full(), 1);
     mbar_init(L.w_ready(), 2);
-    for (int i = 0; i < FP_S_STAGES; ++i) { mbar_init(L.s_full(i), 1); mbar_init(L.s_empty(i), FP_PROD_WARPS); }
-    tma_prefetch_desc(&tmap_e);
-    tma_prefetch_desc(&tmap_p);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc2(smem_u32(L.tmem_ptr), TMEM_COLS);
@@ -155,27 +154,6 @@ joint_fwd3_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
         __syncwarp();
       }
     }
-  } else if (warp == 3) {
-    // ------------------------------------------------------------------ TMA: enc / pred slabs of this CTA's 64 rows
-    Pipe sp;
-    for (int tile = cl; tile < ntiles; tile += ncl) {
-      const int4 ti = p.tiles[tile];
-      const int nu = ti.w;
-      const int fb = (nu == 4) ? 0 : (int)rank;           // 32-frame block of this CTA
-      const int ub = (nu == 4) ? 2 * (int)rank : 0;       // first of its (up to) two label columns
-      const int erow = ti.x * p.T + ti.z + 32 * fb;
-      const int prow = ti.x * p.U1 + ti.y + ub;
-      for (int kb = 0; kb < KB; ++kb) {
-        mbar_wait(L.s_empty(sp.stage), sp.phase ^ 1u, 2);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(L.s_full(sp.stage), 4096u + 256u);
-          tma_load_2d(L.e_stage(sp.stage), &tmap_e, L.s_full(sp.stage), kb * BK, erow);
-          tma_load_2d(L.p_stage(sp.stage), &tmap_p, L.s_full(sp.stage), kb * BK, prow);
-        }
-        __syncwarp();
-        sp.advance(FP_S_STAGES);
-      }
-    }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA; warp-wide loop, one lane issues)
     if (rank == 0) {
@@ -194,15 +172,15 @@ joint_fwd3_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
         if (lane == 0) TC_PROF(1, 101);
         tc_fence_after();
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(L.a_full(ap.stage), ap.phase, 4);
+          if (!(CTCVR_EXP & 4)) mbar_wait(L.a_full(ap.stage), ap.phase, 4);
           if (lane == 0) TC_PROF(1, 50 + kb);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a = tmem_base + FP_A_COL + ap.stage * 32;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint64_t bd = w_desc0 + (uint64_t)((kb * 2 + h) * w_step);
-              const uint32_t d = tmem_base + (uint32_t)(acc * NH + h * NQ);
+            for (int h = 0; h < ((CTCVR_EXP & 16) ? 4 : 2); ++h) {
+              const uint64_t bd = w_desc0 + (uint64_t)((kb * 2 + (h & 1)) * w_step);
+              const uint32_t d = tmem_base + (uint32_t)(acc * NH + (h & 1) * NQ);
               umma2_bf16_ts(d, a, bd, idesc, kb ? 1u : 0u);
               umma2_bf16_ts(d, a + 8, bd + 2, idesc, 1u);
               umma2_bf16_ts(d, a + 16, bd + 4, idesc, 1u);
@@ -299,7 +277,7 @@ joint_fwd3_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) ac[e] += ex2_fast(y[j + e] - nz);
+          for (int e = 0; e < 4; ++e) ac[e] += ((FP_POLY_MASK >> e) & 1) ? ex2_poly(y[j + e] - nz) : ex2_fast(y[j + e] - nz);
         s = s * ex2_fast(m - nz) + ((ac[0] + ac[1]) + (ac[2] + ac[3]));
         m = nm;
       }
@@ -335,44 +313,82 @@ joint_fwd3_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
     }
   } else if (warp >= FP_PROD_WARP0) {
     // ------------------------------------------------------------------ A producers (A operand lives in TMEM)
-    // warp = (TMEM quarter q, k-half kh): thread = lane 32q + lane = row 32(q&1) + lane of this CTA: enc row `lane` of
-    // the slab, pred row q & 1, 32 of the 64 k of a k-block.  tanh(e + p) -> 16 packed bf16x2 -> one tcgen05.st into the
-    // A stage columns of the thread's own lane.  The pair MMA wants row m in TMEM lanes m AND m + 64, so quarters q and
-    // q^2 compute the same values (an exchange through shared memory would halve the tanh count, but the resident
-    // W_out leaves no room for its buffers).
-    const int q = warp & 3, kh = (warp - FP_PROD_WARP0) >> 2;
-    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(FP_A_COL + kh * 16);
-    const uint32_t e_row = (uint32_t)lane * 128u, e_sw = (uint32_t)(lane & 7);
-    const uint32_t p_row = (uint32_t)(q & 1) * 128u + (uint32_t)kh * 64u;
-    Pipe ap, sp;
+    // The pair MMA wants row m of the CTA in TMEM lanes m AND m + 64, so quarters q and q^2 hold the same 32 rows.  The
+    // four warps (q, j), (q^2, j), j = 0, 1 of a row group split the 64 k of a k-block into quarters: warp (q, j)
+    // computes kq = 2 (q >> 1) + j - tanh(e + p) for 16 k -> 8 packed bf16x2 - writes them into its own lanes
+    // (tcgen05.st) and hands them to warp (q^2, j) through shared memory, which writes them into the other lane half:
+    // no tanh is computed twice (MUFU is the busiest pipe of this kernel).  The operands come straight from global
+    // memory (L2) into registers, FP_PF k-blocks ahead: 32 contiguous bytes of the thread's enc row and of the warp's
+    // pred row per k-block - the resident W_out leaves no room for a slab ring, and shared memory has no bandwidth to
+    // spare for it either.
+    const int pw = warp - FP_PROD_WARP0;
+    const int q = warp & 3, j = pw >> 2;
+    const int kq = 2 * (q >> 1) + j;                       // my k-quarter; the partner's is kq ^ 2
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)FP_A_COL;
+    const uint32_t x_mine = L.x_base + (uint32_t)(pw * 1024 + lane * 16);
+    const uint32_t x_peer = L.x_base + (uint32_t)((pw ^ 2) * 1024 + lane * 16);
+    const uint32_t bar_id = 4u + (uint32_t)((q & 1) * 2 + j);   // the pair (q, j) / (q^2, j)
+    Pipe ap;
     int prof_n = 0;
+    // load stream: runs FP_PF k-blocks ahead of the compute stream, across tile boundaries
+    int l_tile = cl, l_kb = 0;
+    const __nv_bfloat16 *l_e = nullptr, *l_p = nullptr;
+    auto l_rows = [&]() {
+      if (l_tile >= ntiles) return;                        // past the end: keep re-reading the last rows (discarded)
+      const int4 ti = p.tiles[l_tile];
+      const int nu = ti.w, lognu = nu >> 1;
+      const int qp = 2 * (int)rank + (q & 1);
+      const int u = min(ti.y + (qp & (nu - 1)), p.U1 - 1);
+      const int t = min(ti.z + (((nu == 1) ? (int)rank : (qp >> lognu)) << 5) + lane, p.T - 1);
+      l_e = p.eb + ((size_t)ti.x * p.T + t) * p.D + kq * 16;
+      l_p = p.pb + ((size_t)ti.x * p.U1 + u) * p.D + kq * 16;
+    };
+    U32x8 eq[FP_PF], pq[FP_PF];
+    auto l_next = [&](U32x8& e2, U32x8& p2) {
+      e2 = ldg256(l_e + l_kb * 64);
+      p2 = ldg256(l_p + l_kb * 64);
+      if (++l_kb == KB) { l_kb = 0; l_tile += ncl; l_rows(); }
+    };
+    if (cl < ntiles) {
+      l_rows();
+#pragma unroll
+      for (int i = 0; i < FP_PF; ++i) l_next(eq[i], pq[i]);
+    }
+    // one k-block; S = its slot of the register ring (compile-time, so the ring is never copied: a register move would
+    // wait for the load it moves)
+    auto body = [&](auto SLOT, int kb) {
+      constexpr int S = decltype(SLOT)::value;
+      uint32_t w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = tanh_add_bf16x2_packed(eq[S].v[i], pq[S].v[i]);
+      l_next(eq[S], pq[S]);                                // the operands FP_PF k-blocks ahead
+      if (tid == FP_PROD_WARP0 * 32) TC_PROF(3, 60 + kb);
+      named_barrier_sync(bar_id, 64);                      // the partner has read my previous slot
+      sts128(x_mine, w[0], w[1], w[2], w[3]);
+      sts128(x_mine + 512u, w[4], w[5], w[6], w[7]);
+      mbar_wait(L.a_empty(ap.stage), ap.phase ^ 1u, 8);
+      if (tid == FP_PROD_WARP0 * 32) TC_PROF(3, kb);
+      tc_fence_after();
+      tmem_st8(tq + (uint32_t)(ap.stage * 32 + kq * 8), w);
+      named_barrier_sync(bar_id, 64);                      // the partner's quarter is in shared memory
+      {
+        const uint4 a0 = lds128(x_peer), a1 = lds128(x_peer + 512u);
+        const uint32_t o[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        tmem_st8(tq + (uint32_t)(ap.stage * 32 + (kq ^ 2) * 8), o);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      warp_arrive(L.a_full(ap.stage));
+      if (tid == FP_PROD_WARP0 * 32) TC_PROF(3, 40 + kb);
+      ap.advance(FP_A_STAGES);
+    };
+    int slot = 0;
     for (int tile = cl; tile < ntiles; tile += ncl) {
       for (int kb = 0; kb < KB; ++kb) {
-        mbar_wait(L.s_full(sp.stage), sp.phase, 7);
-        if (tid == FP_PROD_WARP0 * 32) TC_PROF(3, 20 + kb);
-        const uint32_t eb = L.e_stage(sp.stage) + e_row, pb = L.p_stage(sp.stage) + p_row;
-        uint32_t w[16];
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const uint4 ev = lds128(eb + ((((uint32_t)(kh * 4 + c4)) ^ e_sw) << 4));
-          const uint4 pv = lds128(pb + (uint32_t)c4 * 16u);
-          w[4 * c4 + 0] = tanh_add_bf16x2_packed(ev.x, pv.x);
-          w[4 * c4 + 1] = tanh_add_bf16x2_packed(ev.y, pv.y);
-          w[4 * c4 + 2] = tanh_add_bf16x2_packed(ev.z, pv.z);
-          w[4 * c4 + 3] = tanh_add_bf16x2_packed(ev.w, pv.w);
-        }
-        mbar_wait(L.a_empty(ap.stage), ap.phase ^ 1u, 8);
-        if (tid == FP_PROD_WARP0 * 32) TC_PROF(3, kb);
-        tc_fence_after();
-        tmem_st16(tq + (uint32_t)(ap.stage * 32), w);
-        tmem_st_wait();
-        tc_fence_before();
-        warp_arrive(L.a_full(ap.stage));
-        // the slab is released only now: an arrive issued right behind the loads overtook them (stale rows at scale)
-        warp_arrive(L.s_empty(sp.stage));
-        if (tid == FP_PROD_WARP0 * 32) TC_PROF(3, 40 + kb);
-        ap.advance(FP_A_STAGES);
-        sp.advance(FP_S_STAGES);
+        if (slot == 0) body(std::integral_constant<int, 0>{}, kb);
+        else if (slot == 1) body(std::integral_constant<int, 1>{}, kb);
+        else body(std::integral_constant<int, 2>{}, kb);
+        slot = (slot + 1 == FP_PF) ? 0 : slot + 1;
       }
     }
   }

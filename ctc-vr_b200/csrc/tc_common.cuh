@@ -274,6 +274,16 @@ __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
   return __uint_as_float(r);
 }
+// 32 contiguous, 32-byte aligned bytes of read-only global memory in one request per lane (LDG.256, sm_100+): half the
+// L1 wavefronts of two 16-byte loads when every lane touches a different line
+struct U32x8 { uint32_t v[8]; };
+__device__ __forceinline__ U32x8 ldg256(const void* p) {
+  U32x8 r;
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -334,6 +344,20 @@ __device__ __forceinline__ float ex2_fast(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 2^x for x <= 0 on the FMA pipe (no MUFU): round-to-nearest split x = i + f, |f| <= 0.5, degree-4 minimax polynomial
+// for 2^f (relative error 3.6e-6), exponent restored by an integer add.  The joint kernels are MUFU-bound (tanh of the
+// operand producers + exp of the softmax sweeps); moving the exponentials of a sweep here trades 1 MUFU slot for 9
+// FMA/ALU slots per element.  Inputs below -126 return 0.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;                  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(0.009676037f, f, 0.055922036f);
+  p = fmaf(p, f, 0.24022107f);
+  p = fmaf(p, f, 0.69312103f);
+  p = fmaf(p, f, 1.0000001f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 // tanh(a + b) on packed bf16 pairs: one packed add and one packed MUFU op per two elements.  The sum is rounded to
 // bf16 before the tanh (error <= 2^-9 |x| (1 - z^2) <= 9e-4, below the bf16 rounding of z itself).

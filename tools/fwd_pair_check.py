@@ -2,6 +2,8 @@
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctcvr_b200 as C
+import ctcvr_b200._lib as _L
+if os.environ.get('CTCVR_LIB'): _L.LIB_PATH = os.environ['CTCVR_LIB']
 from ctcvr_b200._lib import call, ptr, query, stream, lib
 dev = 'cuda'
 def run(B, T, U1, D, V, ragged, seed=0, time_it=False):
