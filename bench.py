@@ -10,6 +10,11 @@ all-reduce of the data-parallel step).  A step = joint pre-projections + fused j
 + lattice + fused backward (+ gradient all-reduce when N>1).  `value` is measured with inputs resident in
 HBM; `e2e` goes through the same public API with HOST (pinned) inputs and a device->host read of the loss
 inside the timed region.  L2 is flushed (256 MiB write) before every timed step.
+
+Beside the contract keys the line carries (rank 0, N=1): `parity` - the CPU reference run on the SAME batch and
+weights, per-utterance costs compared with the GPU step; `gpu_reference` - the reference's own data flow on this GPU
+through the library kernels it would use (cuBLAS + torchaudio's rnnt_loss CUDA kernels, ATen ctc_loss); `fp32` - the
+reference-precision path; `eager` - the ungraphed ragged-batch public API; `decode` - the A4-A10 rows with RTF.
 """
 import argparse
 import json
@@ -28,7 +33,6 @@ CFG = dict(B=32, T=250, U=40, D=512, V=412, blank=5)
 METRIC = "fused joint+RNN-T loss fwd/bwd throughput"
 # kernels of libctcvr.so inside one captured step (bf16 activations in place), as counted by ctcvr_launch_count() on
 # an eager step:
-KERNELS_PER_GRAPHED_STEP = 8    # fwd: prep, joint_fwd2, lattice | bwd: prep, joint_bwd2, reduce_denc, dw_gemm_rz, reduce_dw
 UNIT = "utt/s"
 
 
@@ -94,24 +98,33 @@ def make_inputs(seed, device, pinned=False):
     return [t.to(device) for t in ts]
 
 
-def cpu_reference_step(nb, threads):
-    """The reference's own PyTorch CPU path for this seam (joint.py:48-69 -> torchaudio rnnt_loss ->
-    backward), restated in oracle/transducer_oracle.py; bounded sample of `nb` utterances."""
-    from oracle import transducer_oracle as TO
-    torch.set_num_threads(threads)
+def bench_weights(device=None):
+    """The joint of the benchmark: seed 1234, default nn.Linear init.  Built on the CPU so that the GPU arm,
+    the CPU reference and the GPU reference all hold the same parameters."""
     torch.manual_seed(1234)
-    D, V, T, U = CFG["D"], CFG["V"], CFG["T"], CFG["U"]
+    D, V = CFG["D"], CFG["V"]
     lin = lambda o, i: torch.nn.Linear(i, o)
     mods = {"enc_ffn": lin(D, D), "pred_ffn": lin(D, D), "ffn_out": lin(V, D)}
-    w = {f"{k}.{n}": p.detach() for k, m in mods.items() for n, p in m.named_parameters()}
-    enc, pred = torch.randn(nb, T, D), torch.randn(nb, U + 1, D)
-    tgt = torch.randint(6, V, (nb, U), dtype=torch.int32)
-    tl, ul = torch.full((nb,), T, dtype=torch.int32), torch.full((nb,), U, dtype=torch.int32)
+    return {f"{k}.{n}": p.detach().clone() for k, m in mods.items() for n, p in m.named_parameters()}
+
+
+def cpu_reference_step(threads, seed=1234):
+    """The reference's own PyTorch CPU path for this seam (joint.py:48-69 -> torchaudio rnnt_loss -> backward),
+    restated in oracle/transducer_oracle.py, on the FULL batch of the benchmark (same inputs and weights as the GPU
+    arm of rank 0).  step() -> (seconds, per-utterance costs)."""
+    from oracle import transducer_oracle as TO
+    torch.set_num_threads(threads)
+    w = bench_weights()
+    enc, pred, tgt, tl, ul = make_inputs(seed, "cpu")
 
     def step():
         t0 = time.perf_counter()
-        TO.fused_joint_rnnt_reference_call(enc, pred, w, tgt, tl, ul, CFG["blank"])
-        return time.perf_counter() - t0
+        ws = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+        e, p = enc.clone().requires_grad_(True), pred.clone().requires_grad_(True)
+        logits = TO.joint_forward(e, p, ws)
+        costs = TO.rnnt_loss_reference_call(logits, tgt, tl, ul, CFG["blank"], -1.0, "none")
+        costs.mean().backward()
+        return time.perf_counter() - t0, costs.detach()
     return step
 
 
@@ -120,21 +133,65 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    nb = 8
-    step = cpu_reference_step(nb, threads)
+    step = cpu_reference_step(threads)
     for _ in range(max(1, min(args.warmup, 1))):
         step()
-    ts = [step() for _ in range(args.steps)]
-    sec = sum(ts) / len(ts)
-    val = nb / sec
-    sample = f"{nb} of {CFG['B']} utterances per step (same T/U/H/V), {args.steps} timed steps, torch CPU + torchaudio"
+    ts = sorted(step()[0] for _ in range(args.steps))
+    sec = ts[len(ts) // 2]
+    val = CFG["B"] / sec
+    sample = f"the full batch of {CFG['B']} utterances per step, median of {args.steps} timed steps after 1 warm-up, torch CPU + torchaudio"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: B=32,T=250,U=40,H=512,V=412 joint+rnnt_loss fwd/bwd (CPU sample)"},
+            "config": {"workload": "configs[1]: B=32,T=250,U=40,H=D=512,V=412 joint+rnnt_loss fwd/bwd (reference on the host cores)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def gpu_reference(dev, steps=5):
+    """The kernel bar of SURVEY.md 2b / 8d: the reference's data flow for this seam on THIS GPU through the library
+    kernels it would run with Config.device = "cuda" - cuBLAS GEMMs + elementwise add / tanh (joint.py:48-69), torchaudio's
+    sm_100 rnnt_loss kernels, autograd backward - in fp32 and under bf16 autocast.  Same inputs and weights as the GPU
+    arm.  Nothing of libctcvr.so and nothing of oracle/ runs here."""
+    import torchaudio
+    B, T, U, D, V, blank = (CFG[k] for k in ("B", "T", "U", "D", "V", "blank"))
+    w = {k: v.to(dev).requires_grad_(True) for k, v in bench_weights().items()}
+    enc, pred, tgt, tl, ul = make_inputs(1234, dev)
+    enc.requires_grad_(True)
+    pred.requires_grad_(True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    F = torch.nn.functional
+    out = {}
+    for name, ac in (("fp32", False), ("autocast_bf16", True)):
+        def step():
+            for t in list(w.values()) + [enc, pred]:
+                t.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                e, p = F.linear(enc, w["enc_ffn.weight"], w["enc_ffn.bias"]), F.linear(pred, w["pred_ffn.weight"], w["pred_ffn.bias"])
+                logits = F.linear(torch.tanh(e.unsqueeze(2) + p.unsqueeze(1)), w["ffn_out.weight"], w["ffn_out.bias"])
+            costs = torchaudio.functional.rnnt_loss(logits.float(), tgt, tl, ul, blank=blank, reduction="none")
+            costs.mean().backward()
+            return costs
+        for _ in range(2):
+            step()
+        ms = []
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            costs = step()
+            s1.record()
+            torch.cuda.synchronize()
+            ms.append(s0.elapsed_time(s1))
+        ms.sort()
+        out[name] = {"ms_per_step": ms[len(ms) // 2], "value": B / (ms[len(ms) // 2] * 1e-3), "unit": UNIT,
+                     "loss": float(costs.mean())}
+    out["what"] = "cuBLAS + elementwise joint, torchaudio rnnt_loss CUDA kernels, autograd backward; same batch and weights"
+    del flush
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -150,14 +207,24 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, T, U, D, V, blank = (CFG[k] for k in ("B", "T", "U", "D", "V", "blank"))
-    torch.manual_seed(1234)
-    joint = C.TransducerJoint(V, D, D, D).to(dev)
+    joint = C.TransducerJoint(V, D, D, D)
+    joint.load_state_dict(bench_weights())
+    joint = joint.to(dev)
     reducer = GradAllReducer(joint.parameters()) if world > 1 else None
     enc, pred, tgt, tl, ul = make_inputs(1234 + rank, dev)
     enc.requires_grad_(True)
     pred.requires_grad_(True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gB = B * world
+
+    # kernels of libctcvr.so per step, counted on one eager step through the same public API (graph replays do not pass
+    # through the C ABI, so the captured launches are counted here)
+    l_pre = _lib.lib().ctcvr_launch_count()
+    joint.rnnt_loss_fused(enc, pred, tgt, tl, ul, blank, reduction="none", precision=args.precision).sum().backward()
+    torch.cuda.synchronize()
+    launches_per_step = int(_lib.lib().ctcvr_launch_count() - l_pre)
+    joint.zero_grad(set_to_none=True)
+    enc.grad = pred.grad = None
 
     use_graph = not args.no_graph
     graphed = C.GraphedJointRnntStep(joint, B, T, U, blank, global_batch=gB, precision=args.precision) if use_graph else None
@@ -203,8 +270,8 @@ def run_ours(args):
             tot_ms += s.elapsed_time(e_)
         barrier()
         launches = _lib.lib().ctcvr_launch_count() - l0
-        if graphed is not None:      # replays do not pass through the C ABI: count the captured launches
-            launches = args.steps * KERNELS_PER_GRAPHED_STEP
+        if graphed is not None:      # replays do not pass through the C ABI: the captured launches, counted above
+            launches = args.steps * launches_per_step
         # ---- e2e: host (pinned) inputs -> H2D -> step -> D2H of the loss, every step.  As in a real input pipeline the
         # H2D copy of step i+1 runs on a copy stream while step i computes (double-buffered staging) and the loss of
         # step i is read back while step i+1 runs; every step still pays its own copy and its own loss read-back, and
@@ -291,22 +358,23 @@ def run_ours(args):
         M = B * T * (U + 1)
         flops_bwd = 4.0 * M * D * V
         flops_fwd = 2.0 * M * D * V
-        peak = pk["tf_sust"] if args.precision == "bf16" else None
         ach_bwd = flops_bwd / (kern["bwd_ms"] * 1e-3) / 1e12
         ach_fwd = flops_fwd / (kern["fwd_ms"] * 1e-3) / 1e12
+        step_tf = 6.0 * M * D * V / (ms_step * 1e-3) / 1e12
+        # `frac` is against the sustained cuBLAS figure (the step is a long tensor-bound region); `frac_burst` against the
+        # burst figure, the right denominator for the entry points timed alone between L2 flushes
         roof = {"bound": "tensor", "kernel": "joint_rnnt_bwd (dominant)", "achieved": ach_bwd,
-                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach_bwd / pk["tf_sust"], "traffic": _ncu_traffic(),
-                "peak_source": pk["src"] + " bf16 sustained",
-                "step_frac": (6.0 * M * D * V / (ms_step * 1e-3) / 1e12) / pk["tf_sust"],
-                "fwd": {"achieved": ach_fwd, "frac": ach_fwd / pk["tf_sust"], "ms": kern["fwd_ms"]},
-                "bwd": {"achieved": ach_bwd, "frac": ach_bwd / pk["tf_sust"], "ms": kern["bwd_ms"]},
+                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach_bwd / pk["tf_sust"],
+                "frac_burst": ach_bwd / pk["tf_burst"], "peak_burst": pk["tf_burst"], "traffic": None,
+                "peak_source": pk["src"] + " bf16 sustained / burst",
+                "step_achieved": step_tf, "step_frac": step_tf / pk["tf_sust"], "step_frac_burst": step_tf / pk["tf_burst"],
+                "fwd": {"achieved": ach_fwd, "frac": ach_fwd / pk["tf_sust"], "frac_burst": ach_fwd / pk["tf_burst"],
+                        "ms": kern["fwd_ms"]},
+                "bwd": {"achieved": ach_bwd, "frac": ach_bwd / pk["tf_sust"], "frac_burst": ach_bwd / pk["tf_burst"],
+                        "ms": kern["bwd_ms"]},
                 "lattice": {"ms": kern["lat_ms"], "achieved_GBps": 24.0 * M / (kern["lat_ms"] * 1e-3) / 1e9,
                             "frac_hbm": 24.0 * M / (kern["lat_ms"] * 1e-3) / 1e9 / pk["hbm"]}}
-        threads = os.cpu_count() or 1
-        nb = 4
-        cstep = cpu_reference_step(nb, threads)
-        cstep()
-        csec = min(cstep(), cstep())
+        roof.update(_ncu_traffic())
         line = {"metric": METRIC, "value": gB / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
@@ -315,10 +383,40 @@ def run_ours(args):
                            "precision": args.precision, "cuda_graph": bool(graphed is not None)},
                 "e2e": {"value": gB / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "h2d_GBps_measured": h2d_gbps, "h2d_ms_per_step": h2d / (h2d_gbps * 1e9) * 1e3},
-                "gpu_launches": int(launches), "roofline": roof,
-                "cpu_baseline": {"value": nb / csec, "unit": UNIT, "cores": threads, "kind": "port",
-                                 "sample": f"{nb} of {B} utterances per step, best of 2 after 1 warm-up, torch CPU + torchaudio"},
+                "gpu_launches": int(launches), "gpu_launches_per_step": launches_per_step, "roofline": roof,
                 "clocks": clk.summary(), "loss": float(loss.item()) * world}
+        if world == 1:
+            # ---- the CPU reference on the SAME batch and weights: baseline timing (full batch, median of 3 after one
+            # warm-up) and the parity check that rides in every record
+            threads = os.cpu_count() or 1
+            cstep = cpu_reference_step(threads)
+            cstep()
+            runs = sorted((cstep() for _ in range(3)), key=lambda r: r[0])
+            csec, ccosts = runs[1]
+            line["cpu_baseline"] = {"value": B / csec, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"the full batch of {B} utterances per step, median of 3 after 1 warm-up, torch CPU + torchaudio"}
+            par = {"reference": "oracle: joint.py:48-69 + torchaudio.functional.rnnt_loss on the host, same batch and weights",
+                   "tolerance": {"fp32": 1e-4, "bf16": 2e-3}}
+            for prec in ("fp32", "bf16"):
+                with torch.no_grad():
+                    g = joint.rnnt_loss_fused(enc.detach(), pred.detach(), tgt, tl, ul, blank, reduction="none", precision=prec).cpu()
+                rel = float(((g - ccosts).abs() / ccosts.abs()).max())
+                par[prec] = {"max_rel_err_per_utterance_cost": rel, "loss": float(g.mean()), "ok": bool(rel <= par["tolerance"][prec])}
+            par["reference_loss"] = float(ccosts.mean())
+            par["step_loss_rel_err"] = abs(line["loss"] - par["reference_loss"]) / abs(par["reference_loss"])
+            line["parity"] = par
+            if not (par["fp32"]["ok"] and par["bf16"]["ok"]):
+                raise RuntimeError(f"bench.py: the GPU costs disagree with the CPU reference on the benchmark batch: {par}")
+            # ---- the reference-precision path (fp32 SIMT kernels, 1e-4): its own step time and denominator
+            line["fp32"] = time_fp32_step(C, joint, B, T, U, blank, enc, pred, tgt, tl, ul, flush)
+            # ---- the ungraphed public API on a ragged batch (what a train loop with varying shapes hits)
+            line["eager"] = time_eager_ragged(joint, enc, pred, tgt, blank, args.precision, flush)
+            line["gpu_reference"] = gpu_reference(dev)
+            line["gpu_reference"]["speedup_vs_fp32"] = line["value"] / line["gpu_reference"]["fp32"]["value"]
+            line["gpu_reference"]["speedup_vs_autocast_bf16"] = line["value"] / line["gpu_reference"]["autocast_bf16"]["value"]
+            if not args.no_decode:
+                import bench_decode
+                line["decode"] = bench_decode.run_rows(quick=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -326,15 +424,89 @@ def run_ours(args):
         print(json.dumps(line))
 
 
+def time_fp32_step(C, joint, B, T, U, blank, enc, pred, tgt, tl, ul, flush, reps=3):
+    """precision='fp32': the SIMT kernels that meet the reference's 1e-4.  Denominator: the fp32 FMA peak of the chip
+    (148 SMs x 128 lanes x 2 flop x max SM clock), since this path does not touch the tensor cores."""
+    e, p = enc.detach().clone().requires_grad_(True), pred.detach().clone().requires_grad_(True)
+
+    def step():
+        joint.zero_grad(set_to_none=True)
+        e.grad = p.grad = None
+        joint.rnnt_loss_fused(e, p, tgt, tl, ul, blank, reduction="none", precision="fp32").sum().div(B).backward()
+    step()
+    ms = []
+    for _ in range(reps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        step()
+        s1.record()
+        torch.cuda.synchronize()
+        ms.append(s0.elapsed_time(s1))
+    ms.sort()
+    med = ms[len(ms) // 2]
+    joint.zero_grad(set_to_none=True)
+    flops = 8.0 * B * T * (U + 1) * CFG["D"] * CFG["V"]          # executed: fwd 2 + bwd (recompute 2 + dZ 2 + dW 2)
+    peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    return {"value": B / (med * 1e-3), "unit": UNIT, "ms_per_step": med, "tolerance": 1e-4,
+            "roofline": {"bound": "fp32 FMA pipe", "achieved": flops / (med * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": flops / (med * 1e-3) / 1e12 / peak, "peak_source": "nominal 148 SM x 128 FMA x 2 x 1.965 GHz",
+                         "flops": "executed (incl. the logits recompute)"}}
+
+
+def time_eager_ragged(joint, enc, pred, tgt, blank, precision, flush, reps=5):
+    """The ungraphed op on a ragged batch (T_b ~ U[125,250], U_b ~ U[20,40], element 0 at the maximum): new workspaces
+    and ~40 launches per call, no CUDA graph."""
+    B, T = enc.shape[0], enc.shape[1]
+    U = tgt.shape[1]
+    g = torch.Generator().manual_seed(99)
+    tl = torch.randint(T // 2, T + 1, (B,), generator=g, dtype=torch.int32)
+    ul = torch.randint(U // 2, U + 1, (B,), generator=g, dtype=torch.int32)
+    tl[0], ul[0] = T, U
+    cells = int(((tl.long()) * (ul.long() + 1)).sum())
+    tl, ul = tl.to(enc.device), ul.to(enc.device)
+    e, p = enc.detach().clone().requires_grad_(True), pred.detach().clone().requires_grad_(True)
+
+    def step():
+        joint.zero_grad(set_to_none=True)
+        e.grad = p.grad = None
+        joint.rnnt_loss_fused(e, p, tgt, tl, ul, blank, reduction="mean", precision=precision).backward()
+    for _ in range(2):
+        step()
+    ms = []
+    for _ in range(reps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        step()
+        s1.record()
+        torch.cuda.synchronize()
+        ms.append(s0.elapsed_time(s1))
+    ms.sort()
+    med = ms[len(ms) // 2]
+    joint.zero_grad(set_to_none=True)
+    return {"value": B / (med * 1e-3), "unit": UNIT, "ms_per_step": med, "lattice_cells": cells,
+            "cells_vs_full_batch": cells / float(B * T * (U + 1)), "what": "ungraphed rnnt_loss_fused + backward, ragged lengths"}
+
+
 def _ncu_traffic():
-    """DRAM bytes (read + write) of the backward entry point's two tensor-core kernels per call, from the committed
-    `ncu --set full` capture of this round (profiles/r1_v6_traffic.json); None when the file is absent."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_v6_traffic.json")
-    try:
-        k = json.load(open(path))["kernels"]
-        return float(sum(k[n]["dram_read_bytes"] + k[n]["dram_write_bytes"] for n in ("joint_bwd2_kernel", "dw_gemm_rz_kernel")))
-    except (OSError, KeyError, ValueError):
-        return None
+    """DRAM bytes (read + write) per call of the backward entry point's tensor-core kernels, from the newest committed
+    `ncu --set full` capture (profiles/r*_traffic.json: it names the commit it was taken at).  ncu cannot run inside a
+    timed benchmark, so this is a recorded measurement of the same code, not a live one."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    for path in reversed(files):
+        try:
+            d = json.load(open(path))
+            k = d["kernels"]
+            names = [n for n in k if n.startswith("joint_bwd") or n.startswith("dw_gemm")]
+            return {"traffic": float(sum(k[n]["dram_read_bytes"] + k[n]["dram_write_bytes"] for n in names)),
+                    "traffic_source": os.path.basename(path) + " (" + str(d.get("commit", "?")) + "): " + ", ".join(names)}
+        except (OSError, KeyError, ValueError):
+            continue
+    return {"traffic": None}
 
 
 def time_kernels(C, joint, enc, pred, tgt, tl, ul, blank, precision, flush, reps=5):
@@ -391,6 +563,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager step instead of the captured CUDA graph")
     ap.add_argument("--precision", default=os.environ.get("CTCVR_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--no-decode", action="store_true", help="skip the A4-A10 rows (bench_decode.py) in the JSON line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

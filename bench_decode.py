@@ -68,19 +68,30 @@ def _cpu_weights(m):
     return pw, jw
 
 
+_ROWS = []
+
+
 def _line(row, what, value, unit, gpu_s, cpu_value, cpu_sample, extra=None):
     d = {"row": row, "what": what, "value": value, "unit": unit, "gpu_seconds": gpu_s, "n_gpus": 1,
          "cpu_baseline": {"value": cpu_value, "unit": unit, "cores": torch.get_num_threads(), "kind": "port",
                           "sample": cpu_sample}}
     if extra:
         d.update(extra)
-    print(json.dumps(d), flush=True)
+    _ROWS.append(d)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--quick", action="store_true", help="smaller CPU samples")
-    args = ap.parse_args()
+def run_rows(quick=True):
+    """All rows as a list of dicts (bench.py folds them into its JSON line under "decode")."""
+    del _ROWS[:]
+    main(types.SimpleNamespace(quick=quick))
+    return list(_ROWS)
+
+
+def main(args=None):
+    if args is None:
+        ap = argparse.ArgumentParser()
+        ap.add_argument("--quick", action="store_true", help="smaller CPU samples")
+        args = ap.parse_args()
     import ctcvr_b200 as C
     from oracle import ctc_oracle as CO
     from oracle import transducer_oracle as TO
@@ -113,10 +124,21 @@ def main():
         l.backward()
     ctc_cpu()
     t0 = time.perf_counter(); ctc_cpu(); ctc_cpu(); c_s = (time.perf_counter() - t0) / 2
+    # the same tail through ATen's CUDA kernels (the library path the reference runs with Config.device = "cuda")
+    xa = logits.cuda().requires_grad_(True)
+
+    def ctc_aten():
+        xa.grad = None
+        l = torch.nn.functional.ctc_loss(xa.transpose(0, 1).log_softmax(2), ysd, hld, yld, blank=BLANK, reduction="sum",
+                                         zero_infinity=True)
+        l.backward()
+        return l
+    a_s, _ = _sync_time(ctc_aten, 20)
     bytes_alg = 2.0 * B * T * V * 4 + 2.0 * B * T * (2 * U + 1) * 4
     _line("A4", "CTC log-softmax + loss fwd/bwd, cfg5 B=32 T=500 V=412 U=40", B / g_s, "utt/s", g_s, nb / c_s,
           f"{nb} of {B} utterances, ATen CPU ctc_loss fwd+bwd", {"achieved_GBps": bytes_alg / g_s / 1e9,
-                                                                "chain_steps": T})
+                                                                "chain_steps": T,
+                                                                "gpu_reference_aten_utt_per_s": B / a_s})
 
     # ------------------------------------------------------------------ A10 / A9: CTC greedy and prefix beam (cfg5)
     lp = torch.log_softmax(logits * 2.0, dim=-1)
@@ -194,3 +216,5 @@ def main():
 
 if __name__ == "__main__":
     main()
+    for r in _ROWS:
+        print(json.dumps(r), flush=True)

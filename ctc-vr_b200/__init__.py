@@ -6,6 +6,7 @@ and no fallback: ops raise RuntimeError without the library or without a CUDA de
 """
 from . import _lib  # noqa: F401
 from . import functional  # noqa: F401
+from . import patch  # noqa: F401
 from .ctc import CTC, OnlineCTC  # noqa: F401
 from .decode import (BeamHypothesis, OnlineBeamState, basic_greedy_search, beam_chunk_online, greedy_batch,  # noqa: F401
                      greedy_chunk, prefix_beam_search)

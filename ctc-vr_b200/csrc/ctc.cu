@@ -44,7 +44,7 @@ __global__ void ctc_loss_kernel(const float* __restrict__ lp, const int64_t* __r
                                 int Sp, int blank, int zero_infinity) {
   extern __shared__ float sm[];
   const int b = blockIdx.x, s = threadIdx.x, nthr = blockDim.x;
-  const int Tb = min(in_lens[b], T), Ub = tgt_lens[b];
+  const int Tb = min(in_lens[b], T), Ub = max(min(tgt_lens[b], Umax), 0);    // lengths beyond the tensors cannot index outside them
   const int S = 2 * Ub + 1;
   float* cur = sm;                  // [Sp] alpha_{t} / beta_{t} exchange
   float* ab = cur + Sp;             // [Sp] alpha+beta at time t
@@ -219,7 +219,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lp, const int64_
                                       int T, int V, int Umax, int Sp, int blank, int zero_infinity) {
   extern __shared__ float sm[];
   const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
-  const int Tb = min(in_lens[b], T), Ub = tgt_lens[b];
+  const int Tb = min(in_lens[b], T), Ub = max(min(tgt_lens[b], Umax), 0);    // lengths beyond the tensors cannot index outside them
   const int S = 2 * Ub + 1;
   float* sel = sm;                               // [Tb][S]  lp[t][label(s)]
   float* ca = sel + (size_t)T * S;               // [2][Sp + 4] alpha exchange, two guard cells on each side
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(128) ctc_grad_kernel(const float* __restrict__
                                                        float* __restrict__ grad, int T, int V, int Sp, int blank) {
   extern __shared__ float sm[];
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int Tb = min(in_lens[b], T), S = 2 * tgt_lens[b] + 1;
+  const int Tb = min(in_lens[b], T), S = min(2 * max(tgt_lens[b], 0) + 1, Sp);
   int* mlab = reinterpret_cast<int*>(sm);        // [3][Sp]
   float* abw = sm + 3 * Sp + warp * Sp;          // [4][Sp] alpha + beta of the warp's row
   float* acc = sm + 7 * Sp + warp * V;           // [4][V] per-label log-sum
@@ -399,8 +399,7 @@ int ctc_loss(const float* lp, const int64_t* targets, const int32_t* in_lens, co
   const int Smax = 2 * Umax + 1;
   // split form when the gathered log-probs of one utterance fit in shared memory
   const size_t smemA = ((size_t)T * Smax + 4 * (Sp + 4)) * sizeof(float) + (size_t)(V + 2 * Sp) * sizeof(int);
-  const char* v1 = getenv("CTCVR_CTC_V1");
-  if (smemA <= 220 * 1024 && 2 * Sp <= 1024 && !(v1 && v1[0] == '1')) {
+  if (smemA <= 220 * 1024 && 2 * Sp <= 1024) {
     CtcWs W = carve_ctc_ws(ws, B, T, Sp);
     const int threads = 2 * Sp < 256 ? 256 : 2 * Sp;
     CTCVR_CHECK_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));

@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(JT_THREADS, 1) joint_tile_kernel(JointTileArgs
   const int lane = tid & 31, warp = tid >> 5;
   const int b = a.b0 + blockIdx.y;
   const int D = a.D, V = a.V, U1 = a.U1, T = a.T;
-  const int Tb = a.t_len ? a.t_len[b] : T;
-  const int Ub = a.u_len ? a.u_len[b] : U1 - 1;
+  const int Tb = a.t_len ? min(a.t_len[b], T) : T;                    // lengths beyond the tensors cannot index outside them
+  const int Ub = a.u_len ? max(min(a.u_len[b], U1 - 1), 0) : U1 - 1;
   const bool dense_enum = (MODE != MODE_STATS);
   const int width = dense_enum ? U1 : (Ub + 1);
   const int ncell = dense_enum ? T * U1 : Tb * (Ub + 1);
@@ -78,7 +78,10 @@ __global__ void __launch_bounds__(JT_THREADS, 1) joint_tile_kernel(JointTileArgs
     rowi[TM + tid] = valid ? t : -1;
     rowi[2 * TM + tid] = u;
     int lab = -1;
-    if (valid && u < Ub && a.targets != nullptr) lab = a.targets[(size_t)b * (U1 - 1) + u];
+    if (valid && u < Ub && a.targets != nullptr) {
+      lab = a.targets[(size_t)b * (U1 - 1) + u];
+      if ((unsigned)lab >= (unsigned)V) lab = a.blank;      // out-of-range ids cannot index outside the tile
+    }
     rowi[tid] = lab;
     if (MODE == MODE_GRAD) {
       float k_all = kNegInf, k_blank = kNegInf, k_label = kNegInf, scale = 0.f;

@@ -612,6 +612,8 @@ static int max_tiles_rect(int B, int T, int U1) {           // upper bound over 
 
 // the forward keeps its A stages in the TMEM columns behind the accumulators: Vp + 96 <= 512
 bool joint_tc_supported(int U1, int D, int V) { return D % 64 == 0 && D >= 64 && D <= 1024 && pad_v(V) <= 416 && U1 <= 128; }
+// the predicate of the bf16 path, both directions (the backward tiles D in 128-lane blocks of dZ^T, at most four)
+bool joint_tc_bwd_supported(int U1, int D, int V) { return joint_tc_supported(U1, D, V) && D % 128 == 0 && D <= 512; }
 
 static int max_tiles_fwd2(int B, int T, int U1) {
   return B * ((U1 >> 2) * ((T + 31) / 32) + (T + 63) / 64 + (T + 63) / 64);
@@ -642,7 +644,10 @@ static FwdWs carve_fwd_ws(void* ws, int B, int T, int U1, int D, int V) {
   return w;
 }
 
-size_t joint_fwd_tc_ws_bytes(int B, int T, int U1, int D, int V) { return carve_fwd_ws(nullptr, B, T, U1, D, V).bytes; }
+size_t joint_fwd_tc_ws_bytes(int B, int T, int U1, int D, int V) {
+  if (!joint_tc_bwd_supported(U1, D, V)) return 256;      // the call itself fails with the reason
+  return carve_fwd_ws(nullptr, B, T, U1, D, V).bytes;
+}
 
 static int sm_count() {
   static int n = 0;
@@ -663,10 +668,9 @@ int joint_fwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
                  int U1, int D, int V, int blank, void* ws, size_t ws_bytes, cudaStream_t st) {
   const float* enc = reinterpret_cast<const float*>(enc_v);
   const float* pred = reinterpret_cast<const float*>(pred_v);
-  if (!joint_tc_supported(U1, D, V)) {  // shapes outside the tensor-core tiling use the fp32 kernels (same GPU)
-    CTCVR_REQUIRE(!in_bf16, "joint_rnnt_fwd: bf16 inputs need D %% 64 == 0, D <= 1024, V <= 512, U+1 <= 128");
-    return joint_fwd_f32(enc, pred, w, bias, targets, t_len, u_len, lse, lp_blank, lp_label, B, T, U1, D, V, blank, st);
-  }
+  // one predicate for both directions, and no silent change of arithmetic: a shape outside the tensor-core tiling is
+  // an error here (the fp32 kernels are ~40x slower and round differently - the caller has to ask for them)
+  CTCVR_REQUIRE(joint_tc_bwd_supported(U1, D, V), "%s: precision = bf16 needs D %% 128 == 0, D <= 512, V <= 416 and U+1 <= 128 (got D=%d V=%d U+1=%d); use precision = fp32 for this shape", "joint_rnnt_fwd", D, V, U1);
   if (check_tc_error("joint_rnnt_fwd")) return 1;
   CTCVR_REQUIRE(ws && ws_bytes >= joint_fwd_tc_ws_bytes(B, T, U1, D, V), "joint_rnnt_fwd bf16: workspace too small");
   CTCVR_REQUIRE(((uintptr_t)enc & 15) == 0 && ((uintptr_t)pred & 15) == 0, "joint_rnnt_fwd bf16: enc_proj / pred_proj must be 16-byte aligned");
@@ -738,9 +742,6 @@ int joint_bwd_f32(const float*, const float*, const float*, const float*, const 
                   const int32_t*, const float*, const float*, const float*, const float*, const float*, float, float*,
                   float*, float*, float*, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 
-bool joint_tc_bwd_supported(int U1, int D, int V) {
-  return joint_tc_supported(U1, D, V) && D % 128 == 0 && D <= 512;
-}
 
 struct BwdWs {
   __nv_bfloat16 *wb, *wtb, *gt, *eb, *pb;
@@ -781,7 +782,7 @@ static BwdWs carve_bwd_ws(void* ws, int B, int T, int U1, int D, int V) {
 }
 
 size_t joint_bwd_tc_ws_bytes(int B, int T, int U1, int D, int V) {
-  if (!joint_tc_bwd_supported(U1, D, V)) return joint_bwd_f32_ws_bytes(B, T, U1, D, V);
+  if (!joint_tc_bwd_supported(U1, D, V)) return 256;      // the call itself fails with the reason
   return carve_bwd_ws(nullptr, B, T, U1, D, V).bytes;
 }
 
@@ -792,11 +793,7 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
                  float* d_b, int B, int T, int U1, int D, int V, int blank, void* ws, size_t ws_bytes, cudaStream_t st) {
   const float* enc = reinterpret_cast<const float*>(enc_v);
   const float* pred = reinterpret_cast<const float*>(pred_v);
-  CTCVR_REQUIRE(!in_bf16 || joint_tc_bwd_supported(U1, D, V),
-                "joint_rnnt_bwd: bf16 inputs need D %% 128 == 0, D <= 512, V <= 512, U+1 <= 128");
-  if (!joint_tc_bwd_supported(U1, D, V))   // shapes outside the tensor-core tiling use the fp32 kernels (same GPU)
-    return joint_bwd_f32(enc, pred, w, bias, targets, t_len, u_len, lse, alpha, beta, costs, grad_costs, clamp, d_enc,
-                         d_pred, d_w, d_b, B, T, U1, D, V, blank, ws, ws_bytes, st);
+  CTCVR_REQUIRE(joint_tc_bwd_supported(U1, D, V), "%s: precision = bf16 needs D %% 128 == 0, D <= 512, V <= 416 and U+1 <= 128 (got D=%d V=%d U+1=%d); use precision = fp32 for this shape", "joint_rnnt_bwd", D, V, U1);
   if (check_tc_error("joint_rnnt_bwd")) return 1;
   CTCVR_REQUIRE(ws && ws_bytes >= joint_bwd_tc_ws_bytes(B, T, U1, D, V), "joint_rnnt_bwd bf16: workspace too small");
   CTCVR_REQUIRE(((uintptr_t)enc & 15) == 0 && ((uintptr_t)pred & 15) == 0, "joint_rnnt_bwd bf16: enc_proj / pred_proj must be 16-byte aligned");

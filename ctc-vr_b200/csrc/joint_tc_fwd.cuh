@@ -224,7 +224,11 @@ joint_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       const bool valid = t < Tb;
       int lab = -1;
       float bias_lab = 0.f;
-      if (eg == 0 && u < Ub) { lab = p.targets[(size_t)b * (p.U1 - 1) + u]; bias_lab = __ldg(p.bias + lab); }
+      if (eg == 0 && u < Ub) {
+        lab = p.targets[(size_t)b * (p.U1 - 1) + u];
+        if ((unsigned)lab >= (unsigned)p.V) lab = p.blank;    // out-of-range ids cannot index outside the tile
+        bias_lab = __ldg(p.bias + lab);
+      }
       pin(lab);
       mbar_wait(L.tmem_full(), tphase, 6);
       if (tid == 128) TC_PROF(2, 1);

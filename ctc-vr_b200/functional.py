@@ -42,8 +42,7 @@ class _FusedJointRnnt(torch.autograd.Function):
         U1 = pred_proj.shape[1]
         V = w.shape[0]
         # bf16 activations (autocast) are consumed in place by the tensor-core path: no fp32 round trip
-        bf16_in = (precision == BF16 and enc_proj.dtype == torch.bfloat16 and pred_proj.dtype == torch.bfloat16
-                   and bool(query("ctcvr_joint_tc_supported", U1, D, V)))
+        bf16_in = precision == BF16 and enc_proj.dtype == torch.bfloat16 and pred_proj.dtype == torch.bfloat16
         if bf16_in:
             e, p = enc_proj.detach().contiguous(), pred_proj.detach().contiguous()
         else:
@@ -54,6 +53,15 @@ class _FusedJointRnnt(torch.autograd.Function):
         if tg.dim() != 2 or tg.shape[0] != B or tg.shape[1] != U1 - 1:
             raise RuntimeError("fused_joint_rnnt_loss: targets must be [B, U] with U == pred_out.size(1) - 1")
         tl, ul = _i32c(t_len, dev), _i32c(u_len, dev)
+        if tl.dim() != 1 or ul.dim() != 1 or tl.shape[0] != B or ul.shape[0] != B:
+            raise RuntimeError("fused_joint_rnnt_loss: logit_lengths / target_lengths must be [B]")
+        if not (0 <= blank < V):
+            raise RuntimeError("fused_joint_rnnt_loss: blank must be within [0, vocab)")
+        # Length / label VALUES are not read back (that would be a host sync in the training step): the kernels clamp
+        # lengths to the tensor extents and treat a label outside [0, V) as blank, so bad values cannot fault the GPU.
+        if precision == BF16 and not bool(query("ctcvr_joint_tc_supported", U1, D, V)):
+            raise RuntimeError(f"fused_joint_rnnt_loss: precision='bf16' needs D % 128 == 0, D <= 512, V <= 416 and "
+                               f"U+1 <= 128 (got D={D}, V={V}, U+1={U1}); use precision='fp32' for this shape")
         lse = torch.empty((B, T, U1), dtype=torch.float32, device=dev)
         lpb, lpl = torch.empty_like(lse), torch.empty_like(lse)
         alpha, beta = torch.empty_like(lse), torch.empty_like(lse)
@@ -99,10 +107,14 @@ class _FusedJointRnnt(torch.autograd.Function):
 
 
 def fused_joint_rnnt_loss(enc_proj, pred_proj, w_out, b_out, targets, logit_lengths, target_lengths,
-                          blank: int, clamp: float = -1.0, reduction: str = "mean", precision="bf16"):
+                          blank: int, clamp: float = -1.0, reduction: str = "mean", precision="fp32"):
     """costs_b = RNN-T negative log-likelihood of utterance b for
     logits = ffn_out(tanh(enc_proj[:, :, None] + pred_proj[:, None])) without materialising them.
-    enc_proj [B,T,D] / pred_proj [B,U+1,D] are the enc_ffn / pred_ffn outputs (joint.py:54-55)."""
+    enc_proj [B,T,D] / pred_proj [B,U+1,D] are the enc_ffn / pred_ffn outputs (joint.py:54-55).
+
+    precision='fp32' (default) is the reference's arithmetic (loss and gradients within 1e-4 of torchaudio's);
+    precision='bf16' is the explicit opt-in to the tcgen05 path (bf16 operands, fp32 accumulation, softmax and
+    lattice; loss within 2e-3, gradients within 3e-2 rel-L2) and raises on shapes outside its tiling."""
     costs = _FusedJointRnnt.apply(enc_proj, pred_proj, w_out, b_out, targets, logit_lengths, target_lengths,
                                   int(blank), float(clamp), _PREC[precision])
     return _reduce(costs, reduction)

@@ -19,7 +19,7 @@ class GraphedJointRnntStep:
     2-GPU box of this round); call `dist.GradAllReducer.reduce()` after `step()`."""
 
     def __init__(self, joint, B: int, T: int, U: int, blank: int, global_batch: Optional[int] = None,
-                 precision: str = "bf16", clamp: float = -1.0, warmup: int = 3):
+                 precision: str = "fp32", clamp: float = -1.0, warmup: int = 3):
         p0 = next(joint.parameters())
         dev = p0.device
         if dev.type != "cuda":

@@ -103,9 +103,10 @@ class TransducerJoint(nn.Module):
         return self.ffn_out(self.activation(out))
 
     def rnnt_loss_fused(self, enc_out, pred_out, targets, logit_lengths, target_lengths, blank: int,
-                        clamp: float = -1.0, reduction: str = "mean", precision: str = "bf16",
+                        clamp: float = -1.0, reduction: str = "mean", precision: str = "fp32",
                         pre_project: bool = True):
-        """joint + log-softmax + RNN-T lattice loss in one op (the seam of transducer.py:172-187)."""
+        """joint + log-softmax + RNN-T lattice loss in one op (the seam of transducer.py:172-187).
+        precision='fp32' keeps the reference's arithmetic; 'bf16' opts into the tcgen05 tensor-core path."""
         if not self.fusable:
             raise RuntimeError("rnnt_loss_fused: only joint_mode='add', activation='tanh', postjoin_linear=False")
         if precision in ("bf16", CF.BF16) and enc_out.is_cuda:

@@ -22,7 +22,7 @@ basic_greedy_search = D.basic_greedy_search
 class Transducer(nn.Module):
     def __init__(self, vocab_size: int, blank: int, encoder: nn.Module, predictor: nn.Module, joint: nn.Module,
                  ctc: Optional[nn.Module] = None, ctc_weight: float = 0.3, ignore_id: int = -1,
-                 transducer_weight: float = 0.7, precision: str = "bf16") -> None:
+                 transducer_weight: float = 0.7, precision: str = "fp32") -> None:
         super().__init__()
         assert ctc_weight + transducer_weight == 1.0
         self.vocab_size = vocab_size
@@ -64,13 +64,13 @@ class Transducer(nn.Module):
 
 
 def compute_rnnt_loss(self, encoder_out, encoder_out_lens, text, text_lengths, clamp: float = -1.0):
-    """Body shared with patch.install(): works on the reference's own Transducer instance too."""
+    """Body shared with `patch.install()` (patch.py): works on the reference's own Transducer instance too."""
     ys_in_pad = add_blank(text, self.blank, self.ignore_id)
     predictor_out = self.predictor(ys_in_pad)
     rnnt_text = text.to(torch.int64)
     rnnt_text = torch.where(rnnt_text == self.ignore_id, 0, rnnt_text).to(torch.int32)
     joint = self.joint
-    precision = getattr(self, "precision", "bf16")
+    precision = getattr(self, "precision", "fp32")      # reference arithmetic unless the model opts into bf16
     from . import functional as CF
     j_ok = getattr(joint, "prejoin_linear", True) and not getattr(joint, "postjoin_linear", False) and \
         isinstance(getattr(joint, "activation", None), nn.Tanh)
