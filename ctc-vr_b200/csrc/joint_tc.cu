@@ -116,6 +116,7 @@ struct Pipe {
 #include "joint_tc_fwd.cuh"
 #include "joint_tc_fwd_pair.cuh"
 #include "joint_tc_bwd.cuh"
+#include "joint_tc_bwd_pair.cuh"
 namespace ctcvr {
 namespace tc {
 
@@ -596,6 +597,7 @@ static long long* g_prof_buf = nullptr;
 // dev switch (ctcvr_debug_set_mode(0)): run the experimental CTA-pair forward kernel (joint_tc_fwd_pair.cuh).  It is
 // correct (tools/fwd_pair_check.py) but at 200 us against 148 us it is not the default: see DESIGN.md section 5.
 static int g_force_single_cta = 1;
+static int g_bwd_single_cta = 0;        // ctcvr_debug_set_mode(2): single-CTA backward kernel (A/B timing against the pair kernel)
 static int pad_v(int V) { return (V + 31) / 32 * 32; }
 static int max_tiles_flat(int B, int T, int U1) { return B * (int)(((long)T * U1 + BM - 1) / BM); }
 // Backward tile geometry: P label columns x TT frames.  Pick the variant with fewer tile rows for this (T, U1);
@@ -801,7 +803,12 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
   BwdWs W = carve_bwd_ws(ws, B, T, U1, D, V);
   const int KBG = (Vp + 63) / 64;
   const int mt = W.mt;
-  const RectGeom G = pick_rect_geom(T, U1);
+  RectGeom G = pick_rect_geom(T, U1);
+  // CTA-pair kernel (joint_tc_bwd_pair.cuh): D in 256-row blocks of dZ^T, tiles paired along the frame axis
+  const size_t smem_pair = G.P == 21 ? bwd4_smem_bytes<21>(NH, Vp, D) : bwd4_smem_bytes<16>(NH, Vp, D);
+  const bool use_pair = D % 256 == 0 && smem_pair <= 232448 && sm_count() >= 2 && bwd4_r1_stages(NH, Vp) >= 4 &&
+                        !g_bwd_single_cta;
+  G.even = use_pair ? 1 : 0;
   // bf16 inputs -> bf16 gradients: d_pred is accumulated in fp32 in the workspace and converted by the d_enc reduction
   float* d_pred_acc = in_bf16 ? W.d_pred_acc : d_pred;
   {
@@ -839,6 +846,20 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
     p.d_enc_part = W.d_enc_part; p.d_pred = d_pred_acc; p.d_bias = d_b;
     p.prof = g_prof_buf;
     tc_error_host_word(&p.err_host);
+    if (use_pair) {
+      CUtensorMap tmap_e2;                 // both tiles' frames in one box (P4 slab)
+      if (make_tmap_bf16_2d(&tmap_e2, W.eb, (uint64_t)B * T, D, D, 2 * G.TT)) return 1;
+      p.r1_stages = bwd4_r1_stages(NH, Vp);
+      const int gridp = std::max(2, std::min(sm_count() & ~1, mt & ~1));
+      if (G.P == 21) {
+        CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd4_kernel<21, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair));
+        joint_bwd4_kernel<21, 6><<<gridp, NTHREADS, smem_pair, st>>>(tmap_e, tmap_e2, tmap_p, p);
+      } else {
+        CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd4_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair));
+        joint_bwd4_kernel<16, 8><<<gridp, NTHREADS, smem_pair, st>>>(tmap_e, tmap_e2, tmap_p, p);
+      }
+      CTCVR_LAUNCH_CHECK();
+    } else {
     const size_t smem = bwd3_smem_bytes(NH, Vp, D);
     CTCVR_REQUIRE(smem <= 232448 && p.r1_stages >= 2, "joint_rnnt_bwd bf16: shared memory budget exceeded (%zu B)", smem);
     if (G.P == 21) {
@@ -849,6 +870,7 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
       CTCVR_CHECK_CUDA(cudaFuncSetAttribute(joint_bwd3_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       joint_bwd3_kernel<16, 8><<<grid, NTHREADS, smem, st>>>(tmap_e, tmap_p, p);
       CTCVR_LAUNCH_CHECK();
+    }
     }
   }
   if (in_bf16)
@@ -881,7 +903,10 @@ int joint_bwd_tc(const void* enc_v, const void* pred_v, int in_bf16, const float
 }
 
 void tc_set_prof(void* buf) { g_prof_buf = reinterpret_cast<long long*>(buf); }
-void tc_set_mode(int single_cta) { g_force_single_cta = single_cta; }
+void tc_set_mode(int mode) {            // bit 0: single-CTA forward (default 1), bit 1: single-CTA backward (default 0)
+  g_force_single_cta = mode & 1;
+  g_bwd_single_cta = (mode >> 1) & 1;
+}
 
 unsigned int tc_error_flag() {
   unsigned int v = 0;

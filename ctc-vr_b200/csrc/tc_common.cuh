@@ -368,6 +368,16 @@ __device__ __forceinline__ uint32_t tanh_add_bf16x2_packed(uint32_t a, uint32_t 
   return r;
 }
 
+// Same, pinned in program order (volatile): the producers release a slab stage right behind these - the MUFU issue
+// waits for its operands, so every load of the stage has completed by the time the arrive that follows is issued.
+// (A plain `asm` may be scheduled below the arrive, which would then overtake the loads.)
+__device__ __forceinline__ uint32_t tanh_add_bf16x2_packed_ordered(uint32_t a, uint32_t b) {
+  uint32_t s, r;
+  asm volatile("add.rn.bf16x2 %0, %1, %2;" : "=r"(s) : "r"(a), "r"(b));
+  asm volatile("tanh.approx.bf16x2 %0, %1;" : "=r"(r) : "r"(s));
+  return r;
+}
+
 // One lane of a converged warp.  Role warps run their loops warp-wide (loop state stays in uniform registers) and
 // guard the single-thread instructions (tcgen05.mma/commit, bulk copies) with this: a `lane == 0` branch around the
 // whole loop forces every descriptor through R2UR and wraps each UTCHMMA in an ELECT/BRA.U.ANY waterfall, which was
