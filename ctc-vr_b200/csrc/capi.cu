@@ -57,6 +57,13 @@ size_t ctc_prefix_beam_ws_bytes(int, int, int, int);
 int ctc_prefix_beam(const float*, const int32_t*, int, int, int, int, int, int32_t*, int32_t*, int32_t*, double*,
                     int32_t*, void*, size_t, cudaStream_t);
 
+int rnnt_prologue(const int64_t*, const void*, int, const int64_t*, int, int, int, int, int64_t*, int32_t*, int32_t*,
+                  int32_t*, cudaStream_t);
+int loss_combine(const float*, int, const float*, float, float, float*, cudaStream_t);
+size_t cer_ws_bytes(int, int, int);
+int cer_batch(const int32_t*, const int32_t*, int, const int32_t*, const int32_t*, int, int, void*, size_t, int32_t*,
+              cudaStream_t);
+
 unsigned int tc_error_flag();
 void tc_set_prof(void*);
 void tc_set_mode(int);
@@ -177,6 +184,30 @@ int ctcvr_joint_rnnt_bwd_bf16in(const void* enc_proj_bf16, const void* pred_proj
   return joint_bwd_tc(enc_proj_bf16, pred_proj_bf16, 1, w_out, b_out, targets, t_len, u_len, lse, lp_blank, lp_label, alpha, beta, costs,
                       grad_costs, clamp, reinterpret_cast<float*>(d_enc_proj_bf16), reinterpret_cast<float*>(d_pred_proj_bf16),
                       d_w_out, d_b_out, B, T, U1, D, V, blank, ws, ws_bytes, ST(stream));
+}
+
+int ctcvr_rnnt_prologue(const int64_t* text, const void* text_lens, int text_lens_are_int64, const int64_t* enc_lens,
+                        int B, int U, int blank, int ignore_id, int64_t* ys_in, int32_t* targets, int32_t* t_len,
+                        int32_t* u_len, void* stream) {
+  CTCVR_REQUIRE(B > 0 && U >= 0, "rnnt_prologue: bad dims");
+  CTCVR_REQUIRE(text_lens && enc_lens && ys_in && t_len && u_len && (U == 0 || (text && targets)), "rnnt_prologue: NULL pointer");
+  return rnnt_prologue(text, text_lens, text_lens_are_int64, enc_lens, B, U, blank, ignore_id, ys_in, targets, t_len, u_len,
+                       ST(stream));
+}
+
+int ctcvr_loss_combine(const float* costs, int B, const float* loss_ctc, float transducer_weight, float ctc_weight,
+                       float* out2, void* stream) {
+  CTCVR_REQUIRE(costs && out2 && B > 0, "loss_combine: bad arguments");
+  return loss_combine(costs, B, loss_ctc, transducer_weight, ctc_weight, out2, ST(stream));
+}
+
+size_t ctcvr_cer_ws_bytes(int N, int Lh, int Lr) { return cer_ws_bytes(N, Lh, Lr); }
+
+int ctcvr_cer_batch(const int32_t* hyp, const int32_t* hyp_len, int Lh, const int32_t* ref, const int32_t* ref_len, int Lr,
+                    int N, void* ws, size_t ws_bytes, int32_t* out_sdin, void* stream) {
+  CTCVR_REQUIRE(N > 0 && Lh >= 0 && Lr >= 0, "cer_batch: bad dims");
+  CTCVR_REQUIRE(hyp_len && ref_len && out_sdin && ws && (Lh == 0 || hyp) && (Lr == 0 || ref), "cer_batch: NULL pointer");
+  return cer_batch(hyp, hyp_len, Lh, ref, ref_len, Lr, N, ws, ws_bytes, out_sdin, ST(stream));
 }
 
 size_t ctcvr_rnnt_loss_dense_ws_bytes(int B, int T, int U1) { return (size_t)5 * B * T * U1 * sizeof(float); }

@@ -15,11 +15,16 @@ class GraphedJointRnntStep:
     arguments into the captured buffers, replays the graph and returns the (device) loss scalar
     `sum_b cost_b / global_batch`.  Gradients land in `joint.<param>.grad`, `self.enc.grad`, `self.pred.grad`
     (static tensors, overwritten by every replay).  Passing no arguments replays on the resident inputs.
-    The data-parallel gradient all-reduce stays outside the graph (capturing the NCCL collective in it hung on the
-    2-GPU box of this round); call `dist.GradAllReducer.reduce()` after `step()`."""
+
+    The data-parallel gradient all-reduce stays outside the graph: a replayed graph that contains the NCCL collective
+    (grouped in round 1, one flat bucket in round 2) hung the 2-GPU bench both times, so `dist.GradAllReducer.reduce()`
+    is called after `step()`.
+    `input_dtype=torch.bfloat16` keeps the captured input buffers in bf16 (the bf16 path rounds its inputs to bf16 in
+    the first kernel anyway): a host pipeline then stages half the bytes per step."""
 
     def __init__(self, joint, B: int, T: int, U: int, blank: int, global_batch: Optional[int] = None,
-                 precision: str = "fp32", clamp: float = -1.0, warmup: int = 3):
+                 precision: str = "fp32", clamp: float = -1.0, warmup: int = 3,
+                 input_dtype: torch.dtype = torch.float32):
         p0 = next(joint.parameters())
         dev = p0.device
         if dev.type != "cuda":
@@ -28,8 +33,8 @@ class GraphedJointRnntStep:
         P = joint.pred_ffn.in_features if joint.pred_ffn is not None else joint.ffn_out.in_features
         self.joint, self.blank, self.precision, self.clamp = joint, int(blank), precision, float(clamp)
         self.gB = float(global_batch if global_batch is not None else B)
-        self.enc = torch.zeros(B, T, E, device=dev, requires_grad=True)
-        self.pred = torch.zeros(B, U + 1, P, device=dev, requires_grad=True)
+        self.enc = torch.zeros(B, T, E, device=dev, dtype=input_dtype, requires_grad=True)
+        self.pred = torch.zeros(B, U + 1, P, device=dev, dtype=input_dtype, requires_grad=True)
         self.targets = torch.full((B, U), max(self.blank + 1, 1) % joint.ffn_out.out_features, dtype=torch.int32, device=dev)
         self.logit_lengths = torch.full((B,), T, dtype=torch.int32, device=dev)
         self.target_lengths = torch.full((B,), U, dtype=torch.int32, device=dev)

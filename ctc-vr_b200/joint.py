@@ -42,7 +42,10 @@ class _Bf16Linear(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1]).to(torch.bfloat16)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = torch.mm(dy2, wb, out_dtype=torch.float32).reshape(ctx.x_shape).to(ctx.x_dtype)
+            if ctx.x_dtype == torch.bfloat16:       # bf16 inputs take bf16 gradients straight from the GEMM
+                dx = torch.mm(dy2, wb).reshape(ctx.x_shape)
+            else:
+                dx = torch.mm(dy2, wb, out_dtype=torch.float32).reshape(ctx.x_shape).to(ctx.x_dtype)
         if ctx.needs_input_grad[1]:
             dw = torch.mm(dy2.t(), xb, out_dtype=torch.float32).to(ctx.w_dtype)
         if ctx.needs_input_grad[2]:

@@ -63,12 +63,33 @@ class Transducer(nn.Module):
         return compute_rnnt_loss(self, encoder_out, encoder_out_lens, text, text_lengths)
 
 
+def rnnt_prologue(text, text_lengths, encoder_out_lens, blank: int, ignore_id: int):
+    """add_blank + the ignore_id remap + the int32 casts of transducer.py:8-19,168,174-178 in one launch
+    (`ctcvr_rnnt_prologue`): -> (ys_in int64 [B,U+1], targets int32 [B,U], logit_lengths int32, target_lengths int32)."""
+    from ._lib import call, ptr, stream
+    dev = text.device
+    B, U = text.shape
+    t64 = text if text.dtype == torch.int64 and text.is_contiguous() else text.to(torch.int64).contiguous()
+    el = encoder_out_lens.to(device=dev, dtype=torch.int64).contiguous()
+    tl = text_lengths.to(dev).contiguous()
+    if tl.dtype not in (torch.int32, torch.int64):
+        tl = tl.to(torch.int32)
+    ys_in = torch.empty((B, U + 1), dtype=torch.int64, device=dev)
+    targets = torch.empty((B, U), dtype=torch.int32, device=dev)
+    t_len = torch.empty((B,), dtype=torch.int32, device=dev)
+    u_len = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        call("ctcvr_rnnt_prologue", ptr(t64), ptr(tl), int(tl.dtype == torch.int64), ptr(el), B, U, int(blank), int(ignore_id),
+             ptr(ys_in), ptr(targets), ptr(t_len), ptr(u_len), stream())
+    return ys_in, targets, t_len, u_len
+
+
 def compute_rnnt_loss(self, encoder_out, encoder_out_lens, text, text_lengths, clamp: float = -1.0):
     """Body shared with `patch.install()` (patch.py): works on the reference's own Transducer instance too."""
-    ys_in_pad = add_blank(text, self.blank, self.ignore_id)
+    if not text.is_cuda:
+        raise RuntimeError("ctcvr_b200 ops run on CUDA (B200) tensors only; there is no CPU path")
+    ys_in_pad, rnnt_text, t_len32, u_len32 = rnnt_prologue(text, text_lengths, encoder_out_lens, self.blank, self.ignore_id)
     predictor_out = self.predictor(ys_in_pad)
-    rnnt_text = text.to(torch.int64)
-    rnnt_text = torch.where(rnnt_text == self.ignore_id, 0, rnnt_text).to(torch.int32)
     joint = self.joint
     precision = getattr(self, "precision", "fp32")      # reference arithmetic unless the model opts into bf16
     from . import functional as CF
@@ -81,6 +102,5 @@ def compute_rnnt_loss(self, encoder_out, encoder_out_lens, text, text_lengths, c
             e, p = joint.enc_ffn(encoder_out), joint.pred_ffn(predictor_out)
     else:
         e, p = joint.enc_ffn(encoder_out), joint.pred_ffn(predictor_out)
-    return CF.fused_joint_rnnt_loss(e, p, joint.ffn_out.weight, joint.ffn_out.bias, rnnt_text,
-                                    encoder_out_lens.to(torch.int32), text_lengths.to(torch.int32),
+    return CF.fused_joint_rnnt_loss(e, p, joint.ffn_out.weight, joint.ffn_out.bias, rnnt_text, t_len32, u_len32,
                                     self.blank, clamp, "mean", precision)

@@ -103,6 +103,24 @@ int ctcvr_joint_rnnt_bwd_bf16in(const void* enc_proj_bf16, const void* pred_proj
                                 void* d_pred_proj_bf16, float* d_w_out, float* d_b_out, int B, int T, int U1, int D,
                                 int V, int blank, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- section 8(f)3: glue of Transducer._compute_rnnt_loss / forward (model/component/transducer.py:8-19,113,168,
+ * 174-178,122-128).  ctcvr_rnnt_prologue: ys_in [B,U+1] int64 = [blank, text]; targets [B,U] int32 = text with
+ * ignore_id -> 0; t_len / u_len [B] int32 from the int64 encoder lengths and the int32 (or int64) text lengths - one
+ * launch.  ctcvr_loss_combine: out2[0] = transducer_weight * mean(costs) + ctc_weight * loss_ctc[0] (loss_ctc may be
+ * NULL), out2[1] = mean(costs). */
+int ctcvr_rnnt_prologue(const int64_t* text, const void* text_lens, int text_lens_are_int64, const int64_t* enc_lens,
+                        int B, int U, int blank, int ignore_id, int64_t* ys_in, int32_t* targets, int32_t* t_len,
+                        int32_t* u_len, void* stream);
+int ctcvr_loss_combine(const float* costs, int B, const float* loss_ctc, float transducer_weight, float ctc_weight,
+                       float* out2, void* stream);
+
+/* ---- section 8(f)4: calculate_cer (rnnt_eval.py:11-56) for N (hypothesis, reference) pairs: hyp [N,Lh], ref [N,Lr]
+ * int32 padded, lengths [N]; out_sdin [N,4] int32 = substitutions, deletions, insertions, reference length, with the
+ * reference's backtrace tie-breaking (match, substitution, deletion, insertion).  ws: ctcvr_cer_ws_bytes. */
+size_t ctcvr_cer_ws_bytes(int N, int Lh, int Lr);
+int ctcvr_cer_batch(const int32_t* hyp, const int32_t* hyp_len, int Lh, const int32_t* ref, const int32_t* ref_len, int Lr,
+                    int N, void* ws, size_t ws_bytes, int32_t* out_sdin, void* stream);
+
 /* ---- A2 on dense logits — torch.ops.torchaudio.rnnt_loss_forward
  * (site-packages/torchaudio/functional/functional.py:1725,1737-1744), fused_log_softmax=True.
  * logits [B,T,U1,V] fp32; costs [B]; grads [B,T,U1,V] (may be NULL) = d cost_b / d logits,

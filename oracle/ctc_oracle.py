@@ -193,3 +193,31 @@ def ctc_prefix_beam_search(ctc_probs: torch.Tensor, ctc_lens, beam_size: int, bl
                             nbest=[list(y[0]) for y in cur], nbest_scores=[y[1].score() for y in cur],
                             nbest_times=[y[1].times() for y in cur]))
     return results
+
+
+# --------------------------------------------------------------------------- CER (section 8f row 4)
+def calculate_cer(pre_tokens, gt_tokens):
+    """rnnt_eval.py:11-56 restated: Levenshtein table, then a backtrace from (m, n) that prefers, in this order, a
+    match, a substitution (diagonal + 1), a deletion (row above + 1) and otherwise an insertion; what is left of either
+    sequence when a border is reached counts as deletions / insertions.  Returns (cer, S, D, I, N)."""
+    m, n = len(pre_tokens), len(gt_tokens)
+    dp = np.zeros((m + 1, n + 1), dtype=np.int64)
+    dp[:, 0] = np.arange(m + 1)
+    dp[0, :] = np.arange(n + 1)
+    for i in range(1, m + 1):
+        for j in range(1, n + 1):
+            cost = 0 if pre_tokens[i - 1] == gt_tokens[j - 1] else 1
+            dp[i, j] = min(dp[i - 1, j] + 1, dp[i, j - 1] + 1, dp[i - 1, j - 1] + cost)
+    i, j, S, D, I = m, n, 0, 0, 0
+    while i > 0 and j > 0:
+        if pre_tokens[i - 1] == gt_tokens[j - 1]:
+            i, j = i - 1, j - 1
+        elif dp[i, j] == dp[i - 1, j - 1] + 1:
+            S, i, j = S + 1, i - 1, j - 1
+        elif dp[i, j] == dp[i - 1, j] + 1:
+            D, i = D + 1, i - 1
+        else:
+            I, j = I + 1, j - 1
+    D += i
+    I += j
+    return ((S + D + I) / n if n != 0 else 0.0), S, D, I, n

@@ -242,5 +242,48 @@ def main():
     print("ctc", fx["off_loss"], fx["on_loss"])
 
 
+def cer_golden():
+    """Section 8f row 4: calculate_cer of the reference (rnnt_eval.py:11-56).  rnnt_eval.py cannot be imported here (it
+    pulls data.dataloader -> librosa), so the function is taken out of the file by its AST node and executed as is."""
+    import ast
+    src = open(os.path.join(REF, "rnnt_eval.py")).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "calculate_cer")
+    ns = {}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), "rnnt_eval.py", "exec"), ns)
+    calculate_cer = ns["calculate_cer"]
+    rng = np.random.default_rng(17)
+    hyps, refs = [], []
+    for i in range(64):
+        n = int(rng.integers(0, 40))
+        ref = rng.integers(6, 30, n).tolist()          # small alphabet: many ties in the backtrace
+        hyp = list(ref)
+        for _ in range(int(rng.integers(0, 12))):       # random edits
+            op = int(rng.integers(0, 3))
+            pos = int(rng.integers(0, len(hyp) + 1))
+            if op == 0 and hyp:
+                hyp[min(pos, len(hyp) - 1)] = int(rng.integers(6, 30))
+            elif op == 1 and hyp:
+                del hyp[min(pos, len(hyp) - 1)]
+            else:
+                hyp.insert(pos, int(rng.integers(6, 30)))
+        if i % 16 == 0:
+            hyp = []
+        hyps.append(hyp)
+        refs.append(ref)
+    fx = dict(n=len(hyps))
+    for i, (h, r) in enumerate(zip(hyps, refs)):
+        cer, S, D, I, N = calculate_cer(h, r)
+        fx[f"hyp_{i}"] = np.array(h, dtype=np.int64)
+        fx[f"ref_{i}"] = np.array(r, dtype=np.int64)
+        fx[f"res_{i}"] = np.array([S, D, I, N], dtype=np.int64)
+        fx[f"cer_{i}"] = cer
+    np.savez_compressed(os.path.join(OUT, "cer_small.npz"), **fx)
+    print("cer", sum(int(fx[f"res_{i}"][:3].sum()) for i in range(len(hyps))), "edits over", len(hyps), "pairs")
+
+
 if __name__ == "__main__":
-    main()
+    if "--cer-only" in sys.argv:
+        cer_golden()
+    else:
+        main()
+        cer_golden()

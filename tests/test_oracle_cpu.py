@@ -142,3 +142,12 @@ def test_decoders_match_reference():
         for i, (hyp, sc) in enumerate(out):
             assert hyp == fx[f"a8_b{beam}_tok_{i}"].tolist()
             np.testing.assert_allclose(sc, fx[f"a8_b{beam}_sc_{i}"], atol=1e-4)
+
+
+def test_cer_restated_matches_reference_golden():
+    """oracle calculate_cer vs the outputs of the reference's rnnt_eval.calculate_cer (tests/golden/cer_small.npz)."""
+    fx = load_golden("cer_small.npz")
+    for i in range(int(fx["n"])):
+        cer, S, D, I, N = CO.calculate_cer(fx[f"hyp_{i}"].tolist(), fx[f"ref_{i}"].tolist())
+        assert [S, D, I, N] == fx[f"res_{i}"].tolist(), i
+        assert abs(cer - float(fx[f"cer_{i}"])) < 1e-12
