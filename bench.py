@@ -210,7 +210,39 @@ def run_ours(args):
     joint = C.TransducerJoint(V, D, D, D)
     joint.load_state_dict(bench_weights())
     joint = joint.to(dev)
-    reducer = GradAllReducer(joint.parameters()) if world > 1 else None
+    # N > 1: the gradient sum is the last kernel of the step graph (csrc/peer_reduce.cu over NVLink peer memory), checked
+    # once here against NCCL on random data; `--allreduce nccl`, a node without peer access or a failed check fall back to
+    # the NCCL all-reduce launched behind the graph
+    reducer, exchange, allreduce_note = None, None, None
+    if world > 1:
+        from ctcvr_b200.dist import PeerGradExchange
+        if args.allreduce == "peer":
+            try:
+                exchange = PeerGradExchange(sum(p.numel() for p in joint.parameters()) + 1)
+                torch.manual_seed(77 + rank)
+                probe = [torch.randn(n, device=dev) for n in (V * D, V, 1, 3 * D + 2)]
+                want = [x.clone() for x in probe]
+                for w_ in want:
+                    dist.all_reduce(w_)
+                try:
+                    exchange.reduce(probe)
+                    torch.cuda.synchronize()
+                    good = all(torch.allclose(a_, b_, rtol=1e-5, atol=1e-5) for a_, b_ in zip(probe, want))
+                except RuntimeError:
+                    good = False
+                ok = torch.tensor([float(good)], device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if float(ok) != 1.0:
+                    raise RuntimeError("sums differ from NCCL's on the probe tensors")
+                allreduce_note = "parameter gradients + loss summed by ONE kernel over NVLink peer memory, captured as the last node of the step graph (checked against NCCL at start-up)"
+            except RuntimeError as ex_err:
+                if exchange is not None:
+                    exchange.close()
+                exchange = None
+                allreduce_note = f"NCCL behind the step graph (peer exchange unavailable: {str(ex_err)[:160]})"
+        if exchange is None:
+            reducer = GradAllReducer(joint.parameters())
+            allreduce_note = allreduce_note or "one grouped NCCL all-reduce of the parameter gradients behind the step graph"
     enc, pred, tgt, tl, ul = make_inputs(1234 + rank, dev)
     enc.requires_grad_(True)
     pred.requires_grad_(True)
@@ -230,7 +262,7 @@ def run_ours(args):
     # bf16 path: the captured input buffers (and the pinned host staging of the e2e loop) are bf16 - the first kernel of
     # the path rounds its inputs to bf16 anyway
     in_dtype = torch.bfloat16 if args.precision == "bf16" else torch.float32
-    gkw = dict(global_batch=gB, precision=args.precision, input_dtype=in_dtype)
+    gkw = dict(global_batch=gB, precision=args.precision, input_dtype=in_dtype, grad_exchange=exchange)
     graphed = C.GraphedJointRnntStep(joint, B, T, U, blank, **gkw) if use_graph else None
     if graphed is not None:
         graphed.load(enc.detach(), pred.detach(), tgt, tl, ul)
@@ -247,6 +279,9 @@ def run_ours(args):
             costs = joint.rnnt_loss_fused(e, p, tg, tl_, ul_, blank, reduction="none", precision=args.precision)
             loss = costs.sum() / gB
             loss.backward()
+            if exchange is not None:
+                loss = loss.detach().clone()
+                exchange.reduce_grads(joint.parameters(), extra=[loss.view(1)])
         if reducer is not None:
             reducer.reduce()
         return loss
@@ -388,12 +423,12 @@ def run_ours(args):
                 "config": {"workload": "configs[1]: B=32/GPU,T=250,U=40,H=D=512,V=412 fused joint+rnnt_loss fwd/bwd",
                            "global_batch": gB, "parallelism": f"dp{world}", "l2": "flushed (256 MiB write) before each step",
                            "precision": args.precision, "cuda_graph": bool(graphed is not None),
-                           "allreduce": "one grouped NCCL all-reduce of the parameter gradients behind the step graph" if world > 1 else None},
+                           "allreduce": allreduce_note},
                 "e2e": {"value": gB / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "input_dtype": str(in_dtype).replace("torch.", "") if graphed is not None else "float32",
                         "h2d_GBps_measured": h2d_gbps, "h2d_ms_per_step": h2d / (h2d_gbps * 1e9) * 1e3},
                 "gpu_launches": int(launches), "gpu_launches_per_step": launches_per_step, "roofline": roof,
-                "clocks": clk.summary(), "loss": float(loss.item()) * world}
+                "clocks": clk.summary(), "loss": float(loss.item()) * (1 if exchange is not None else world)}
         if world == 1:
             # ---- the CPU reference on the SAME batch and weights: baseline timing (full batch, median of 3 after one
             # warm-up) and the parity check that rides in every record
@@ -572,6 +607,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager step instead of the captured CUDA graph")
     ap.add_argument("--precision", default=os.environ.get("CTCVR_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
+                    help="N>1: gradient sum by the in-graph NVLink peer kernel (default) or by NCCL behind the graph")
     ap.add_argument("--no-decode", action="store_true", help="skip the A4-A10 rows (bench_decode.py) in the JSON line")
     args = ap.parse_args()
     if args.impl == "reference":

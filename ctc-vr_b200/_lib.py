@@ -41,6 +41,12 @@ _SIGS = {
     "ctcvr_loss_combine": (I, [P, I, P, F, F, P, P]),
     "ctcvr_cer_ws_bytes": (Z, [I, I, I]),
     "ctcvr_cer_batch": (I, [P, P, I, P, P, I, I, P, Z, P, P]),
+    "ctcvr_peer_create": (I, [I, I, Z, P, P]),
+    "ctcvr_peer_connect": (I, [P, P, P]),
+    "ctcvr_peer_local_buffer": (P, [P]),
+    "ctcvr_peer_set_timeout_ms": (I, [P, c_long]),
+    "ctcvr_peer_allreduce": (I, [P, P, P, I, I, P]),
+    "ctcvr_peer_destroy": (I, [P]),
     "ctcvr_rnnt_loss_dense_ws_bytes": (Z, [I, I, I]),
     "ctcvr_rnnt_loss_dense": (I, [P, P, P, P, P, P, I, I, I, I, I, F, P, Z, P]),
     "ctcvr_log_softmax": (I, [P, P, c_long, I, P]),

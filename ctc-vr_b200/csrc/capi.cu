@@ -64,6 +64,13 @@ size_t cer_ws_bytes(int, int, int);
 int cer_batch(const int32_t*, const int32_t*, int, const int32_t*, const int32_t*, int, int, void*, size_t, int32_t*,
               cudaStream_t);
 
+int peer_create(int, int, size_t, void**, void*);
+int peer_connect(void*, const void*, void* const*);
+void* peer_local_buffer(void*);
+int peer_set_timeout_ms(void*, long);
+int peer_allreduce(void*, void* const*, const long*, int, int, cudaStream_t);
+int peer_destroy(void*);
+
 unsigned int tc_error_flag();
 void tc_set_prof(void*);
 void tc_set_mode(int);
@@ -209,6 +216,17 @@ int ctcvr_cer_batch(const int32_t* hyp, const int32_t* hyp_len, int Lh, const in
   CTCVR_REQUIRE(hyp_len && ref_len && out_sdin && ws && (Lh == 0 || hyp) && (Lr == 0 || ref), "cer_batch: NULL pointer");
   return cer_batch(hyp, hyp_len, Lh, ref, ref_len, Lr, N, ws, ws_bytes, out_sdin, ST(stream));
 }
+
+int ctcvr_peer_create(int rank, int world, size_t max_floats, void** out_ctx, void* out_handle64) {
+  return peer_create(rank, world, max_floats, out_ctx, out_handle64);
+}
+int ctcvr_peer_connect(void* ctx, const void* handles, void* const* local_ptrs) { return peer_connect(ctx, handles, local_ptrs); }
+void* ctcvr_peer_local_buffer(void* ctx) { return peer_local_buffer(ctx); }
+int ctcvr_peer_set_timeout_ms(void* ctx, long ms) { return peer_set_timeout_ms(ctx, ms); }
+int ctcvr_peer_allreduce(void* ctx, void* const* seg_ptrs, const long* seg_floats, int nseg, int ctas, void* stream) {
+  return peer_allreduce(ctx, seg_ptrs, seg_floats, nseg, ctas, ST(stream));
+}
+int ctcvr_peer_destroy(void* ctx) { return peer_destroy(ctx); }
 
 size_t ctcvr_rnnt_loss_dense_ws_bytes(int B, int T, int U1) { return (size_t)5 * B * T * U1 * sizeof(float); }
 

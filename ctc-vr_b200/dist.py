@@ -8,6 +8,7 @@ gradients equal those of the single-process run on the concatenated batch (also 
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Iterable, List, Optional, Sequence
 
 import torch
@@ -62,6 +63,104 @@ class GradAllReducer:
                 p.grad = torch.empty_like(p)
             p.grad.copy_(self._flat[off:off + k].view_as(p))
             off += k
+
+
+class PeerGradExchange:
+    """Sum of fp32 gradient tensors over the ranks of ONE node by a single kernel over NVLink peer memory
+    (`csrc/peer_reduce.cu`, `ctcvr_peer_allreduce`): pack -> flag barrier -> each rank reduces its slice from all peers
+    and stores it to all peers -> flag barrier -> unpack, in place on the tensors passed to `reduce()`.  Unlike an NCCL
+    call it is an ordinary kernel launch, so `GraphedJointRnntStep(grad_exchange=...)` captures it inside the step graph
+    (a replayed graph holding the NCCL all-reduce hung, see graph.py).  Sums are taken in rank order on the owning rank,
+    so every rank holds bit-identical results.
+
+    `torch.distributed` is used once, to pass the 64-byte CUDA IPC handles around.  Every rank must call `reduce()` with
+    tensors of the same sizes in the same order.  No fallback: a node without peer access raises."""
+
+    MAX_TENSORS = 24
+
+    def __init__(self, max_floats: int, group=None, ctas: int = 32, _ctx=None, _rank=0, _world=1):
+        from . import _lib
+        self._L = _lib
+        self.ctas = int(ctas)
+        self._cache = {}
+        if _ctx is not None:                                       # ranks simulated inside one process (tests)
+            self.ctx, self.rank, self.world = _ctx, _rank, _world
+            return
+        if not dist.is_initialized():
+            raise RuntimeError("PeerGradExchange needs an initialised torch.distributed process group (one process per GPU)")
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if not torch.cuda.is_available():
+            raise RuntimeError("PeerGradExchange runs on CUDA (B200) devices only; there is no CPU path")
+        ctx = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        _lib.call("ctcvr_peer_create", self.rank, self.world, int(max_floats) + 4 * self.MAX_TENSORS, ctypes.byref(ctx), handle)
+        self.ctx = ctx
+        handles: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        blob = ctypes.create_string_buffer(b"".join(handles), 64 * self.world)
+        err = None
+        try:
+            _lib.call("ctcvr_peer_connect", self.ctx, blob, None)
+        except RuntimeError as e:
+            err = str(e)
+        # nobody launches before every rank has mapped its peers, and all ranks fail together if one could not
+        errs: List[Optional[str]] = [None] * self.world
+        dist.all_gather_object(errs, err, group=group)
+        bad = [f"rank {r}: {e}" for r, e in enumerate(errs) if e]
+        if bad:
+            self.close()
+            raise RuntimeError("PeerGradExchange: " + "; ".join(bad))
+
+    @classmethod
+    def local_group(cls, world: int, max_floats: int, ctas: int = 32) -> List["PeerGradExchange"]:
+        """`world` ranks inside this process, all on the current device (buffers addressed directly, no IPC): the
+        single-GPU test of the kernel - the ranks' kernels must then be launched on DIFFERENT streams."""
+        from . import _lib
+        ctxs = []
+        for r in range(world):
+            ctx = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(64)
+            _lib.call("ctcvr_peer_create", r, world, int(max_floats) + 4 * cls.MAX_TENSORS, ctypes.byref(ctx), handle)
+            ctxs.append(ctx)
+        bufs = (ctypes.c_void_p * world)(*[_lib.lib().ctcvr_peer_local_buffer(c) for c in ctxs])
+        for c in ctxs:
+            _lib.call("ctcvr_peer_connect", c, None, bufs)
+        return [cls(max_floats, ctas=ctas, _ctx=c, _rank=r, _world=world) for r, c in enumerate(ctxs)]
+
+    def set_timeout_ms(self, ms: int):
+        self._L.call("ctcvr_peer_set_timeout_ms", self.ctx, int(ms))
+
+    def reduce(self, tensors: Sequence[torch.Tensor]):
+        """In-place sum over ranks of `tensors` (fp32, contiguous, CUDA) on the current stream."""
+        if self.world == 1:
+            return
+        ts = list(tensors)
+        for t in ts:
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() > 0):
+                raise RuntimeError("PeerGradExchange.reduce: tensors must be non-empty contiguous fp32 CUDA tensors")
+        key = tuple((t.data_ptr(), t.numel()) for t in ts)
+        args = self._cache.get(key)
+        if args is None:
+            if len(self._cache) > 64:
+                self._cache.clear()
+            args = ((ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts]), (ctypes.c_long * len(ts))(*[t.numel() for t in ts]))
+            self._cache[key] = args
+        self._L.call("ctcvr_peer_allreduce", self.ctx, args[0], args[1], len(ts), self.ctas, self._L.stream())
+
+    def reduce_grads(self, params: Iterable[torch.nn.Parameter], extra: Sequence[torch.Tensor] = ()):
+        grads = []
+        for p in params:
+            if not p.requires_grad:
+                continue
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            grads.append(p.grad)
+        self.reduce(grads + list(extra))
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None:
+            self._L.lib().ctcvr_peer_destroy(self.ctx)
+            self.ctx = None
 
 
 def dp_loss_and_backward(loss_fn, global_batch: int, reducer: Optional[GradAllReducer] = None):

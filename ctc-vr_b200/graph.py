@@ -16,15 +16,17 @@ class GraphedJointRnntStep:
     `sum_b cost_b / global_batch`.  Gradients land in `joint.<param>.grad`, `self.enc.grad`, `self.pred.grad`
     (static tensors, overwritten by every replay).  Passing no arguments replays on the resident inputs.
 
-    The data-parallel gradient all-reduce stays outside the graph: a replayed graph that contains the NCCL collective
-    (grouped in round 1, one flat bucket in round 2) hung the 2-GPU bench both times, so `dist.GradAllReducer.reduce()`
-    is called after `step()`.
+    Data parallel: with `grad_exchange=dist.PeerGradExchange(...)` the sum of the parameter gradients (and of the loss)
+    over the ranks is the LAST kernel of the captured step (`csrc/peer_reduce.cu`, flags and 16-byte loads / stores over
+    NVLink peer memory).  An NCCL collective cannot take that place: a replayed graph that contained it (grouped in round
+    1, one flat bucket in round 2) hung the 2-GPU bench both times; with `grad_exchange=None` call
+    `dist.GradAllReducer.reduce()` after `step()`.
     `input_dtype=torch.bfloat16` keeps the captured input buffers in bf16 (the bf16 path rounds its inputs to bf16 in
     the first kernel anyway): a host pipeline then stages half the bytes per step."""
 
     def __init__(self, joint, B: int, T: int, U: int, blank: int, global_batch: Optional[int] = None,
                  precision: str = "fp32", clamp: float = -1.0, warmup: int = 3,
-                 input_dtype: torch.dtype = torch.float32):
+                 input_dtype: torch.dtype = torch.float32, grad_exchange=None):
         p0 = next(joint.parameters())
         dev = p0.device
         if dev.type != "cuda":
@@ -33,6 +35,7 @@ class GraphedJointRnntStep:
         P = joint.pred_ffn.in_features if joint.pred_ffn is not None else joint.ffn_out.in_features
         self.joint, self.blank, self.precision, self.clamp = joint, int(blank), precision, float(clamp)
         self.gB = float(global_batch if global_batch is not None else B)
+        self.grad_exchange = grad_exchange
         self.enc = torch.zeros(B, T, E, device=dev, dtype=input_dtype, requires_grad=True)
         self.pred = torch.zeros(B, U + 1, P, device=dev, dtype=input_dtype, requires_grad=True)
         self.targets = torch.full((B, U), max(self.blank + 1, 1) % joint.ffn_out.out_features, dtype=torch.int32, device=dev)
@@ -66,6 +69,8 @@ class GraphedJointRnntStep:
         # sum / div / fill / mul / expand kernels of the scalar-loss autograd chain), the value is one dot product
         torch.autograd.backward(costs, grad_tensors=self._seed)
         self.loss = torch.dot(costs.detach(), self._seed)
+        if self.grad_exchange is not None:
+            self.grad_exchange.reduce([p.grad for p in self.joint.parameters() if p.grad is not None] + [self.loss.view(1)])
 
     @torch.no_grad()
     def load(self, enc_out, pred_out, targets, logit_lengths, target_lengths):

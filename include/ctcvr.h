@@ -121,6 +121,23 @@ size_t ctcvr_cer_ws_bytes(int N, int Lh, int Lr);
 int ctcvr_cer_batch(const int32_t* hyp, const int32_t* hyp_len, int Lh, const int32_t* ref, const int32_t* ref_len, int Lr,
                     int N, void* ws, size_t ws_bytes, int32_t* out_sdin, void* stream);
 
+/* ---- section 8(e): data-parallel gradient exchange over NVLink peer memory (replaces the all-reduce the reference
+ * gets from torch DistributedDataParallel around the train step, rnnt_train.py:60-75).  One rank = one process = one
+ * GPU of a node.  ctcvr_peer_create allocates the rank's staging buffer (room for max_floats payload floats) and
+ * returns its 64-byte CUDA IPC handle; the host exchanges the handles (any transport), ctcvr_peer_connect maps the
+ * peers' buffers (handles: world x 64 bytes; or local_ptrs[world] = buffers of ranks living in THIS process, then
+ * handles may be NULL).  ctcvr_peer_allreduce launches ONE kernel on `stream` that sums nseg fp32 tensors
+ * (seg_ptrs[i], seg_floats[i] floats, <= 24 per call) over all ranks in place, in rank order 0..world-1, so every rank
+ * ends with bit-identical sums; it can be captured in a CUDA graph.  Every rank must pass the same segment sizes and
+ * the same `ctas` (<= 64, 0 = 32).  A rank that waits longer than the timeout (default 10 s) for a peer gives up and the
+ * NEXT call returns an error.  world == 1: no launch. */
+int ctcvr_peer_create(int rank, int world, size_t max_floats, void** out_ctx, void* out_handle64);
+int ctcvr_peer_connect(void* ctx, const void* handles, void* const* local_ptrs);
+void* ctcvr_peer_local_buffer(void* ctx);
+int ctcvr_peer_set_timeout_ms(void* ctx, long ms);
+int ctcvr_peer_allreduce(void* ctx, void* const* seg_ptrs, const long* seg_floats, int nseg, int ctas, void* stream);
+int ctcvr_peer_destroy(void* ctx);
+
 /* ---- A2 on dense logits — torch.ops.torchaudio.rnnt_loss_forward
  * (site-packages/torchaudio/functional/functional.py:1725,1737-1744), fused_log_softmax=True.
  * logits [B,T,U1,V] fp32; costs [B]; grads [B,T,U1,V] (may be NULL) = d cost_b / d logits,

@@ -1,6 +1,7 @@
 """Data-parallel step on real GPUs over NCCL (skipped with fewer than 2 GPUs): the summed gradients of N ranks on
 shards of a batch equal the single-process gradients on the whole batch, through the NCCL branch of
-`GradAllReducer` (grouped in-place collective) behind an eager step and behind a graphed step."""
+`GradAllReducer` (grouped in-place collective) behind an eager step and behind a graphed step, and through the NVLink
+peer exchange (`PeerGradExchange`) alone and captured inside the step graph."""
 import os
 import socket
 
@@ -21,7 +22,7 @@ def _free_port():
 def _worker(rank, world, port, out):
     import torch.distributed as dist
     import ctcvr_b200 as C
-    from ctcvr_b200.dist import GradAllReducer, shard_bounds
+    from ctcvr_b200.dist import GradAllReducer, PeerGradExchange, shard_bounds
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dev = torch.device("cuda", rank)
     torch.cuda.set_device(dev)
@@ -48,6 +49,27 @@ def _worker(rank, world, port, out):
     red.reduce()
     torch.cuda.synchronize()
     res["graph"] = {n: p.grad.detach().float().cpu() for n, p in joint.named_parameters()}
+    # (3) the NVLink peer exchange (csrc/peer_reduce.cu) against NCCL on the same tensors: a + b is commutative, so at
+    # world size 2 the sums must be bit-identical
+    ex = PeerGradExchange(sum(p.numel() for p in joint.parameters()) + 1)
+    torch.manual_seed(100 + rank)
+    xs = [torch.randn(n, device=dev) for n in (412 * 512, 412, 1, 77, 512 * 512)]
+    want = [x.clone() for x in xs]
+    for w in want:
+        dist.all_reduce(w)
+    for _ in range(3):                                   # repeated calls: the flags are step counters, nothing is reset
+        got = [x.clone() for x in xs]
+        ex.reduce(got)
+        torch.cuda.synchronize()
+        res.setdefault("peer_exact", True)
+        res["peer_exact"] = res["peer_exact"] and all(torch.equal(a, b) for a, b in zip(got, want))
+    # (4) graphed step with the exchange captured as the last kernel of the graph, replayed twice
+    g2 = C.GraphedJointRnntStep(joint, hi - lo, T, U, blank, global_batch=B, precision="bf16", grad_exchange=ex)
+    for _ in range(2):
+        loss = g2.step(sh(enc), sh(pred), sh(tgt), sh(tl), sh(ul))
+    torch.cuda.synchronize()
+    res["graph_peer"] = {n: p.grad.detach().float().cpu() for n, p in joint.named_parameters()}
+    res["graph_peer_loss"] = float(loss)
     if rank == 0:
         # single-process truth on the whole batch
         joint.zero_grad(set_to_none=True)
@@ -55,8 +77,10 @@ def _worker(rank, world, port, out):
                                       precision="bf16")
         (costs.sum() / B).backward()
         res["single"] = {n: p.grad.detach().float().cpu() for n, p in joint.named_parameters()}
+        res["single_loss"] = float(costs.sum() / B)
         torch.save(res, out)
     dist.barrier()
+    ex.close()
     dist.destroy_process_group()
 
 
@@ -67,7 +91,9 @@ def test_nccl_dp_step_matches_single_process(tmp_path):
     out = str(tmp_path / "res.pt")
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     res = torch.load(out)
-    for kind in ("eager", "graph"):
+    assert res["peer_exact"]
+    assert abs(res["graph_peer_loss"] - res["single_loss"]) < 2e-3 * abs(res["single_loss"])
+    for kind in ("eager", "graph", "graph_peer"):
         for n, want in res["single"].items():
             got = res[kind][n]
             err = float((got - want).norm() / max(float(want.norm()), 1e-30))
