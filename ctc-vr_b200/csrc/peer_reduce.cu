@@ -25,9 +25,9 @@ namespace {
 
 constexpr int PR_MAX_WORLD = 8;
 constexpr int PR_MAX_SEG = 24;
-constexpr int PR_MAX_CTAS = 64;
+constexpr int PR_MAX_CTAS = 128;
 constexpr int PR_THREADS = 512;
-constexpr size_t PR_HEADER = 4096;   // flags [PR_MAX_CTAS][PR_MAX_WORLD] u32 | epoch [PR_MAX_CTAS] u32
+constexpr size_t PR_HEADER = 8192;   // flags [PR_MAX_CTAS][PR_MAX_WORLD] u32 | epoch [PR_MAX_CTAS] u32
 
 struct PeerCtx {
   int rank = 0, world = 1, device = 0;
@@ -102,52 +102,93 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs& a, unsigned int val
 }
 
 // Payload floats [4u, 4u+4) live in one segment (offsets and padded lengths are multiples of 4).
-template <bool kPack>
-__device__ __forceinline__ void move_unit(const PeerArgs& a, long u, float4* stage) {
+struct UnitRef { float* g; long left; bool whole; };   // left = floats of the segment from g on (<= 0: pure padding)
+__device__ __forceinline__ UnitRef locate_unit(const PeerArgs& a, long u) {
   const long f = u * 4;
   int s = 0;
 #pragma unroll 1
   for (int i = 1; i < a.nseg; ++i)
     if (f >= a.seg_off[i]) s = i;
   const long j = f - a.seg_off[s];
-  const long n = a.seg_n[s];
-  float* g = a.seg_ptr[s] + j;
-  const bool whole = j + 4 <= n && ((reinterpret_cast<uintptr_t>(g) & 15u) == 0);
-  if (kPack) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (whole) v = *reinterpret_cast<const float4*>(g);
-    else {
-      if (j + 0 < n) v.x = g[0];
-      if (j + 1 < n) v.y = g[1];
-      if (j + 2 < n) v.z = g[2];
-      if (j + 3 < n) v.w = g[3];
-    }
-    stage[u] = v;
-  } else {
-    const float4 v = ld_sys_f4(stage + u);
-    if (whole) *reinterpret_cast<float4*>(g) = v;
-    else {
-      if (j + 0 < n) g[0] = v.x;
-      if (j + 1 < n) g[1] = v.y;
-      if (j + 2 < n) g[2] = v.z;
-      if (j + 3 < n) g[3] = v.w;
+  UnitRef r;
+  r.g = a.seg_ptr[s] + j;
+  r.left = a.seg_n[s] - j;
+  r.whole = r.left >= 4 && ((reinterpret_cast<uintptr_t>(r.g) & 15u) == 0);
+  return r;
+}
+__device__ __forceinline__ float4 load_unit(const UnitRef& r) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r.whole) return *reinterpret_cast<const float4*>(r.g);
+  if (r.left > 0) v.x = r.g[0];
+  if (r.left > 1) v.y = r.g[1];
+  if (r.left > 2) v.z = r.g[2];
+  if (r.left > 3) v.w = r.g[3];
+  return v;
+}
+__device__ __forceinline__ void store_unit(const UnitRef& r, const float4 v) {
+  if (r.whole) { *reinterpret_cast<float4*>(r.g) = v; return; }
+  if (r.left > 0) r.g[0] = v.x;
+  if (r.left > 1) r.g[1] = v.y;
+  if (r.left > 2) r.g[2] = v.z;
+  if (r.left > 3) r.g[3] = v.w;
+}
+
+// pack (tensors -> staging buffer) / unpack (staging buffer -> tensors) of this CTA's units of every slice, R loads in
+// flight per thread.  Unit (slice r, index i) is flat unit r * slice4 + i.
+template <bool kPack>
+__device__ __forceinline__ void move_units(const PeerArgs& a, int i0, int stride, float4* stage) {
+  constexpr int R = 4;
+  for (int r = 0; r < a.world; ++r) {
+    const long base = (long)r * a.slice4;
+    for (long i = i0; i < a.slice4; i += (long)R * stride) {
+      float4 v[R];
+      UnitRef ref[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const long ik = i + (long)k * stride;
+        if (ik < a.slice4) {
+          ref[k] = locate_unit(a, base + ik);
+          v[k] = kPack ? load_unit(ref[k]) : ld_sys_f4(stage + base + ik);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const long ik = i + (long)k * stride;
+        if (ik < a.slice4) {
+          if (kPack) stage[base + ik] = v[k];
+          else store_unit(ref[k], v[k]);
+        }
+      }
     }
   }
 }
 
+// A remote 16-byte load is a ~2 us round trip and the L1-bypassing loads are not reordered by the compiler, so each thread
+// issues the loads of R units (R * N requests in flight) before it sums and stores any of them.
+template <int N, int R>
+__device__ __forceinline__ void reduce_units(const PeerArgs& a, long base, long i, int stride, long end) {
+  float4 v[R][N];
+#pragma unroll
+  for (int k = 0; k < R; ++k)
+    if (i + (long)k * stride < end) {
+#pragma unroll
+      for (int q = 0; q < N; ++q) v[k][q] = ld_sys_f4(data_of(a.peer[q]) + base + i + (long)k * stride);
+    }
+#pragma unroll
+  for (int k = 0; k < R; ++k)
+    if (i + (long)k * stride < end) {
+      float4 s = v[k][0];
+#pragma unroll
+      for (int q = 1; q < N; ++q) { s.x += v[k][q].x; s.y += v[k][q].y; s.z += v[k][q].z; s.w += v[k][q].w; }
+#pragma unroll
+      for (int q = 0; q < N; ++q) data_of(a.peer[q])[base + i + (long)k * stride] = s;
+    }
+}
 template <int N>
 __device__ __forceinline__ void reduce_slice(const PeerArgs& a, int i0, int stride) {
+  constexpr int R = N <= 2 ? 4 : (N <= 4 ? 2 : 1);
   const long base = (long)a.rank * a.slice4;
-  for (long i = i0; i < a.slice4; i += stride) {
-    float4 v[N];
-#pragma unroll
-    for (int q = 0; q < N; ++q) v[q] = ld_sys_f4(data_of(a.peer[q]) + base + i);
-    float4 s = v[0];
-#pragma unroll
-    for (int q = 1; q < N; ++q) { s.x += v[q].x; s.y += v[q].y; s.z += v[q].z; s.w += v[q].w; }
-#pragma unroll
-    for (int q = 0; q < N; ++q) data_of(a.peer[q])[base + i] = s;
-  }
+  for (long i = i0; i < a.slice4; i += (long)R * stride) reduce_units<N, R>(a, base, i, stride, a.slice4);
 }
 
 __global__ void __launch_bounds__(PR_THREADS, 1) peer_allreduce_kernel(const PeerArgs a) {
@@ -159,8 +200,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) peer_allreduce_kernel(const Pee
   const int i0 = blockIdx.x * PR_THREADS + threadIdx.x, stride = gridDim.x * PR_THREADS;
   float4* stage = data_of(local);
 
-  for (int r = 0; r < a.world; ++r)
-    for (long i = i0; i < a.slice4; i += stride) move_unit<true>(a, (long)r * a.slice4 + i, stage);
+  move_units<true>(a, i0, stride, stage);
   peer_barrier(a, 2u * e + 1u, 1);
   switch (a.world) {
     case 2: reduce_slice<2>(a, i0, stride); break;
@@ -173,8 +213,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) peer_allreduce_kernel(const Pee
     default: break;
   }
   peer_barrier(a, 2u * e + 2u, 2);
-  for (int r = 0; r < a.world; ++r)
-    for (long i = i0; i < a.slice4; i += stride) move_unit<false>(a, (long)r * a.slice4 + i, stage);
+  move_units<false>(a, i0, stride, stage);
   if (threadIdx.x == 0) *epoch_of(local, blockIdx.x) = e + 1u;
 }
 
@@ -279,7 +318,7 @@ int peer_allreduce(void* ctx, void* const* seg_ptrs, const long* seg_floats, int
   for (int q = 0; q < c->world; ++q) a.peer[q] = c->peer[q];
   a.err = c->err_d;
   a.timeout_ns = c->timeout_ns;
-  if (ctas <= 0) ctas = 32;
+  if (ctas <= 0) ctas = 64;
   ctas = std::min(ctas, PR_MAX_CTAS);
   peer_allreduce_kernel<<<ctas, PR_THREADS, 0, st>>>(a);
   CTCVR_LAUNCH_CHECK();

@@ -21,6 +21,8 @@ class GraphedJointRnntStep:
     NVLink peer memory).  An NCCL collective cannot take that place: a replayed graph that contained it (grouped in round
     1, one flat bucket in round 2) hung the 2-GPU bench both times; with `grad_exchange=None` call
     `dist.GradAllReducer.reduce()` after `step()`.
+    Construct it before (or after dropping every reference to) eager autograd graphs over the same parameters: a live
+    graph pins their AccumulateGrad nodes to the stream it ran on, and the capture may not synchronise with that stream.
     `input_dtype=torch.bfloat16` keeps the captured input buffers in bf16 (the bf16 path rounds its inputs to bf16 in
     the first kernel anyway): a host pipeline then stages half the bytes per step."""
 

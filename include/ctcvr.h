@@ -129,7 +129,7 @@ int ctcvr_cer_batch(const int32_t* hyp, const int32_t* hyp_len, int Lh, const in
  * handles may be NULL).  ctcvr_peer_allreduce launches ONE kernel on `stream` that sums nseg fp32 tensors
  * (seg_ptrs[i], seg_floats[i] floats, <= 24 per call) over all ranks in place, in rank order 0..world-1, so every rank
  * ends with bit-identical sums; it can be captured in a CUDA graph.  Every rank must pass the same segment sizes and
- * the same `ctas` (<= 64, 0 = 32).  A rank that waits longer than the timeout (default 10 s) for a peer gives up and the
+ * the same `ctas` (<= 128, 0 = 64).  A rank that waits longer than the timeout (default 10 s) for a peer gives up and the
  * NEXT call returns an error.  world == 1: no launch. */
 int ctcvr_peer_create(int rank, int world, size_t max_floats, void** out_ctx, void* out_handle64);
 int ctcvr_peer_connect(void* ctx, const void* handles, void* const* local_ptrs);

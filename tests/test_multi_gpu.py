@@ -43,6 +43,9 @@ def _worker(rank, world, port, out):
     (costs.sum() / B).backward()
     red.reduce()
     res["eager"] = {n: p.grad.detach().float().cpu() for n, p in joint.named_parameters()}
+    # an autograd graph kept alive over the same parameters pins their AccumulateGrad nodes to the default stream, which
+    # a capture on another stream may not touch (cudaErrorStreamCaptureImplicit)
+    del costs
     # (2) graphed step, the collective behind the replay
     g = C.GraphedJointRnntStep(joint, hi - lo, T, U, blank, global_batch=B, precision="bf16")
     g.step(sh(enc), sh(pred), sh(tgt), sh(tl), sh(ul))
@@ -51,9 +54,10 @@ def _worker(rank, world, port, out):
     res["graph"] = {n: p.grad.detach().float().cpu() for n, p in joint.named_parameters()}
     # (3) the NVLink peer exchange (csrc/peer_reduce.cu) against NCCL on the same tensors: a + b is commutative, so at
     # world size 2 the sums must be bit-identical
-    ex = PeerGradExchange(sum(p.numel() for p in joint.parameters()) + 1)
+    sizes = (412 * 512, 412, 1, 77, 512 * 512)
+    ex = PeerGradExchange(max(sum(sizes), sum(p.numel() for p in joint.parameters()) + 1))
     torch.manual_seed(100 + rank)
-    xs = [torch.randn(n, device=dev) for n in (412 * 512, 412, 1, 77, 512 * 512)]
+    xs = [torch.randn(n, device=dev) for n in sizes]
     want = [x.clone() for x in xs]
     for w in want:
         dist.all_reduce(w)
