@@ -297,17 +297,19 @@ def run_ours(args):
     barrier()
     l0 = _lib.lib().ctcvr_launch_count()
     with ClockSampler(local) as clk:
-        tot_ms = 0.0
+        # K steps between one barrier + synchronize on each side.  Every step is bracketed by its own pair of events so
+        # that the L2 flush in front of it is not counted; the host does not synchronise inside the region (at N > 1 the
+        # ranks pace each other through the gradient exchange, as in a train loop).
+        evs = []
         for _ in range(args.steps):
             flush.zero_()
-            barrier()
             s, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             loss = step(*resident)
             e_.record()
-            torch.cuda.synchronize()
-            tot_ms += s.elapsed_time(e_)
+            evs.append((s, e_))
         barrier()
+        tot_ms = sum(s.elapsed_time(e_) for s, e_ in evs)
         launches = _lib.lib().ctcvr_launch_count() - l0
         if graphed is not None:      # replays do not pass through the C ABI: the captured launches, counted above
             launches = args.steps * launches_per_step

@@ -70,6 +70,7 @@ void* peer_local_buffer(void*);
 int peer_set_timeout_ms(void*, long);
 int peer_allreduce(void*, void* const*, const long*, int, int, cudaStream_t);
 int peer_destroy(void*);
+void peer_set_prof(void*);
 
 unsigned int tc_error_flag();
 void tc_set_prof(void*);
@@ -99,7 +100,7 @@ extern "C" {
 const char* ctcvr_last_error(void) { return g_err; }
 int ctcvr_version(void) { return 100; }
 unsigned int ctcvr_debug_tc_error(void) { return tc_error_flag(); }
-void ctcvr_debug_set_prof(void* buf) { tc_set_prof(buf); }
+void ctcvr_debug_set_prof(void* buf) { tc_set_prof(buf); peer_set_prof(buf); }
 void ctcvr_debug_set_mode(int single_cta) { tc_set_mode(single_cta); }
 unsigned long long ctcvr_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 

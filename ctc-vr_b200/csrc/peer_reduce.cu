@@ -1,20 +1,23 @@
 // Data-parallel gradient exchange over NVLink peer memory (replaces the DDP all-reduce the
 // reference's train loop gets from torch DistributedDataParallel, rnnt_train.py:60-75).
 //
-// ONE kernel per step, capturable in the step's CUDA graph (no NCCL call, no host round trip):
-//   pack      the rank's gradient tensors (a table of segments) are copied into its staging buffer
-//   barrier A every rank's staging buffer is complete (flags written into the peers' buffers over NVLink)
-//   reduce    rank r sums slice r of all N staging buffers (16-byte loads over NVLink, fixed order 0..N-1, so every rank
-//             ends with bit-identical sums) and stores the sum into slice r of all N buffers
-//   barrier B every slice of the local buffer has been written by its owner
-//   unpack    the staging buffer is copied back into the gradient tensors
+// ONE kernel per step, capturable in the step's CUDA graph (no NCCL call, no host round trip).  All NVLink traffic is
+// POSTED STORES - a remote load is a ~2 us round trip per dependent step, a remote store is fire-and-forget:
+//   scatter   the rank's gradient tensors (a table of segments) are read once; the part that falls into slice r is stored
+//             into rank r's inbox, slot [this rank]
+//   barrier A every rank's inbox is complete (flags written into the peers' buffers over NVLink)
+//   reduce    rank r sums the N slots of its inbox (local loads, fixed order 0..N-1, so all ranks end with bit-identical
+//             sums) and stores the sum into slice r of every rank's result area
+//   barrier B every slice of the local result area has been written by its owner
+//   unpack    the result area is copied back into the gradient tensors
 // A payload of a few MB is latency-bound: NCCL's launch + protocol cost ~75-110 us per step on 2-8 B200s when called
-// behind the step graph (profiles/README.md, round 1); this kernel is bounded by two NVLink round trips plus ~3 MB of peer
-// reads and writes per rank.
+// behind the step graph (profiles/README.md, round 1); this kernel is bounded by two flag round trips plus 2 x 7/8 of the
+// payload in posted stores per rank.
 //
-// No grid-wide synchronisation: float4 unit i of a slice belongs to CTA (i / blockDim) % gridDim on EVERY rank, for the
-// pack, the reduction and the unpack alike, and CTA c only ever synchronises with CTA c of the peers.  Flags are
-// monotonic step counters (no reset, replay-safe); waits are bounded and report through a mapped host word.
+// No grid-wide synchronisation: float4 unit i of a slice belongs to CTA (i / blockDim) % gridDim on EVERY rank, in all
+// three phases, and CTA c only ever synchronises with CTA c of the peers.  Flags are monotonic step counters (no reset,
+// replay-safe; a peer can run at most one barrier ahead, which the two areas make safe); waits are bounded and report
+// through a mapped host word.
 #include <algorithm>
 
 #include "common.cuh"
@@ -31,7 +34,7 @@ constexpr size_t PR_HEADER = 8192;   // flags [PR_MAX_CTAS][PR_MAX_WORLD] u32 | 
 
 struct PeerCtx {
   int rank = 0, world = 1, device = 0;
-  size_t cap_floats = 0;                 // payload capacity (floats), multiple of 4 * world
+  size_t cap_floats = 0;                 // payload capacity (floats), multiple of 4 * world; the buffer holds it twice
   uint8_t* local = nullptr;
   uint8_t* peer[PR_MAX_WORLD] = {};
   bool imported[PR_MAX_WORLD] = {};
@@ -48,9 +51,14 @@ struct PeerArgs {
   long seg_n[PR_MAX_SEG];                // floats
   int nseg, rank, world;
   long slice4;                           // float4 units per slice
+  long result4;                          // float4 offset of the result area (fixed by the capacity: calls of different
+                                         // payload sizes must not let one step's inbox overlap the previous step's result)
   unsigned int* err;
   long long timeout_ns;
+  long long* prof;                       // dev tool: 8 globaltimer stamps per CTA (ctcvr_debug_set_prof), else NULL
 };
+
+static void* g_peer_prof = nullptr;
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -78,7 +86,9 @@ __device__ __forceinline__ unsigned int* flags_of(uint8_t* base, int cta) {
 __device__ __forceinline__ unsigned int* epoch_of(uint8_t* base, int cta) {
   return reinterpret_cast<unsigned int*>(base + PR_MAX_CTAS * PR_MAX_WORLD * 4) + cta;
 }
-__device__ __forceinline__ float4* data_of(uint8_t* base) { return reinterpret_cast<float4*>(base + PR_HEADER); }
+// inbox: [world][slice4] float4 (slot q = rank q's part of MY slice) | result: [world * slice4] float4 (the reduced payload)
+__device__ __forceinline__ float4* inbox_of(uint8_t* base) { return reinterpret_cast<float4*>(base + PR_HEADER); }
+__device__ __forceinline__ float4* result_of(uint8_t* base, long result4) { return inbox_of(base) + result4; }
 
 // All of the CTA's earlier writes are ordered before the flag stores (bar.sync + release at system scope); the flag of
 // this rank is raised in CTA c's row of every peer, then the CTA waits until all N flags of its own row reached `value`.
@@ -133,13 +143,15 @@ __device__ __forceinline__ void store_unit(const UnitRef& r, const float4 v) {
   if (r.left > 3) r.g[3] = v.w;
 }
 
-// pack (tensors -> staging buffer) / unpack (staging buffer -> tensors) of this CTA's units of every slice, R loads in
-// flight per thread.  Unit (slice r, index i) is flat unit r * slice4 + i.
-template <bool kPack>
-__device__ __forceinline__ void move_units(const PeerArgs& a, int i0, int stride, float4* stage) {
+// scatter (tensors -> the owners' inboxes) / unpack (local result area -> tensors) of this CTA's units of every slice,
+// R loads in flight per thread.  Unit (slice r, index i) is flat payload unit r * slice4 + i.
+template <bool kScatter>
+__device__ __forceinline__ void move_units(const PeerArgs& a, int i0, int stride) {
   constexpr int R = 4;
+  const float4* result = result_of(a.peer[a.rank], a.result4);
   for (int r = 0; r < a.world; ++r) {
     const long base = (long)r * a.slice4;
+    float4* inbox = inbox_of(a.peer[r]) + (long)a.rank * a.slice4;
     for (long i = i0; i < a.slice4; i += (long)R * stride) {
       float4 v[R];
       UnitRef ref[R];
@@ -148,14 +160,14 @@ __device__ __forceinline__ void move_units(const PeerArgs& a, int i0, int stride
         const long ik = i + (long)k * stride;
         if (ik < a.slice4) {
           ref[k] = locate_unit(a, base + ik);
-          v[k] = kPack ? load_unit(ref[k]) : ld_sys_f4(stage + base + ik);
+          v[k] = kScatter ? load_unit(ref[k]) : ld_sys_f4(result + base + ik);
         }
       }
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         const long ik = i + (long)k * stride;
         if (ik < a.slice4) {
-          if (kPack) stage[base + ik] = v[k];
+          if (kScatter) inbox[ik] = v[k];
           else store_unit(ref[k], v[k]);
         }
       }
@@ -163,32 +175,30 @@ __device__ __forceinline__ void move_units(const PeerArgs& a, int i0, int stride
   }
 }
 
-// A remote 16-byte load is a ~2 us round trip and the L1-bypassing loads are not reordered by the compiler, so each thread
-// issues the loads of R units (R * N requests in flight) before it sums and stores any of them.
-template <int N, int R>
-__device__ __forceinline__ void reduce_units(const PeerArgs& a, long base, long i, int stride, long end) {
-  float4 v[R][N];
-#pragma unroll
-  for (int k = 0; k < R; ++k)
-    if (i + (long)k * stride < end) {
-#pragma unroll
-      for (int q = 0; q < N; ++q) v[k][q] = ld_sys_f4(data_of(a.peer[q]) + base + i + (long)k * stride);
-    }
-#pragma unroll
-  for (int k = 0; k < R; ++k)
-    if (i + (long)k * stride < end) {
-      float4 s = v[k][0];
-#pragma unroll
-      for (int q = 1; q < N; ++q) { s.x += v[k][q].x; s.y += v[k][q].y; s.z += v[k][q].z; s.w += v[k][q].w; }
-#pragma unroll
-      for (int q = 0; q < N; ++q) data_of(a.peer[q])[base + i + (long)k * stride] = s;
-    }
-}
+// Sum of the N inbox slots of this rank's slice (local, L1-bypassing: the peers wrote them), stored to every rank's result area.
 template <int N>
 __device__ __forceinline__ void reduce_slice(const PeerArgs& a, int i0, int stride) {
   constexpr int R = N <= 2 ? 4 : (N <= 4 ? 2 : 1);
+  const float4* inbox = inbox_of(a.peer[a.rank]);
   const long base = (long)a.rank * a.slice4;
-  for (long i = i0; i < a.slice4; i += (long)R * stride) reduce_units<N, R>(a, base, i, stride, a.slice4);
+  for (long i = i0; i < a.slice4; i += (long)R * stride) {
+    float4 v[R][N];
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+      if (i + (long)k * stride < a.slice4) {
+#pragma unroll
+        for (int q = 0; q < N; ++q) v[k][q] = ld_sys_f4(inbox + (long)q * a.slice4 + i + (long)k * stride);
+      }
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+      if (i + (long)k * stride < a.slice4) {
+        float4 s = v[k][0];
+#pragma unroll
+        for (int q = 1; q < N; ++q) { s.x += v[k][q].x; s.y += v[k][q].y; s.z += v[k][q].z; s.w += v[k][q].w; }
+#pragma unroll
+        for (int q = 0; q < N; ++q) result_of(a.peer[q], a.result4)[base + i + (long)k * stride] = s;
+      }
+  }
 }
 
 __global__ void __launch_bounds__(PR_THREADS, 1) peer_allreduce_kernel(const PeerArgs a) {
@@ -198,10 +208,13 @@ __global__ void __launch_bounds__(PR_THREADS, 1) peer_allreduce_kernel(const Pee
   __syncthreads();
   const unsigned int e = s_epoch;
   const int i0 = blockIdx.x * PR_THREADS + threadIdx.x, stride = gridDim.x * PR_THREADS;
-  float4* stage = data_of(local);
+#define PEER_STAMP(k) do { if (a.prof && threadIdx.x == 0) a.prof[blockIdx.x * 8 + (k)] = globaltimer_ns(); } while (0)
 
-  move_units<true>(a, i0, stride, stage);
+  PEER_STAMP(0);
+  move_units<true>(a, i0, stride);
+  PEER_STAMP(1);
   peer_barrier(a, 2u * e + 1u, 1);
+  PEER_STAMP(2);
   switch (a.world) {
     case 2: reduce_slice<2>(a, i0, stride); break;
     case 3: reduce_slice<3>(a, i0, stride); break;
@@ -212,8 +225,12 @@ __global__ void __launch_bounds__(PR_THREADS, 1) peer_allreduce_kernel(const Pee
     case 8: reduce_slice<8>(a, i0, stride); break;
     default: break;
   }
+  PEER_STAMP(3);
   peer_barrier(a, 2u * e + 2u, 2);
-  move_units<false>(a, i0, stride, stage);
+  PEER_STAMP(4);
+  move_units<false>(a, i0, stride);
+  __syncthreads();
+  PEER_STAMP(5);
   if (threadIdx.x == 0) *epoch_of(local, blockIdx.x) = e + 1u;
 }
 
@@ -226,7 +243,7 @@ int peer_create(int rank, int world, size_t max_floats, void** out_ctx, void* ha
   c->rank = rank; c->world = world;
   // every segment is padded to a multiple of 4 floats (<= 3 per segment) and the total to a multiple of 4 * world
   c->cap_floats = align_up(max_floats + 4 * PR_MAX_SEG, (size_t)4 * world);
-  const size_t bytes = PR_HEADER + c->cap_floats * 4;
+  const size_t bytes = PR_HEADER + 2 * c->cap_floats * 4;      // inbox + result area
   if (cudaGetDevice(&c->device) != cudaSuccess || cudaMalloc(reinterpret_cast<void**>(&c->local), bytes) != cudaSuccess ||
       cudaMemset(c->local, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
     set_error("peer_create: cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
@@ -315,15 +332,19 @@ int peer_allreduce(void* ctx, void* const* seg_ptrs, const long* seg_floats, int
   CTCVR_REQUIRE((size_t)total <= c->cap_floats, "peer_allreduce: payload of %ld floats exceeds the %zu the exchange was created for", total, c->cap_floats);
   a.nseg = nseg; a.rank = c->rank; a.world = c->world;
   a.slice4 = total / 4 / c->world;
+  a.result4 = (long)(c->cap_floats / 4);
   for (int q = 0; q < c->world; ++q) a.peer[q] = c->peer[q];
   a.err = c->err_d;
   a.timeout_ns = c->timeout_ns;
-  if (ctas <= 0) ctas = 64;
+  a.prof = static_cast<long long*>(g_peer_prof);
+  if (ctas <= 0) ctas = 128;
   ctas = std::min(ctas, PR_MAX_CTAS);
   peer_allreduce_kernel<<<ctas, PR_THREADS, 0, st>>>(a);
   CTCVR_LAUNCH_CHECK();
   return 0;
 }
+
+void peer_set_prof(void* buf) { g_peer_prof = buf; }
 
 int peer_destroy(void* ctx) {
   PeerCtx* c = static_cast<PeerCtx*>(ctx);

@@ -78,7 +78,7 @@ class PeerGradExchange:
 
     MAX_TENSORS = 24
 
-    def __init__(self, max_floats: int, group=None, ctas: int = 64, _ctx=None, _rank=0, _world=1):
+    def __init__(self, max_floats: int, group=None, ctas: int = 128, _ctx=None, _rank=0, _world=1):
         from . import _lib
         self._L = _lib
         self.ctas = int(ctas)
@@ -112,7 +112,7 @@ class PeerGradExchange:
             raise RuntimeError("PeerGradExchange: " + "; ".join(bad))
 
     @classmethod
-    def local_group(cls, world: int, max_floats: int, ctas: int = 64) -> List["PeerGradExchange"]:
+    def local_group(cls, world: int, max_floats: int, ctas: int = 128) -> List["PeerGradExchange"]:
         """`world` ranks inside this process, all on the current device (buffers addressed directly, no IPC): the
         single-GPU test of the kernel - the ranks' kernels must then be launched on DIFFERENT streams."""
         from . import _lib

@@ -123,13 +123,14 @@ int ctcvr_cer_batch(const int32_t* hyp, const int32_t* hyp_len, int Lh, const in
 
 /* ---- section 8(e): data-parallel gradient exchange over NVLink peer memory (replaces the all-reduce the reference
  * gets from torch DistributedDataParallel around the train step, rnnt_train.py:60-75).  One rank = one process = one
- * GPU of a node.  ctcvr_peer_create allocates the rank's staging buffer (room for max_floats payload floats) and
+ * GPU of a node.  ctcvr_peer_create allocates the rank's staging buffer (room for max_floats payload floats, the
+ * same value on every rank) and
  * returns its 64-byte CUDA IPC handle; the host exchanges the handles (any transport), ctcvr_peer_connect maps the
  * peers' buffers (handles: world x 64 bytes; or local_ptrs[world] = buffers of ranks living in THIS process, then
  * handles may be NULL).  ctcvr_peer_allreduce launches ONE kernel on `stream` that sums nseg fp32 tensors
  * (seg_ptrs[i], seg_floats[i] floats, <= 24 per call) over all ranks in place, in rank order 0..world-1, so every rank
  * ends with bit-identical sums; it can be captured in a CUDA graph.  Every rank must pass the same segment sizes and
- * the same `ctas` (<= 128, 0 = 64).  A rank that waits longer than the timeout (default 10 s) for a peer gives up and the
+ * the same `ctas` (<= 128, 0 = 128).  A rank that waits longer than the timeout (default 10 s) for a peer gives up and the
  * NEXT call returns an error.  world == 1: no launch. */
 int ctcvr_peer_create(int rank, int world, size_t max_floats, void** out_ctx, void* out_handle64);
 int ctcvr_peer_connect(void* ctx, const void* handles, void* const* local_ptrs);

@@ -30,5 +30,21 @@ for ctas in (16, 32, 64, 128):
         for _ in range(10): ex.reduce(xs)
     res[f"peer_{ctas}ctas_graph_us"] = timeit(g.replay, 20) / 10
     dist.barrier(); ex.close()
+# phase stamps of one call (globaltimer ns, thread 0 of every CTA): scatter | barrier A | reduce | barrier B | unpack
+from ctcvr_b200._lib import lib
+import ctypes
+ex = PeerGradExchange(sum(sizes), ctas=64)
+prof = torch.zeros(128 * 8, dtype=torch.int64, device=dev)
+for _ in range(5): ex.reduce(xs)
+dist.barrier(); torch.cuda.synchronize()
+lib().ctcvr_debug_set_prof(ctypes.c_void_p(prof.data_ptr()))
+ex.reduce(xs); ex.reduce(xs); torch.cuda.synchronize()
+lib().ctcvr_debug_set_prof(None)
+p_ = prof.view(128, 8)[:64, :6].cpu().double()
+t0 = p_[:, 0].min()
+if rank == 0:
+    print("phase end (us after first CTA start), mean / max over CTAs:",
+          [(round(float((p_[:, k] - t0).mean()) / 1e3, 1), round(float((p_[:, k] - t0).max()) / 1e3, 1)) for k in range(6)])
+dist.barrier(); ex.close()
 if rank == 0: print({k: round(v, 1) for k, v in res.items()}, "world", dist.get_world_size(), "MB", sum(sizes) * 4 / 1e6)
 dist.barrier(); dist.destroy_process_group()
