@@ -21,3 +21,25 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+def cfg_decoder_weights(fx):
+    """Predictor / joint / CTC-head weights and encoder frames of decode_cfg.npz: exact integer-hash tensors rebuilt by
+    tests/golden/synth.py (the fixture stores only what the reference decoded from them)."""
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    import synth
+    H, V, blank = int(fx["H"]), int(fx["V"]), int(fx["blank"])
+    shapes = {
+        "predictor": {"embed.weight": (V, H), "rnn.weight_ih_l0": (4 * H, H), "rnn.weight_hh_l0": (4 * H, H),
+                      "rnn.bias_ih_l0": (4 * H,), "rnn.bias_hh_l0": (4 * H,), "projection.weight": (H, H),
+                      "projection.bias": (H,)},
+        "joint": {"enc_ffn.weight": (H, H), "enc_ffn.bias": (H,), "pred_ffn.weight": (H, H), "pred_ffn.bias": (H,),
+                  "ffn_out.weight": (V, H), "ffn_out.bias": (V,)},
+        "ctc": {"ctc_lo.weight": (V, H), "ctc_lo.bias": (V,)},
+    }
+    out = {k: synth.decoder_state(v, f"cfg/{k}", blank, scales={"ffn_out.weight": float(fx["ffn_out_scale"])},
+                                  blank_bias=float(fx["blank_bias"])) for k, v in shapes.items()}
+    out["enc"] = synth.synth((2, 500, H), "cfg/enc", 2.0)
+    out["synth"] = synth
+    return out

@@ -242,6 +242,86 @@ def main():
     print("ctc", fx["off_loss"], fx["on_loss"])
 
 
+CFG_BLANK_BIAS, CFG_SCALES = 4.0, {"ffn_out.weight": 0.25}
+
+
+def decode_cfg_golden():
+    """decode_cfg.npz: the reference decoders at BASELINE.json's config sizes - cfg3 (H=256, V=412, T'=249, chunk 16:
+    A5 offline greedy, A6 streaming greedy) and cfg5 (beam 10, T'=500: A7 online beam, A8 wenet prefix beam with CTC
+    fusion; A9 ctc_prefix_beam_search on 32 x 500 x 412).  Weights and inputs are the exact integer-hash tensors of
+    synth.py (loaded into the unmodified reference modules here, rebuilt in the GPU tests), so the fixture holds only the
+    expected hypotheses."""
+    _shims()
+    sys.path.insert(0, OUT)
+    import synth
+    from model.component.predictor import RNNPredictor
+    from model.component.transducer import basic_greedy_search
+    from model.online_rnnt_model import OnlineRNNTModel
+    from wenet.transformer.search import ctc_prefix_beam_search
+    from wenet.transducer.search import prefix_beam_search as pbs_mod
+    H, V, blank = 256, 412, 5
+    om = OnlineRNNTModel(input_dim=H, hidden_dim=H, vocab_size=V, blank_id=blank, predictor_dropout=0.0,
+                         ctc_dropout_rate=0.0).eval()
+    om.encoder = StubEncoder()
+    for mod, tag in ((om.predictor, "cfg/predictor"), (om.joint, "cfg/joint"), (om.ctc_head, "cfg/ctc")):
+        st = synth.decoder_state({k: tuple(v.shape) for k, v in mod.state_dict().items()}, tag, blank,
+                                 scales=CFG_SCALES, blank_bias=CFG_BLANK_BIAS)
+        mod.load_state_dict({k: torch.from_numpy(v) for k, v in st.items()})
+    enc = torch.from_numpy(synth.synth((2, 500, H), "cfg/enc", 2.0))
+    fx = dict(H=H, V=V, blank=blank, blank_bias=CFG_BLANK_BIAS, ffn_out_scale=CFG_SCALES["ffn_out.weight"])
+    lp = RNNPredictor(V, H, H, 0.0, H, 1, dropout=0.0).eval()
+    lp.load_state_dict(om.predictor.state_dict())
+    holder = types.SimpleNamespace(predictor=lp, joint=om.joint, blank=blank)
+    with torch.no_grad():
+        # cfg3 / A5: offline greedy, two utterances of T' = 249 and 180
+        hyps = basic_greedy_search(holder, enc[:, :249], torch.tensor([249, 180]), n_steps=64)
+        for b, h in enumerate(hyps):
+            fx[f"a5_hyp_{b}"] = np.array(h, dtype=np.int64)
+        # cfg3 / A6: streaming greedy over T' = 249 in chunks of 16 encoder frames, predictor state carried
+        om.reset_streaming_cache(torch.device("cpu"))
+        toks, st, last = [], None, blank
+        for s in range(0, 249, 16):
+            c, _, _, st, last = om._decode_chunk_streaming_logic(enc[1:2, s:min(s + 16, 249)], 0, 0, om.streaming_att_cache,
+                                                                  om.streaming_cnn_cache, st, last)
+            toks += c
+        fx["a6_hyp"], fx["a6_last"] = np.array(toks, dtype=np.int64), last
+        # cfg5 / A7: online beam search, beam 10, T' = 500 in chunks of 16
+        hy = None
+        for s in range(0, 500, 16):
+            hy, _, _ = om._decode_chunk_beam_search(enc[:1, s:s + 16], 0, 0, om.streaming_att_cache, om.streaming_cnn_cache,
+                                                    hy, beam_size=10)
+        fx["a7_n"] = len(hy)
+        for i, h in enumerate(hy):
+            fx[f"a7_tok_{i}"] = np.array(h.tokens, dtype=np.int64)
+            fx[f"a7_lp_{i}"] = h.log_prob
+        # cfg5 / A8: wenet prefix beam with CTC fusion, beam 10, T' = 500 (list-form log_add patched in, module docstring)
+        def log_add_list(xs):
+            if all(a == -float("inf") for a in xs):
+                return -float("inf")
+            m = max(xs)
+            return m + math.log(sum(math.exp(a - m) for a in xs))
+        pbs_mod.log_add = log_add_list
+        searcher = pbs_mod.PrefixBeamSearch(om.encoder, om.predictor, om.joint, om.ctc_head, blank)
+        seqs, _ = searcher.prefix_beam_search(enc[1:2], torch.tensor([500]), beam_size=10)
+        fx["a8_n"] = len(seqs)
+        for i, s in enumerate(seqs):
+            fx[f"a8_tok_{i}"] = np.array(s.hyp, dtype=np.int64)
+            fx[f"a8_sc_{i}"] = s.score
+    # cfg5 / A9: CTC prefix beam search on 32 x 500 x 412 scores, ragged lengths
+    B, T = 32, 500
+    lens = np.array([T - 13 * (b % 7) if b % 5 else T for b in range(B)], dtype=np.int64)
+    res = ctc_prefix_beam_search(torch.from_numpy(synth.ctc_logp(B, T, V, blank)), torch.from_numpy(lens), 10, blank_id=blank)
+    fx["a9_lens"] = lens
+    for i, r in enumerate(res):
+        fx[f"a9_nbest_len_{i}"] = np.array([len(x) for x in r.nbest], dtype=np.int64)
+        fx[f"a9_nbest_flat_{i}"] = np.array([t for x in r.nbest for t in x], dtype=np.int64)
+        fx[f"a9_nbest_scores_{i}"] = np.array(r.nbest_scores)
+        fx[f"a9_times_{i}"] = np.array(r.times, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "decode_cfg.npz"), **fx)
+    print("cfg A5", [len(h) for h in hyps], "A6", len(toks), "A7", len(hy), len(hy[0].tokens), "A8", len(seqs), len(seqs[0].hyp),
+          "A9 best lens", [int(fx[f"a9_nbest_len_{i}"][0]) for i in range(4)])
+
+
 def cer_golden():
     """Section 8f row 4: calculate_cer of the reference (rnnt_eval.py:11-56).  rnnt_eval.py cannot be imported here (it
     pulls data.dataloader -> librosa), so the function is taken out of the file by its AST node and executed as is."""
@@ -284,6 +364,9 @@ def cer_golden():
 if __name__ == "__main__":
     if "--cer-only" in sys.argv:
         cer_golden()
+    elif "--decode-cfg-only" in sys.argv:
+        decode_cfg_golden()
     else:
         main()
         cer_golden()
+        decode_cfg_golden()

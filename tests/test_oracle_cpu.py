@@ -144,6 +144,34 @@ def test_decoders_match_reference():
             np.testing.assert_allclose(sc, fx[f"a8_b{beam}_sc_{i}"], atol=1e-4)
 
 
+def test_decoders_match_reference_at_config_sizes():
+    """The oracle against the reference's hypotheses at BASELINE.json cfg3 / cfg5 sizes (decode_cfg.npz; H=256, V=412).
+    Bounded to keep the CPU suite short: A5 on the 180-frame utterance, A6 over all 249 frames, A9 on four of the 32
+    utterances of 500 frames.  A7 / A8 need minutes per 500-frame utterance in the Python oracle: the oracle's beam
+    decoders are pinned on the small fixture above, the CUDA ones against this fixture at full length (-m gpu)."""
+    from conftest import cfg_decoder_weights
+    fx = load_golden("decode_cfg.npz")
+    w = cfg_decoder_weights(fx)
+    blank, V = int(fx["blank"]), int(fx["V"])
+    pw = {k: T(v) for k, v in w["predictor"].items()}
+    jw = {k: T(v) for k, v in w["joint"].items()}
+    enc = T(w["enc"])
+    hy = TO.greedy_search_offline(pw, jw, blank, enc[1:2, :180], torch.tensor([180]), 64)
+    assert hy[0] == fx["a5_hyp_1"].tolist()
+    toks, st, last = [], None, blank
+    for s in range(0, 249, 16):
+        c, st, last = TO.greedy_chunk_streaming(pw, jw, blank, enc[1, s:min(s + 16, 249)], st, last, 10)
+        toks += c
+    assert toks == fx["a6_hyp"].tolist() and last == int(fx["a6_last"])
+    pick = [0, 1, 7, 31]
+    lp = T(w["synth"].ctc_logp(32, 500, V, blank))[pick]
+    res = CO.ctc_prefix_beam_search(lp, fx["a9_lens"][pick], 10, blank)
+    for r, i in zip(res, pick):
+        assert [t for x in r["nbest"] for t in x] == fx[f"a9_nbest_flat_{i}"].tolist()
+        np.testing.assert_allclose(r["nbest_scores"], fx[f"a9_nbest_scores_{i}"], rtol=1e-9, atol=1e-9)
+        assert r["times"] == fx[f"a9_times_{i}"].tolist()
+
+
 def test_cer_restated_matches_reference_golden():
     """oracle calculate_cer vs the outputs of the reference's rnnt_eval.calculate_cer (tests/golden/cer_small.npz)."""
     fx = load_golden("cer_small.npz")
