@@ -206,6 +206,10 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.global_batch:
+        # BASELINE.json configs[3] read as a strong split: a fixed global batch sharded over the ranks
+        assert args.global_batch % world == 0, "--global-batch must be divisible by the number of ranks"
+        CFG["B"] = args.global_batch // world
     B, T, U, D, V, blank = (CFG[k] for k in ("B", "T", "U", "D", "V", "blank"))
     joint = C.TransducerJoint(V, D, D, D)
     joint.load_state_dict(bench_weights())
@@ -420,9 +424,11 @@ def run_ours(args):
                             "frac_hbm": 24.0 * M / (kern["lat_ms"] * 1e-3) / 1e9 / pk["hbm"]}}
         roof.update(_ncu_traffic())
         line = {"metric": METRIC, "value": gB / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-                "config": {"workload": "configs[1]: B=32/GPU,T=250,U=40,H=D=512,V=412 fused joint+rnnt_loss fwd/bwd",
+                "config": {"workload": (f"configs[3] strong split: global B={gB} ({B}/GPU),T=250,U=40,H=D=512,V=412 fused joint+rnnt_loss fwd/bwd"
+                                        if args.global_batch else
+                                        "configs[1]: B=32/GPU,T=250,U=40,H=D=512,V=412 fused joint+rnnt_loss fwd/bwd"),
                            "global_batch": gB, "parallelism": f"dp{world}", "l2": "flushed (256 MiB write) before each step",
                            "precision": args.precision, "cuda_graph": bool(graphed is not None),
                            "allreduce": allreduce_note},
@@ -431,7 +437,7 @@ def run_ours(args):
                         "h2d_GBps_measured": h2d_gbps, "h2d_ms_per_step": h2d / (h2d_gbps * 1e9) * 1e3},
                 "gpu_launches": int(launches), "gpu_launches_per_step": launches_per_step, "roofline": roof,
                 "clocks": clk.summary(), "loss": float(loss.item()) * (1 if exchange is not None else world)}
-        if world == 1:
+        if world == 1 and not args.global_batch:
             # ---- the CPU reference on the SAME batch and weights: baseline timing (full batch, median of 3 after one
             # warm-up) and the parity check that rides in every record
             threads = os.cpu_count() or 1
@@ -456,7 +462,7 @@ def run_ours(args):
             # ---- the reference-precision path (fp32 SIMT kernels, 1e-4): its own step time and denominator
             line["fp32"] = time_fp32_step(C, joint, B, T, U, blank, enc, pred, tgt, tl, ul, flush)
             # ---- the ungraphed public API on a ragged batch (what a train loop with varying shapes hits)
-            line["eager"] = time_eager_ragged(joint, enc, pred, tgt, blank, args.precision, flush)
+            line["eager"], line["bucketed"] = time_ragged(C, joint, enc, pred, tgt, blank, args.precision, flush, in_dtype)
             line["gpu_reference"] = gpu_reference(dev)
             line["gpu_reference"]["speedup_vs_fp32"] = line["value"] / line["gpu_reference"]["fp32"]["value"]
             line["gpu_reference"]["speedup_vs_autocast_bf16"] = line["value"] / line["gpu_reference"]["autocast_bf16"]["value"]
@@ -501,40 +507,61 @@ def time_fp32_step(C, joint, B, T, U, blank, enc, pred, tgt, tl, ul, flush, reps
                          "flops": "executed (incl. the logits recompute)"}}
 
 
-def time_eager_ragged(joint, enc, pred, tgt, blank, precision, flush, reps=5):
-    """The ungraphed op on a ragged batch (T_b ~ U[125,250], U_b ~ U[20,40], element 0 at the maximum): new workspaces
-    and ~40 launches per call, no CUDA graph."""
+def time_ragged(C, joint, enc, pred, tgt, blank, precision, flush, in_dtype, reps=3):
+    """A train loop whose batches change shape: six ragged batches (T_b ~ U[Tmax/2, Tmax], U_b ~ U[Umax/2, Umax], the
+    batch maxima Tmax in 229..250 and Umax in 36..40, element 0 at the maximum), stepped (a) through the ungraphed public
+    op - new workspaces and ~40 launches per call - and (b) through BucketedJointRnntStep (T rounded up to 16 frames, U to
+    8 labels: two captured graphs serve the six shapes).  Median step time over `reps` passes after one warm-up pass."""
     B, T = enc.shape[0], enc.shape[1]
     U = tgt.shape[1]
     g = torch.Generator().manual_seed(99)
-    tl = torch.randint(T // 2, T + 1, (B,), generator=g, dtype=torch.int32)
-    ul = torch.randint(U // 2, U + 1, (B,), generator=g, dtype=torch.int32)
-    tl[0], ul[0] = T, U
-    cells = int(((tl.long()) * (ul.long() + 1)).sum())
-    tl, ul = tl.to(enc.device), ul.to(enc.device)
-    e, p = enc.detach().clone().requires_grad_(True), pred.detach().clone().requires_grad_(True)
+    batches, cells = [], 0
+    for Tm, Um in ((250, 40), (238, 37), (245, 39), (250, 40), (229, 36), (241, 38)):
+        Tm, Um = min(Tm, T), min(Um, U)
+        tl = torch.randint(Tm // 2, Tm + 1, (B,), generator=g, dtype=torch.int32)
+        ul = torch.randint(Um // 2, Um + 1, (B,), generator=g, dtype=torch.int32)
+        tl[0], ul[0] = Tm, Um
+        cells += int(((tl.long()) * (ul.long() + 1)).sum())
+        batches.append((enc.detach()[:, :Tm].contiguous(), pred.detach()[:, :Um + 1].contiguous(), tgt[:, :Um].contiguous(),
+                        tl.to(enc.device), ul.to(enc.device)))
 
-    def step():
+    def timed(step_fn):
+        for b_ in batches:
+            step_fn(*b_)
+        ms = []
+        for _ in range(reps):
+            for b_ in batches:
+                flush.zero_()
+                torch.cuda.synchronize()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                step_fn(*b_)
+                s1.record()
+                torch.cuda.synchronize()
+                ms.append(s0.elapsed_time(s1))
+        ms.sort()
+        return ms[len(ms) // 2]
+
+    def eager_step(e, p, tg, tl, ul):
         joint.zero_grad(set_to_none=True)
+        e, p = e.requires_grad_(True), p.requires_grad_(True)
         e.grad = p.grad = None
-        joint.rnnt_loss_fused(e, p, tgt, tl, ul, blank, reduction="mean", precision=precision).backward()
-    for _ in range(2):
-        step()
-    ms = []
-    for _ in range(reps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        step()
-        s1.record()
-        torch.cuda.synchronize()
-        ms.append(s0.elapsed_time(s1))
-    ms.sort()
-    med = ms[len(ms) // 2]
+        joint.rnnt_loss_fused(e, p, tg, tl, ul, blank, reduction="mean", precision=precision).backward()
+
+    med_e = timed(eager_step)
+    for e, p, *_ in batches:
+        e.requires_grad_(False)
+        p.requires_grad_(False)
+        e.grad = p.grad = None
     joint.zero_grad(set_to_none=True)
-    return {"value": B / (med * 1e-3), "unit": UNIT, "ms_per_step": med, "lattice_cells": cells,
-            "cells_vs_full_batch": cells / float(B * T * (U + 1)), "what": "ungraphed rnnt_loss_fused + backward, ragged lengths"}
+    stepper = C.BucketedJointRnntStep(joint, blank, t_bucket=16, u_bucket=8, precision=precision, input_dtype=in_dtype)
+    med_b = timed(stepper.step)
+    joint.zero_grad(set_to_none=True)
+    frac = cells / float(len(batches) * B * T * (U + 1))
+    common = {"unit": UNIT, "lattice_cells_per_step": cells // len(batches), "cells_vs_full_batch": frac}
+    return ({"value": B / (med_e * 1e-3), "ms_per_step": med_e, "what": "ungraphed rnnt_loss_fused + backward, six ragged batch shapes", **common},
+            {"value": B / (med_b * 1e-3), "ms_per_step": med_b, "graphs_captured": stepper.captures,
+             "what": "BucketedJointRnntStep (shape-bucketed CUDA graph cache, input copy included), same six ragged batch shapes", **common})
 
 
 def _ncu_traffic():
@@ -609,6 +636,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager step instead of the captured CUDA graph")
     ap.add_argument("--precision", default=os.environ.get("CTCVR_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling (configs[3]): fixed global batch split over the ranks; the headline extras are skipped")
     ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
                     help="N>1: gradient sum by the in-graph NVLink peer kernel (default) or by NCCL behind the graph")
     ap.add_argument("--no-decode", action="store_true", help="skip the A4-A10 rows (bench_decode.py) in the JSON line")

@@ -13,7 +13,7 @@ from .decode import (BeamHypothesis, OnlineBeamState, basic_greedy_search, beam_
                      greedy_chunk, prefix_beam_search)
 from .functional import (ctc_greedy_search as ctc_greedy_hyps, ctc_loss_from_logits, fused_joint_rnnt_loss,  # noqa: F401
                          joint_logits, rnnt_loss)
-from .graph import GraphedJointRnntStep  # noqa: F401
+from .graph import BucketedJointRnntStep, GraphedJointRnntStep  # noqa: F401
 from .joint import TransducerJoint  # noqa: F401
 from .predictor import RNNPredictor  # noqa: F401
 from .search import DecodeResult, ctc_greedy_search, ctc_prefix_beam_search  # noqa: F401

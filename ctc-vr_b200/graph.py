@@ -83,6 +83,22 @@ class GraphedJointRnntStep:
         self.logit_lengths.copy_(logit_lengths, non_blocking=True)
         self.target_lengths.copy_(target_lengths, non_blocking=True)
 
+    @torch.no_grad()
+    def load_padded(self, enc_out, pred_out, targets, logit_lengths, target_lengths):
+        """Copy a batch whose T / U are SMALLER than the captured ones into the leading corner of the input buffers.
+        The kernels only visit cells below the per-utterance lengths, so whatever an earlier batch left beyond them is
+        never read (the buffers start as zeros and only ever hold finite values)."""
+        T, U1, U = enc_out.shape[1], pred_out.shape[1], targets.shape[1]
+        if enc_out.shape[0] != self.enc.shape[0] or T > self.enc.shape[1] or U1 > self.pred.shape[1] or U1 != U + 1:
+            raise RuntimeError(f"load_padded: batch {tuple(enc_out.shape)} / {tuple(pred_out.shape)} does not fit the captured "
+                               f"{tuple(self.enc.shape)} / {tuple(self.pred.shape)}")
+        self.enc[:, :T].copy_(enc_out, non_blocking=True)
+        self.pred[:, :U1].copy_(pred_out, non_blocking=True)
+        if U:
+            self.targets[:, :U].copy_(targets, non_blocking=True)
+        self.logit_lengths.copy_(logit_lengths, non_blocking=True)
+        self.target_lengths.copy_(target_lengths, non_blocking=True)
+
     def step(self, enc_out=None, pred_out=None, targets=None, logit_lengths=None, target_lengths=None):
         if enc_out is not None:
             self.load(enc_out, pred_out, targets, logit_lengths, target_lengths)
@@ -96,5 +112,50 @@ class GraphedJointRnntStep:
         """The captured input tensors [enc, pred, targets, logit_lengths, target_lengths]: a loader may copy the next
         batch straight into them (e.g. H2D on a copy stream) once the previous replay of THIS graph has finished."""
         return [self.enc, self.pred, self.targets, self.logit_lengths, self.target_lengths]
+
+    __call__ = step
+
+
+
+class BucketedJointRnntStep:
+    """Graph replay for a train loop whose batches change shape: (B, T, U) is rounded up to a bucket (T to a multiple of
+    `t_bucket` frames, U to a multiple of `u_bucket` labels), one `GraphedJointRnntStep` is captured per bucket on first
+    use and kept (least recently used evicted beyond `max_graphs`), and a batch is copied into the leading corner of its
+    bucket's buffers.  The per-utterance lengths are device tensors read by the kernels, so the padding costs no tiles:
+    a ragged batch runs in the time of its real cells, without the ~40 launches and workspace allocations of the eager
+    path (`bench.py` prints both).
+
+    `step()` returns the device loss scalar; parameter gradients land in `joint.<param>.grad`; the gradients of the inputs
+    are `enc_grad` [B,T,E] / `pred_grad` [B,U+1,P] (views into the bucket's buffers, valid until its next replay)."""
+
+    def __init__(self, joint, blank: int, t_bucket: int = 16, u_bucket: int = 8, max_graphs: int = 16, **graph_kwargs):
+        if t_bucket < 1 or u_bucket < 1 or max_graphs < 1:
+            raise ValueError("t_bucket, u_bucket and max_graphs must be positive")
+        self.joint, self.blank = joint, int(blank)
+        self.t_bucket, self.u_bucket, self.max_graphs = int(t_bucket), int(u_bucket), int(max_graphs)
+        self.graph_kwargs = graph_kwargs
+        self._graphs = {}                       # (B, Tb, Ub) -> GraphedJointRnntStep, in LRU order
+        self.captures = 0
+        self.enc_grad = self.pred_grad = None
+
+    def bucket_of(self, B: int, T: int, U: int):
+        up = lambda x, m: max(m, (x + m - 1) // m * m)
+        return (int(B), up(T, self.t_bucket), up(U, self.u_bucket))
+
+    def step(self, enc_out, pred_out, targets, logit_lengths, target_lengths):
+        B, T = enc_out.shape[0], enc_out.shape[1]
+        U = targets.shape[1]
+        key = self.bucket_of(B, T, U)
+        g = self._graphs.pop(key, None)
+        if g is None:
+            if len(self._graphs) >= self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))          # least recently used
+            g = GraphedJointRnntStep(self.joint, key[0], key[1], key[2], self.blank, **self.graph_kwargs)
+            self.captures += 1
+        self._graphs[key] = g
+        g.load_padded(enc_out, pred_out, targets, logit_lengths, target_lengths)
+        loss = g.step()
+        self.enc_grad, self.pred_grad = g.enc.grad[:, :T], g.pred.grad[:, :U + 1]
+        return loss
 
     __call__ = step
