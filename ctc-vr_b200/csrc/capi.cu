@@ -293,7 +293,7 @@ int ctcvr_rnnt_beam_chunk(const ctcvr_decoder_weights* w, const float* enc_proj,
                           int n_steps, int max_out, int blank, int32_t* out_n, int32_t* out_tokens, int32_t* out_lens,
                           double* out_scores, float* out_h, float* out_c, void* stream) {
   if (int rc = check_weights("rnnt_beam_chunk", w)) return rc;
-  CTCVR_REQUIRE(enc_proj && beam_state && out_n && out_tokens && out_lens && out_scores, "rnnt_beam_chunk: NULL pointer");
+  CTCVR_REQUIRE((enc_proj || T == 0) && beam_state && out_n && out_tokens && out_lens && out_scores, "rnnt_beam_chunk: NULL pointer");
   CTCVR_REQUIRE(T >= 0 && beam > 0 && n_steps > 0 && max_out > 0, "rnnt_beam_chunk: bad dims");
   CTCVR_REQUIRE(blank >= 0 && blank < w->V, "rnnt_beam_chunk: blank out of range");
   return rnnt_beam_chunk(*w, enc_proj, T, beam_state, beam, n_steps, max_out, blank, out_n, out_tokens, out_lens,
