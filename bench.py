@@ -51,11 +51,49 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.source = "nvidia-smi"
         self._stop = threading.Event()
         self._th = threading.Thread(target=self._run, daemon=True)
 
+    def _nvml_handle(self):
+        """NVML handle of CUDA device `index` (by PCI bus id: CUDA_VISIBLE_DEVICES may renumber), or None."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(self.index)
+            try:
+                bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            return pynvml, h
+        except Exception:
+            return None, None
+
     def _run(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        nv, h = self._nvml_handle()
+        if nv is not None:
+            # NVML in-process: a query takes ~0.1 ms, so a timed region of a few ms still gets samples (nvidia-smi: ~100 ms)
+            self.source = "nvml"
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            try:
+                self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            except Exception:
+                pass
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                    mask = int(get(h))
+                    for n, b_ in bits.items():
+                        if mask & b_:
+                            self.reasons.add(n)
+                except Exception:
+                    pass
+                self._stop.wait(0.001)
+            return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
@@ -80,8 +118,8 @@ class ClockSampler:
 
     def summary(self):
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_min_mhz": s[0] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s), "source": self.source}
 
 
 def make_inputs(seed, device, pinned=False):
