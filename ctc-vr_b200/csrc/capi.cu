@@ -71,6 +71,7 @@ int peer_set_timeout_ms(void*, long);
 int peer_allreduce(void*, void* const*, const long*, int, int, cudaStream_t);
 int peer_destroy(void*);
 void peer_set_prof(void*);
+void peer_set_mode(int);
 
 unsigned int tc_error_flag();
 void tc_set_prof(void*);
@@ -101,7 +102,7 @@ const char* ctcvr_last_error(void) { return g_err; }
 int ctcvr_version(void) { return 100; }
 unsigned int ctcvr_debug_tc_error(void) { return tc_error_flag(); }
 void ctcvr_debug_set_prof(void* buf) { tc_set_prof(buf); peer_set_prof(buf); }
-void ctcvr_debug_set_mode(int single_cta) { tc_set_mode(single_cta); }
+void ctcvr_debug_set_mode(int mode) { tc_set_mode(mode & 3); peer_set_mode(mode >> 2); }
 unsigned long long ctcvr_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int ctcvr_joint_logits(const float* enc_proj, const float* pred_proj, const float* w_out, const float* b_out,

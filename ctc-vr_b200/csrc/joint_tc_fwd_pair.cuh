@@ -1,5 +1,7 @@
-// Forward kernel of the bf16 tcgen05 path on CTA PAIRS (included by joint_tc.cu) - the default whenever the CTA's half
-// of W_out fits in shared memory (V = 412, D = 512 does: 208 KB).
+// Forward kernel of the bf16 tcgen05 path on CTA PAIRS (included by joint_tc.cu).  PARKED: correct (tools/fwd_pair_check.py,
+// 1e-6 against the single-CTA kernel) but slower at cfg2 (199-232 us against 142 us), so joint_fwd_tc only takes it after
+// ctcvr_debug_set_mode(0); DESIGN.md section 5 has the measurements.  It needs the CTA's half of W_out resident in shared
+// memory (V = 412, D = 512: 208 KB).
 //
 //   z      = tanh(enc_proj[b,t,:] + pred_proj[b,u,:])        model/component/joint.py:57-67
 //   logits = z . W_out^T + b_out                             model/component/joint.py:68

@@ -56,9 +56,11 @@ struct PeerArgs {
   unsigned int* err;
   long long timeout_ns;
   long long* prof;                       // dev tool: 8 globaltimer stamps per CTA (ctcvr_debug_set_prof), else NULL
+  int mode;                              // dev tool: timing experiments (ctcvr_debug_set_mode bits 2..), 0 in production
 };
 
 static void* g_peer_prof = nullptr;
+static int g_peer_mode = 0;
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -96,7 +98,9 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs& a, unsigned int val
   __syncthreads();
   const int t = threadIdx.x;
   if (t < a.world) {
-    __threadfence_system();
+    // the release store orders the CTA's earlier writes (bar.sync above + cumulativity); an extra __threadfence_system()
+    // (fence.sc.sys) in front of it cost ~3 us per barrier (tools/peer_time.py, mode bit 0)
+    if (a.mode & 1) __threadfence_system();
     st_release_sys(flags_of(a.peer[t], blockIdx.x) + a.rank, value);
     const unsigned int* mine = flags_of(a.peer[a.rank], blockIdx.x) + t;
     const long long t0 = globaltimer_ns();
@@ -149,7 +153,10 @@ template <bool kScatter>
 __device__ __forceinline__ void move_units(const PeerArgs& a, int i0, int stride) {
   constexpr int R = 4;
   const float4* result = result_of(a.peer[a.rank], a.result4);
-  for (int r = 0; r < a.world; ++r) {
+  for (int k0 = 0; k0 < a.world; ++k0) {
+    // destinations in plain order; the rotated order (rank + 1, rank + 2, ..: every rank on a different peer at any
+    // moment) measured no better on NVSwitch (tools/peer_time.py, mode bit 1)
+    const int r = (a.mode & 2) ? (a.rank + 1 + k0) % a.world : k0;
     const long base = (long)r * a.slice4;
     float4* inbox = inbox_of(a.peer[r]) + (long)a.rank * a.slice4;
     for (long i = i0; i < a.slice4; i += (long)R * stride) {
@@ -196,7 +203,10 @@ __device__ __forceinline__ void reduce_slice(const PeerArgs& a, int i0, int stri
 #pragma unroll
         for (int q = 1; q < N; ++q) { s.x += v[k][q].x; s.y += v[k][q].y; s.z += v[k][q].z; s.w += v[k][q].w; }
 #pragma unroll
-        for (int q = 0; q < N; ++q) result_of(a.peer[q], a.result4)[base + i + (long)k * stride] = s;
+        for (int q0 = 0; q0 < N; ++q0) {
+          const int q = (a.mode & 2) ? (a.rank + 1 + q0) % N : q0;
+          result_of(a.peer[q], a.result4)[base + i + (long)k * stride] = s;
+        }
       }
   }
 }
@@ -337,6 +347,7 @@ int peer_allreduce(void* ctx, void* const* seg_ptrs, const long* seg_floats, int
   a.err = c->err_d;
   a.timeout_ns = c->timeout_ns;
   a.prof = static_cast<long long*>(g_peer_prof);
+  a.mode = g_peer_mode;
   if (ctas <= 0) ctas = 128;
   ctas = std::min(ctas, PR_MAX_CTAS);
   peer_allreduce_kernel<<<ctas, PR_THREADS, 0, st>>>(a);
@@ -345,6 +356,7 @@ int peer_allreduce(void* ctx, void* const* seg_ptrs, const long* seg_floats, int
 }
 
 void peer_set_prof(void* buf) { g_peer_prof = buf; }
+void peer_set_mode(int mode) { g_peer_mode = mode; }
 
 int peer_destroy(void* ctx) {
   PeerCtx* c = static_cast<PeerCtx*>(ctx);

@@ -41,8 +41,10 @@ unsigned long long ctcvr_launch_count(void);
 unsigned int ctcvr_debug_tc_error(void);
 /* debug: device buffer of 4*2048 int64 receiving a per-role timeline of CTA 0 of the next tcgen05 forward (NULL = off) */
 void ctcvr_debug_set_prof(void* device_buf);
-/* debug: non-zero = run the single-CTA tcgen05 kernels where a CTA-pair kernel is the default (A/B timing) */
-void ctcvr_debug_set_mode(int single_cta);
+/* debug (A/B timing): bit 0 = single-CTA forward kernel (default 1; 0 runs the parked CTA-pair forward), bit 1 =
+ * single-CTA backward kernel where the CTA-pair kernel is the default, bits 2.. = experiment switches of the peer
+ * exchange kernel (tools/peer_time.py).  Production value: 1. */
+void ctcvr_debug_set_mode(int mode);
 
 /* ---- A1: TransducerJoint.forward dense logits — model/component/joint.py:57-68
  * logits[b,t,u,:] = W_out · tanh(enc_proj[b,t,:] + pred_proj[b,u,:]) + b_out.

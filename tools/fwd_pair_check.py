@@ -36,7 +36,7 @@ def run(B, T, U1, D, V, ragged, seed=0, time_it=False):
                 a.record(); f(); c.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(c) * 1e3)
             ts.sort(); ms = ts[len(ts) // 2]
         outs.append((lse, lpb, lpl, err, ms))
-    lib().ctcvr_debug_set_mode(0)
+    lib().ctcvr_debug_set_mode(1)
     mask = (torch.arange(T, device=dev)[None, :, None] < tl[:, None, None]) & (torch.arange(U1, device=dev)[None, None, :] <= ul[:, None, None])
     d = []
     for i, n in enumerate(("lse", "lpb", "lpl")):

@@ -22,7 +22,16 @@ def nccl():
         for x in xs: dist.all_reduce(x)
 flat = torch.randn(sum(sizes), device=dev)
 res = {"nccl_grouped_us": timeit(nccl), "nccl_flat_us": timeit(lambda: dist.all_reduce(flat))}
-for ctas in (16, 32, 64, 128):
+from ctcvr_b200._lib import lib as _lib0
+# experiment bits of the exchange kernel (ctcvr_debug_set_mode bits 2..): 1 = extra __threadfence_system before the release
+# store, 2 = destinations in rotated order (every rank on a different peer at any moment) instead of 0..N-1
+for mode in (0, 1, 2, 3):
+    _lib0().ctcvr_debug_set_mode(1 | (mode << 2))
+    ex = PeerGradExchange(sum(sizes), ctas=128)
+    res[f"peer_mode{mode}_us"] = timeit(lambda: ex.reduce(xs))
+    dist.barrier(); ex.close()
+_lib0().ctcvr_debug_set_mode(1)
+for ctas in (64, 128):
     ex = PeerGradExchange(sum(sizes), ctas=ctas)
     res[f"peer_{ctas}ctas_us"] = timeit(lambda: ex.reduce(xs))
     g = torch.cuda.CUDAGraph()
