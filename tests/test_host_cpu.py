@@ -72,6 +72,35 @@ def test_module_surface_matches_reference_names():
     assert ys.tolist() == [[5, 7, 8, 0]]
 
 
+def test_bucketed_step_host_logic_and_peer_exchange_fail_loudly():
+    """Host logic that needs no GPU: the bucket rounding of BucketedJointRnntStep, its refusal to run on a CPU joint,
+    and PeerGradExchange / the peer entry points failing loudly (no fallback) without a process group or a device."""
+    import ctypes
+    import ctcvr_b200 as C
+    from ctcvr_b200 import _lib
+    from ctcvr_b200.dist import PeerGradExchange
+    joint = C.TransducerJoint(40, 128, 128, 128)
+    st = C.BucketedJointRnntStep(joint, 5, t_bucket=16, u_bucket=8)
+    assert st.bucket_of(4, 1, 1) == (4, 16, 8) and st.bucket_of(4, 16, 8) == (4, 16, 8) and st.bucket_of(4, 17, 9) == (4, 32, 16)
+    assert st.bucket_of(32, 250, 40) == (32, 256, 40)
+    with pytest.raises(ValueError):
+        C.BucketedJointRnntStep(joint, 5, t_bucket=0)
+    x = torch.zeros(4, 10, 128)
+    with pytest.raises(RuntimeError):                       # capture needs the joint on a CUDA device
+        st.step(x, torch.zeros(4, 4, 128), torch.zeros(4, 3, dtype=torch.int32), torch.full((4,), 10, dtype=torch.int32),
+                torch.full((4,), 3, dtype=torch.int32))
+    with pytest.raises(RuntimeError):                       # one process per GPU: needs an initialised process group
+        PeerGradExchange(1024)
+    ctx, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+    with pytest.raises(RuntimeError):                       # bad rank / world are rejected before any CUDA call
+        _lib.call("ctcvr_peer_create", 3, 2, 1024, ctypes.byref(ctx), handle)
+    with pytest.raises(RuntimeError):
+        _lib.call("ctcvr_peer_create", 0, 9, 1024, ctypes.byref(ctx), handle)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):                   # no device: cudaMalloc fails -> error, not a host buffer
+            _lib.call("ctcvr_peer_create", 0, 2, 1024, ctypes.byref(ctx), handle)
+
+
 def test_shard_bounds():
     from ctcvr_b200.dist import shard_bounds
     for n, w in ((256, 8), (10, 4), (3, 8)):
