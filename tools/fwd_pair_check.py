@@ -1,4 +1,5 @@
-"""Dev tool: CTA-pair forward kernel against the single-CTA kernel (same bf16 operands) - max differences and timing."""
+"""Dev tool: a forward-kernel variant against the single-CTA joint_fwd2_kernel (same bf16 operands) - max differences and
+timing.  FWD_MODE selects the variant by its ctcvr_debug_set_mode value (0 = the parked CTA-pair kernel, the default here)."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctcvr_b200 as C
@@ -19,7 +20,7 @@ def run(B, T, U1, D, V, ragged, seed=0, time_it=False):
         tl = torch.full((B,), T, dtype=torch.int32, device=dev); ul = torch.full((B,), U1 - 1, dtype=torch.int32, device=dev)
     ws = torch.empty(query("ctcvr_joint_rnnt_fwd_ws_bytes", B, T, U1, D, V, 1), dtype=torch.uint8, device=dev)
     outs = []
-    for mode in (1, 0):
+    for mode in (1, int(os.environ.get('FWD_MODE', '0'))):
         lib().ctcvr_debug_set_mode(mode)
         lse = torch.full((B, T, U1), float('nan'), device=dev); lpb = lse.clone(); lpl = lse.clone()
         def f():
@@ -50,4 +51,4 @@ def run(B, T, U1, D, V, ragged, seed=0, time_it=False):
 import sys
 for a in sys.argv[1:]:
     B,T,U1,D,V,r = [int(x) for x in a.split(',')]
-    run(B,T,U1,D,V,bool(r), time_it=(r==0))
+    run(B,T,U1,D,V,bool(r & 1), time_it=bool(r & 2) or r == 0)

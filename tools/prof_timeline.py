@@ -5,6 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctcvr_b200 as C
 from ctcvr_b200._lib import call, ptr, query, stream, lib
 torch.manual_seed(0)
+lib().ctcvr_debug_set_mode(int(os.environ.get('FWD_MODE', '1')))
 B,T,U1,D,V,blank=32,250,41,512,412,5
 dev='cuda'
 e=torch.randn(B,T,D,device=dev); p=torch.randn(B,U1,D,device=dev)
@@ -29,7 +30,7 @@ for r in range(4):
     tags=(ev>>48); clk=(ev & 0xffffffffffff)-t0
     print(names[r], len(ev))
     # print first 3 tiles worth
-    lim={'TMA':48,'MMA':90,'EPI':8,'PROD':140}[names[r]]
+    lim={'TMA':48,'MMA':90,'EPI':int(os.environ.get('EPI_LIM', '8')),'PROD':140}[names[r]]
     print(' '.join(f"{int(a)}:{int(c)}" for a,c in zip(tags[:lim],clk[:lim])))
     print(' ... last:', ' '.join(f"{int(a)}:{int(c)}" for a,c in zip(tags[-6:],clk[-6:])))
 
