@@ -321,8 +321,9 @@ def run_ours(args):
             costs = joint.rnnt_loss_fused(e, p, tg, tl_, ul_, blank, reduction="none", precision=args.precision)
             loss = costs.sum() / gB
             loss.backward()
+            loss = loss.detach().clone()         # no live autograd graph over the parameters after the step (graph.py)
+            del costs
             if exchange is not None:
-                loss = loss.detach().clone()
                 exchange.reduce_grads(joint.parameters(), extra=[loss.view(1)])
         if reducer is not None:
             reducer.reduce()
@@ -365,6 +366,7 @@ def run_ours(args):
         h = [t.cpu().pin_memory() for t in h]
         h2d = sum(t.numel() * t.element_size() for t in h)
         copy_stream = torch.cuda.Stream(device=dev)
+        rb_stream = torch.cuda.Stream(device=dev)
         # graph mode: one captured step per staging slot, so the H2D copies land directly in the graph's own input
         # buffers (no device-to-device copy in front of the replay); eager mode: plain staging tensors
         graphs = None
@@ -406,8 +408,13 @@ def run_ours(args):
                     e_in, p_in = d[0].detach().requires_grad_(True), d[1].detach().requires_grad_(True)
                     lv = step(e_in, p_in, d[2], d[3], d[4])
                 consumed[i % 2].record(torch.cuda.current_stream())
-                host_loss[i:i + 1].copy_(lv.detach().reshape(1), non_blocking=True)      # D2H read of the step's loss
-                done[i].record(torch.cuda.current_stream())
+                # D2H read of the step's loss, on the read-back stream: the next step's graph does not queue behind the copy
+                # (each graph writes its own loss buffer, which is not rewritten before step i + 2)
+                rb_stream.wait_event(consumed[i % 2])
+                lv.record_stream(rb_stream)
+                with torch.cuda.stream(rb_stream):
+                    host_loss[i:i + 1].copy_(lv.detach().reshape(1), non_blocking=True)
+                    done[i].record(rb_stream)
                 if i >= 1:
                     done[i - 1].synchronize()
                     losses.append(float(host_loss[i - 1]))
@@ -429,8 +436,13 @@ def run_ours(args):
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
-        e2e_run(args.steps)
+        e2e_losses = e2e_run(args.steps)
         e2e_ms = (time.perf_counter() - t0) * 1e3
+        # every e2e step stages the same batch: each loss read back from the device must be the resident step's loss
+        # (the all-reduced one when the exchange sums it) - a stale or torn read-back would show here
+        want = float(loss.item())
+        if not all(abs(x - want) <= 1e-3 * abs(want) for x in e2e_losses):
+            raise RuntimeError(f"bench.py: e2e losses {e2e_losses[:4]}.. differ from the resident step's {want}")
     ms = torch.tensor([tot_ms / args.steps, e2e_ms / args.steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -471,6 +483,7 @@ def run_ours(args):
                            "precision": args.precision, "cuda_graph": bool(graphed is not None),
                            "allreduce": allreduce_note},
                 "e2e": {"value": gB / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "loss_checked_every_step": True,
                         "input_dtype": str(in_dtype).replace("torch.", "") if graphed is not None else "float32",
                         "h2d_GBps_measured": h2d_gbps, "h2d_ms_per_step": h2d / (h2d_gbps * 1e9) * 1e3},
                 "gpu_launches": int(launches), "gpu_launches_per_step": launches_per_step, "roofline": roof,
