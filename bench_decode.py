@@ -1,5 +1,5 @@
 """Secondary measurements for the hot-path rows outside the headline metric (A4 CTC loss, A5/A6 greedy,
-A7/A8 RNN-T beams, A9 CTC prefix beam, A10 CTC greedy) on ONE B200, each next to the reference's CPU arithmetic timed
+A7/A8 RNN-T beams (one stream, and A7b/A8b: 296 utterances per launch), A9 CTC prefix beam, A10 CTC greedy) on ONE B200, each next to the reference's CPU arithmetic timed
 on a bounded sample on the same box.  One JSON line per row:
 
     python bench_decode.py [--quick]
@@ -204,6 +204,17 @@ def main(args=None):
     t0 = time.perf_counter(); TO.beam_chunk_online(pw, jw, BLANK, e5[0, :tq].cpu(), None, 10, 10); c_s = time.perf_counter() - t0
     _line("A7", "online RNN-T beam search, beam 10, 500 frames in 16-frame chunks", 1 / g_s, "utt/s", g_s, (tq / Tb) / c_s,
           f"first {tq} of 500 frames, Python algorithm of the reference", {"rtf": g_s / (Tb * FRAME_S)})
+    a7_cpu = (tq / Tb) / c_s
+    # the same search for S utterances in one launch (one CTA per utterance; the reference API is batch 1): whole-job
+    # throughput of an offline decode, RTF = wall / total audio
+    S = 296                                                      # two waves of CTAs on 148 SMs
+    torch.manual_seed(8)
+    eS = torch.randn(S, Tb, H, device=dev)
+    lS = torch.full((S,), Tb, dtype=torch.int32, device=dev)
+    g_s, hyS = _sync_time(lambda: C.beam_search_batch(m, eS, lS, beam_size=10, n_steps=10), 2)
+    _line("A7b", f"online RNN-T beam search, beam 10, {S} utterances x 500 frames in ONE launch", S / g_s, "utt/s", g_s, a7_cpu,
+          f"first {tq} of 500 frames of one utterance, Python algorithm of the reference",
+          {"rtf": g_s / (S * Tb * FRAME_S), "mean_tokens_best": sum(len(h[0].tokens) for h in hyS) / S})
     ctc_w = torch.randn(V, H, device=dev) / H ** 0.5
     ctc_logp = torch.log_softmax(e5[0] @ ctc_w.T, dim=-1)
     g_s, _ = _sync_time(lambda: C.prefix_beam_search(m, e5[0], ctc_logp, beam_size=10), 2)
@@ -212,6 +223,11 @@ def main(args=None):
     c_s = time.perf_counter() - t0
     _line("A8", "wenet prefix beam search with CTC fusion, beam 10, 500 frames", 1 / g_s, "utt/s", g_s, (tq / Tb) / c_s,
           f"first {tq} of 500 frames, Python algorithm of the reference", {"rtf": g_s / (Tb * FRAME_S)})
+    ctcS = torch.log_softmax(eS @ ctc_w.T, dim=-1)
+    g_s, _ = _sync_time(lambda: C.prefix_beam_search_batch(m, eS, lS, ctcS, beam_size=10), 2)
+    _line("A8b", f"wenet prefix beam search with CTC fusion, beam 10, {S} utterances x 500 frames in ONE launch", S / g_s, "utt/s",
+          g_s, (tq / Tb) / c_s, f"first {tq} of 500 frames of one utterance, Python algorithm of the reference",
+          {"rtf": g_s / (S * Tb * FRAME_S)})
 
 
 if __name__ == "__main__":

@@ -9,8 +9,8 @@ from . import functional  # noqa: F401
 from . import patch  # noqa: F401
 from .ctc import CTC, OnlineCTC  # noqa: F401
 from .evaluate import calculate_cer, calculate_cer_batch  # noqa: F401
-from .decode import (BeamHypothesis, OnlineBeamState, basic_greedy_search, beam_chunk_online, greedy_batch,  # noqa: F401
-                     greedy_chunk, prefix_beam_search)
+from .decode import (BeamHypothesis, OnlineBeamState, basic_greedy_search, beam_chunk_online, beam_search_batch,  # noqa: F401
+                     greedy_batch, greedy_chunk, prefix_beam_search, prefix_beam_search_batch)
 from .functional import (ctc_greedy_search as ctc_greedy_hyps, ctc_loss_from_logits, fused_joint_rnnt_loss,  # noqa: F401
                          joint_logits, rnnt_loss)
 from .graph import BucketedJointRnntStep, GraphedJointRnntStep  # noqa: F401

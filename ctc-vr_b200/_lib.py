@@ -58,8 +58,11 @@ _SIGS = {
     "ctcvr_rnnt_beam_state_bytes": (Z, [P, I, I, I]),
     "ctcvr_rnnt_beam_reset": (I, [P, P, I, I, I, P]),
     "ctcvr_rnnt_beam_chunk": (I, [P, P, I, P, I, I, I, I, P, P, P, P, P, P, P]),
+    "ctcvr_rnnt_beam_reset_batch": (I, [P, P, I, I, I, I, P]),
+    "ctcvr_rnnt_beam_chunk_batch": (I, [P, P, P, I, I, P, I, I, I, I, P, P, P, P, P, P, P]),
     "ctcvr_rnnt_prefix_beam_ws_bytes": (Z, [P, I, I]),
     "ctcvr_rnnt_prefix_beam": (I, [P, P, P, I, I, I, F, F, P, P, P, P, P, Z, P]),
+    "ctcvr_rnnt_prefix_beam_batch": (I, [P, P, P, P, I, I, I, I, F, F, P, P, P, P, P, Z, P]),
     "ctcvr_ctc_prefix_beam_ws_bytes": (Z, [I, I, I, I]),
     "ctcvr_ctc_prefix_beam": (I, [P, P, I, I, I, I, I, P, P, P, P, P, P, Z, P]),
 }

@@ -1,4 +1,4 @@
-// On-device RNN-T beam decoders, one stream per launch, hypotheses advancing in
+// On-device RNN-T beam decoders, one stream per CTA (grid = streams of the call), hypotheses advancing in
 // lock-step inside ONE CTA so that every predictor / joint weight fetched from L2 feeds all of them:
 //   A7  OnlineRNNTModel._decode_chunk_beam_search        model/online_rnnt_model.py:389-522
 //   A8  PrefixBeamSearch.prefix_beam_search              wenet/transducer/search/prefix_beam_search.py:42-148
@@ -118,11 +118,25 @@ __global__ void __launch_bounds__(BM_THREADS, 1) rnnt_beam_chunk_kernel(
     ctcvr_decoder_weights w, const float* __restrict__ enc_proj, int T, unsigned char* __restrict__ state, int beam,
     int n_steps, int max_out, int blank, int32_t* __restrict__ out_n, int32_t* __restrict__ out_tokens,
     int32_t* __restrict__ out_lens, double* __restrict__ out_scores, float* __restrict__ out_h,
-    float* __restrict__ out_c) {
+    float* __restrict__ out_c, const int32_t* __restrict__ chunk_lens, size_t state_stride) {
   extern __shared__ __align__(16) float smf[];
   DecodeSmem<NB> s;
   s.carve(smf, w, true);
   const BeamLayout lay = beam_layout(w.L, w.H, beam, n_steps, max_out);
+  {
+    // one CTA per stream (grid = number of streams): every per-stream array is offset by the stream index; a stream's
+    // chunk may be shorter than T (chunk_lens), its rows beyond that are not read
+    const size_t sidx = blockIdx.x;
+    enc_proj += sidx * (size_t)T * w.D;
+    state += sidx * state_stride;
+    out_n += sidx;
+    out_tokens += sidx * (size_t)beam * max_out;
+    out_lens += sidx * beam;
+    out_scores += sidx * beam;
+    out_h += sidx * (size_t)beam * w.L * w.H;
+    out_c += sidx * (size_t)beam * w.L * w.H;
+    if (chunk_lens) T = max(0, min(T, chunk_lens[sidx]));
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = BM_THREADS / 32;
   const int LH = w.L * w.H, V = w.V;
   int* hdr = reinterpret_cast<int*>(state);
@@ -329,7 +343,9 @@ __global__ void __launch_bounds__(BM_THREADS, 1) rnnt_beam_chunk_kernel(
   }
 }
 
-__global__ void rnnt_beam_reset_kernel(unsigned char* state, int L, int H, int beam, int n_steps, int max_out) {
+__global__ void rnnt_beam_reset_kernel(unsigned char* state, int L, int H, int beam, int n_steps, int max_out,
+                                       size_t state_stride) {
+  state += (size_t)blockIdx.x * state_stride;
   const BeamLayout lay = beam_layout(L, H, beam, n_steps, max_out);
   int* hdr = reinterpret_cast<int*>(state);
   if (threadIdx.x == 0) {
@@ -349,44 +365,48 @@ size_t rnnt_beam_state_bytes(const ctcvr_decoder_weights& w, int beam, int n_ste
   return beam_layout(w.L, w.H, beam, n_steps, max_out).total;
 }
 
-int rnnt_beam_reset(void* state, const ctcvr_decoder_weights& w, int beam, int n_steps, int max_out, cudaStream_t st) {
-  CTCVR_REQUIRE(state, "rnnt_beam_reset: NULL state");
+int rnnt_beam_reset(void* state, const ctcvr_decoder_weights& w, int S, int beam, int n_steps, int max_out, cudaStream_t st) {
+  CTCVR_REQUIRE(state && S >= 1, "rnnt_beam_reset: NULL state or no stream");
   CTCVR_REQUIRE(beam >= 1 && beam <= BM_BEAM_MAX && n_steps >= 1 && n_steps <= BM_STEPS_MAX,
                 "rnnt_beam: beam must be within [1,%d] and n_steps within [1,%d]", BM_BEAM_MAX, BM_STEPS_MAX);
-  rnnt_beam_reset_kernel<<<1, 256, 0, st>>>(reinterpret_cast<unsigned char*>(state), w.L, w.H, beam, n_steps, max_out);
+  rnnt_beam_reset_kernel<<<S, 256, 0, st>>>(reinterpret_cast<unsigned char*>(state), w.L, w.H, beam, n_steps, max_out,
+                                            rnnt_beam_state_bytes(w, beam, n_steps, max_out));
   CTCVR_LAUNCH_CHECK();
   return 0;
 }
 
 template <int NB>
-static int launch_beam_chunk(const ctcvr_decoder_weights& w, const float* enc_proj, int T, void* state, int beam,
-                             int n_steps, int max_out, int blank, int32_t* out_n, int32_t* out_tokens,
-                             int32_t* out_lens, double* out_scores, float* out_h, float* out_c, cudaStream_t st) {
+static int launch_beam_chunk(const ctcvr_decoder_weights& w, const float* enc_proj, const int32_t* chunk_lens, int S, int T,
+                             void* state, int beam, int n_steps, int max_out, int blank, int32_t* out_n,
+                             int32_t* out_tokens, int32_t* out_lens, double* out_scores, float* out_h, float* out_c,
+                             cudaStream_t st) {
   const size_t smem = beam_smem<NB>(w);
   CTCVR_CHECK_CUDA(cudaFuncSetAttribute(rnnt_beam_chunk_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rnnt_beam_chunk_kernel<NB><<<1, BM_THREADS, smem, st>>>(w, enc_proj, T, reinterpret_cast<unsigned char*>(state), beam,
+  rnnt_beam_chunk_kernel<NB><<<S, BM_THREADS, smem, st>>>(w, enc_proj, T, reinterpret_cast<unsigned char*>(state), beam,
                                                           n_steps, max_out, blank, out_n, out_tokens, out_lens,
-                                                          out_scores, out_h, out_c);
+                                                          out_scores, out_h, out_c, chunk_lens,
+                                                          rnnt_beam_state_bytes(w, beam, n_steps, max_out));
   CTCVR_LAUNCH_CHECK();
   return 0;
 }
 
-int rnnt_beam_chunk(const ctcvr_decoder_weights& w, const float* enc_proj, int T, void* state, int beam, int n_steps,
-                    int max_out, int blank, int32_t* out_n, int32_t* out_tokens, int32_t* out_lens, double* out_scores,
-                    float* out_h, float* out_c, cudaStream_t st) {
+int rnnt_beam_chunk(const ctcvr_decoder_weights& w, const float* enc_proj, const int32_t* chunk_lens, int S, int T,
+                    void* state, int beam, int n_steps, int max_out, int blank, int32_t* out_n, int32_t* out_tokens,
+                    int32_t* out_lens, double* out_scores, float* out_h, float* out_c, cudaStream_t st) {
+  CTCVR_REQUIRE(S >= 1, "rnnt_beam: no stream");
   CTCVR_REQUIRE(beam >= 1 && beam <= BM_BEAM_MAX && n_steps >= 1 && n_steps <= BM_STEPS_MAX,
                 "rnnt_beam: beam must be within [1,%d] and n_steps within [1,%d]", BM_BEAM_MAX, BM_STEPS_MAX);
   CTCVR_REQUIRE(w.V - 1 >= 1, "rnnt_beam: vocabulary too small");
   const size_t lim = 220 * 1024;
   // one warp per hypothesis inside a group: the candidate append order (hypothesis-major) needs NB <= #warps
   if (beam > 8 && beam_smem<16>(w) <= lim)
-    return launch_beam_chunk<16>(w, enc_proj, T, state, beam, n_steps, max_out, blank, out_n, out_tokens, out_lens, out_scores, out_h, out_c, st);
+    return launch_beam_chunk<16>(w, enc_proj, chunk_lens, S, T, state, beam, n_steps, max_out, blank, out_n, out_tokens, out_lens, out_scores, out_h, out_c, st);
   if (beam > 4 && beam_smem<8>(w) <= lim)
-    return launch_beam_chunk<8>(w, enc_proj, T, state, beam, n_steps, max_out, blank, out_n, out_tokens, out_lens, out_scores, out_h, out_c, st);
+    return launch_beam_chunk<8>(w, enc_proj, chunk_lens, S, T, state, beam, n_steps, max_out, blank, out_n, out_tokens, out_lens, out_scores, out_h, out_c, st);
   if (beam > 1 && beam_smem<4>(w) <= lim)
-    return launch_beam_chunk<4>(w, enc_proj, T, state, beam, n_steps, max_out, blank, out_n, out_tokens, out_lens, out_scores, out_h, out_c, st);
+    return launch_beam_chunk<4>(w, enc_proj, chunk_lens, S, T, state, beam, n_steps, max_out, blank, out_n, out_tokens, out_lens, out_scores, out_h, out_c, st);
   CTCVR_REQUIRE(beam_smem<1>(w) <= lim, "rnnt_beam: predictor too large for shared memory (H=%d L=%d)", w.H, w.L);
-  return launch_beam_chunk<1>(w, enc_proj, T, state, beam, n_steps, max_out, blank, out_n, out_tokens, out_lens, out_scores, out_h, out_c, st);
+  return launch_beam_chunk<1>(w, enc_proj, chunk_lens, S, T, state, beam, n_steps, max_out, blank, out_n, out_tokens, out_lens, out_scores, out_h, out_c, st);
 }
 
 // =============================================================================================================
@@ -428,13 +448,26 @@ template <int NB>
 __global__ void __launch_bounds__(BM_THREADS, 1) rnnt_prefix_beam_kernel(
     ctcvr_decoder_weights w, const float* __restrict__ enc_proj, const float* __restrict__ ctc_logp, int T, int beam,
     int blank, float ctc_weight, float tr_weight, int32_t* __restrict__ out_n, int32_t* __restrict__ out_tokens,
-    int32_t* __restrict__ out_lens, double* __restrict__ out_scores, unsigned char* __restrict__ ws) {
+    int32_t* __restrict__ out_lens, double* __restrict__ out_scores, unsigned char* __restrict__ ws,
+    const int32_t* __restrict__ lens, size_t ws_stride) {
   extern __shared__ __align__(16) float smf[];
   DecodeSmem<NB> s;
   s.carve(smf, w, true);
-  const PrefixLayout lay = prefix_layout(w.L, w.H, beam, T);
+  const PrefixLayout lay = prefix_layout(w.L, w.H, beam, T);      // sized for the longest utterance of the batch
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = BM_THREADS / 32;
   const int LH = w.L * w.H, V = w.V, ML = T + 1;
+  {
+    // one CTA per utterance (grid = batch): per-utterance arrays are offset by the utterance index
+    const size_t sidx = blockIdx.x;
+    enc_proj += sidx * (size_t)T * w.D;
+    ctc_logp += sidx * (size_t)T * V;
+    ws += sidx * ws_stride;
+    out_n += sidx;
+    out_tokens += sidx * (size_t)beam * ML;
+    out_lens += sidx * beam;
+    out_scores += sidx * beam;
+    if (lens) T = max(0, min(T, lens[sidx]));
+  }
   auto b_score = [&](int bf) { return reinterpret_cast<double*>(ws + lay.off_buf[bf] + lay.o_score); };
   auto b_len = [&](int bf) { return reinterpret_cast<int*>(ws + lay.off_buf[bf] + lay.o_len); };
   auto b_tok = [&](int bf) { return reinterpret_cast<int*>(ws + lay.off_buf[bf] + lay.o_tok); };
@@ -606,29 +639,33 @@ size_t rnnt_prefix_beam_ws_bytes(const ctcvr_decoder_weights& w, int beam, int T
 }
 
 template <int NB>
-static int launch_prefix(const ctcvr_decoder_weights& w, const float* enc_proj, const float* ctc_logp, int T, int beam,
-                         int blank, float cw, float tw, int32_t* out_n, int32_t* out_tokens, int32_t* out_lens,
-                         double* out_scores, void* ws, cudaStream_t st) {
+static int launch_prefix(const ctcvr_decoder_weights& w, const float* enc_proj, const float* ctc_logp, const int32_t* lens,
+                         int S, int T, int beam, int blank, float cw, float tw, int32_t* out_n, int32_t* out_tokens,
+                         int32_t* out_lens, double* out_scores, void* ws, cudaStream_t st) {
   const size_t smem = beam_smem<NB>(w);
   CTCVR_CHECK_CUDA(cudaFuncSetAttribute(rnnt_prefix_beam_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rnnt_prefix_beam_kernel<NB><<<1, BM_THREADS, smem, st>>>(w, enc_proj, ctc_logp, T, beam, blank, cw, tw, out_n,
+  rnnt_prefix_beam_kernel<NB><<<S, BM_THREADS, smem, st>>>(w, enc_proj, ctc_logp, T, beam, blank, cw, tw, out_n,
                                                            out_tokens, out_lens, out_scores,
-                                                           reinterpret_cast<unsigned char*>(ws));
+                                                           reinterpret_cast<unsigned char*>(ws), lens,
+                                                           rnnt_prefix_beam_ws_bytes(w, beam, T));
   CTCVR_LAUNCH_CHECK();
   return 0;
 }
 
-int rnnt_prefix_beam(const ctcvr_decoder_weights& w, const float* enc_proj, const float* ctc_logp, int T, int beam,
-                     int blank, float ctc_weight, float transducer_weight, int32_t* out_n, int32_t* out_tokens,
-                     int32_t* out_lens, double* out_scores, void* ws, size_t ws_bytes, cudaStream_t st) {
+int rnnt_prefix_beam(const ctcvr_decoder_weights& w, const float* enc_proj, const float* ctc_logp, const int32_t* lens,
+                     int S, int T, int beam, int blank, float ctc_weight, float transducer_weight, int32_t* out_n,
+                     int32_t* out_tokens, int32_t* out_lens, double* out_scores, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
   CTCVR_REQUIRE(beam >= 1 && beam <= BM_BEAM_MAX, "rnnt_prefix_beam: beam must be within [1,%d]", BM_BEAM_MAX);
-  CTCVR_REQUIRE(ws && ws_bytes >= rnnt_prefix_beam_ws_bytes(w, beam, T), "rnnt_prefix_beam: workspace too small");
+  CTCVR_REQUIRE(S >= 1, "rnnt_prefix_beam: no utterance");
+  CTCVR_REQUIRE(ws && ws_bytes >= (size_t)S * rnnt_prefix_beam_ws_bytes(w, beam, T),
+                "rnnt_prefix_beam: workspace too small (%d x ctcvr_rnnt_prefix_beam_ws_bytes)", S);
   const size_t lim = 220 * 1024;
-  if (beam > 8 && beam_smem<16>(w) <= lim) return launch_prefix<16>(w, enc_proj, ctc_logp, T, beam, blank, ctc_weight, transducer_weight, out_n, out_tokens, out_lens, out_scores, ws, st);
-  if (beam > 4 && beam_smem<8>(w) <= lim) return launch_prefix<8>(w, enc_proj, ctc_logp, T, beam, blank, ctc_weight, transducer_weight, out_n, out_tokens, out_lens, out_scores, ws, st);
-  if (beam > 1 && beam_smem<4>(w) <= lim) return launch_prefix<4>(w, enc_proj, ctc_logp, T, beam, blank, ctc_weight, transducer_weight, out_n, out_tokens, out_lens, out_scores, ws, st);
+  if (beam > 8 && beam_smem<16>(w) <= lim) return launch_prefix<16>(w, enc_proj, ctc_logp, lens, S, T, beam, blank, ctc_weight, transducer_weight, out_n, out_tokens, out_lens, out_scores, ws, st);
+  if (beam > 4 && beam_smem<8>(w) <= lim) return launch_prefix<8>(w, enc_proj, ctc_logp, lens, S, T, beam, blank, ctc_weight, transducer_weight, out_n, out_tokens, out_lens, out_scores, ws, st);
+  if (beam > 1 && beam_smem<4>(w) <= lim) return launch_prefix<4>(w, enc_proj, ctc_logp, lens, S, T, beam, blank, ctc_weight, transducer_weight, out_n, out_tokens, out_lens, out_scores, ws, st);
   CTCVR_REQUIRE(beam_smem<1>(w) <= lim, "rnnt_prefix_beam: predictor too large for shared memory (H=%d L=%d)", w.H, w.L);
-  return launch_prefix<1>(w, enc_proj, ctc_logp, T, beam, blank, ctc_weight, transducer_weight, out_n, out_tokens, out_lens, out_scores, ws, st);
+  return launch_prefix<1>(w, enc_proj, ctc_logp, lens, S, T, beam, blank, ctc_weight, transducer_weight, out_n, out_tokens, out_lens, out_scores, ws, st);
 }
 
 }  // namespace ctcvr

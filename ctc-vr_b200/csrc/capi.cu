@@ -47,12 +47,12 @@ int ctc_greedy(const float*, const int32_t*, int32_t*, int32_t*, int, int, int, 
 int rnnt_greedy(const ctcvr_decoder_weights&, const float*, const int32_t*, float*, float*, int32_t*, int32_t*,
                 int32_t*, int, int, int, int, int, cudaStream_t);
 size_t rnnt_beam_state_bytes(const ctcvr_decoder_weights&, int, int, int);
-int rnnt_beam_reset(void*, const ctcvr_decoder_weights&, int, int, int, cudaStream_t);
-int rnnt_beam_chunk(const ctcvr_decoder_weights&, const float*, int, void*, int, int, int, int, int32_t*, int32_t*,
-                    int32_t*, double*, float*, float*, cudaStream_t);
+int rnnt_beam_reset(void*, const ctcvr_decoder_weights&, int, int, int, int, cudaStream_t);
+int rnnt_beam_chunk(const ctcvr_decoder_weights&, const float*, const int32_t*, int, int, void*, int, int, int, int, int32_t*,
+                    int32_t*, int32_t*, double*, float*, float*, cudaStream_t);
 size_t rnnt_prefix_beam_ws_bytes(const ctcvr_decoder_weights&, int, int);
-int rnnt_prefix_beam(const ctcvr_decoder_weights&, const float*, const float*, int, int, int, float, float, int32_t*,
-                     int32_t*, int32_t*, double*, void*, size_t, cudaStream_t);
+int rnnt_prefix_beam(const ctcvr_decoder_weights&, const float*, const float*, const int32_t*, int, int, int, int, float,
+                     float, int32_t*, int32_t*, int32_t*, double*, void*, size_t, cudaStream_t);
 size_t ctc_prefix_beam_ws_bytes(int, int, int, int);
 int ctc_prefix_beam(const float*, const int32_t*, int, int, int, int, int, int32_t*, int32_t*, int32_t*, double*,
                     int32_t*, void*, size_t, cudaStream_t);
@@ -287,7 +287,14 @@ int ctcvr_rnnt_beam_reset(void* beam_state, const ctcvr_decoder_weights* w, int 
                           void* stream) {
   if (int rc = check_weights("rnnt_beam_reset", w)) return rc;
   CTCVR_REQUIRE(beam_state && beam > 0 && n_steps > 0 && max_out > 0, "rnnt_beam_reset: bad arguments");
-  return rnnt_beam_reset(beam_state, *w, beam, n_steps, max_out, ST(stream));
+  return rnnt_beam_reset(beam_state, *w, 1, beam, n_steps, max_out, ST(stream));
+}
+
+int ctcvr_rnnt_beam_reset_batch(void* beam_states, const ctcvr_decoder_weights* w, int S, int beam, int n_steps,
+                                int max_out, void* stream) {
+  if (int rc = check_weights("rnnt_beam_reset_batch", w)) return rc;
+  CTCVR_REQUIRE(beam_states && S > 0 && beam > 0 && n_steps > 0 && max_out > 0, "rnnt_beam_reset_batch: bad arguments");
+  return rnnt_beam_reset(beam_states, *w, S, beam, n_steps, max_out, ST(stream));
 }
 
 int ctcvr_rnnt_beam_chunk(const ctcvr_decoder_weights* w, const float* enc_proj, int T, void* beam_state, int beam,
@@ -297,8 +304,21 @@ int ctcvr_rnnt_beam_chunk(const ctcvr_decoder_weights* w, const float* enc_proj,
   CTCVR_REQUIRE((enc_proj || T == 0) && beam_state && out_n && out_tokens && out_lens && out_scores, "rnnt_beam_chunk: NULL pointer");
   CTCVR_REQUIRE(T >= 0 && beam > 0 && n_steps > 0 && max_out > 0, "rnnt_beam_chunk: bad dims");
   CTCVR_REQUIRE(blank >= 0 && blank < w->V, "rnnt_beam_chunk: blank out of range");
-  return rnnt_beam_chunk(*w, enc_proj, T, beam_state, beam, n_steps, max_out, blank, out_n, out_tokens, out_lens,
+  return rnnt_beam_chunk(*w, enc_proj, nullptr, 1, T, beam_state, beam, n_steps, max_out, blank, out_n, out_tokens, out_lens,
                          out_scores, out_h, out_c, ST(stream));
+}
+
+int ctcvr_rnnt_beam_chunk_batch(const ctcvr_decoder_weights* w, const float* enc_proj, const int32_t* chunk_lens, int S,
+                                int T, void* beam_states, int beam, int n_steps, int max_out, int blank, int32_t* out_n,
+                                int32_t* out_tokens, int32_t* out_lens, double* out_scores, float* out_h, float* out_c,
+                                void* stream) {
+  if (int rc = check_weights("rnnt_beam_chunk_batch", w)) return rc;
+  CTCVR_REQUIRE((enc_proj || T == 0) && beam_states && out_n && out_tokens && out_lens && out_scores && out_h && out_c,
+                "rnnt_beam_chunk_batch: NULL pointer");
+  CTCVR_REQUIRE(S > 0 && T >= 0 && beam > 0 && n_steps > 0 && max_out > 0, "rnnt_beam_chunk_batch: bad dims");
+  CTCVR_REQUIRE(blank >= 0 && blank < w->V, "rnnt_beam_chunk_batch: blank out of range");
+  return rnnt_beam_chunk(*w, enc_proj, chunk_lens, S, T, beam_states, beam, n_steps, max_out, blank, out_n, out_tokens,
+                         out_lens, out_scores, out_h, out_c, ST(stream));
 }
 
 size_t ctcvr_rnnt_prefix_beam_ws_bytes(const ctcvr_decoder_weights* w, int beam, int T) {
@@ -312,7 +332,18 @@ int ctcvr_rnnt_prefix_beam(const ctcvr_decoder_weights* w, const float* enc_proj
   if (int rc = check_weights("rnnt_prefix_beam", w)) return rc;
   CTCVR_REQUIRE(enc_proj && ctc_logp && out_n && out_tokens && out_lens && out_scores && ws, "rnnt_prefix_beam: NULL pointer");
   CTCVR_REQUIRE(T > 0 && beam > 0, "rnnt_prefix_beam: bad dims");
-  return rnnt_prefix_beam(*w, enc_proj, ctc_logp, T, beam, blank, ctc_weight, transducer_weight, out_n, out_tokens,
+  return rnnt_prefix_beam(*w, enc_proj, ctc_logp, nullptr, 1, T, beam, blank, ctc_weight, transducer_weight, out_n, out_tokens,
+                          out_lens, out_scores, ws, ws_bytes, ST(stream));
+}
+
+int ctcvr_rnnt_prefix_beam_batch(const ctcvr_decoder_weights* w, const float* enc_proj, const float* ctc_logp,
+                                 const int32_t* lens, int S, int T, int beam, int blank, float ctc_weight,
+                                 float transducer_weight, int32_t* out_n, int32_t* out_tokens, int32_t* out_lens,
+                                 double* out_scores, void* ws, size_t ws_bytes, void* stream) {
+  if (int rc = check_weights("rnnt_prefix_beam_batch", w)) return rc;
+  CTCVR_REQUIRE(enc_proj && ctc_logp && out_n && out_tokens && out_lens && out_scores && ws, "rnnt_prefix_beam_batch: NULL pointer");
+  CTCVR_REQUIRE(S > 0 && T > 0 && beam > 0, "rnnt_prefix_beam_batch: bad dims");
+  return rnnt_prefix_beam(*w, enc_proj, ctc_logp, lens, S, T, beam, blank, ctc_weight, transducer_weight, out_n, out_tokens,
                           out_lens, out_scores, ws, ws_bytes, ST(stream));
 }
 

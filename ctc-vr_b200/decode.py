@@ -215,6 +215,43 @@ def beam_chunk_online(model, encoder_out_chunk: torch.Tensor, state: Optional[On
     return hyps, state
 
 
+@torch.no_grad()
+def beam_search_batch(model, encoder_out: torch.Tensor, encoder_out_lens: torch.Tensor, beam_size: int = 4,
+                      n_steps: int = 10, max_out: Optional[int] = None) -> List[List[BeamHypothesis]]:
+    """The search of `_decode_chunk_beam_search` (model/online_rnnt_model.py:425-522) over whole utterances, for S
+    utterances in ONE kernel launch (one CTA per utterance; `ctcvr_rnnt_beam_chunk_batch`).  The reference decodes one
+    stream at a time (batch 1 is asserted, online_rnnt_model.py:277-278); chunk boundaries only matter to the encoder, so
+    utterance s gets exactly the hypotheses (tokens, order, scores) of feeding its frames through `beam_chunk_online`.
+    encoder_out [S,T,H], encoder_out_lens [S].  Returns, per utterance, the beam as a list of BeamHypothesis."""
+    w = _prepared(model).get()
+    blank = _blank_of(model)
+    ep = _enc_proj(model, encoder_out).contiguous()
+    S, T = ep.shape[0], ep.shape[1]
+    dev = ep.device
+    beam = int(beam_size)
+    lens = encoder_out_lens.to(device=dev, dtype=torch.int32).contiguous()
+    mo = int(max_out) if max_out is not None else max(16, T * int(n_steps) + 1)      # a frame appends at most n_steps tokens
+    LH = w.L * w.H
+    with torch.cuda.device(dev):
+        nbytes = int(query("ctcvr_rnnt_beam_state_bytes", ctypes.byref(w), beam, int(n_steps), mo))
+        states = torch.zeros(S * nbytes, dtype=torch.uint8, device=dev)
+        out_n = torch.zeros((S,), dtype=torch.int32, device=dev)
+        out_tok = torch.zeros((S, beam, mo), dtype=torch.int32, device=dev)
+        out_len = torch.zeros((S, beam), dtype=torch.int32, device=dev)
+        out_sc = torch.zeros((S, beam), dtype=torch.float64, device=dev)
+        out_h = torch.zeros((S, beam, w.L, w.H), dtype=torch.float32, device=dev)
+        out_c = torch.zeros_like(out_h)
+        call("ctcvr_rnnt_beam_reset_batch", ptr(states), ctypes.byref(w), S, beam, int(n_steps), mo, stream())
+        call("ctcvr_rnnt_beam_chunk_batch", ctypes.byref(w), ptr(ep), ptr(lens), S, T, ptr(states), beam, int(n_steps), mo,
+             blank, ptr(out_n), ptr(out_tok), ptr(out_len), ptr(out_sc), ptr(out_h), ptr(out_c), stream())
+    ns, ls, toks, sc = out_n.cpu(), out_len.cpu(), out_tok.cpu(), out_sc.cpu()
+    res = []
+    for s_ in range(S):
+        res.append([BeamHypothesis(toks[s_, i, :int(ls[s_, i])].tolist(), float(sc[s_, i]),
+                                   [out_h[s_, i].unsqueeze(1), out_c[s_, i].unsqueeze(1)]) for i in range(int(ns[s_]))])
+    return res
+
+
 # ------------------------------------------------------------------------------------------------ A8
 @torch.no_grad()
 def prefix_beam_search(model, encoder_out: torch.Tensor, ctc_logp: torch.Tensor, beam_size: int = 5,
@@ -242,3 +279,35 @@ def prefix_beam_search(model, encoder_out: torch.Tensor, ctc_logp: torch.Tensor,
     n = int(out_n.item())
     lens, toks, sc = out_len.cpu(), out_tok.cpu(), out_sc.cpu()
     return [(toks[i, :int(lens[i])].tolist(), float(sc[i])) for i in range(n)]
+
+
+@torch.no_grad()
+def prefix_beam_search_batch(model, encoder_out: torch.Tensor, encoder_out_lens: torch.Tensor, ctc_logp: torch.Tensor,
+                             beam_size: int = 5, ctc_weight: float = 0.3,
+                             transducer_weight: float = 0.7) -> List[List[Tuple[List[int], float]]]:
+    """`prefix_beam_search` (wenet/transducer/search/prefix_beam_search.py:42-148 below the encoder call) for S
+    utterances in ONE launch (one CTA per utterance; `ctcvr_rnnt_prefix_beam_batch`): encoder_out [S,T,H],
+    encoder_out_lens [S], ctc_logp [S,T,V].  Per utterance the same [(hyp incl. the leading blank, score)] list, best
+    first, as the single-utterance call on its first encoder_out_lens[s] frames."""
+    w = _prepared(model).get()
+    blank = _blank_of(model)
+    ep = _enc_proj(model, encoder_out).contiguous()
+    S, T = ep.shape[0], ep.shape[1]
+    dev = ep.device
+    cl = ctc_logp.detach().float().contiguous().to(dev)
+    if cl.shape[0] != S or cl.shape[1] != T:
+        raise RuntimeError("prefix_beam_search_batch: ctc_logp must be [S,T,V] for encoder_out [S,T,H]")
+    lens = encoder_out_lens.to(device=dev, dtype=torch.int32).contiguous()
+    beam = int(beam_size)
+    out_n = torch.zeros((S,), dtype=torch.int32, device=dev)
+    out_tok = torch.zeros((S, beam, T + 1), dtype=torch.int32, device=dev)
+    out_len = torch.zeros((S, beam), dtype=torch.int32, device=dev)
+    out_sc = torch.zeros((S, beam), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = int(query("ctcvr_rnnt_prefix_beam_ws_bytes", ctypes.byref(w), beam, T))
+        ws = torch.empty(max(S * nbytes, 256), dtype=torch.uint8, device=dev)
+        call("ctcvr_rnnt_prefix_beam_batch", ctypes.byref(w), ptr(ep), ptr(cl), ptr(lens), S, T, beam, blank,
+             float(ctc_weight), float(transducer_weight), ptr(out_n), ptr(out_tok), ptr(out_len), ptr(out_sc), ptr(ws),
+             ws.numel(), stream())
+    ns, ls, toks, sc = out_n.cpu(), out_len.cpu(), out_tok.cpu(), out_sc.cpu()
+    return [[(toks[s_, i, :int(ls[s_, i])].tolist(), float(sc[s_, i])) for i in range(int(ns[s_]))] for s_ in range(S)]

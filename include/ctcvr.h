@@ -214,6 +214,18 @@ int ctcvr_rnnt_beam_chunk(const ctcvr_decoder_weights* w, const float* enc_proj,
                           int32_t* out_n, int32_t* out_tokens, int32_t* out_lens,
                           double* out_scores, float* out_h, float* out_c, void* stream);
 
+/* A7 for S independent streams in ONE launch (one CTA per stream; the reference decodes one stream at a time,
+ * online_rnnt_model.py:277-278 - the per-stream arithmetic is unchanged, so every stream's hypotheses equal the
+ * single-stream call's).  beam_states: S consecutive states of ctcvr_rnnt_beam_state_bytes each; enc_proj [S,T,D];
+ * chunk_lens [S] frames of each stream's chunk (<= T; NULL = T for all); outputs carry a leading S dimension:
+ * out_n [S], out_tokens [S,beam,max_out], out_lens / out_scores [S,beam], out_h / out_c [S,beam,L,H]. */
+int ctcvr_rnnt_beam_reset_batch(void* beam_states, const ctcvr_decoder_weights* w, int S, int beam, int n_steps,
+                                int max_out, void* stream);
+int ctcvr_rnnt_beam_chunk_batch(const ctcvr_decoder_weights* w, const float* enc_proj, const int32_t* chunk_lens,
+                                int S, int T, void* beam_states, int beam, int n_steps, int max_out, int blank,
+                                int32_t* out_n, int32_t* out_tokens, int32_t* out_lens, double* out_scores,
+                                float* out_h, float* out_c, void* stream);
+
 /* ---- A8 wenet transducer prefix beam with CTC shallow fusion —
  * wenet/transducer/search/prefix_beam_search.py:42-148.  enc_proj [T,D]; ctc_logp [T,V] (log-probs);
  * out_tokens [beam][T+1] (every hypothesis starts with the blank, as in the reference), out_lens [beam],
@@ -224,6 +236,14 @@ int ctcvr_rnnt_prefix_beam(const ctcvr_decoder_weights* w, const float* enc_proj
                            float transducer_weight, int32_t* out_n, int32_t* out_tokens,
                            int32_t* out_lens, double* out_scores, void* ws, size_t ws_bytes,
                            void* stream);
+
+/* A8 for S utterances in ONE launch (one CTA per utterance): enc_proj [S,T,D], ctc_logp [S,T,V], lens [S] frames per
+ * utterance (<= T; NULL = T), out_n [S], out_tokens [S,beam,T+1], out_lens / out_scores [S,beam];
+ * ws: S x ctcvr_rnnt_prefix_beam_ws_bytes(w, beam, T). */
+int ctcvr_rnnt_prefix_beam_batch(const ctcvr_decoder_weights* w, const float* enc_proj, const float* ctc_logp,
+                                 const int32_t* lens, int S, int T, int beam, int blank, float ctc_weight,
+                                 float transducer_weight, int32_t* out_n, int32_t* out_tokens, int32_t* out_lens,
+                                 double* out_scores, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- A9 CTC prefix beam search — wenet/transformer/search.py:125-247 (context_graph=None).
  * ctc_probs [B,T,V] log-probs; per utterance up to `beam` hyps: out_tokens [B,beam,T],
