@@ -87,11 +87,65 @@ def run_rows(quick=True):
     return list(_ROWS)
 
 
+def sharded():
+    """cfg3 / cfg5 decode sharded over the ranks of one node (launch under torchrun): utterances are dealt out evenly,
+    every rank decodes its shard with the same weights, NO collective on the data path (SURVEY.md 8e: replicas only);
+    time = max over ranks between two barriers.  Rows: A5 (1 000 utterances x 249 frames, greedy) and A7b (1 184
+    utterances x 500 frames, online beam 10)."""
+    import torch.distributed as dist
+    import ctcvr_b200 as C
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    m = _decode_model(C, 256)                     # seeded: identical weights on every rank
+
+    def timed(fn, reps=2):
+        fn()
+        tot = 0.0
+        for _ in range(reps):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot += float(t)
+        return tot / reps
+
+    rows = []
+    for row, total, frames, what, fn in (
+            ("A5", 1000, 249, "RNN-T greedy search, 1000 utterances x 249 frames, H=256, n_steps=64",
+             lambda e, l: C.basic_greedy_search(m, e, l, n_steps=64)),
+            ("A7b", 1184, 500, "online RNN-T beam search, beam 10, 1184 utterances x 500 frames",
+             lambda e, l: C.beam_search_batch(m, e, l, beam_size=10, n_steps=10))):
+        lo, hi = rank * total // world, (rank + 1) * total // world
+        g = torch.Generator().manual_seed(100 + rank)
+        e = torch.randn(hi - lo, frames, 256, generator=g).to(dev)
+        l = torch.full((hi - lo,), frames, dtype=torch.int32, device=dev)
+        sec = timed(lambda: fn(e, l))
+        rows.append({"row": row, "what": what, "value": total / sec, "unit": "utt/s", "gpu_seconds": sec, "n_gpus": world,
+                     "rtf": sec / (total * frames * FRAME_S), "sharding": "utterances dealt evenly to ranks, no collective"})
+    if rank == 0:
+        for r in rows:
+            print(json.dumps(r), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main(args=None):
     if args is None:
         ap = argparse.ArgumentParser()
         ap.add_argument("--quick", action="store_true", help="smaller CPU samples")
+        ap.add_argument("--sharded", action="store_true", help="under torchrun: A5 / A7b with the utterances sharded over the ranks")
         args = ap.parse_args()
+    if getattr(args, "sharded", False):
+        return sharded()
     import ctcvr_b200 as C
     from oracle import ctc_oracle as CO
     from oracle import transducer_oracle as TO
