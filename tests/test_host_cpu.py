@@ -28,6 +28,21 @@ def test_library_exports_every_declared_symbol():
     assert ctcvr_b200.__version__
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/ctcvr.h is the drop-in boundary: it must compile as C99 (no C++ types, no torch) and as C++."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "ctcvr.h"\nint main(void) { int (*f)(void) = ctcvr_version; return f == (int (*)(void))0; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src)],
+                ["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-I", inc, "-x", "c++", str(src)]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
 def test_ws_queries_need_no_gpu():
     from ctcvr_b200._lib import query
     assert query("ctcvr_rnnt_loss_dense_ws_bytes", 2, 10, 5) == 5 * 2 * 10 * 5 * 4
