@@ -117,12 +117,11 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs& a, unsigned int val
 
 // Payload floats [4u, 4u+4) live in one segment (offsets and padded lengths are multiples of 4).
 struct UnitRef { float* g; long left; bool whole; };   // left = floats of the segment from g on (<= 0: pure padding)
-__device__ __forceinline__ UnitRef locate_unit(const PeerArgs& a, long u) {
+// `s` is the caller's segment cursor: a thread visits its units in increasing order, so the cursor only moves forward
+// (a full scan of the table per 16-byte unit made the pack / unpack phases compute-bound at 13 MB payloads).
+__device__ __forceinline__ UnitRef locate_unit(const PeerArgs& a, long u, int& s) {
   const long f = u * 4;
-  int s = 0;
-#pragma unroll 1
-  for (int i = 1; i < a.nseg; ++i)
-    if (f >= a.seg_off[i]) s = i;
+  while (s + 1 < a.nseg && f >= a.seg_off[s + 1]) ++s;
   const long j = f - a.seg_off[s];
   UnitRef r;
   r.g = a.seg_ptr[s] + j;
@@ -153,10 +152,12 @@ template <bool kScatter>
 __device__ __forceinline__ void move_units(const PeerArgs& a, int i0, int stride) {
   constexpr int R = 4;
   const float4* result = result_of(a.peer[a.rank], a.result4);
+  int seg = 0;                                   // plain destination order 0..N-1: the units of a thread only increase
   for (int k0 = 0; k0 < a.world; ++k0) {
     // destinations in plain order; the rotated order (rank + 1, rank + 2, ..: every rank on a different peer at any
     // moment) measured no better on NVSwitch (tools/peer_time.py, mode bit 1)
     const int r = (a.mode & 2) ? (a.rank + 1 + k0) % a.world : k0;
+    if (a.mode & 2) seg = 0;                     // rotated order (experiment switch): the cursor restarts per slice
     const long base = (long)r * a.slice4;
     float4* inbox = inbox_of(a.peer[r]) + (long)a.rank * a.slice4;
     for (long i = i0; i < a.slice4; i += (long)R * stride) {
@@ -166,7 +167,7 @@ __device__ __forceinline__ void move_units(const PeerArgs& a, int i0, int stride
       for (int k = 0; k < R; ++k) {
         const long ik = i + (long)k * stride;
         if (ik < a.slice4) {
-          ref[k] = locate_unit(a, base + ik);
+          ref[k] = locate_unit(a, base + ik, seg);
           v[k] = kScatter ? load_unit(ref[k]) : ld_sys_f4(result + base + ik);
         }
       }

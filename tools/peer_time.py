@@ -6,7 +6,9 @@ from ctcvr_b200.dist import PeerGradExchange
 rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 dev = torch.device("cuda", local); torch.cuda.set_device(dev)
 dist.init_process_group("nccl", device_id=dev)
-sizes = [512 * 512, 512, 512 * 512, 512, 412 * 512, 412, 1]
+sizes = [512 * 512, 512, 512 * 512, 512, 412 * 512, 412, 1]        # the joint's parameters (2.95 MB)
+if os.environ.get("PAYLOAD") == "predictor":                         # + the predictor at H = 512: 13.2 MB
+    sizes += [412 * 512, 2048 * 512, 2048 * 512, 2048, 2048, 512 * 512, 512]
 xs = [torch.randn(n, device=dev) for n in sizes]
 def timeit(f, n=200):
     for _ in range(10): f()
