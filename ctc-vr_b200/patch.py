@@ -178,8 +178,13 @@ def _make_prefix_beam_search(seq_cls):
 
 
 # ------------------------------------------------------------------------------------------------ install
-def install(namespace=None) -> Dict[str, List[str]]:
-    """Patch whatever of the reference is present in `namespace` (None: import it).  Returns what was patched."""
+def install(namespace=None, precision: Optional[str] = None) -> Dict[str, List[str]]:
+    """Patch whatever of the reference is present in `namespace` (None: import it).  Returns what was patched.
+    `precision` ("fp32" | "bf16") becomes the class default of the patched `Transducer` (the fused loss reads
+    `self.precision`, fp32 when absent), so an unchanged train script opts into the tcgen05 path with
+    `install(precision="bf16")`; a model instance can still override it with its own `precision` attribute."""
+    if precision not in (None, "fp32", "bf16"):
+        raise ValueError("precision must be None, 'fp32' or 'bf16'")
     done: Dict[str, List[str]] = {}
 
     def note(mod, name):
@@ -194,6 +199,9 @@ def install(namespace=None) -> Dict[str, List[str]]:
         if hasattr(m, "Transducer"):
             _set(m.Transducer, "_compute_rnnt_loss", _transducer_compute_rnnt_loss)
             note("transducer", "Transducer._compute_rnnt_loss")
+            if precision is not None:
+                _set(m.Transducer, "precision", precision)
+                note("transducer", f"Transducer.precision = {precision}")
         if hasattr(m, "basic_greedy_search"):
             _set(m, "basic_greedy_search", D.basic_greedy_search)
             note("transducer", "basic_greedy_search")

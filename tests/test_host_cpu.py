@@ -116,6 +116,27 @@ def test_bucketed_step_host_logic_and_peer_exchange_fail_loudly():
             _lib.call("ctcvr_peer_create", 0, 2, 1024, ctypes.byref(ctx), handle)
 
 
+def test_patch_install_precision_default_and_uninstall():
+    """patch.install(namespace, precision=...) on stand-in modules: the patched Transducer class gets the precision
+    default, uninstall restores everything; an unknown precision is rejected."""
+    import types
+    import ctcvr_b200 as C
+
+    class Transducer:
+        def _compute_rnnt_loss(self, *a):
+            return "reference"
+
+    ns = types.SimpleNamespace(transducer=types.SimpleNamespace(Transducer=Transducer, basic_greedy_search=lambda *a: "ref"))
+    done = C.patch.install(ns, precision="bf16")
+    assert "Transducer._compute_rnnt_loss" in done["transducer"] and Transducer.precision == "bf16"
+    assert Transducer._compute_rnnt_loss is not None and ns.transducer.basic_greedy_search is C.basic_greedy_search
+    C.patch.uninstall()
+    assert not hasattr(Transducer, "precision") and Transducer()._compute_rnnt_loss() == "reference"
+    assert ns.transducer.basic_greedy_search() == "ref"
+    with pytest.raises(ValueError):
+        C.patch.install(ns, precision="fp16")
+
+
 def test_shard_bounds():
     from ctcvr_b200.dist import shard_bounds
     for n, w in ((256, 8), (10, 4), (3, 8)):
