@@ -426,57 +426,74 @@ int ctc_loss(const float* lp, const int64_t* targets, const int32_t* in_lens, co
   return 0;
 }
 
-// ---------------------------------------------------------------- CTC greedy: one CTA per utterance
-__global__ void ctc_greedy_kernel(const float* __restrict__ scores, const int32_t* __restrict__ lens,
-                                  int32_t* __restrict__ out_tokens, int32_t* __restrict__ out_lens, int T, int V,
-                                  int blank) {
-  extern __shared__ int ids[];      // [T]
-  const int b = blockIdx.x;
-  const int Tb = min(lens[b], T);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int t = warp; t < Tb; t += nw) {
-    const float* x = scores + ((size_t)b * T + t) * V;
-    float best = kNegInf;
-    int bi = V;
+// ---------------------------------------------------------------- CTC greedy (A10)
+// Two launches.  (1) argmax of every frame, one warp per frame, frames of all utterances spread over the whole GPU (one
+// CTA per utterance - the first version - left 116 of 148 SMs idle at B = 32 and walked 62 frames per warp in sequence:
+// 130 us for 26 MB).  First maximum = lowest index on ties, as torch.argmax / topk(1).  The ids land in the output token
+// array itself.  (2) collapse in place, one warp per utterance: keep[t] = id != blank && id != id[t-1], ordered
+// compaction by ballot; a 32-frame group is read before anything of it is overwritten and writes only go to positions
+// <= the ones already read.
+constexpr int GREEDY_FRAMES_PER_CTA = 8;         // 8 warps, one frame each
+__global__ void __launch_bounds__(256) ctc_argmax_kernel(const float* __restrict__ scores, const int32_t* __restrict__ lens,
+                                                         int32_t* __restrict__ ids, int T, int V) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y, t = blockIdx.x * GREEDY_FRAMES_PER_CTA + warp;
+  if (t >= min(lens[b], T)) return;
+  const float* x = scores + ((size_t)b * T + t) * V;
+  float best = kNegInf;
+  int bi = V;
+  if ((V & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0)) {
+    for (int v = 4 * lane; v < V; v += 128) {          // ascending within the lane: the first maximum survives
+      const float4 q = __ldg(reinterpret_cast<const float4*>(x + v));
+      if (q.x > best) { best = q.x; bi = v; }
+      if (q.y > best) { best = q.y; bi = v + 1; }
+      if (q.z > best) { best = q.z; bi = v + 2; }
+      if (q.w > best) { best = q.w; bi = v + 3; }
+    }
+  } else {
     for (int v = lane; v < V; v += 32) {
-      float xv = x[v];
-      if (xv > best) { best = xv; bi = v; }          // first maximum within the lane (ascending v)
+      const float xv = x[v];
+      if (xv > best) { best = xv; bi = v; }
     }
+  }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-    }
-    if (lane == 0) ids[t] = bi;
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
   }
-  __syncthreads();
-  if (warp == 0) {                  // keep[t] = id!=blank && id!=id[t-1]; ordered compaction by ballot
-    int count = 0;
-    for (int t0 = 0; t0 < Tb; t0 += 32) {
-      int t = t0 + lane;
-      bool keep = false;
-      int id = 0;
-      if (t < Tb) {
-        id = ids[t];
-        int prev = (t > 0) ? ids[t - 1] : -1;
-        keep = (id != blank) && (id != prev);
-      }
-      unsigned m = __ballot_sync(0xffffffffu, keep);
-      if (keep) out_tokens[(size_t)b * T + count + __popc(m & ((1u << lane) - 1))] = id;
-      count += __popc(m);
-    }
-    if (lane == 0) out_lens[b] = count;
+  if (lane == 0) ids[(size_t)b * T + t] = bi;
+}
+
+__global__ void __launch_bounds__(128) ctc_collapse_kernel(const int32_t* __restrict__ lens, int32_t* __restrict__ tokens,
+                                                           int32_t* __restrict__ out_lens, int B, int T, int blank) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int Tb = min(lens[b], T);
+  int32_t* row = tokens + (size_t)b * T;
+  int count = 0, carry = -1;                      // carry = id of the frame in front of the group
+  for (int t0 = 0; t0 < Tb; t0 += 32) {
+    const int t = t0 + lane;
+    const int id = (t < Tb) ? row[t] : blank;
+    int prev = __shfl_up_sync(0xffffffffu, id, 1);
+    if (lane == 0) prev = carry;
+    carry = __shfl_sync(0xffffffffu, id, 31);
+    const bool keep = (t < Tb) && (id != blank) && (id != prev);
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();                                 // every lane holds its id before the group is overwritten
+    if (keep) row[count + __popc(m & ((1u << lane) - 1))] = id;
+    count += __popc(m);
   }
+  if (lane == 0) out_lens[b] = count;
 }
 
 int ctc_greedy(const float* scores, const int32_t* lens, int32_t* out_tokens, int32_t* out_lens, int B, int T, int V,
                int blank, cudaStream_t st) {
   if (B == 0) return 0;
-  size_t smem = (size_t)T * sizeof(int);
-  CTCVR_REQUIRE(smem <= 200 * 1024, "ctc_greedy: T=%d too long", T);
-  CTCVR_CHECK_CUDA(cudaFuncSetAttribute(ctc_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ctc_greedy_kernel<<<B, 256, smem, st>>>(scores, lens, out_tokens, out_lens, T, V, blank);
+  ctc_argmax_kernel<<<dim3(cdiv(T, GREEDY_FRAMES_PER_CTA), B), 256, 0, st>>>(scores, lens, out_tokens, T, V);
+  CTCVR_LAUNCH_CHECK();
+  ctc_collapse_kernel<<<cdiv(B, 4), 128, 0, st>>>(lens, out_tokens, out_lens, B, T, blank);
   CTCVR_LAUNCH_CHECK();
   return 0;
 }

@@ -120,10 +120,10 @@ def greedy_batch(model, encoder_out, encoder_out_lens, n_steps: int, h=None, c=N
     with torch.cuda.device(dev):
         call("ctcvr_rnnt_greedy", ctypes.byref(w), ptr(ep), ptr(lens), ptr(h), ptr(c), ptr(last_token), ptr(toks),
              ptr(nout), N, T, max_out, blank, int(n_steps), None, 0, stream())
-    nh = nout.cpu()
-    width = int(nh.max()) if N > 0 else 0
-    th = toks[:, :max(width, 1)].cpu()
-    hyps = [th[i, :int(nh[i])].tolist() for i in range(N)]
+    nh = nout.cpu().tolist()
+    width = max(nh) if N > 0 else 0
+    th = toks[:, :max(width, 1)].cpu().numpy()          # numpy rows: per-utterance slicing of a torch tensor costs ~5 us each
+    hyps = [th[i, :nh[i]].tolist() for i in range(N)]
     return hyps, h, c, last_token
 
 
@@ -244,11 +244,13 @@ def beam_search_batch(model, encoder_out: torch.Tensor, encoder_out_lens: torch.
         call("ctcvr_rnnt_beam_reset_batch", ptr(states), ctypes.byref(w), S, beam, int(n_steps), mo, stream())
         call("ctcvr_rnnt_beam_chunk_batch", ctypes.byref(w), ptr(ep), ptr(lens), S, T, ptr(states), beam, int(n_steps), mo,
              blank, ptr(out_n), ptr(out_tok), ptr(out_len), ptr(out_sc), ptr(out_h), ptr(out_c), stream())
-    ns, ls, toks, sc = out_n.cpu(), out_len.cpu(), out_tok.cpu(), out_sc.cpu()
+    ns, ls, sc = out_n.cpu().tolist(), out_len.cpu().numpy(), out_sc.cpu().numpy()
+    width = max(int(ls.max()), 1)                           # only the used part of the token arrays crosses PCIe
+    toks = out_tok[:, :, :width].contiguous().cpu().numpy()
     res = []
     for s_ in range(S):
-        res.append([BeamHypothesis(toks[s_, i, :int(ls[s_, i])].tolist(), float(sc[s_, i]),
-                                   [out_h[s_, i].unsqueeze(1), out_c[s_, i].unsqueeze(1)]) for i in range(int(ns[s_]))])
+        res.append([BeamHypothesis(toks[s_, i, :ls[s_, i]].tolist(), float(sc[s_, i]),
+                                   [out_h[s_, i].unsqueeze(1), out_c[s_, i].unsqueeze(1)]) for i in range(ns[s_])])
     return res
 
 
@@ -309,5 +311,7 @@ def prefix_beam_search_batch(model, encoder_out: torch.Tensor, encoder_out_lens:
         call("ctcvr_rnnt_prefix_beam_batch", ctypes.byref(w), ptr(ep), ptr(cl), ptr(lens), S, T, beam, blank,
              float(ctc_weight), float(transducer_weight), ptr(out_n), ptr(out_tok), ptr(out_len), ptr(out_sc), ptr(ws),
              ws.numel(), stream())
-    ns, ls, toks, sc = out_n.cpu(), out_len.cpu(), out_tok.cpu(), out_sc.cpu()
-    return [[(toks[s_, i, :int(ls[s_, i])].tolist(), float(sc[s_, i])) for i in range(int(ns[s_]))] for s_ in range(S)]
+    ns, ls, sc = out_n.cpu().tolist(), out_len.cpu().numpy(), out_sc.cpu().numpy()
+    width = max(int(ls.max()), 1)
+    toks = out_tok[:, :, :width].contiguous().cpu().numpy()
+    return [[(toks[s_, i, :ls[s_, i]].tolist(), float(sc[s_, i])) for i in range(ns[s_])] for s_ in range(S)]

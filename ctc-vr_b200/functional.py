@@ -277,9 +277,10 @@ def ctc_greedy_search(scores, lens, blank: int):
     B, T, V = x.shape
     dev = x.device
     ln = _i32c(lens, dev)
-    toks = torch.empty((B, T), dtype=torch.int32, device=dev)
-    n = torch.empty((B,), dtype=torch.int32, device=dev)
+    buf = torch.empty((B * T + B,), dtype=torch.int32, device=dev)      # tokens [B,T] | lengths [B]: one D2H copy
+    toks, n = buf[:B * T].view(B, T), buf[B * T:]
     with torch.cuda.device(dev):
         call("ctcvr_ctc_greedy", ptr(x), ptr(ln), ptr(toks), ptr(n), B, T, V, int(blank), stream())
-    toks_h, n_h = toks.cpu(), n.cpu()
-    return [toks_h[b, :int(n_h[b])].tolist() for b in range(B)]
+    host = buf.cpu().numpy()
+    toks_h, n_h = host[:B * T].reshape(B, T), host[B * T:].tolist()
+    return [toks_h[b, :n_h[b]].tolist() for b in range(B)]

@@ -52,12 +52,15 @@ def ctc_prefix_beam_search(ctc_probs: torch.Tensor, ctc_lens: torch.Tensor, beam
         ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
         call("ctcvr_ctc_prefix_beam", ptr(x), ptr(lens), B, T, V, beam, int(blank_id), ptr(out_n), ptr(out_tok),
              ptr(out_len), ptr(out_sc), ptr(out_tm), ptr(ws), ws.numel(), stream())
-    n_h, tok_h, len_h, sc_h, tm_h = out_n.cpu(), out_tok.cpu(), out_len.cpu(), out_sc.cpu(), out_tm.cpu()
+    n_h, len_h, sc_h = out_n.cpu().tolist(), out_len.cpu().numpy(), out_sc.cpu().numpy()
+    width = max(int(len_h.max()), 1)                        # only the used part of the token / time arrays crosses PCIe
+    tok_h = out_tok[:, :, :width].contiguous().cpu().numpy()
+    tm_h = out_tm[:, :, :width].contiguous().cpu().numpy()
     results = []
     for b in range(B):
-        n = int(n_h[b])
-        nbest = [tuple(tok_h[b, i, :int(len_h[b, i])].tolist()) for i in range(n)]
-        times = [tm_h[b, i, :int(len_h[b, i])].tolist() for i in range(n)]
+        n = n_h[b]
+        nbest = [tuple(tok_h[b, i, :len_h[b, i]].tolist()) for i in range(n)]
+        times = [tm_h[b, i, :len_h[b, i]].tolist() for i in range(n)]
         scores = [float(sc_h[b, i]) for i in range(n)]
         results.append(DecodeResult(tokens=nbest[0], score=scores[0], times=times[0], nbest=nbest,
                                     nbest_scores=scores, nbest_times=times))
