@@ -399,8 +399,12 @@ int rnnt_beam_chunk(const ctcvr_decoder_weights& w, const float* enc_proj, const
   CTCVR_REQUIRE(w.V - 1 >= 1, "rnnt_beam: vocabulary too small");
   const size_t lim = 220 * 1024;
   // one warp per hypothesis inside a group: the candidate append order (hypothesis-major) needs NB <= #warps
-  if (beam > 8 && beam_smem<16>(w) <= lim)
+  // the lock-step group is as wide as the template: 12 slots for beams of 9..12 (beam 10 of BASELINE.json's cfg5 would
+  // otherwise spend 6 of 16 FMA lanes per weight on empty slots)
+  if (beam > 12 && beam_smem<16>(w) <= lim)
     return launch_beam_chunk<16>(w, enc_proj, chunk_lens, S, T, state, beam, n_steps, max_out, blank, out_n, out_tokens, out_lens, out_scores, out_h, out_c, st);
+  if (beam > 8 && beam_smem<12>(w) <= lim)
+    return launch_beam_chunk<12>(w, enc_proj, chunk_lens, S, T, state, beam, n_steps, max_out, blank, out_n, out_tokens, out_lens, out_scores, out_h, out_c, st);
   if (beam > 4 && beam_smem<8>(w) <= lim)
     return launch_beam_chunk<8>(w, enc_proj, chunk_lens, S, T, state, beam, n_steps, max_out, blank, out_n, out_tokens, out_lens, out_scores, out_h, out_c, st);
   if (beam > 1 && beam_smem<4>(w) <= lim)
@@ -661,7 +665,8 @@ int rnnt_prefix_beam(const ctcvr_decoder_weights& w, const float* enc_proj, cons
   CTCVR_REQUIRE(ws && ws_bytes >= (size_t)S * rnnt_prefix_beam_ws_bytes(w, beam, T),
                 "rnnt_prefix_beam: workspace too small (%d x ctcvr_rnnt_prefix_beam_ws_bytes)", S);
   const size_t lim = 220 * 1024;
-  if (beam > 8 && beam_smem<16>(w) <= lim) return launch_prefix<16>(w, enc_proj, ctc_logp, lens, S, T, beam, blank, ctc_weight, transducer_weight, out_n, out_tokens, out_lens, out_scores, ws, st);
+  if (beam > 12 && beam_smem<16>(w) <= lim) return launch_prefix<16>(w, enc_proj, ctc_logp, lens, S, T, beam, blank, ctc_weight, transducer_weight, out_n, out_tokens, out_lens, out_scores, ws, st);
+  if (beam > 8 && beam_smem<12>(w) <= lim) return launch_prefix<12>(w, enc_proj, ctc_logp, lens, S, T, beam, blank, ctc_weight, transducer_weight, out_n, out_tokens, out_lens, out_scores, ws, st);
   if (beam > 4 && beam_smem<8>(w) <= lim) return launch_prefix<8>(w, enc_proj, ctc_logp, lens, S, T, beam, blank, ctc_weight, transducer_weight, out_n, out_tokens, out_lens, out_scores, ws, st);
   if (beam > 1 && beam_smem<4>(w) <= lim) return launch_prefix<4>(w, enc_proj, ctc_logp, lens, S, T, beam, blank, ctc_weight, transducer_weight, out_n, out_tokens, out_lens, out_scores, ws, st);
   CTCVR_REQUIRE(beam_smem<1>(w) <= lim, "rnnt_prefix_beam: predictor too large for shared memory (H=%d L=%d)", w.H, w.L);

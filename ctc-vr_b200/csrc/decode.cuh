@@ -11,33 +11,88 @@ namespace ctcvr {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
+// two IEEE fp32 FMAs in one instruction (FFMA2, sm_100+): {d.lo, d.hi} = {a.lo * b.lo + c.lo, a.hi * b.hi + c.hi} -
+// bit-identical to two fmaf() calls, half the issue slots
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
 // out[j][n] = init(j,n) + sum_k Wt[k*J + j] * xs[k*NB + n]   for j in [0,J)
+// Per output row the sum runs over k in ascending order with one fused multiply-add per term - the same arithmetic for
+// every NB and for the packed form, so hypotheses do not depend on how many advance in lock-step.
+// 16 weight loads in flight per thread: with 4, a 512-thread CTA kept ~8 KB in flight against an L2 latency of ~600
+// cycles (~25 GB/s per SM) and the weight stream, not the FMAs, set the step time.  The loop is then issue-bound
+// (NB FMAs + NB/4 shared loads per weight and thread): the packed FFMA2 halves the FMA issue slots.
 template <int NB, class Init, class Store>
 __device__ __forceinline__ void gemv_t(const float* __restrict__ Wt, int J, int K, const float* xs, Init init,
                                        Store store) {
-  for (int j = threadIdx.x; j < J; j += blockDim.x) {
-    float acc[NB];
+  if constexpr (NB % 2 == 0) {
+    constexpr int NP = NB / 2;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+      unsigned long long acc[NP];
 #pragma unroll
-    for (int n = 0; n < NB; ++n) acc[n] = init(j, n);
-    // 16 weight loads in flight per thread: with 4, a 512-thread CTA kept ~8 KB in flight against an L2 latency of
-    // ~600 cycles (~25 GB/s per SM) and the weight stream, not the FMAs, set the step time
-    int k = 0;
-    for (; k + 16 <= K; k += 16) {
-      float w[16];
+      for (int m = 0; m < NP; ++m) acc[m] = pack2(init(j, 2 * m), init(j, 2 * m + 1));
+      int k = 0;
+      for (; k + 16 <= K; k += 16) {
+        float w[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) w[i] = __ldg(Wt + (size_t)(k + i) * J + j);
+        for (int i = 0; i < 16; ++i) w[i] = __ldg(Wt + (size_t)(k + i) * J + j);
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
+        for (int i = 0; i < 16; ++i) {
+          const unsigned long long wp = pack2(w[i], w[i]);
+          const unsigned long long* xr = reinterpret_cast<const unsigned long long*>(xs + (size_t)(k + i) * NB);
 #pragma unroll
-        for (int n = 0; n < NB; ++n) acc[n] = fmaf(w[i], xs[(k + i) * NB + n], acc[n]);
+          for (int m = 0; m < NP; ++m) acc[m] = fma2(wp, xr[m], acc[m]);
+        }
+      }
+      for (; k < K; ++k) {
+        const float w = __ldg(Wt + (size_t)k * J + j);
+        const unsigned long long wp = pack2(w, w);
+        const unsigned long long* xr = reinterpret_cast<const unsigned long long*>(xs + (size_t)k * NB);
+#pragma unroll
+        for (int m = 0; m < NP; ++m) acc[m] = fma2(wp, xr[m], acc[m]);
+      }
+#pragma unroll
+      for (int m = 0; m < NP; ++m) {
+        float lo, hi;
+        unpack2(acc[m], lo, hi);
+        store(j, 2 * m, lo);
+        store(j, 2 * m + 1, hi);
+      }
     }
-    for (; k < K; ++k) {
-      const float w = __ldg(Wt + (size_t)k * J + j);
+  } else {
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+      float acc[NB];
 #pragma unroll
-      for (int n = 0; n < NB; ++n) acc[n] = fmaf(w, xs[k * NB + n], acc[n]);
+      for (int n = 0; n < NB; ++n) acc[n] = init(j, n);
+      int k = 0;
+      for (; k + 16 <= K; k += 16) {
+        float w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = __ldg(Wt + (size_t)(k + i) * J + j);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+#pragma unroll
+          for (int n = 0; n < NB; ++n) acc[n] = fmaf(w[i], xs[(k + i) * NB + n], acc[n]);
+      }
+      for (; k < K; ++k) {
+        const float w = __ldg(Wt + (size_t)k * J + j);
+#pragma unroll
+        for (int n = 0; n < NB; ++n) acc[n] = fmaf(w, xs[k * NB + n], acc[n]);
+      }
+#pragma unroll
+      for (int n = 0; n < NB; ++n) store(j, n, acc[n]);
     }
-#pragma unroll
-    for (int n = 0; n < NB; ++n) store(j, n, acc[n]);
   }
 }
 
