@@ -14,6 +14,7 @@ namespace ctcvr {
 constexpr int BM_THREADS = 512;
 constexpr int BM_BEAM_MAX = 16;
 constexpr int BM_STEPS_MAX = 16;
+constexpr int BM_SORT_SMEM = 512;          // candidates whose scores are sorted from shared memory (A7)
 
 // ---- beam state (device, opaque to the caller) ------------------------------------------------------------
 // header | per buffer (x2): lens[beam] | scores[beam] (f64) | tokens[beam][max_out] | h[beam][L*H] | c[beam][L*H]
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(BM_THREADS, 1) rnnt_beam_chunk_kernel(
   __shared__ double sh_lp[NB];
   __shared__ unsigned long long sh_hash[NB][BM_STEPS_MAX + 1];    // hash of hyp tokens + walk prefix
   __shared__ int sh_ncand, sh_any, sh_keep[BM_BEAM_MAX], sh_nkeep;
+  __shared__ double sh_sc[BM_SORT_SMEM];
 
   int buf = hdr[1];
   const int k = min(beam, V - 1);
@@ -310,14 +312,30 @@ __global__ void __launch_bounds__(BM_THREADS, 1) rnnt_beam_chunk_kernel(
     __syncthreads();
     const int nc = sh_ncand;
     int* c_list = c_rank + lay.ncand;
-    for (int a = tid; a < nc; a += BM_THREADS) {
-      const double sa = c_score[c_list[a]];
-      int rank = 0;
-      for (int bq = 0; bq < nc; ++bq) {
-        const double sb = c_score[c_list[bq]];
-        rank += (sb > sa) || (sb == sa && bq < a);
+    if (nc <= BM_SORT_SMEM) {
+      // the scores of the compact list staged in shared memory: the rank loop otherwise makes nc^2 dependent pairs of
+      // global loads (c_list -> c_score), 8 % of the kernel in the cycle-counter build
+      for (int a = tid; a < nc; a += BM_THREADS) sh_sc[a] = c_score[c_list[a]];
+      __syncthreads();
+      for (int a = tid; a < nc; a += BM_THREADS) {
+        const double sa = sh_sc[a];
+        int rank = 0;
+        for (int bq = 0; bq < nc; ++bq) {
+          const double sb = sh_sc[bq];
+          rank += (sb > sa) || (sb == sa && bq < a);
+        }
+        c_rank[rank] = c_list[a];
       }
-      c_rank[rank] = c_list[a];
+    } else {
+      for (int a = tid; a < nc; a += BM_THREADS) {
+        const double sa = c_score[c_list[a]];
+        int rank = 0;
+        for (int bq = 0; bq < nc; ++bq) {
+          const double sb = c_score[c_list[bq]];
+          rank += (sb > sa) || (sb == sa && bq < a);
+        }
+        c_rank[rank] = c_list[a];
+      }
     }
     __syncthreads();
     // ---- de-duplicate by token sequence, first occurrence wins, stop at `beam`
@@ -352,15 +370,15 @@ __global__ void __launch_bounds__(BM_THREADS, 1) rnnt_beam_chunk_kernel(
     __syncthreads();
     // ---- new beam into the other buffer
     const int nk = sh_nkeep, nbuf = buf ^ 1;
-    for (int e = 0; e < nk; ++e) {
+    for (int e = warp; e < nk; e += nwarp) {                 // one warp per kept hypothesis: the copies' latencies overlap
       const int c = sh_keep[e];
       const int j = c_src[c] & 0xff, st = c_src[c] >> 8;
       const int len = min(c_len[c], max_out);
-      for (int pos = tid; pos < len; pos += BM_THREADS) b_tok(nbuf)[(size_t)e * max_out + pos] = tok_at(c, pos);
+      for (int pos = lane; pos < len; pos += 32) b_tok(nbuf)[(size_t)e * max_out + pos] = tok_at(c, pos);
       // blank candidate keeps the state before step st, a token candidate takes the state after it
       const float* cj = chain + ((size_t)j * (n_steps + 1) + st) * 2 * LH + (c_extra[c] >= 0 ? 2 * LH : 0);
-      for (int i = tid; i < LH; i += BM_THREADS) { b_h(nbuf)[(size_t)e * LH + i] = cj[i]; b_c(nbuf)[(size_t)e * LH + i] = cj[LH + i]; }
-      if (tid == 0) { b_len(nbuf)[e] = len; b_score(nbuf)[e] = c_score[c]; }
+      for (int i = lane; i < LH; i += 32) { b_h(nbuf)[(size_t)e * LH + i] = cj[i]; b_c(nbuf)[(size_t)e * LH + i] = cj[LH + i]; }
+      if (lane == 0) { b_len(nbuf)[e] = len; b_score(nbuf)[e] = c_score[c]; }
     }
     __syncthreads();
     if (tid == 0) { hdr[0] = nk; hdr[1] = nbuf; }
