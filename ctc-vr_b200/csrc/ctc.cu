@@ -212,6 +212,11 @@ static CtcWs carve_ctc_ws(void* ws, int B, int T, int Sp) {
   return w;
 }
 
+// NJ > 0: ONE warp per direction, lane l owns the NJ consecutive states l*NJ .. l*NJ+NJ-1 (Sp = 32 NJ), so the neighbours
+// s-1 / s-2 (alpha) and s+1 / s+2 (beta) are registers of the same lane or two shuffles away - no shared-memory exchange and
+// no barrier on the T dependent steps (the barrier form below, NJ = 0, spent ~500 cycles per step on a chain of ~170).
+// Same operations per state as the barrier form, in the same order: bit-identical alpha / beta.
+template <int NJ>
 __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lp, const int64_t* __restrict__ targets,
                                       const int32_t* __restrict__ in_lens, const int32_t* __restrict__ tgt_lens,
                                       float* __restrict__ nll_out, float* __restrict__ alpha_ws,
@@ -267,9 +272,103 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lp, const int64_
     }
     return;
   }
-  const int lab = lab_s[s];
   float* ga = alpha_ws + (size_t)b * T * Sp;
   float* gbt = beta_ws + (size_t)b * T * Sp;
+  if (NJ > 0) {
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp > 1) return;
+    constexpr int NQ = NJ > 0 ? NJ : 1;
+    const int s0 = lane * NQ;
+    bool live[NQ], skp[NQ];
+    float prev[NQ], xn[NQ];
+    if (warp == 0) {
+      // ---- alpha_t(s) = lse(alpha_{t-1}(s), alpha_{t-1}(s-1), [alpha_{t-1}(s-2)]) + lp_t(label(s))
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const int q = s0 + i;
+        live[i] = q < S;
+        skp[i] = (q < S && (q & 1) && q >= 2) && (lab_s[q] != lab_s[q - 2]);
+        prev[i] = (live[i] && q < 2) ? sel[q] : kCtcNeg;
+        ga[q] = prev[i];
+        xn[i] = (live[i] && Tb > 1) ? sel[S + q] : kCtcNeg;
+      }
+      for (int t = 1; t < Tb; ++t) {
+        float x[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) x[i] = xn[i];
+        if (t + 1 < Tb) {
+#pragma unroll
+          for (int i = 0; i < NQ; ++i) xn[i] = live[i] ? sel[(t + 1) * S + s0 + i] : kCtcNeg;     // next step's log-probs
+        }
+        // states s0 - 1 and s0 - 2 live in the lane below
+        float m1 = __shfl_up_sync(0xffffffffu, prev[NQ - 1], 1);
+        float m2 = (NQ >= 2) ? __shfl_up_sync(0xffffffffu, prev[NQ >= 2 ? NQ - 2 : 0], 1) : __shfl_up_sync(0xffffffffu, prev[0], 2);
+        if (lane == 0) { m1 = kCtcNeg; m2 = kCtcNeg; }
+        if (NQ == 1 && lane == 1) m2 = kCtcNeg;
+        float nv[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          const float a1 = (i >= 1) ? prev[i >= 1 ? i - 1 : 0] : m1;
+          const float a2 = (i >= 2) ? prev[i >= 2 ? i - 2 : 0] : (i == 1 ? m1 : m2);
+          float v = ctc_lse3(prev[i], a1, skp[i] ? a2 : kCtcNeg) + x[i];
+          nv[i] = live[i] ? fmaxf(v, kCtcNeg) : kCtcNeg;
+        }
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) { prev[i] = nv[i]; ga[(size_t)t * Sp + s0 + i] = nv[i]; }
+      }
+      // log-likelihood = lse(alpha_{T-1}(S-1), alpha_{T-1}(S-2)): fetch the two states from their lanes
+      float a1 = kCtcNeg, a2 = kCtcNeg;
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const float v1 = __shfl_sync(0xffffffffu, prev[i], (S - 1) / NQ);
+        const float v2 = __shfl_sync(0xffffffffu, prev[i], S > 1 ? (S - 2) / NQ : 0);
+        if ((S - 1) % NQ == i) a1 = v1;
+        if (S > 1 && (S - 2) % NQ == i) a2 = v2;
+      }
+      if (lane == 0) {
+        const float ll = ctc_lse3(a1, a2, kCtcNeg);
+        const bool inf = ll < -1.0e29f;
+        nll_out[b] = inf ? (zero_infinity ? 0.f : INFINITY) : -ll;
+        flags[b] = inf ? 1 : 0;
+      }
+    } else {
+      // ---- beta_t(s) = lse(beta_{t+1}(s), beta_{t+1}(s+1), [beta_{t+1}(s+2)]) + lp_t(label(s))
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const int q = s0 + i;
+        live[i] = q < S;
+        skp[i] = (q < S && (q & 1) && q + 2 < S) && (lab_s[q] != lab_s[q + 2]);
+        prev[i] = (live[i] && q >= S - 2) ? sel[(Tb - 1) * S + q] : kCtcNeg;
+        gbt[(size_t)(Tb - 1) * Sp + q] = prev[i];
+        xn[i] = (live[i] && Tb > 1) ? sel[(Tb - 2) * S + q] : kCtcNeg;
+      }
+      for (int t = Tb - 2; t >= 0; --t) {
+        float x[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) x[i] = xn[i];
+        if (t >= 1) {
+#pragma unroll
+          for (int i = 0; i < NQ; ++i) xn[i] = live[i] ? sel[(t - 1) * S + s0 + i] : kCtcNeg;
+        }
+        float p1 = __shfl_down_sync(0xffffffffu, prev[0], 1);
+        float p2 = (NQ >= 2) ? __shfl_down_sync(0xffffffffu, prev[NQ >= 2 ? 1 : 0], 1) : __shfl_down_sync(0xffffffffu, prev[0], 2);
+        if (lane == 31) { p1 = kCtcNeg; p2 = kCtcNeg; }
+        if (NQ == 1 && lane == 30) p2 = kCtcNeg;
+        float nv[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          const float b1 = (i + 1 < NQ) ? prev[i + 1 < NQ ? i + 1 : 0] : p1;
+          const float b2 = (i + 2 < NQ) ? prev[i + 2 < NQ ? i + 2 : 0] : (i + 1 < NQ ? p1 : p2);
+          float v = ctc_lse3(prev[i], b1, skp[i] ? b2 : kCtcNeg) + x[i];
+          nv[i] = live[i] ? fmaxf(v, kCtcNeg) : kCtcNeg;
+        }
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) { prev[i] = nv[i]; gbt[(size_t)t * Sp + s0 + i] = nv[i]; }
+      }
+    }
+    return;
+  }
+  const int lab = lab_s[s];
   if (grp == 0) {
     // ---- alpha_t(s) = lse(alpha_{t-1}(s), alpha_{t-1}(s-1), [alpha_{t-1}(s-2)]) + lp_t(label(s))
     const bool skip = (s < S && (s & 1) && s >= 2) && (lab != lab_s[s - 2]);
@@ -402,9 +501,24 @@ int ctc_loss(const float* lp, const int64_t* targets, const int32_t* in_lens, co
   if (smemA <= 220 * 1024 && 2 * Sp <= 1024) {
     CtcWs W = carve_ctc_ws(ws, B, T, Sp);
     const int threads = 2 * Sp < 256 ? 256 : 2 * Sp;
-    CTCVR_CHECK_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-    ctc_alpha_beta_kernel<<<B, threads, smemA, st>>>(lp, targets, in_lens, tgt_lens, nll, W.alpha, W.beta, W.meta, W.flags,
-                                                     T, V, Umax, Sp, blank, zero_infinity);
+#define CTCVR_AB_LAUNCH(NJ_)                                                                                                   \
+  do {                                                                                                                       \
+    CTCVR_CHECK_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel<NJ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA)); \
+    ctc_alpha_beta_kernel<NJ_><<<B, threads, smemA, st>>>(lp, targets, in_lens, tgt_lens, nll, W.alpha, W.beta, W.meta, W.flags, \
+                                                          T, V, Umax, Sp, blank, zero_infinity);                              \
+  } while (0)
+    switch (Sp / 32) {                       // states per lane of the shuffle form; longer targets take the barrier form
+      case 1: CTCVR_AB_LAUNCH(1); break;
+      case 2: CTCVR_AB_LAUNCH(2); break;
+      case 3: CTCVR_AB_LAUNCH(3); break;
+      case 4: CTCVR_AB_LAUNCH(4); break;
+      case 5: CTCVR_AB_LAUNCH(5); break;
+      case 6: CTCVR_AB_LAUNCH(6); break;
+      case 7: CTCVR_AB_LAUNCH(7); break;
+      case 8: CTCVR_AB_LAUNCH(8); break;
+      default: CTCVR_AB_LAUNCH(0); break;
+    }
+#undef CTCVR_AB_LAUNCH
     CTCVR_LAUNCH_CHECK();
     if (grad) {
       const size_t smemB = ((size_t)7 * Sp + (size_t)4 * V) * sizeof(float);
