@@ -502,9 +502,11 @@ joint_bwd3_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
       mbar_wait(L.tmem_full(), ph, 30);
       if (tid == 128) TC_PROF(2, 2);
       tc_fence_after();
-      // 16-column pieces (two per 32-column chunk wg, wg+3, ..); the next piece's TMEM load is in flight during the math
-      const int npieces = 2 * ((p.Vp / 32 - wg + 2) / 3);
-      auto piece_col = [&](int i) { return wg * 32 + (i >> 1) * 96 + (i & 1) * 16; };
+      // 16-column pieces wg, wg+3, ..; the next piece's TMEM load is in flight during the math
+      // pieces dealt round-robin to the three warp groups (26 pieces at Vp = 416: 9 / 9 / 8; by 32-column chunks it was
+      // 10 / 8 / 8 and the phase ended with two groups waiting for the first)
+      const int npieces = (p.Vp / 16 - wg + 2) / 3;
+      auto piece_col = [&](int i) { return (wg + 3 * i) * 16; };
       float v[16];
       if (npieces > 0) tmem_ld16(tq + piece_col(0), v);
       for (int pi = 0; pi < npieces; ++pi) {
@@ -546,7 +548,7 @@ joint_bwd3_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
           sts128(gb + (((ch0 + i) ^ (r & 7)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
       }
       // exact (fp32, single rounding) blank and label entries of row r, from the forward's log-probs: the warp group that
-      // wrote the 32-column chunk of the column patches it (program order within the thread - no barrier needed)
+      // wrote the 16-column piece of the column patches it (program order within the thread - no barrier needed)
       if (valid) {
         auto entry = [&](float lp, float b1, float b2) {
           float gv = __expf(lp + a_c + be) - __expf(lp + a_c + b1);
@@ -559,8 +561,8 @@ joint_bwd3_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_const
           const uint32_t a = L.g_kblock(col >> 6) + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4) + (col & 7) * 2;
           asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(h) : "memory");
         };
-        if (((p.blank >> 5) % 3) == wg) put(p.blank, entry(lpb, bnext, (lab == p.blank) ? bl1 : kNegInf));
-        if (lab >= 0 && lab != p.blank && ((lab >> 5) % 3) == wg) put(lab, entry(lpl, bl1, kNegInf));
+        if (((p.blank >> 4) % 3) == wg) put(p.blank, entry(lpb, bnext, (lab == p.blank) ? bl1 : kNegInf));
+        if (lab >= 0 && lab != p.blank && ((lab >> 4) % 3) == wg) put(lab, entry(lpl, bl1, kNegInf));
       }
       fence_proxy_async();
       tc_fence_before();
