@@ -41,6 +41,10 @@ _SIGS = {
     "ctcvr_loss_combine": (I, [P, I, P, F, F, P, P]),
     "ctcvr_cer_ws_bytes": (Z, [I, I, I]),
     "ctcvr_cer_batch": (I, [P, P, I, P, P, I, I, P, Z, P, P]),
+    "ctcvr_lstm_seq_supported": (I, [I, I]),
+    "ctcvr_lstm_seq_ws_bytes": (Z, [I, I]),
+    "ctcvr_lstm_seq_fwd": (I, [P] * 9 + [I, I, I, P, Z, P]),
+    "ctcvr_lstm_seq_bwd": (I, [P] * 10 + [I, I, I, P, Z, P]),
     "ctcvr_peer_create": (I, [I, I, Z, P, P]),
     "ctcvr_peer_connect": (I, [P, P, P]),
     "ctcvr_peer_local_buffer": (P, [P]),

@@ -64,6 +64,13 @@ size_t cer_ws_bytes(int, int, int);
 int cer_batch(const int32_t*, const int32_t*, int, const int32_t*, const int32_t*, int, int, void*, size_t, int32_t*,
               cudaStream_t);
 
+int lstm_seq_supported(int, int);
+size_t lstm_seq_ws_bytes(int, int);
+int lstm_seq_fwd(const float*, const float*, const float*, const float*, float*, float*, float*, float*, float*, int, int, int,
+                 void*, size_t, cudaStream_t);
+int lstm_seq_bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, float*,
+                 float*, float*, int, int, int, void*, size_t, cudaStream_t);
+
 int peer_create(int, int, size_t, void**, void*);
 int peer_connect(void*, const void*, void* const*);
 void* peer_local_buffer(void*);
@@ -217,6 +224,24 @@ int ctcvr_cer_batch(const int32_t* hyp, const int32_t* hyp_len, int Lh, const in
   CTCVR_REQUIRE(N > 0 && Lh >= 0 && Lr >= 0, "cer_batch: bad dims");
   CTCVR_REQUIRE(hyp_len && ref_len && out_sdin && ws && (Lh == 0 || hyp) && (Lr == 0 || ref), "cer_batch: NULL pointer");
   return cer_batch(hyp, hyp_len, Lh, ref, ref_len, Lr, N, ws, ws_bytes, out_sdin, ST(stream));
+}
+
+int ctcvr_lstm_seq_supported(int B, int H) { return lstm_seq_supported(B, H); }
+size_t ctcvr_lstm_seq_ws_bytes(int B, int H) { return (B > 0 && H > 0) ? lstm_seq_ws_bytes(B, H) : 0; }
+
+int ctcvr_lstm_seq_fwd(const float* xg, const float* w_hh, const float* h0, const float* c0, float* out, float* cs,
+                       float* act, float* hn, float* cn, int B, int U1, int H, void* ws, size_t ws_bytes, void* stream) {
+  CTCVR_REQUIRE(B > 0 && U1 > 0 && H > 0, "lstm_seq_fwd: bad dims");
+  CTCVR_REQUIRE(xg && w_hh && out && hn && cn && ws, "lstm_seq_fwd: NULL pointer");
+  return lstm_seq_fwd(xg, w_hh, h0, c0, out, cs, act, hn, cn, B, U1, H, ws, ws_bytes, ST(stream));
+}
+
+int ctcvr_lstm_seq_bwd(const float* act, const float* cs, const float* c0, const float* w_hh, const float* d_out,
+                       const float* d_hn, const float* d_cn, float* dgates, float* d_h0, float* d_c0, int B, int U1,
+                       int H, void* ws, size_t ws_bytes, void* stream) {
+  CTCVR_REQUIRE(B > 0 && U1 > 0 && H > 0, "lstm_seq_bwd: bad dims");
+  CTCVR_REQUIRE(act && cs && w_hh && dgates && d_h0 && d_c0 && ws, "lstm_seq_bwd: NULL pointer");
+  return lstm_seq_bwd(act, cs, c0, w_hh, d_out, d_hn, d_cn, dgates, d_h0, d_c0, B, U1, H, ws, ws_bytes, ST(stream));
 }
 
 int ctcvr_peer_create(int rank, int world, size_t max_floats, void** out_ctx, void* out_handle64) {

@@ -1,0 +1,476 @@
+// Predictor LSTM over a whole label sequence, forward and backward.
+//
+// Replaces the library LSTM behind RNNPredictor.forward (model/component/predictor.py:43-63: embed -> nn.LSTM ->
+// projection; one layer, hidden 256 in both reference models, 512 at BASELINE.json's cfg2 shape) for the U+1 = 41
+// sequential steps of a training batch.  Gate order and arithmetic are torch's (i, f, g, o; c' = f*c + i*g;
+// h' = o*tanh(c')), fp32 throughout with IEEE expf / tanhf: the reference-precision path.
+//
+// The input projection x_t W_ih^T + b_ih + b_hh of all steps is one plain GEMM done by the caller (`xg`); what is
+// sequential is h_{t-1} W_hh^T.  One persistent cooperative launch walks the sequence:
+//   * the H hidden units are dealt to G = ceil(H / HS) CTAs (HS = 1, 2, 4 or 8 so that G <= 148: one CTA per SM); a CTA
+//     keeps the 4*HS rows of W_hh that produce its units' gates resident in shared memory for the whole sequence
+//     (forward), or the HS columns it needs for dh_{t-1} (backward), so the 4 MB of W_hh are read from HBM once;
+//   * a step exchanges h_t (forward, [H][B]) or the gate gradients (backward, [4H][B]) through a ping-pong buffer in
+//     L2: every CTA stores its slice, raises its own step flag (st.release.gpu), and waits until all G flags have
+//     reached the step (ld.acquire.gpu by one thread per flag) - no atomics, no grid-wide counter;
+//   * inside a CTA warp w owns a 1/16 slice of the reduction dimension and lane b one batch row: the operand row
+//     exchange[k][b] is one coalesced 128-byte L2 load per warp (ld.global.cg, the lines are rewritten by other SMs every
+//     second step), the weights are shared-memory broadcasts, and each lane keeps 4*HS (forward) or HS (backward)
+//     accumulators; the 16 partial sums meet in shared memory;
+//   * the per-step tensors that do not depend on the recurrence (xg; the saved gates, cell states and dL/dh_t) are
+//     loaded into registers BEFORE the flag wait, so their latency hides under the barrier.
+// Batches beyond 32 rows run as chunks of 32 inside a step.  Waits are bounded (2 s): a CTA that gives up writes a
+// mapped host word and the next call fails loudly.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ctcvr {
+namespace {
+
+constexpr int LSTM_THREADS = 512;
+constexpr int LSTM_WARPS = 16;
+constexpr long long LSTM_TIMEOUT_NS = 2LL * 1000 * 1000 * 1000;
+
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ long long gtime_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+struct LstmFwdArgs {
+  const float* xg;      // [B, U1, 4H]  x_t W_ih^T + b_ih + b_hh
+  const float* w_hh;    // [4H, H]
+  const float* h0;      // [B, H] or NULL (zeros)
+  const float* c0;      // [B, H] or NULL
+  float* out;           // [B, U1, H]  h_t
+  float* cs;            // [B, U1, H]  c_t            (NULL: not kept)
+  float* act;           // [B, U1, 4H] activated gates (NULL: not kept)
+  float* hn;            // [B, H]
+  float* cn;            // [B, H]
+  float* hx;            // workspace: 2 x [H][Bp]
+  unsigned int* flags;  // workspace: [G], zeroed before the launch
+  unsigned int* err;    // mapped host word
+  int B, U1, H, Bp, G;
+};
+
+struct LstmBwdArgs {
+  const float* act;     // [B, U1, 4H]
+  const float* cs;      // [B, U1, H]
+  const float* c0;      // [B, H] or NULL
+  const float* w_hh;    // [4H, H]
+  const float* d_out;   // [B, U1, H] dL/dh_t from the layers above (NULL: zeros)
+  const float* d_hn;    // [B, H] or NULL
+  const float* d_cn;    // [B, H] or NULL
+  float* dgates;        // [B, U1, 4H] dL/d(pre-activation gates)
+  float* d_h0;          // [B, H]
+  float* d_c0;          // [B, H]
+  float* dgx;           // workspace: 2 x [4H][Bp]
+  unsigned int* flags;
+  unsigned int* err;
+  int B, U1, H, Bp, G;
+};
+
+// Every CTA has stored its slice of step `value - 1`: raise my flag, then wait for all G flags.
+__device__ __forceinline__ void publish(unsigned int* flags, unsigned int value) {
+  __syncthreads();                        // the CTA's stores are ordered before thread 0's release (cumulativity)
+  if (threadIdx.x == 0) {
+    __threadfence();
+    st_release_gpu(flags + blockIdx.x, value);
+  }
+}
+// `dead` (shared memory) is set by the first wait of this CTA that times out: later waits return at once, so a broken
+// launch ends after ~2 s instead of 2 s per step.
+__device__ __forceinline__ void wait_all(const unsigned int* flags, int G, unsigned int value, unsigned int* err, int site,
+                                         volatile int* dead) {
+  if ((int)threadIdx.x < G && !*dead) {
+    const long long t0 = gtime_ns();
+    int spins = 0;
+    while ((int)(ld_acquire_gpu(flags + threadIdx.x) - value) < 0) {
+      if ((++spins & 255) == 0 && (*dead || gtime_ns() - t0 > LSTM_TIMEOUT_NS)) {
+        if (err) *reinterpret_cast<volatile unsigned int*>(err) = 0x80000000u | ((unsigned)site << 24) | ((unsigned)threadIdx.x << 12) | blockIdx.x;
+        *dead = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------------
+template <int HS>
+__global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_fwd_kernel(const LstmFwdArgs a) {
+  extern __shared__ __align__(16) unsigned char lstm_smem[];
+  __shared__ int s_dead;
+  if (threadIdx.x == 0) s_dead = 0;
+  const int H = a.H, B = a.B, Bp = a.Bp, nb = Bp >> 5, U1 = a.U1;
+  float4* Wsm = reinterpret_cast<float4*>(lstm_smem);                    // [H + 16][HS] {i, f, g, o} weights of (k, unit)
+  float* red = reinterpret_cast<float*>(Wsm + (size_t)(H + 16) * HS);    // [16][4*HS][32]
+  float* sums = red + LSTM_WARPS * 4 * HS * 32;                          // [4*HS][32]
+  float* c_sm = sums + 4 * HS * 32;                                      // [Bp][HS]
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int unit0 = blockIdx.x * HS;
+  const size_t H4 = (size_t)4 * H;
+
+  for (int idx = tid; idx < (H + 16) * HS; idx += LSTM_THREADS) {        // idx = u * (H+16) + k: coalesced over k
+    const int u = idx / (H + 16), k = idx - u * (H + 16), unit = unit0 + u;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < H && unit < H) {
+      v.x = a.w_hh[((size_t)0 * H + unit) * H + k];
+      v.y = a.w_hh[((size_t)1 * H + unit) * H + k];
+      v.z = a.w_hh[((size_t)2 * H + unit) * H + k];
+      v.w = a.w_hh[((size_t)3 * H + unit) * H + k];
+    }
+    Wsm[(size_t)k * HS + u] = v;
+  }
+  for (int idx = tid; idx < Bp * HS; idx += LSTM_THREADS) {              // idx = u * Bp + b: coalesced exchange stores
+    const int u = idx / Bp, b = idx - u * Bp, unit = unit0 + u;
+    const bool ok = b < B && unit < H;
+    c_sm[b * HS + u] = (ok && a.c0) ? a.c0[(size_t)b * H + unit] : 0.f;
+    if (unit < H) a.hx[(size_t)unit * Bp + b] = (ok && a.h0) ? a.h0[(size_t)b * H + unit] : 0.f;
+  }
+  publish(a.flags, 1u);
+
+  const int Kc = (H + LSTM_WARPS - 1) / LSTM_WARPS;
+  const int k0 = min(H, w * Kc), k1 = min(H, k0 + Kc);
+  for (int t = 0; t < U1; ++t) {
+    const float* hprev = a.hx + (size_t)(t & 1) * H * Bp;
+    float* hnext = a.hx + (size_t)((t + 1) & 1) * H * Bp;
+    // the finishing warps (w < HS: unit w, batch row = lane) fetch chunk 0's input projection ahead of the wait
+    float xg_pf[4] = {0.f, 0.f, 0.f, 0.f};
+    if (w < HS && unit0 + w < H && lane < B) {
+      const float* q = a.xg + ((size_t)lane * U1 + t) * H4 + unit0 + w;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) xg_pf[g] = __ldg(q + (size_t)g * H);
+    }
+    wait_all(a.flags, a.G, (unsigned)(t + 1), a.err, 1, &s_dead);
+    for (int ch = 0; ch < nb; ++ch) {
+      float acc[HS][4];
+#pragma unroll
+      for (int u = 0; u < HS; ++u) acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f;
+      const float* hp = hprev + ch * 32 + lane;
+      for (int k = k0; k < k1; k += 16) {
+        float hv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hv[i] = (k + i < k1) ? __ldcg(hp + (size_t)(k + i) * Bp) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+#pragma unroll
+          for (int u = 0; u < HS; ++u) {
+            const float4 wv = Wsm[(size_t)(k + i) * HS + u];
+            acc[u][0] = fmaf(hv[i], wv.x, acc[u][0]);
+            acc[u][1] = fmaf(hv[i], wv.y, acc[u][1]);
+            acc[u][2] = fmaf(hv[i], wv.z, acc[u][2]);
+            acc[u][3] = fmaf(hv[i], wv.w, acc[u][3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < HS; ++u)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) red[((w * 4 * HS) + u * 4 + g) * 32 + lane] = acc[u][g];
+      __syncthreads();
+      for (int combo = w; combo < 4 * HS; combo += LSTM_WARPS) {
+        float s = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < LSTM_WARPS; ++ww) s += red[((ww * 4 * HS) + combo) * 32 + lane];
+        sums[combo * 32 + lane] = s;
+      }
+      __syncthreads();
+      if (w < HS) {
+        const int u = w, unit = unit0 + u, b = ch * 32 + lane;
+        if (unit < H && b < B) {
+          float x4[4];
+          if (ch == 0) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) x4[g] = xg_pf[g];
+          } else {
+            const float* q = a.xg + ((size_t)b * U1 + t) * H4 + unit;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) x4[g] = __ldg(q + (size_t)g * H);
+          }
+          const float gi = sigmoidf_(sums[(u * 4 + 0) * 32 + lane] + x4[0]);
+          const float gf = sigmoidf_(sums[(u * 4 + 1) * 32 + lane] + x4[1]);
+          const float gg = tanhf(sums[(u * 4 + 2) * 32 + lane] + x4[2]);
+          const float go = sigmoidf_(sums[(u * 4 + 3) * 32 + lane] + x4[3]);
+          const float c = gf * c_sm[b * HS + u] + gi * gg;
+          const float h = go * tanhf(c);
+          c_sm[b * HS + u] = c;
+          hnext[(size_t)unit * Bp + b] = h;
+          const size_t row = (size_t)b * U1 + t;
+          a.out[row * H + unit] = h;
+          if (a.cs) a.cs[row * H + unit] = c;
+          if (a.act) {
+            float* q = a.act + row * H4 + unit;
+            q[0] = gi; q[(size_t)H] = gf; q[(size_t)2 * H] = gg; q[(size_t)3 * H] = go;
+          }
+          if (t == U1 - 1) {
+            a.hn[(size_t)b * H + unit] = h;
+            a.cn[(size_t)b * H + unit] = c;
+          }
+        } else if (unit < H) {
+          hnext[(size_t)unit * Bp + b] = 0.f;               // padded batch rows stay finite
+        }
+      }
+      // the next chunk's partial sums are written after its accumulation; the publish / wait below also separate them
+      if (ch + 1 < nb) __syncthreads();
+    }
+    publish(a.flags, (unsigned)(t + 2));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward: dL/d(gates) of every step, dL/dh0, dL/dc0
+// ---------------------------------------------------------------------------------------------------------------
+struct BwdStepIn { float gi, gf, gg, go, c, cprev, dh; };
+
+__device__ __forceinline__ BwdStepIn load_step(const LstmBwdArgs& a, int b, int t, int unit) {
+  const int H = a.H, U1 = a.U1;
+  const size_t row = (size_t)b * U1 + t;
+  const float* q = a.act + row * 4 * H + unit;
+  BwdStepIn s;
+  s.gi = __ldg(q); s.gf = __ldg(q + (size_t)H); s.gg = __ldg(q + (size_t)2 * H); s.go = __ldg(q + (size_t)3 * H);
+  s.c = __ldg(a.cs + row * H + unit);
+  s.cprev = t > 0 ? __ldg(a.cs + (row - 1) * H + unit) : (a.c0 ? __ldg(a.c0 + (size_t)b * H + unit) : 0.f);
+  s.dh = a.d_out ? __ldg(a.d_out + row * H + unit) : 0.f;
+  return s;
+}
+
+template <int HS>
+__global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_bwd_kernel(const LstmBwdArgs a) {
+  extern __shared__ __align__(16) unsigned char lstm_smem[];
+  __shared__ int s_dead;
+  if (threadIdx.x == 0) s_dead = 0;
+  const int H = a.H, B = a.B, Bp = a.Bp, nb = Bp >> 5, U1 = a.U1;
+  const int J = 4 * H;
+  float* Wc = reinterpret_cast<float*>(lstm_smem);        // [4H + 16][HS]: W_hh[j][unit0 + u]
+  float* red = Wc + (size_t)(J + 16) * HS;                 // [16][HS][32]
+  float* dh_sm = red + LSTM_WARPS * HS * 32;               // [Bp][HS] dL/dh_t arriving through the recurrence
+  float* dc_sm = dh_sm + (size_t)Bp * HS;                  // [Bp][HS] dL/dc_t arriving from step t+1
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int unit0 = blockIdx.x * HS;
+
+  for (int idx = tid; idx < (J + 16) * HS; idx += LSTM_THREADS) {
+    const int j = idx / HS, u = idx - j * HS, unit = unit0 + u;
+    Wc[idx] = (j < J && unit < H) ? a.w_hh[(size_t)j * H + unit] : 0.f;
+  }
+  for (int idx = tid; idx < Bp * HS; idx += LSTM_THREADS) {
+    const int b = idx / HS, u = idx - b * HS, unit = unit0 + u;
+    const bool ok = b < B && unit < H;
+    dh_sm[idx] = (ok && a.d_hn) ? a.d_hn[(size_t)b * H + unit] : 0.f;
+    dc_sm[idx] = (ok && a.d_cn) ? a.d_cn[(size_t)b * H + unit] : 0.f;
+  }
+  __syncthreads();
+
+  const int Jc = (J + LSTM_WARPS - 1) / LSTM_WARPS;
+  const int j0 = min(J, w * Jc), j1 = min(J, j0 + Jc);
+  const bool fin = w < HS && unit0 + w < H;                // finishing warp: unit w, batch row = lane
+  BwdStepIn pf{};
+  if (fin && lane < B) pf = load_step(a, lane, U1 - 1, unit0 + w);
+
+  for (int s = 0; s < U1; ++s) {
+    const int t = U1 - 1 - s;
+    float* dgx = a.dgx + (size_t)(s & 1) * J * Bp;
+    // A. pointwise gradients of step t for my units
+    if (fin) {
+      const int u = w, unit = unit0 + u;
+      for (int ch = 0; ch < nb; ++ch) {
+        const int b = ch * 32 + lane;
+        if (b < B) {
+          const BwdStepIn in = (ch == 0) ? pf : load_step(a, b, t, unit);
+          const float dh = in.dh + dh_sm[b * HS + u];
+          const float tc = tanhf(in.c);
+          const float dc = dc_sm[b * HS + u] + dh * in.go * (1.f - tc * tc);
+          const float d_o = dh * tc * in.go * (1.f - in.go);
+          const float d_i = dc * in.gg * in.gi * (1.f - in.gi);
+          const float d_f = dc * in.cprev * in.gf * (1.f - in.gf);
+          const float d_g = dc * in.gi * (1.f - in.gg * in.gg);
+          dc_sm[b * HS + u] = dc * in.gf;
+          float* q = a.dgates + ((size_t)b * U1 + t) * J + unit;
+          q[0] = d_i; q[(size_t)H] = d_f; q[(size_t)2 * H] = d_g; q[(size_t)3 * H] = d_o;
+          dgx[(size_t)(0 * H + unit) * Bp + b] = d_i;
+          dgx[(size_t)(1 * H + unit) * Bp + b] = d_f;
+          dgx[(size_t)(2 * H + unit) * Bp + b] = d_g;
+          dgx[(size_t)(3 * H + unit) * Bp + b] = d_o;
+        } else {
+          dgx[(size_t)(0 * H + unit) * Bp + b] = 0.f;       // padded batch rows stay finite
+          dgx[(size_t)(1 * H + unit) * Bp + b] = 0.f;
+          dgx[(size_t)(2 * H + unit) * Bp + b] = 0.f;
+          dgx[(size_t)(3 * H + unit) * Bp + b] = 0.f;
+        }
+      }
+    }
+    publish(a.flags, (unsigned)(s + 1));
+    if (fin && lane < B && t > 0) pf = load_step(a, lane, t - 1, unit0 + w);   // next step's operands, under the wait
+    wait_all(a.flags, a.G, (unsigned)(s + 1), a.err, 2, &s_dead);
+    // D. dh_{t-1}[b][my units] = sum_j dgates_t[b][j] * W_hh[j][unit]
+    for (int ch = 0; ch < nb; ++ch) {
+      float acc[HS];
+#pragma unroll
+      for (int u = 0; u < HS; ++u) acc[u] = 0.f;
+      const float* gp = dgx + ch * 32 + lane;
+      for (int j = j0; j < j1; j += 16) {
+        float gv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) gv[i] = (j + i < j1) ? __ldcg(gp + (size_t)(j + i) * Bp) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float* wr = Wc + (size_t)(j + i) * HS;
+#pragma unroll
+          for (int u = 0; u < HS; ++u) acc[u] = fmaf(gv[i], wr[u], acc[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < HS; ++u) red[(w * HS + u) * 32 + lane] = acc[u];
+      __syncthreads();
+      if (w < HS) {
+        float sum = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < LSTM_WARPS; ++ww) sum += red[(ww * HS + w) * 32 + lane];
+        dh_sm[(ch * 32 + lane) * HS + w] = sum;
+      }
+      __syncthreads();
+    }
+  }
+  if (fin) {
+    const int u = w, unit = unit0 + u;
+    for (int b = lane; b < B; b += 32) {
+      a.d_h0[(size_t)b * H + unit] = dh_sm[b * HS + u];
+      a.d_c0[(size_t)b * H + unit] = dc_sm[b * HS + u];
+    }
+  }
+}
+
+int pick_hs(int H, int sms) {
+  int hs = 1;
+  while (hs < 8 && (H + hs - 1) / hs > sms) hs *= 2;
+  return hs;
+}
+int lstm_sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = 0;
+      return 148;
+    }
+  }
+  return n;
+}
+size_t fwd_smem(int H, int hs, int Bp) {
+  return (size_t)(H + 16) * hs * 16 + (size_t)LSTM_WARPS * 4 * hs * 32 * 4 + (size_t)4 * hs * 32 * 4 + (size_t)Bp * hs * 4;
+}
+size_t bwd_smem(int H, int hs, int Bp) {
+  return (size_t)(4 * H + 16) * hs * 4 + (size_t)LSTM_WARPS * hs * 32 * 4 + (size_t)2 * Bp * hs * 4;
+}
+
+unsigned int* lstm_error_host_word(unsigned int** dev_ptr) {
+  static unsigned int* h = nullptr;
+  static unsigned int* d = nullptr;
+  if (!h) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h), sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess) { h = nullptr; cudaGetLastError(); }
+    else { *h = 0u; if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0) != cudaSuccess) { d = nullptr; cudaGetLastError(); } }
+  }
+  if (dev_ptr) *dev_ptr = d;
+  return h;
+}
+int check_lstm_error(const char* where) {
+  unsigned int* h = lstm_error_host_word(nullptr);
+  if (h && *reinterpret_cast<volatile unsigned int*>(h) != 0u) {
+    const unsigned int code = *h;
+    *h = 0u;
+    set_error("%s: an earlier LSTM sequence kernel gave up waiting for a step flag (0x%08x: site %u, flag %u, CTA %u); the "
+              "results of that call are invalid", where, code, (code >> 24) & 0x7fu, (code >> 12) & 0xfffu, code & 0xfffu);
+    return 1;
+  }
+  return 0;
+}
+
+struct LstmWs { unsigned int* flags; float* xch; size_t bytes; };
+LstmWs carve_lstm_ws(void* ws, int B, int H) {
+  const int Bp = (B + 31) / 32 * 32;
+  LstmWs W;
+  W.flags = reinterpret_cast<unsigned int*>(ws);
+  W.xch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + 1024);
+  W.bytes = 1024 + (size_t)2 * 4 * H * Bp * sizeof(float);
+  return W;
+}
+
+template <typename Args>
+int launch_coop(void (*kern)(const Args), int G, size_t smem, const Args& a, cudaStream_t st) {
+  CTCVR_CHECK_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(kern), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* params[] = {const_cast<Args*>(&a)};
+  CTCVR_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(G), dim3(LSTM_THREADS), params, smem, st));
+  CTCVR_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+int lstm_seq_supported(int B, int H) {
+  if (B < 1 || H < 1) return 0;
+  const int sms = lstm_sm_count();
+  const int hs = pick_hs(H, sms), Bp = (B + 31) / 32 * 32;
+  if ((H + hs - 1) / hs > sms || (H + hs - 1) / hs > 256) return 0;
+  return fwd_smem(H, hs, Bp) <= 232448 && bwd_smem(H, hs, Bp) <= 232448;
+}
+
+size_t lstm_seq_ws_bytes(int B, int H) { return carve_lstm_ws(nullptr, B, H).bytes; }
+
+int lstm_seq_fwd(const float* xg, const float* w_hh, const float* h0, const float* c0, float* out, float* cs, float* act,
+                 float* hn, float* cn, int B, int U1, int H, void* ws, size_t ws_bytes, cudaStream_t st) {
+  CTCVR_REQUIRE(lstm_seq_supported(B, H), "lstm_seq_fwd: hidden size %d / batch %d do not fit one CTA per SM (H <= 8 x SMs, shared memory)", H, B);
+  if (check_lstm_error("lstm_seq_fwd")) return 1;
+  CTCVR_REQUIRE(ws_bytes >= lstm_seq_ws_bytes(B, H), "lstm_seq_fwd: workspace too small");
+  const int hs = pick_hs(H, lstm_sm_count()), Bp = (B + 31) / 32 * 32, G = (H + hs - 1) / hs;
+  LstmWs W = carve_lstm_ws(ws, B, H);
+  LstmFwdArgs a{};
+  a.xg = xg; a.w_hh = w_hh; a.h0 = h0; a.c0 = c0; a.out = out; a.cs = cs; a.act = act; a.hn = hn; a.cn = cn;
+  a.hx = W.xch; a.flags = W.flags; a.B = B; a.U1 = U1; a.H = H; a.Bp = Bp; a.G = G;
+  lstm_error_host_word(&a.err);
+  CTCVR_CHECK_CUDA(cudaMemsetAsync(W.flags, 0, 1024, st));
+  const size_t smem = fwd_smem(H, hs, Bp);
+  switch (hs) {
+    case 1: return launch_coop(lstm_seq_fwd_kernel<1>, G, smem, a, st);
+    case 2: return launch_coop(lstm_seq_fwd_kernel<2>, G, smem, a, st);
+    case 4: return launch_coop(lstm_seq_fwd_kernel<4>, G, smem, a, st);
+    default: return launch_coop(lstm_seq_fwd_kernel<8>, G, smem, a, st);
+  }
+}
+
+int lstm_seq_bwd(const float* act, const float* cs, const float* c0, const float* w_hh, const float* d_out, const float* d_hn,
+                 const float* d_cn, float* dgates, float* d_h0, float* d_c0, int B, int U1, int H, void* ws, size_t ws_bytes,
+                 cudaStream_t st) {
+  CTCVR_REQUIRE(lstm_seq_supported(B, H), "lstm_seq_bwd: hidden size %d / batch %d do not fit one CTA per SM (H <= 8 x SMs, shared memory)", H, B);
+  if (check_lstm_error("lstm_seq_bwd")) return 1;
+  CTCVR_REQUIRE(ws_bytes >= lstm_seq_ws_bytes(B, H), "lstm_seq_bwd: workspace too small");
+  const int hs = pick_hs(H, lstm_sm_count()), Bp = (B + 31) / 32 * 32, G = (H + hs - 1) / hs;
+  LstmWs W = carve_lstm_ws(ws, B, H);
+  LstmBwdArgs a{};
+  a.act = act; a.cs = cs; a.c0 = c0; a.w_hh = w_hh; a.d_out = d_out; a.d_hn = d_hn; a.d_cn = d_cn;
+  a.dgates = dgates; a.d_h0 = d_h0; a.d_c0 = d_c0; a.dgx = W.xch; a.flags = W.flags;
+  a.B = B; a.U1 = U1; a.H = H; a.Bp = Bp; a.G = G;
+  lstm_error_host_word(&a.err);
+  CTCVR_CHECK_CUDA(cudaMemsetAsync(W.flags, 0, 1024, st));
+  const size_t smem = bwd_smem(H, hs, Bp);
+  switch (hs) {
+    case 1: return launch_coop(lstm_seq_bwd_kernel<1>, G, smem, a, st);
+    case 2: return launch_coop(lstm_seq_bwd_kernel<2>, G, smem, a, st);
+    case 4: return launch_coop(lstm_seq_bwd_kernel<4>, G, smem, a, st);
+    default: return launch_coop(lstm_seq_bwd_kernel<8>, G, smem, a, st);
+  }
+}
+
+}  // namespace ctcvr

@@ -8,6 +8,8 @@
   ctc_loss               — drop-in for F.log_softmax + nn.CTCLoss(zero_infinity=True) tails
                            (model/rnnt_model.py:55-58, model/online_rnnt_model.py:29-30).
   joint_logits           — dense TransducerJoint tail (model/component/joint.py:57-68).
+  lstm_sequence          — one layer of the predictor's nn.LSTM over a whole label sequence, forward and backward
+                           (model/component/predictor.py:58).
 """
 from __future__ import annotations
 
@@ -268,6 +270,81 @@ def ctc_loss_from_logits(logits, targets, input_lengths, target_lengths, blank: 
     else:
         raise ValueError(f"{reduction} is not a valid value for reduction")
     return loss, lp
+
+
+class _LstmSeq(torch.autograd.Function):
+    """One LSTM layer over [B,U1,*] (batch_first, fp32).  The sequential part runs in the two persistent kernels of
+    csrc/lstm_seq.cu; the input projection and the three weight / input gradient products are plain library GEMMs
+    over all B*U1 rows at once."""
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, h0, c0):
+        _lib.require_cuda(x, w_ih, w_hh, h0, c0)
+        dev = x.device
+        B, U1, E = x.shape
+        H = w_hh.shape[1]
+        if w_ih.shape != (4 * H, E) or w_hh.shape != (4 * H, H) or h0.shape != (B, H) or c0.shape != (B, H):
+            raise RuntimeError("lstm_sequence: inconsistent shapes")
+        if U1 == 0:
+            raise RuntimeError("lstm_sequence: empty sequence")
+        if not bool(query("ctcvr_lstm_seq_supported", B, H)):
+            raise RuntimeError(f"lstm_sequence: hidden size {H} with batch {B} does not fit the persistent kernel "
+                               "(H <= 8 x SM count and the per-CTA shared memory)")
+        x2 = _f32c(x).view(B * U1, E)
+        wi, wh = _f32c(w_ih), _f32c(w_hh)
+        bias = None
+        if b_ih is not None:
+            bias = _f32c(b_ih) + _f32c(b_hh)
+        xg = torch.addmm(bias, x2, wi.t()) if bias is not None else torch.mm(x2, wi.t())
+        h0c, c0c = _f32c(h0), _f32c(c0)
+        keep = any(ctx.needs_input_grad)
+        out = torch.empty((B, U1, H), dtype=torch.float32, device=dev)
+        hn = torch.empty((B, H), dtype=torch.float32, device=dev)
+        cn = torch.empty_like(hn)
+        cs = torch.empty_like(out) if keep else None
+        act = torch.empty((B, U1, 4 * H), dtype=torch.float32, device=dev) if keep else None
+        with torch.cuda.device(dev):
+            ws = _ws(query("ctcvr_lstm_seq_ws_bytes", B, H), dev)
+            call("ctcvr_lstm_seq_fwd", ptr(xg), ptr(wh), ptr(h0c), ptr(c0c), ptr(out), ptr(cs), ptr(act), ptr(hn), ptr(cn),
+                 B, U1, H, ptr(ws), ws.numel(), stream())
+        if keep:
+            ctx.save_for_backward(x2, wi, wh, h0c, c0c, out, cs, act)
+        ctx.has_bias = b_ih is not None
+        ctx.dims = (B, U1, E, H)
+        return out, hn, cn
+
+    @staticmethod
+    def backward(ctx, d_out, d_hn, d_cn):
+        x2, wi, wh, h0c, c0c, out, cs, act = ctx.saved_tensors
+        B, U1, E, H = ctx.dims
+        dev = x2.device
+        d_out = _f32c(d_out) if d_out is not None else None
+        d_hn = _f32c(d_hn) if d_hn is not None else None
+        d_cn = _f32c(d_cn) if d_cn is not None else None
+        dg = torch.empty((B, U1, 4 * H), dtype=torch.float32, device=dev)
+        d_h0 = torch.empty((B, H), dtype=torch.float32, device=dev)
+        d_c0 = torch.empty_like(d_h0)
+        with torch.cuda.device(dev):
+            ws = _ws(query("ctcvr_lstm_seq_ws_bytes", B, H), dev)
+            call("ctcvr_lstm_seq_bwd", ptr(act), ptr(cs), ptr(c0c), ptr(wh), ptr(d_out), ptr(d_hn), ptr(d_cn), ptr(dg),
+                 ptr(d_h0), ptr(d_c0), B, U1, H, ptr(ws), ws.numel(), stream())
+        dg2 = dg.view(B * U1, 4 * H)
+        ng = ctx.needs_input_grad
+        dx = torch.mm(dg2, wi).view(B, U1, E) if ng[0] else None
+        d_wi = torch.mm(dg2.t(), x2) if ng[1] else None
+        d_wh = None
+        if ng[2]:
+            h_prev = torch.cat([h0c.unsqueeze(1), out[:, :-1]], dim=1).reshape(B * U1, H)
+            d_wh = torch.mm(dg2.t(), h_prev)
+        db = dg2.sum(0) if ctx.has_bias and (ng[3] or ng[4]) else None
+        return dx, d_wi, d_wh, (db if ctx.has_bias and ng[3] else None), (db if ctx.has_bias and ng[4] else None), \
+            (d_h0 if ng[5] else None), (d_c0 if ng[6] else None)
+
+
+def lstm_sequence(x, w_ih, w_hh, b_ih, b_hh, h0, c0):
+    """`out, (h_n, c_n) = nn.LSTM(batch_first=True)(x, (h0, c0))` for ONE layer: x [B,U1,E], w_ih [4H,E], w_hh [4H,H],
+    biases [4H] (or both None), h0 / c0 [B,H].  Returns (out [B,U1,H], h_n [B,H], c_n [B,H]) in fp32, differentiable
+    in every argument.  This is the reference predictor's recurrence (model/component/predictor.py:58)."""
+    return _LstmSeq.apply(x, w_ih, w_hh, b_ih, b_hh, h0, c0)
 
 
 def ctc_greedy_search(scores, lens, blank: int):

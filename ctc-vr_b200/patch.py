@@ -19,12 +19,14 @@ import torch
 
 from . import decode as D
 from . import functional as CF
+from .predictor import lstm_stack
 from .transducer import compute_rnnt_loss
 
 _SAVED: List[tuple] = []
 
 _MODULES = {
     "joint": "model.component.joint",
+    "predictor": "model.component.predictor",
     "transducer": "model.component.transducer",
     "rnnt_model": "model.rnnt_model",
     "online": "model.online_rnnt_model",
@@ -76,6 +78,31 @@ def _joint_forward(self, enc_out: torch.Tensor, pred_out: torch.Tensor, pre_proj
     if getattr(self, "postjoin_linear", False) and self.post_ffn is not None:
         out = self.post_ffn(out)
     return self.ffn_out(self.activation(out))
+
+
+def _predictor_forward(self, input_tensor: torch.Tensor, cache: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
+    """RNNPredictor.forward (model/component/predictor.py:43-63): embed -> dropout -> LSTM -> projection with the
+    recurrence in the sequence kernels (csrc/lstm_seq.cu) instead of the library LSTM."""
+    embed = self.dropout(self.embed(input_tensor))
+    if cache is None:
+        st = self.init_state(batch_size=input_tensor.size(0), device=input_tensor.device)
+        h0, c0 = st[0], st[1]
+    else:
+        assert len(cache) == 2
+        h0, c0 = cache[0], cache[1]
+    out, _, _ = lstm_stack(self.rnn, embed, h0, c0, self.training)
+    return self.projection(out)
+
+
+def _predictor_forward_step(self, input_tensor: torch.Tensor, padding: torch.Tensor, cache: List[torch.Tensor]):
+    """RNNPredictor.forward_step (model/component/predictor.py:79-98)."""
+    assert len(cache) == 2
+    state_m, state_c = cache[0], cache[1]
+    embed = self.dropout(self.embed(input_tensor.to(self.embed.weight.device)))
+    out, m, c = lstm_stack(self.rnn, embed, state_m, state_c, self.training)
+    out = self.projection(out)
+    pad = padding.unsqueeze(0)
+    return out, [pad * state_m + m * (1 - pad), pad * state_c + c * (1 - pad)]
 
 
 def _transducer_compute_rnnt_loss(self, encoder_out, encoder_out_lens, text, text_lengths):
@@ -194,6 +221,11 @@ def install(namespace=None, precision: Optional[str] = None) -> Dict[str, List[s
     if m is not None and hasattr(m, "TransducerJoint"):
         _set(m.TransducerJoint, "forward", _joint_forward)
         note("joint", "TransducerJoint.forward")
+    m = _resolve(namespace, "predictor")
+    if m is not None and hasattr(m, "RNNPredictor"):
+        _set(m.RNNPredictor, "forward", _predictor_forward)
+        _set(m.RNNPredictor, "forward_step", _predictor_forward_step)
+        note("predictor", "RNNPredictor.forward/forward_step")
     m = _resolve(namespace, "transducer")
     if m is not None:
         if hasattr(m, "Transducer"):

@@ -116,6 +116,23 @@ int ctcvr_rnnt_prologue(const int64_t* text, const void* text_lens, int text_len
 int ctcvr_loss_combine(const float* costs, int B, const float* loss_ctc, float transducer_weight, float ctc_weight,
                        float* out2, void* stream);
 
+/* ---- section 8(f)2: the predictor's LSTM over a whole label sequence (model/component/predictor.py:43-63,
+ * `out, (m, c) = self.rnn(embed, states)`; one call per layer).  fp32, torch's gate order (i, f, g, o).
+ * xg [B,U1,4H] = x_t W_ih^T + b_ih + b_hh for every step (one plain GEMM on the caller's side); w_hh [4H,H];
+ * h0 / c0 [B,H] (NULL = zeros).  Forward writes out [B,U1,H] = h_t, hn / cn [B,H], and - for a later backward -
+ * cs [B,U1,H] = c_t and act [B,U1,4H] = the activated gates (both may be NULL).  Backward takes d_out [B,U1,H] =
+ * dL/dh_t (NULL = zeros), d_hn / d_cn [B,H] (NULL = zeros) and writes dgates [B,U1,4H] = dL/d(pre-activation gates)
+ * - from which dW_ih, dW_hh, the bias gradients and dx are three plain GEMMs and a column sum - and d_h0 / d_c0 [B,H].
+ * One persistent cooperative launch per call: needs H <= 8 x SM count (ctcvr_lstm_seq_supported); a CTA that waits
+ * longer than 2 s for a step flag gives up and the NEXT call returns an error.  ws: ctcvr_lstm_seq_ws_bytes. */
+int ctcvr_lstm_seq_supported(int B, int H);
+size_t ctcvr_lstm_seq_ws_bytes(int B, int H);
+int ctcvr_lstm_seq_fwd(const float* xg, const float* w_hh, const float* h0, const float* c0, float* out, float* cs,
+                       float* act, float* hn, float* cn, int B, int U1, int H, void* ws, size_t ws_bytes, void* stream);
+int ctcvr_lstm_seq_bwd(const float* act, const float* cs, const float* c0, const float* w_hh, const float* d_out,
+                       const float* d_hn, const float* d_cn, float* dgates, float* d_h0, float* d_c0, int B, int U1,
+                       int H, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- section 8(f)4: calculate_cer (rnnt_eval.py:11-56) for N (hypothesis, reference) pairs: hyp [N,Lh], ref [N,Lr]
  * int32 padded, lengths [N]; out_sdin [N,4] int32 = substitutions, deletions, insertions, reference length, with the
  * reference's backtrace tie-breaking (match, substitution, deletion, insertion).  ws: ctcvr_cer_ws_bytes. */

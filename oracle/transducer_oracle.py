@@ -177,7 +177,8 @@ def predictor_init_state(pw: Weights, batch: int = 1) -> List[torch.Tensor]:
     """model/component/predictor.py:65-77 / wenet/transducer/predictor.py:165-183."""
     L = n_layers_of(pw)
     H = pw["rnn.weight_hh_l0"].size(1)
-    return [torch.zeros(L, batch, H), torch.zeros(L, batch, H)]
+    dt = pw["rnn.weight_hh_l0"].dtype
+    return [torch.zeros(L, batch, H, dtype=dt), torch.zeros(L, batch, H, dtype=dt)]
 
 
 def predictor_forward_step(pw: Weights, token: torch.Tensor, state: List[torch.Tensor]):
@@ -209,6 +210,16 @@ def predictor_forward(pw: Weights, ys_in: torch.Tensor) -> torch.Tensor:
         o, st = predictor_forward_step(pw, ys_in[:, i], st)
         outs.append(o)
     return torch.stack(outs, dim=1)
+
+
+def predictor_forward_backward(pw: Weights, ys_in: torch.Tensor, d_out: torch.Tensor):
+    """Forward + backward of model/component/predictor.py:43-63 through the restated cell above: returns
+    (out [B,U1,P], {parameter name: gradient of sum(out * d_out)}).  The arithmetic runs in the dtype of `pw`
+    (float64 weights give the ground truth the section 8f row 2 kernels are compared with)."""
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in pw.items()}
+    out = predictor_forward(leaf, ys_in)
+    (out * d_out.to(out.dtype)).sum().backward()
+    return out.detach(), {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaf.items()}
 
 
 def _joint_step(jw: Weights, enc_t: torch.Tensor, pred_u: torch.Tensor) -> torch.Tensor:

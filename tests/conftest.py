@@ -43,3 +43,19 @@ def cfg_decoder_weights(fx):
     out["enc"] = synth.synth((2, 500, H), "cfg/enc", 2.0)
     out["synth"] = synth
     return out
+
+
+def predictor_case(fx, tag):
+    """One case of predictor_small.npz: (dims, {state_dict key: fp32 array}, ys [B,U1] int64, r [B,U1,H]) - the
+    weights, token ids and cotangent are rebuilt from tests/golden/synth.py, the fixture holds the reference's results."""
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    import synth
+    V, H, L, B, U1 = (int(x) for x in fx[f"{tag}_dims"])
+    shapes = {"embed.weight": (V, H)}
+    for l in range(L):
+        shapes.update({f"rnn.weight_ih_l{l}": (4 * H, H), f"rnn.weight_hh_l{l}": (4 * H, H),
+                       f"rnn.bias_ih_l{l}": (4 * H,), f"rnn.bias_hh_l{l}": (4 * H,)})
+    shapes.update({"projection.weight": (H, H), "projection.bias": (H,)})
+    ys, r = synth.predictor_case(tag, V, H, B, U1)
+    return (V, H, L, B, U1), synth.predictor_state(shapes, f"pred/{tag}"), ys, r

@@ -361,12 +361,40 @@ def cer_golden():
     print("cer", sum(int(fx[f"res_{i}"][:3].sum()) for i in range(len(hyps))), "edits over", len(hyps), "pairs")
 
 
+def predictor_golden():
+    """predictor_small.npz: the reference RNNPredictor (model/component/predictor.py:11-63)
+    forward + backward on synth.py weights - one layer at V=412, H=128 (the models' layout at half width) and a
+    two-layer H=32 case for the layer stacking.  The loss is sum(out * r) with a synthetic cotangent r, so the fixture
+    holds out and the gradient of every parameter."""
+    _shims()
+    sys.path.insert(0, OUT)
+    import synth
+    from model.component.predictor import RNNPredictor
+    fx = {}
+    for tag, (V, H, L, B, U1) in {"p1": (412, 128, 1, 3, 9), "p2": (20, 32, 2, 5, 7)}.items():
+        pr = RNNPredictor(V, H, H, 0.0, H, L, dropout=0.0).eval()
+        shapes = {k: tuple(v.shape) for k, v in pr.state_dict().items()}
+        st = synth.predictor_state(shapes, f"pred/{tag}")
+        pr.load_state_dict({k: torch.from_numpy(v) for k, v in st.items()})
+        ys, r = synth.predictor_case(tag, V, H, B, U1)
+        out = pr(torch.from_numpy(ys))
+        (out * torch.from_numpy(r)).sum().backward()
+        fx.update({f"{tag}_dims": np.array([V, H, L, B, U1]), f"{tag}_out": out.detach().numpy()})
+        for k, v in pr.named_parameters():
+            fx[f"{tag}_d_{k}"] = v.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "predictor_small.npz"), **fx)
+    print("predictor", {k: float(np.abs(v).max()) for k, v in fx.items() if k.endswith("_out")})
+
+
 if __name__ == "__main__":
     if "--cer-only" in sys.argv:
         cer_golden()
     elif "--decode-cfg-only" in sys.argv:
         decode_cfg_golden()
+    elif "--predictor-only" in sys.argv:
+        predictor_golden()
     else:
         main()
         cer_golden()
         decode_cfg_golden()
+        predictor_golden()

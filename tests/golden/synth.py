@@ -46,6 +46,23 @@ def decoder_state(shapes, tag, blank, scales=None, blank_bias=4.0):
     return out
 
 
+def predictor_state(shapes, tag):
+    """Synthetic RNNPredictor parameters for predictor_small.npz: {state_dict key: fp32 array}, any number of layers."""
+    sc = {"embed.weight": 2.0, "weight_ih": 0.25, "weight_hh": 0.125, "bias": 0.0625, "projection.weight": 0.25,
+          "projection.bias": 0.0625}
+    out = {}
+    for k, shp in shapes.items():
+        key = next(n for n in sc if n in k)
+        out[k] = synth(tuple(shp), f"{tag}/{k}", sc[key])
+    return out
+
+
+def predictor_case(tag, V, H, B, U1):
+    """Token ids [B,U1] int64 and the cotangent r [B,U1,H] of a predictor_small.npz case."""
+    ys = (synth((B, U1), f"pred/{tag}/ys", 32768.0).astype(np.int64) + 32768) % V
+    return ys, synth((B, U1, H), f"pred/{tag}/r", 1.0)
+
+
 def ctc_logp(B, T, V, blank, name="cfg5/ctc_logp"):
     """[B,T,V] fp32 scores shaped like CTC log-posteriors (a peaked frame distribution with frequent blanks); they are
     exact grid values, not normalised - the prefix beam search only adds and compares them."""

@@ -3,7 +3,7 @@ and vs fixtures produced by the reference modules themselves (tests/golden/make_
 import numpy as np
 import torch
 
-from conftest import load_golden
+from conftest import load_golden, predictor_case
 from oracle import ctc_oracle as CO
 from oracle import transducer_oracle as TO
 
@@ -179,3 +179,22 @@ def test_cer_restated_matches_reference_golden():
         cer, S, D, I, N = CO.calculate_cer(fx[f"hyp_{i}"].tolist(), fx[f"ref_{i}"].tolist())
         assert [S, D, I, N] == fx[f"res_{i}"].tolist(), i
         assert abs(cer - float(fx[f"cer_{i}"])) < 1e-12
+
+
+def test_predictor_restated_matches_reference_golden():
+    """Section 8f row 2: the restated predictor (embed -> LSTM cells -> projection) and its gradients against what
+    the reference RNNPredictor (model/component/predictor.py:43-63) produced (predictor_small.npz), one and two
+    layers; and against torch's own nn.LSTM on the same weights (the library call the reference makes)."""
+    fx = load_golden("predictor_small.npz")
+    for tag in ("p1", "p2"):
+        (V, H, L, B, U1), st, ys, r = predictor_case(fx, tag)
+        pw = {k: T(v).double() for k, v in st.items()}
+        out, g = TO.predictor_forward_backward(pw, T(ys), T(r))
+        assert rel_l2(out.numpy(), fx[f"{tag}_out"]) < 1e-6
+        for k in st:
+            assert rel_l2(g[k].numpy(), fx[f"{tag}_d_{k}"]) < 2e-6, (tag, k)
+        lstm = torch.nn.LSTM(H, H, L, batch_first=True).double()
+        lstm.load_state_dict({k[4:]: v for k, v in pw.items() if k.startswith("rnn.")})
+        y, _ = lstm(pw["embed.weight"][T(ys)])
+        y = y @ pw["projection.weight"].T + pw["projection.bias"]
+        assert rel_l2(y.detach().numpy(), out.numpy()) < 1e-12
