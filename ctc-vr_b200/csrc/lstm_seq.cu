@@ -11,14 +11,18 @@
 //     keeps the 4*HS rows of W_hh that produce its units' gates resident in shared memory for the whole sequence
 //     (forward), or the HS columns it needs for dh_{t-1} (backward), so the 4 MB of W_hh are read from HBM once;
 //   * a step exchanges h_t (forward, [H][B]) or the gate gradients (backward, [4H][B]) through a ping-pong buffer in
-//     L2: every CTA stores its slice, raises its own step flag (st.release.gpu), and waits until all G flags have
-//     reached the step (ld.acquire.gpu by one thread per flag) - no atomics, no grid-wide counter;
+//     L2 whose elements validate themselves: every element is one 8-byte word {fp32 value, step tag} written and read
+//     with single 64-bit relaxed accesses (the pattern NCCL's LL protocol uses over NVLink).  A consumer simply re-reads
+//     an element until its tag is the step it waits for, so a step costs one store -> L2 -> load trip: there is no
+//     flag barrier, no fence and no atomic on the critical path (the first version of this kernel raised one release
+//     flag per CTA and step and polled all G of them: 7 us per step with nothing else to do);
+//     the buffer is zeroed before the launch, tags start at 1;
 //   * inside a CTA warp w owns a 1/16 slice of the reduction dimension and lane b one batch row: the operand row
-//     exchange[k][b] is one coalesced 128-byte L2 load per warp (ld.global.cg, the lines are rewritten by other SMs every
-//     second step), the weights are shared-memory broadcasts, and each lane keeps 4*HS (forward) or HS (backward)
-//     accumulators; the 16 partial sums meet in shared memory;
+//     exchange[k][b] is one coalesced 256-byte L2 load per warp, 16 of them in flight per warp, the weights are
+//     shared-memory broadcasts, and each lane keeps 4*HS (forward) or HS (backward) accumulators fed by packed
+//     fma.rn.f32x2 (two IEEE FMAs per issue slot); the 16 partial sums meet in shared memory;
 //   * the per-step tensors that do not depend on the recurrence (xg; the saved gates, cell states and dL/dh_t) are
-//     loaded into registers BEFORE the flag wait, so their latency hides under the barrier.
+//     loaded into registers BEFORE the first exchange load, so their latency hides under the wait.
 // Batches beyond 32 rows run as chunks of 32 inside a step.  Waits are bounded (2 s): a CTA that gives up writes a
 // mapped host word and the next call fails loudly.
 #include <algorithm>
@@ -31,21 +35,37 @@ namespace {
 constexpr int LSTM_THREADS = 512;
 constexpr int LSTM_WARPS = 16;
 constexpr long long LSTM_TIMEOUT_NS = 2LL * 1000 * 1000 * 1000;
+typedef unsigned long long u64;
 
-__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_relaxed_u64(u64* p, u64 v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 tagged(float v, unsigned int tag) { return ((u64)tag << 32) | (u64)__float_as_uint(v); }
 __device__ __forceinline__ long long gtime_ns() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// two IEEE fp32 FMAs in one issue slot (bit-identical to two fmaf calls)
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
 
 struct LstmFwdArgs {
   const float* xg;      // [B, U1, 4H]  x_t W_ih^T + b_ih + b_hh
@@ -57,10 +77,9 @@ struct LstmFwdArgs {
   float* act;           // [B, U1, 4H] activated gates (NULL: not kept)
   float* hn;            // [B, H]
   float* cn;            // [B, H]
-  float* hx;            // workspace: 2 x [H][Bp]
-  unsigned int* flags;  // workspace: [G], zeroed before the launch
+  u64* hx;              // workspace: 2 x [H][Bp] {value, tag}, zeroed before the launch
   unsigned int* err;    // mapped host word
-  int B, U1, H, Bp, G;
+  int B, U1, H, Bp;
 };
 
 struct LstmBwdArgs {
@@ -74,36 +93,44 @@ struct LstmBwdArgs {
   float* dgates;        // [B, U1, 4H] dL/d(pre-activation gates)
   float* d_h0;          // [B, H]
   float* d_c0;          // [B, H]
-  float* dgx;           // workspace: 2 x [4H][Bp]
-  unsigned int* flags;
+  u64* dgx;             // workspace: 2 x [4H][Bp] {value, tag}, zeroed before the launch
   unsigned int* err;
-  int B, U1, H, Bp, G;
+  int B, U1, H, Bp;
 };
 
-// Every CTA has stored its slice of step `value - 1`: raise my flag, then wait for all G flags.
-__device__ __forceinline__ void publish(unsigned int* flags, unsigned int value) {
-  __syncthreads();                        // the CTA's stores are ordered before thread 0's release (cumulativity)
-  if (threadIdx.x == 0) {
-    __threadfence();
-    st_release_gpu(flags + blockIdx.x, value);
+// Load rows r0 .. r0+15 (those below r1) of the exchange buffer for this lane's batch row, re-reading an element until
+// it carries `tag`.  All pending loads are issued before the first tag is looked at.  `dead` (shared memory) is set by
+// the first wait of this CTA that times out: later waits return at once, so a broken launch ends after ~2 s.
+__device__ __forceinline__ void load16(const u64* p, size_t stride, int r0, int r1, unsigned int tag, float (&v)[16],
+                                       unsigned int* err, int site, volatile int* dead) {
+  unsigned int pend = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    v[i] = 0.f;
+    if (r0 + i < r1) pend |= 1u << i;
   }
-}
-// `dead` (shared memory) is set by the first wait of this CTA that times out: later waits return at once, so a broken
-// launch ends after ~2 s instead of 2 s per step.
-__device__ __forceinline__ void wait_all(const unsigned int* flags, int G, unsigned int value, unsigned int* err, int site,
-                                         volatile int* dead) {
-  if ((int)threadIdx.x < G && !*dead) {
-    const long long t0 = gtime_ns();
-    int spins = 0;
-    while ((int)(ld_acquire_gpu(flags + threadIdx.x) - value) < 0) {
-      if ((++spins & 255) == 0 && (*dead || gtime_ns() - t0 > LSTM_TIMEOUT_NS)) {
-        if (err) *reinterpret_cast<volatile unsigned int*>(err) = 0x80000000u | ((unsigned)site << 24) | ((unsigned)threadIdx.x << 12) | blockIdx.x;
+  int spins = 0;
+  long long t0 = 0;
+  while (pend) {
+    u64 raw[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if ((pend >> i) & 1u) raw[i] = ld_relaxed_u64(p + (size_t)(r0 + i) * stride);
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (((pend >> i) & 1u) && (unsigned int)(raw[i] >> 32) == tag) {
+        v[i] = __uint_as_float((unsigned int)raw[i]);
+        pend &= ~(1u << i);
+      }
+    if (pend && (++spins & 63) == 0) {
+      if (t0 == 0) t0 = gtime_ns();
+      if (*dead || gtime_ns() - t0 > LSTM_TIMEOUT_NS) {
+        if (err) *reinterpret_cast<volatile unsigned int*>(err) = 0x80000000u | ((unsigned)site << 24) | ((unsigned)(tag & 0xfffu) << 12) | (blockIdx.x & 0xfffu);
         *dead = 1;
         break;
       }
     }
   }
-  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -138,15 +165,16 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_fwd_kernel(const Lst
     const int u = idx / Bp, b = idx - u * Bp, unit = unit0 + u;
     const bool ok = b < B && unit < H;
     c_sm[b * HS + u] = (ok && a.c0) ? a.c0[(size_t)b * H + unit] : 0.f;
-    if (unit < H) a.hx[(size_t)unit * Bp + b] = (ok && a.h0) ? a.h0[(size_t)b * H + unit] : 0.f;
+    if (unit < H) st_relaxed_u64(a.hx + (size_t)unit * Bp + b, tagged((ok && a.h0) ? a.h0[(size_t)b * H + unit] : 0.f, 1u));
   }
-  publish(a.flags, 1u);
+  __syncthreads();
 
+  const ulonglong2* Wsm2 = reinterpret_cast<const ulonglong2*>(Wsm);     // {W_i, W_f}, {W_g, W_o}
   const int Kc = (H + LSTM_WARPS - 1) / LSTM_WARPS;
   const int k0 = min(H, w * Kc), k1 = min(H, k0 + Kc);
   for (int t = 0; t < U1; ++t) {
-    const float* hprev = a.hx + (size_t)(t & 1) * H * Bp;
-    float* hnext = a.hx + (size_t)((t + 1) & 1) * H * Bp;
+    const u64* hprev = a.hx + (size_t)(t & 1) * H * Bp;
+    u64* hnext = a.hx + (size_t)((t + 1) & 1) * H * Bp;
     // the finishing warps (w < HS: unit w, batch row = lane) fetch chunk 0's input projection ahead of the wait
     float xg_pf[4] = {0.f, 0.f, 0.f, 0.f};
     if (w < HS && unit0 + w < H && lane < B) {
@@ -154,32 +182,33 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_fwd_kernel(const Lst
 #pragma unroll
       for (int g = 0; g < 4; ++g) xg_pf[g] = __ldg(q + (size_t)g * H);
     }
-    wait_all(a.flags, a.G, (unsigned)(t + 1), a.err, 1, &s_dead);
     for (int ch = 0; ch < nb; ++ch) {
-      float acc[HS][4];
+      u64 acc[HS][2];
 #pragma unroll
-      for (int u = 0; u < HS; ++u) acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f;
-      const float* hp = hprev + ch * 32 + lane;
+      for (int u = 0; u < HS; ++u) acc[u][0] = acc[u][1] = 0ull;
+      const u64* hp = hprev + ch * 32 + lane;
       for (int k = k0; k < k1; k += 16) {
         float hv[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) hv[i] = (k + i < k1) ? __ldcg(hp + (size_t)(k + i) * Bp) : 0.f;
+        load16(hp, (size_t)Bp, k, k1, (unsigned)(t + 1), hv, a.err, 1, &s_dead);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
+          const u64 hh = pack2(hv[i], hv[i]);
 #pragma unroll
           for (int u = 0; u < HS; ++u) {
-            const float4 wv = Wsm[(size_t)(k + i) * HS + u];
-            acc[u][0] = fmaf(hv[i], wv.x, acc[u][0]);
-            acc[u][1] = fmaf(hv[i], wv.y, acc[u][1]);
-            acc[u][2] = fmaf(hv[i], wv.z, acc[u][2]);
-            acc[u][3] = fmaf(hv[i], wv.w, acc[u][3]);
+            const ulonglong2 wv = Wsm2[(size_t)(k + i) * HS + u];
+            acc[u][0] = fma2(hh, wv.x, acc[u][0]);
+            acc[u][1] = fma2(hh, wv.y, acc[u][1]);
           }
         }
       }
 #pragma unroll
-      for (int u = 0; u < HS; ++u)
-#pragma unroll
-        for (int g = 0; g < 4; ++g) red[((w * 4 * HS) + u * 4 + g) * 32 + lane] = acc[u][g];
+      for (int u = 0; u < HS; ++u) {
+        float s0, s1, s2, s3;
+        unpack2(acc[u][0], s0, s1);
+        unpack2(acc[u][1], s2, s3);
+        float* q = red + ((w * 4 * HS) + u * 4) * 32 + lane;
+        q[0] = s0; q[32] = s1; q[64] = s2; q[96] = s3;
+      }
       __syncthreads();
       for (int combo = w; combo < 4 * HS; combo += LSTM_WARPS) {
         float s = 0.f;
@@ -188,6 +217,8 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_fwd_kernel(const Lst
         sums[combo * 32 + lane] = s;
       }
       __syncthreads();
+      // (the next red / sums writes happen behind the two barriers of the next chunk or step, which the finishing
+      // warps only reach after this block)
       if (w < HS) {
         const int u = w, unit = unit0 + u, b = ch * 32 + lane;
         if (unit < H && b < B) {
@@ -207,7 +238,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_fwd_kernel(const Lst
           const float c = gf * c_sm[b * HS + u] + gi * gg;
           const float h = go * tanhf(c);
           c_sm[b * HS + u] = c;
-          hnext[(size_t)unit * Bp + b] = h;
+          st_relaxed_u64(hnext + (size_t)unit * Bp + b, tagged(h, (unsigned)(t + 2)));    // first: the others wait for it
           const size_t row = (size_t)b * U1 + t;
           a.out[row * H + unit] = h;
           if (a.cs) a.cs[row * H + unit] = c;
@@ -220,13 +251,10 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_fwd_kernel(const Lst
             a.cn[(size_t)b * H + unit] = c;
           }
         } else if (unit < H) {
-          hnext[(size_t)unit * Bp + b] = 0.f;               // padded batch rows stay finite
+          st_relaxed_u64(hnext + (size_t)unit * Bp + b, tagged(0.f, (unsigned)(t + 2)));  // padded batch rows
         }
       }
-      // the next chunk's partial sums are written after its accumulation; the publish / wait below also separate them
-      if (ch + 1 < nb) __syncthreads();
     }
-    publish(a.flags, (unsigned)(t + 2));
   }
 }
 
@@ -281,54 +309,60 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_bwd_kernel(const Lst
 
   for (int s = 0; s < U1; ++s) {
     const int t = U1 - 1 - s;
-    float* dgx = a.dgx + (size_t)(s & 1) * J * Bp;
+    const unsigned int tag = (unsigned)(s + 1);
+    u64* dgx = a.dgx + (size_t)(s & 1) * J * Bp;
     // A. pointwise gradients of step t for my units
     if (fin) {
       const int u = w, unit = unit0 + u;
       for (int ch = 0; ch < nb; ++ch) {
         const int b = ch * 32 + lane;
+        float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f;
         if (b < B) {
           const BwdStepIn in = (ch == 0) ? pf : load_step(a, b, t, unit);
           const float dh = in.dh + dh_sm[b * HS + u];
           const float tc = tanhf(in.c);
           const float dc = dc_sm[b * HS + u] + dh * in.go * (1.f - tc * tc);
-          const float d_o = dh * tc * in.go * (1.f - in.go);
-          const float d_i = dc * in.gg * in.gi * (1.f - in.gi);
-          const float d_f = dc * in.cprev * in.gf * (1.f - in.gf);
-          const float d_g = dc * in.gi * (1.f - in.gg * in.gg);
+          d_o = dh * tc * in.go * (1.f - in.go);
+          d_i = dc * in.gg * in.gi * (1.f - in.gi);
+          d_f = dc * in.cprev * in.gf * (1.f - in.gf);
+          d_g = dc * in.gi * (1.f - in.gg * in.gg);
           dc_sm[b * HS + u] = dc * in.gf;
+        }
+        st_relaxed_u64(dgx + (size_t)(0 * H + unit) * Bp + b, tagged(d_i, tag));    // padded batch rows carry zeros
+        st_relaxed_u64(dgx + (size_t)(1 * H + unit) * Bp + b, tagged(d_f, tag));
+        st_relaxed_u64(dgx + (size_t)(2 * H + unit) * Bp + b, tagged(d_g, tag));
+        st_relaxed_u64(dgx + (size_t)(3 * H + unit) * Bp + b, tagged(d_o, tag));
+        if (b < B) {
           float* q = a.dgates + ((size_t)b * U1 + t) * J + unit;
           q[0] = d_i; q[(size_t)H] = d_f; q[(size_t)2 * H] = d_g; q[(size_t)3 * H] = d_o;
-          dgx[(size_t)(0 * H + unit) * Bp + b] = d_i;
-          dgx[(size_t)(1 * H + unit) * Bp + b] = d_f;
-          dgx[(size_t)(2 * H + unit) * Bp + b] = d_g;
-          dgx[(size_t)(3 * H + unit) * Bp + b] = d_o;
-        } else {
-          dgx[(size_t)(0 * H + unit) * Bp + b] = 0.f;       // padded batch rows stay finite
-          dgx[(size_t)(1 * H + unit) * Bp + b] = 0.f;
-          dgx[(size_t)(2 * H + unit) * Bp + b] = 0.f;
-          dgx[(size_t)(3 * H + unit) * Bp + b] = 0.f;
         }
       }
+      if (lane < B && t > 0) pf = load_step(a, lane, t - 1, unit);   // next step's operands, under the wait below
     }
-    publish(a.flags, (unsigned)(s + 1));
-    if (fin && lane < B && t > 0) pf = load_step(a, lane, t - 1, unit0 + w);   // next step's operands, under the wait
-    wait_all(a.flags, a.G, (unsigned)(s + 1), a.err, 2, &s_dead);
     // D. dh_{t-1}[b][my units] = sum_j dgates_t[b][j] * W_hh[j][unit]
     for (int ch = 0; ch < nb; ++ch) {
       float acc[HS];
 #pragma unroll
       for (int u = 0; u < HS; ++u) acc[u] = 0.f;
-      const float* gp = dgx + ch * 32 + lane;
+      const u64* gp = dgx + ch * 32 + lane;
       for (int j = j0; j < j1; j += 16) {
         float gv[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) gv[i] = (j + i < j1) ? __ldcg(gp + (size_t)(j + i) * Bp) : 0.f;
+        load16(gp, (size_t)Bp, j, j1, tag, gv, a.err, 2, &s_dead);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float* wr = Wc + (size_t)(j + i) * HS;
+          if (HS >= 2) {
+            const u64 gg2 = pack2(gv[i], gv[i]);
+            const u64* wr2 = reinterpret_cast<const u64*>(wr);
 #pragma unroll
-          for (int u = 0; u < HS; ++u) acc[u] = fmaf(gv[i], wr[u], acc[u]);
+            for (int u = 0; u < HS / 2; ++u) {
+              u64 c2 = pack2(acc[2 * u], acc[2 * u + 1]);
+              c2 = fma2(gg2, wr2[u], c2);
+              unpack2(c2, acc[2 * u], acc[2 * u + 1]);
+            }
+          } else {
+            acc[0] = fmaf(gv[i], wr[0], acc[0]);
+          }
         }
       }
 #pragma unroll
@@ -391,22 +425,15 @@ int check_lstm_error(const char* where) {
   if (h && *reinterpret_cast<volatile unsigned int*>(h) != 0u) {
     const unsigned int code = *h;
     *h = 0u;
-    set_error("%s: an earlier LSTM sequence kernel gave up waiting for a step flag (0x%08x: site %u, flag %u, CTA %u); the "
+    set_error("%s: an earlier LSTM sequence kernel gave up waiting for a step's operands (0x%08x: site %u, step tag %u, CTA %u); the "
               "results of that call are invalid", where, code, (code >> 24) & 0x7fu, (code >> 12) & 0xfffu, code & 0xfffu);
     return 1;
   }
   return 0;
 }
 
-struct LstmWs { unsigned int* flags; float* xch; size_t bytes; };
-LstmWs carve_lstm_ws(void* ws, int B, int H) {
-  const int Bp = (B + 31) / 32 * 32;
-  LstmWs W;
-  W.flags = reinterpret_cast<unsigned int*>(ws);
-  W.xch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + 1024);
-  W.bytes = 1024 + (size_t)2 * 4 * H * Bp * sizeof(float);
-  return W;
-}
+// exchange buffer: 2 x [rows][Bp] 8-byte {value, tag} words; rows = H (forward) or 4H (backward)
+size_t xch_bytes(int rows, int Bp) { return (size_t)2 * rows * Bp * sizeof(u64); }
 
 template <typename Args>
 int launch_coop(void (*kern)(const Args), int G, size_t smem, const Args& a, cudaStream_t st) {
@@ -427,7 +454,7 @@ int lstm_seq_supported(int B, int H) {
   return fwd_smem(H, hs, Bp) <= 232448 && bwd_smem(H, hs, Bp) <= 232448;
 }
 
-size_t lstm_seq_ws_bytes(int B, int H) { return carve_lstm_ws(nullptr, B, H).bytes; }
+size_t lstm_seq_ws_bytes(int B, int H) { return xch_bytes(4 * H, (B + 31) / 32 * 32); }
 
 int lstm_seq_fwd(const float* xg, const float* w_hh, const float* h0, const float* c0, float* out, float* cs, float* act,
                  float* hn, float* cn, int B, int U1, int H, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -435,12 +462,12 @@ int lstm_seq_fwd(const float* xg, const float* w_hh, const float* h0, const floa
   if (check_lstm_error("lstm_seq_fwd")) return 1;
   CTCVR_REQUIRE(ws_bytes >= lstm_seq_ws_bytes(B, H), "lstm_seq_fwd: workspace too small");
   const int hs = pick_hs(H, lstm_sm_count()), Bp = (B + 31) / 32 * 32, G = (H + hs - 1) / hs;
-  LstmWs W = carve_lstm_ws(ws, B, H);
+  CTCVR_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "lstm_seq_fwd: workspace must be 8-byte aligned");
   LstmFwdArgs a{};
   a.xg = xg; a.w_hh = w_hh; a.h0 = h0; a.c0 = c0; a.out = out; a.cs = cs; a.act = act; a.hn = hn; a.cn = cn;
-  a.hx = W.xch; a.flags = W.flags; a.B = B; a.U1 = U1; a.H = H; a.Bp = Bp; a.G = G;
+  a.hx = reinterpret_cast<u64*>(ws); a.B = B; a.U1 = U1; a.H = H; a.Bp = Bp;
   lstm_error_host_word(&a.err);
-  CTCVR_CHECK_CUDA(cudaMemsetAsync(W.flags, 0, 1024, st));
+  CTCVR_CHECK_CUDA(cudaMemsetAsync(ws, 0, xch_bytes(H, Bp), st));
   const size_t smem = fwd_smem(H, hs, Bp);
   switch (hs) {
     case 1: return launch_coop(lstm_seq_fwd_kernel<1>, G, smem, a, st);
@@ -457,13 +484,13 @@ int lstm_seq_bwd(const float* act, const float* cs, const float* c0, const float
   if (check_lstm_error("lstm_seq_bwd")) return 1;
   CTCVR_REQUIRE(ws_bytes >= lstm_seq_ws_bytes(B, H), "lstm_seq_bwd: workspace too small");
   const int hs = pick_hs(H, lstm_sm_count()), Bp = (B + 31) / 32 * 32, G = (H + hs - 1) / hs;
-  LstmWs W = carve_lstm_ws(ws, B, H);
+  CTCVR_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "lstm_seq_bwd: workspace must be 8-byte aligned");
   LstmBwdArgs a{};
   a.act = act; a.cs = cs; a.c0 = c0; a.w_hh = w_hh; a.d_out = d_out; a.d_hn = d_hn; a.d_cn = d_cn;
-  a.dgates = dgates; a.d_h0 = d_h0; a.d_c0 = d_c0; a.dgx = W.xch; a.flags = W.flags;
-  a.B = B; a.U1 = U1; a.H = H; a.Bp = Bp; a.G = G;
+  a.dgates = dgates; a.d_h0 = d_h0; a.d_c0 = d_c0; a.dgx = reinterpret_cast<u64*>(ws);
+  a.B = B; a.U1 = U1; a.H = H; a.Bp = Bp;
   lstm_error_host_word(&a.err);
-  CTCVR_CHECK_CUDA(cudaMemsetAsync(W.flags, 0, 1024, st));
+  CTCVR_CHECK_CUDA(cudaMemsetAsync(ws, 0, xch_bytes(4 * H, Bp), st));
   const size_t smem = bwd_smem(H, hs, Bp);
   switch (hs) {
     case 1: return launch_coop(lstm_seq_bwd_kernel<1>, G, smem, a, st);
