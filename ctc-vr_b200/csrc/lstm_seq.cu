@@ -134,24 +134,47 @@ __device__ __forceinline__ void load16(const u64* p, size_t stride, int r0, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Work split.  A CTA owns UC = UG * HSL hidden units (UG = 32 / BW unit groups of HSL units) and the batch rows of its
+// row groups (BW = 8 rows each; blockIdx.y = first row group, stride gridDim.y).  Lane = (bl, ug): batch row bl of the
+// row group, unit group ug - so a warp-wide exchange load only touches BW distinct elements (64 bytes with BW = 8
+// instead of 256 with one batch row per lane: the per-step L2 -> SM volume, which bounds the step at H = 512, drops 4x)
+// while the per-lane arithmetic (HSL units x its k slice) is unchanged.
+// ---------------------------------------------------------------------------------------------------------------
+struct LaneMap {
+  int bl, ug;
+};
+template <int BW>
+__device__ __forceinline__ LaneMap lane_map(int lane) {
+  LaneMap m;
+  m.bl = lane & (BW - 1);
+  m.ug = lane / BW;
+  return m;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------------
-template <int HS>
+template <int HSL, int BW>
 __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_fwd_kernel(const LstmFwdArgs a) {
+  constexpr int UG = 32 / BW, UC = UG * HSL;
   extern __shared__ __align__(16) unsigned char lstm_smem[];
   __shared__ int s_dead;
   if (threadIdx.x == 0) s_dead = 0;
-  const int H = a.H, B = a.B, Bp = a.Bp, nb = Bp >> 5, U1 = a.U1;
-  float4* Wsm = reinterpret_cast<float4*>(lstm_smem);                    // [H + 16][HS] {i, f, g, o} weights of (k, unit)
-  float* red = reinterpret_cast<float*>(Wsm + (size_t)(H + 16) * HS);    // [16][4*HS][32]
-  float* sums = red + LSTM_WARPS * 4 * HS * 32;                          // [4*HS][32]
-  float* c_sm = sums + 4 * HS * 32;                                      // [Bp][HS]
+  const int H = a.H, B = a.B, Bp = a.Bp, U1 = a.U1;
+  const int RG = Bp / BW, NBS = gridDim.y, bs = blockIdx.y;
+  const int nch = (RG - bs + NBS - 1) / NBS;                            // row groups of this CTA: bs, bs + NBS, ...
+  float4* Wsm = reinterpret_cast<float4*>(lstm_smem);                    // [H + 16][HSL][UG] {i, f, g, o} weights of (k, unit)
+  float* red = reinterpret_cast<float*>(Wsm + (size_t)(H + 16) * UC);    // [16][4*HSL][32]
+  float* sums = red + LSTM_WARPS * 4 * HSL * 32;                         // [4*HSL][32]
+  float* c_sm = sums + 4 * HSL * 32;                                     // [nch][32][HSL]
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const int unit0 = blockIdx.x * HS;
+  const LaneMap lm = lane_map<BW>(lane);
+  const int unit0 = blockIdx.x * UC;
   const size_t H4 = (size_t)4 * H;
 
-  for (int idx = tid; idx < (H + 16) * HS; idx += LSTM_THREADS) {        // idx = u * (H+16) + k: coalesced over k
-    const int u = idx / (H + 16), k = idx - u * (H + 16), unit = unit0 + u;
+  for (int idx = tid; idx < (H + 16) * UC; idx += LSTM_THREADS) {        // idx = uc * (H+16) + k: coalesced over k
+    const int uc = idx / (H + 16), k = idx - uc * (H + 16), unit = unit0 + uc;
+    const int ug = uc / HSL, ui = uc - ug * HSL;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k < H && unit < H) {
       v.x = a.w_hh[((size_t)0 * H + unit) * H + k];
@@ -159,13 +182,18 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_fwd_kernel(const Lst
       v.z = a.w_hh[((size_t)2 * H + unit) * H + k];
       v.w = a.w_hh[((size_t)3 * H + unit) * H + k];
     }
-    Wsm[(size_t)k * HS + u] = v;
+    Wsm[((size_t)k * HSL + ui) * UG + ug] = v;
   }
-  for (int idx = tid; idx < Bp * HS; idx += LSTM_THREADS) {              // idx = u * Bp + b: coalesced exchange stores
-    const int u = idx / Bp, b = idx - u * Bp, unit = unit0 + u;
-    const bool ok = b < B && unit < H;
-    c_sm[b * HS + u] = (ok && a.c0) ? a.c0[(size_t)b * H + unit] : 0.f;
-    if (unit < H) st_relaxed_u64(a.hx + (size_t)unit * Bp + b, tagged((ok && a.h0) ? a.h0[(size_t)b * H + unit] : 0.f, 1u));
+  // finishing threads (w < HSL): unit = unit0 + ug * HSL + w, batch row b = rg * BW + bl
+  const int my_unit = unit0 + lm.ug * HSL + w;
+  const bool fin = w < HSL && my_unit < H;
+  if (w < HSL) {
+    for (int c = 0; c < nch; ++c) {
+      const int b = (bs + c * NBS) * BW + lm.bl;
+      const bool ok = fin && b < B;
+      c_sm[(c * 32 + lane) * HSL + w] = (ok && a.c0) ? a.c0[(size_t)b * H + my_unit] : 0.f;
+      if (fin) st_relaxed_u64(a.hx + (size_t)my_unit * Bp + b, tagged((ok && a.h0) ? a.h0[(size_t)b * H + my_unit] : 0.f, 1u));
+    }
   }
   __syncthreads();
 
@@ -175,18 +203,19 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_fwd_kernel(const Lst
   for (int t = 0; t < U1; ++t) {
     const u64* hprev = a.hx + (size_t)(t & 1) * H * Bp;
     u64* hnext = a.hx + (size_t)((t + 1) & 1) * H * Bp;
-    // the finishing warps (w < HS: unit w, batch row = lane) fetch chunk 0's input projection ahead of the wait
+    // the finishing threads fetch their first row group's input projection ahead of the wait
     float xg_pf[4] = {0.f, 0.f, 0.f, 0.f};
-    if (w < HS && unit0 + w < H && lane < B) {
-      const float* q = a.xg + ((size_t)lane * U1 + t) * H4 + unit0 + w;
+    if (fin && bs * BW + lm.bl < B) {
+      const float* q = a.xg + ((size_t)(bs * BW + lm.bl) * U1 + t) * H4 + my_unit;
 #pragma unroll
       for (int g = 0; g < 4; ++g) xg_pf[g] = __ldg(q + (size_t)g * H);
     }
-    for (int ch = 0; ch < nb; ++ch) {
-      u64 acc[HS][2];
+    for (int c = 0; c < nch; ++c) {
+      const int b = (bs + c * NBS) * BW + lm.bl;
+      u64 acc[HSL][2];
 #pragma unroll
-      for (int u = 0; u < HS; ++u) acc[u][0] = acc[u][1] = 0ull;
-      const u64* hp = hprev + ch * 32 + lane;
+      for (int u = 0; u < HSL; ++u) acc[u][0] = acc[u][1] = 0ull;
+      const u64* hp = hprev + b;
       for (int k = k0; k < k1; k += 16) {
         float hv[16];
         load16(hp, (size_t)Bp, k, k1, (unsigned)(t + 1), hv, a.err, 1, &s_dead);
@@ -194,40 +223,40 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_fwd_kernel(const Lst
         for (int i = 0; i < 16; ++i) {
           const u64 hh = pack2(hv[i], hv[i]);
 #pragma unroll
-          for (int u = 0; u < HS; ++u) {
-            const ulonglong2 wv = Wsm2[(size_t)(k + i) * HS + u];
+          for (int u = 0; u < HSL; ++u) {
+            const ulonglong2 wv = Wsm2[((size_t)(k + i) * HSL + u) * UG + lm.ug];
             acc[u][0] = fma2(hh, wv.x, acc[u][0]);
             acc[u][1] = fma2(hh, wv.y, acc[u][1]);
           }
         }
       }
 #pragma unroll
-      for (int u = 0; u < HS; ++u) {
+      for (int u = 0; u < HSL; ++u) {
         float s0, s1, s2, s3;
         unpack2(acc[u][0], s0, s1);
         unpack2(acc[u][1], s2, s3);
-        float* q = red + ((w * 4 * HS) + u * 4) * 32 + lane;
+        float* q = red + ((w * 4 * HSL) + u * 4) * 32 + lane;
         q[0] = s0; q[32] = s1; q[64] = s2; q[96] = s3;
       }
       __syncthreads();
-      for (int combo = w; combo < 4 * HS; combo += LSTM_WARPS) {
+      for (int combo = w; combo < 4 * HSL; combo += LSTM_WARPS) {
         float s = 0.f;
 #pragma unroll
-        for (int ww = 0; ww < LSTM_WARPS; ++ww) s += red[((ww * 4 * HS) + combo) * 32 + lane];
+        for (int ww = 0; ww < LSTM_WARPS; ++ww) s += red[((ww * 4 * HSL) + combo) * 32 + lane];
         sums[combo * 32 + lane] = s;
       }
       __syncthreads();
-      // (the next red / sums writes happen behind the two barriers of the next chunk or step, which the finishing
+      // (the next red / sums writes happen behind the two barriers of the next row group or step, which the finishing
       // warps only reach after this block)
-      if (w < HS) {
-        const int u = w, unit = unit0 + u, b = ch * 32 + lane;
-        if (unit < H && b < B) {
+      if (fin) {
+        const int u = w;
+        if (b < B) {
           float x4[4];
-          if (ch == 0) {
+          if (c == 0) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) x4[g] = xg_pf[g];
           } else {
-            const float* q = a.xg + ((size_t)b * U1 + t) * H4 + unit;
+            const float* q = a.xg + ((size_t)b * U1 + t) * H4 + my_unit;
 #pragma unroll
             for (int g = 0; g < 4; ++g) x4[g] = __ldg(q + (size_t)g * H);
           }
@@ -235,23 +264,24 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_fwd_kernel(const Lst
           const float gf = sigmoidf_(sums[(u * 4 + 1) * 32 + lane] + x4[1]);
           const float gg = tanhf(sums[(u * 4 + 2) * 32 + lane] + x4[2]);
           const float go = sigmoidf_(sums[(u * 4 + 3) * 32 + lane] + x4[3]);
-          const float c = gf * c_sm[b * HS + u] + gi * gg;
-          const float h = go * tanhf(c);
-          c_sm[b * HS + u] = c;
-          st_relaxed_u64(hnext + (size_t)unit * Bp + b, tagged(h, (unsigned)(t + 2)));    // first: the others wait for it
+          float* cp = c_sm + (c * 32 + lane) * HSL + u;
+          const float cc = gf * *cp + gi * gg;
+          const float h = go * tanhf(cc);
+          *cp = cc;
+          st_relaxed_u64(hnext + (size_t)my_unit * Bp + b, tagged(h, (unsigned)(t + 2)));    // first: the others wait for it
           const size_t row = (size_t)b * U1 + t;
-          a.out[row * H + unit] = h;
-          if (a.cs) a.cs[row * H + unit] = c;
+          a.out[row * H + my_unit] = h;
+          if (a.cs) a.cs[row * H + my_unit] = cc;
           if (a.act) {
-            float* q = a.act + row * H4 + unit;
+            float* q = a.act + row * H4 + my_unit;
             q[0] = gi; q[(size_t)H] = gf; q[(size_t)2 * H] = gg; q[(size_t)3 * H] = go;
           }
           if (t == U1 - 1) {
-            a.hn[(size_t)b * H + unit] = h;
-            a.cn[(size_t)b * H + unit] = c;
+            a.hn[(size_t)b * H + my_unit] = h;
+            a.cn[(size_t)b * H + my_unit] = cc;
           }
-        } else if (unit < H) {
-          st_relaxed_u64(hnext + (size_t)unit * Bp + b, tagged(0.f, (unsigned)(t + 2)));  // padded batch rows
+        } else {
+          st_relaxed_u64(hnext + (size_t)my_unit * Bp + b, tagged(0.f, (unsigned)(t + 2)));  // padded batch rows
         }
       }
     }
@@ -275,37 +305,45 @@ __device__ __forceinline__ BwdStepIn load_step(const LstmBwdArgs& a, int b, int 
   return s;
 }
 
-template <int HS>
+template <int HSL, int BW>
 __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_bwd_kernel(const LstmBwdArgs a) {
+  constexpr int UG = 32 / BW, UC = UG * HSL;
   extern __shared__ __align__(16) unsigned char lstm_smem[];
   __shared__ int s_dead;
   if (threadIdx.x == 0) s_dead = 0;
-  const int H = a.H, B = a.B, Bp = a.Bp, nb = Bp >> 5, U1 = a.U1;
+  const int H = a.H, B = a.B, Bp = a.Bp, U1 = a.U1;
+  const int RG = Bp / BW, NBS = gridDim.y, bs = blockIdx.y;
+  const int nch = (RG - bs + NBS - 1) / NBS;
   const int J = 4 * H;
-  float* Wc = reinterpret_cast<float*>(lstm_smem);        // [4H + 16][HS]: W_hh[j][unit0 + u]
-  float* red = Wc + (size_t)(J + 16) * HS;                 // [16][HS][32]
-  float* dh_sm = red + LSTM_WARPS * HS * 32;               // [Bp][HS] dL/dh_t arriving through the recurrence
-  float* dc_sm = dh_sm + (size_t)Bp * HS;                  // [Bp][HS] dL/dc_t arriving from step t+1
+  float* Wc = reinterpret_cast<float*>(lstm_smem);        // [4H + 16][UG][HSL]: W_hh[j][unit0 + ug * HSL + ui]
+  float* red = Wc + (size_t)(J + 16) * UC;                 // [16][HSL][32]
+  float* dh_sm = red + LSTM_WARPS * HSL * 32;              // [nch][32][HSL] dL/dh_t arriving through the recurrence
+  float* dc_sm = dh_sm + (size_t)nch * 32 * HSL;           // [nch][32][HSL] dL/dc_t arriving from step t+1
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const int unit0 = blockIdx.x * HS;
+  const LaneMap lm = lane_map<BW>(lane);
+  const int unit0 = blockIdx.x * UC;
 
-  for (int idx = tid; idx < (J + 16) * HS; idx += LSTM_THREADS) {
-    const int j = idx / HS, u = idx - j * HS, unit = unit0 + u;
+  for (int idx = tid; idx < (J + 16) * UC; idx += LSTM_THREADS) {
+    const int j = idx / UC, uc = idx - j * UC, unit = unit0 + uc;       // [ug][ui] order == unit order inside the CTA
     Wc[idx] = (j < J && unit < H) ? a.w_hh[(size_t)j * H + unit] : 0.f;
   }
-  for (int idx = tid; idx < Bp * HS; idx += LSTM_THREADS) {
-    const int b = idx / HS, u = idx - b * HS, unit = unit0 + u;
-    const bool ok = b < B && unit < H;
-    dh_sm[idx] = (ok && a.d_hn) ? a.d_hn[(size_t)b * H + unit] : 0.f;
-    dc_sm[idx] = (ok && a.d_cn) ? a.d_cn[(size_t)b * H + unit] : 0.f;
+  const int my_unit = unit0 + lm.ug * HSL + w;
+  const bool fin = w < HSL && my_unit < H;                 // finishing thread: unit my_unit, batch row rg * BW + bl
+  if (w < HSL) {
+    for (int c = 0; c < nch; ++c) {
+      const int b = (bs + c * NBS) * BW + lm.bl;
+      const bool ok = fin && b < B;
+      dh_sm[(c * 32 + lane) * HSL + w] = (ok && a.d_hn) ? a.d_hn[(size_t)b * H + my_unit] : 0.f;
+      dc_sm[(c * 32 + lane) * HSL + w] = (ok && a.d_cn) ? a.d_cn[(size_t)b * H + my_unit] : 0.f;
+    }
   }
   __syncthreads();
 
   const int Jc = (J + LSTM_WARPS - 1) / LSTM_WARPS;
   const int j0 = min(J, w * Jc), j1 = min(J, j0 + Jc);
-  const bool fin = w < HS && unit0 + w < H;                // finishing warp: unit w, batch row = lane
+  const int b_first = bs * BW + lm.bl;
   BwdStepIn pf{};
-  if (fin && lane < B) pf = load_step(a, lane, U1 - 1, unit0 + w);
+  if (fin && b_first < B) pf = load_step(a, b_first, U1 - 1, my_unit);
 
   for (int s = 0; s < U1; ++s) {
     const int t = U1 - 1 - s;
@@ -313,49 +351,52 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_bwd_kernel(const Lst
     u64* dgx = a.dgx + (size_t)(s & 1) * J * Bp;
     // A. pointwise gradients of step t for my units
     if (fin) {
-      const int u = w, unit = unit0 + u;
-      for (int ch = 0; ch < nb; ++ch) {
-        const int b = ch * 32 + lane;
+      const int u = w;
+      for (int c = 0; c < nch; ++c) {
+        const int b = (bs + c * NBS) * BW + lm.bl;
         float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f;
         if (b < B) {
-          const BwdStepIn in = (ch == 0) ? pf : load_step(a, b, t, unit);
-          const float dh = in.dh + dh_sm[b * HS + u];
+          const BwdStepIn in = (c == 0) ? pf : load_step(a, b, t, my_unit);
+          float* dhp = dh_sm + (c * 32 + lane) * HSL + u;
+          float* dcp = dc_sm + (c * 32 + lane) * HSL + u;
+          const float dh = in.dh + *dhp;
           const float tc = tanhf(in.c);
-          const float dc = dc_sm[b * HS + u] + dh * in.go * (1.f - tc * tc);
+          const float dc = *dcp + dh * in.go * (1.f - tc * tc);
           d_o = dh * tc * in.go * (1.f - in.go);
           d_i = dc * in.gg * in.gi * (1.f - in.gi);
           d_f = dc * in.cprev * in.gf * (1.f - in.gf);
           d_g = dc * in.gi * (1.f - in.gg * in.gg);
-          dc_sm[b * HS + u] = dc * in.gf;
+          *dcp = dc * in.gf;
         }
-        st_relaxed_u64(dgx + (size_t)(0 * H + unit) * Bp + b, tagged(d_i, tag));    // padded batch rows carry zeros
-        st_relaxed_u64(dgx + (size_t)(1 * H + unit) * Bp + b, tagged(d_f, tag));
-        st_relaxed_u64(dgx + (size_t)(2 * H + unit) * Bp + b, tagged(d_g, tag));
-        st_relaxed_u64(dgx + (size_t)(3 * H + unit) * Bp + b, tagged(d_o, tag));
+        st_relaxed_u64(dgx + (size_t)(0 * H + my_unit) * Bp + b, tagged(d_i, tag));    // padded batch rows carry zeros
+        st_relaxed_u64(dgx + (size_t)(1 * H + my_unit) * Bp + b, tagged(d_f, tag));
+        st_relaxed_u64(dgx + (size_t)(2 * H + my_unit) * Bp + b, tagged(d_g, tag));
+        st_relaxed_u64(dgx + (size_t)(3 * H + my_unit) * Bp + b, tagged(d_o, tag));
         if (b < B) {
-          float* q = a.dgates + ((size_t)b * U1 + t) * J + unit;
+          float* q = a.dgates + ((size_t)b * U1 + t) * J + my_unit;
           q[0] = d_i; q[(size_t)H] = d_f; q[(size_t)2 * H] = d_g; q[(size_t)3 * H] = d_o;
         }
       }
-      if (lane < B && t > 0) pf = load_step(a, lane, t - 1, unit);   // next step's operands, under the wait below
+      if (b_first < B && t > 0) pf = load_step(a, b_first, t - 1, my_unit);   // next step's operands, under the wait below
     }
     // D. dh_{t-1}[b][my units] = sum_j dgates_t[b][j] * W_hh[j][unit]
-    for (int ch = 0; ch < nb; ++ch) {
-      float acc[HS];
+    for (int c = 0; c < nch; ++c) {
+      const int b = (bs + c * NBS) * BW + lm.bl;
+      float acc[HSL];
 #pragma unroll
-      for (int u = 0; u < HS; ++u) acc[u] = 0.f;
-      const u64* gp = dgx + ch * 32 + lane;
+      for (int u = 0; u < HSL; ++u) acc[u] = 0.f;
+      const u64* gp = dgx + b;
       for (int j = j0; j < j1; j += 16) {
         float gv[16];
         load16(gp, (size_t)Bp, j, j1, tag, gv, a.err, 2, &s_dead);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float* wr = Wc + (size_t)(j + i) * HS;
-          if (HS >= 2) {
+          const float* wr = Wc + ((size_t)(j + i) * UG + lm.ug) * HSL;
+          if (HSL >= 2) {
             const u64 gg2 = pack2(gv[i], gv[i]);
             const u64* wr2 = reinterpret_cast<const u64*>(wr);
 #pragma unroll
-            for (int u = 0; u < HS / 2; ++u) {
+            for (int u = 0; u < HSL / 2; ++u) {
               u64 c2 = pack2(acc[2 * u], acc[2 * u + 1]);
               c2 = fma2(gg2, wr2[u], c2);
               unpack2(c2, acc[2 * u], acc[2 * u + 1]);
@@ -366,31 +407,31 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_bwd_kernel(const Lst
         }
       }
 #pragma unroll
-      for (int u = 0; u < HS; ++u) red[(w * HS + u) * 32 + lane] = acc[u];
+      for (int u = 0; u < HSL; ++u) red[(w * HSL + u) * 32 + lane] = acc[u];
       __syncthreads();
-      if (w < HS) {
+      if (w < HSL) {
         float sum = 0.f;
 #pragma unroll
-        for (int ww = 0; ww < LSTM_WARPS; ++ww) sum += red[(ww * HS + w) * 32 + lane];
-        dh_sm[(ch * 32 + lane) * HS + w] = sum;
+        for (int ww = 0; ww < LSTM_WARPS; ++ww) sum += red[(ww * HSL + w) * 32 + lane];
+        dh_sm[(c * 32 + lane) * HSL + w] = sum;
       }
       __syncthreads();
     }
   }
   if (fin) {
-    const int u = w, unit = unit0 + u;
-    for (int b = lane; b < B; b += 32) {
-      a.d_h0[(size_t)b * H + unit] = dh_sm[b * HS + u];
-      a.d_c0[(size_t)b * H + unit] = dc_sm[b * HS + u];
+    for (int c = 0; c < nch; ++c) {
+      const int b = (bs + c * NBS) * BW + lm.bl;
+      if (b < B) {
+        a.d_h0[(size_t)b * H + my_unit] = dh_sm[(c * 32 + lane) * HSL + w];
+        a.d_c0[(size_t)b * H + my_unit] = dc_sm[(c * 32 + lane) * HSL + w];
+      }
     }
   }
 }
 
-int pick_hs(int H, int sms) {
-  int hs = 1;
-  while (hs < 8 && (H + hs - 1) / hs > sms) hs *= 2;
-  return hs;
-}
+constexpr int LSTM_BW = 8;                       // batch rows per row group (lane map above)
+constexpr int LSTM_UG = 32 / LSTM_BW;
+
 int lstm_sm_count() {
   static int n = 0;
   if (!n) {
@@ -403,11 +444,28 @@ int lstm_sm_count() {
   }
   return n;
 }
-size_t fwd_smem(int H, int hs, int Bp) {
-  return (size_t)(H + 16) * hs * 16 + (size_t)LSTM_WARPS * 4 * hs * 32 * 4 + (size_t)4 * hs * 32 * 4 + (size_t)Bp * hs * 4;
-}
-size_t bwd_smem(int H, int hs, int Bp) {
-  return (size_t)(4 * H + 16) * hs * 4 + (size_t)LSTM_WARPS * hs * 32 * 4 + (size_t)2 * Bp * hs * 4;
+
+// Grid of one launch: gx CTAs along the hidden units (UG * hsl units each) x gy along the row groups, gx * gy <= SMs.
+struct LstmCfg { int hsl, gx, gy, nch, Bp; bool ok; size_t smem_f, smem_b; };
+LstmCfg pick_cfg(int B, int H) {
+  const int sms = lstm_sm_count();
+  const int RG = (B + LSTM_BW - 1) / LSTM_BW;
+  LstmCfg best{};
+  long best_cost = -1;
+  for (int hsl = 1; hsl <= 4; hsl *= 2) {
+    const int uc = LSTM_UG * hsl, gx = (H + uc - 1) / uc;
+    if (gx > sms) continue;
+    const int gy = std::max(1, std::min(RG, sms / gx)), nch = (RG + gy - 1) / gy;
+    LstmCfg c{};
+    c.hsl = hsl; c.gx = gx; c.gy = gy; c.nch = nch; c.Bp = RG * LSTM_BW;
+    c.smem_f = (size_t)(H + 16) * uc * 16 + (size_t)LSTM_WARPS * 4 * hsl * 32 * 4 + (size_t)4 * hsl * 32 * 4 + (size_t)nch * 32 * hsl * 4;
+    c.smem_b = (size_t)(4 * H + 16) * uc * 4 + (size_t)LSTM_WARPS * hsl * 32 * 4 + (size_t)2 * nch * 32 * hsl * 4;
+    c.ok = c.smem_f <= 232448 - 64 && c.smem_b <= 232448 - 64;
+    if (!c.ok) continue;
+    const long cost = (long)nch * (hsl + 2);       // per step: nch passes of (hsl units of arithmetic + a fixed latency)
+    if (best_cost < 0 || cost < best_cost) { best = c; best_cost = cost; }
+  }
+  return best;
 }
 
 unsigned int* lstm_error_host_word(unsigned int** dev_ptr) {
@@ -436,10 +494,10 @@ int check_lstm_error(const char* where) {
 size_t xch_bytes(int rows, int Bp) { return (size_t)2 * rows * Bp * sizeof(u64); }
 
 template <typename Args>
-int launch_coop(void (*kern)(const Args), int G, size_t smem, const Args& a, cudaStream_t st) {
+int launch_coop(void (*kern)(const Args), const LstmCfg& c, size_t smem, const Args& a, cudaStream_t st) {
   CTCVR_CHECK_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(kern), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* params[] = {const_cast<Args*>(&a)};
-  CTCVR_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(G), dim3(LSTM_THREADS), params, smem, st));
+  CTCVR_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(c.gx, c.gy), dim3(LSTM_THREADS), params, smem, st));
   CTCVR_LAUNCH_CHECK();
   return 0;
 }
@@ -448,55 +506,48 @@ int launch_coop(void (*kern)(const Args), int G, size_t smem, const Args& a, cud
 
 int lstm_seq_supported(int B, int H) {
   if (B < 1 || H < 1) return 0;
-  const int sms = lstm_sm_count();
-  const int hs = pick_hs(H, sms), Bp = (B + 31) / 32 * 32;
-  if ((H + hs - 1) / hs > sms || (H + hs - 1) / hs > 256) return 0;
-  return fwd_smem(H, hs, Bp) <= 232448 && bwd_smem(H, hs, Bp) <= 232448;
+  return pick_cfg(B, H).ok ? 1 : 0;
 }
 
-size_t lstm_seq_ws_bytes(int B, int H) { return xch_bytes(4 * H, (B + 31) / 32 * 32); }
+size_t lstm_seq_ws_bytes(int B, int H) { return xch_bytes(4 * H, (B + LSTM_BW - 1) / LSTM_BW * LSTM_BW); }
 
 int lstm_seq_fwd(const float* xg, const float* w_hh, const float* h0, const float* c0, float* out, float* cs, float* act,
                  float* hn, float* cn, int B, int U1, int H, void* ws, size_t ws_bytes, cudaStream_t st) {
-  CTCVR_REQUIRE(lstm_seq_supported(B, H), "lstm_seq_fwd: hidden size %d / batch %d do not fit one CTA per SM (H <= 8 x SMs, shared memory)", H, B);
+  const LstmCfg c = pick_cfg(B, H);
+  CTCVR_REQUIRE(c.ok, "lstm_seq_fwd: hidden size %d / batch %d do not fit one CTA per SM (H <= 16 x SMs, shared memory)", H, B);
   if (check_lstm_error("lstm_seq_fwd")) return 1;
   CTCVR_REQUIRE(ws_bytes >= lstm_seq_ws_bytes(B, H), "lstm_seq_fwd: workspace too small");
-  const int hs = pick_hs(H, lstm_sm_count()), Bp = (B + 31) / 32 * 32, G = (H + hs - 1) / hs;
   CTCVR_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "lstm_seq_fwd: workspace must be 8-byte aligned");
   LstmFwdArgs a{};
   a.xg = xg; a.w_hh = w_hh; a.h0 = h0; a.c0 = c0; a.out = out; a.cs = cs; a.act = act; a.hn = hn; a.cn = cn;
-  a.hx = reinterpret_cast<u64*>(ws); a.B = B; a.U1 = U1; a.H = H; a.Bp = Bp;
+  a.hx = reinterpret_cast<u64*>(ws); a.B = B; a.U1 = U1; a.H = H; a.Bp = c.Bp;
   lstm_error_host_word(&a.err);
-  CTCVR_CHECK_CUDA(cudaMemsetAsync(ws, 0, xch_bytes(H, Bp), st));
-  const size_t smem = fwd_smem(H, hs, Bp);
-  switch (hs) {
-    case 1: return launch_coop(lstm_seq_fwd_kernel<1>, G, smem, a, st);
-    case 2: return launch_coop(lstm_seq_fwd_kernel<2>, G, smem, a, st);
-    case 4: return launch_coop(lstm_seq_fwd_kernel<4>, G, smem, a, st);
-    default: return launch_coop(lstm_seq_fwd_kernel<8>, G, smem, a, st);
+  CTCVR_CHECK_CUDA(cudaMemsetAsync(ws, 0, xch_bytes(H, c.Bp), st));
+  switch (c.hsl) {
+    case 1: return launch_coop(lstm_seq_fwd_kernel<1, LSTM_BW>, c, c.smem_f, a, st);
+    case 2: return launch_coop(lstm_seq_fwd_kernel<2, LSTM_BW>, c, c.smem_f, a, st);
+    default: return launch_coop(lstm_seq_fwd_kernel<4, LSTM_BW>, c, c.smem_f, a, st);
   }
 }
 
 int lstm_seq_bwd(const float* act, const float* cs, const float* c0, const float* w_hh, const float* d_out, const float* d_hn,
                  const float* d_cn, float* dgates, float* d_h0, float* d_c0, int B, int U1, int H, void* ws, size_t ws_bytes,
                  cudaStream_t st) {
-  CTCVR_REQUIRE(lstm_seq_supported(B, H), "lstm_seq_bwd: hidden size %d / batch %d do not fit one CTA per SM (H <= 8 x SMs, shared memory)", H, B);
+  const LstmCfg c = pick_cfg(B, H);
+  CTCVR_REQUIRE(c.ok, "lstm_seq_bwd: hidden size %d / batch %d do not fit one CTA per SM (H <= 16 x SMs, shared memory)", H, B);
   if (check_lstm_error("lstm_seq_bwd")) return 1;
   CTCVR_REQUIRE(ws_bytes >= lstm_seq_ws_bytes(B, H), "lstm_seq_bwd: workspace too small");
-  const int hs = pick_hs(H, lstm_sm_count()), Bp = (B + 31) / 32 * 32, G = (H + hs - 1) / hs;
   CTCVR_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "lstm_seq_bwd: workspace must be 8-byte aligned");
   LstmBwdArgs a{};
   a.act = act; a.cs = cs; a.c0 = c0; a.w_hh = w_hh; a.d_out = d_out; a.d_hn = d_hn; a.d_cn = d_cn;
   a.dgates = dgates; a.d_h0 = d_h0; a.d_c0 = d_c0; a.dgx = reinterpret_cast<u64*>(ws);
-  a.B = B; a.U1 = U1; a.H = H; a.Bp = Bp;
+  a.B = B; a.U1 = U1; a.H = H; a.Bp = c.Bp;
   lstm_error_host_word(&a.err);
-  CTCVR_CHECK_CUDA(cudaMemsetAsync(ws, 0, xch_bytes(4 * H, Bp), st));
-  const size_t smem = bwd_smem(H, hs, Bp);
-  switch (hs) {
-    case 1: return launch_coop(lstm_seq_bwd_kernel<1>, G, smem, a, st);
-    case 2: return launch_coop(lstm_seq_bwd_kernel<2>, G, smem, a, st);
-    case 4: return launch_coop(lstm_seq_bwd_kernel<4>, G, smem, a, st);
-    default: return launch_coop(lstm_seq_bwd_kernel<8>, G, smem, a, st);
+  CTCVR_CHECK_CUDA(cudaMemsetAsync(ws, 0, xch_bytes(4 * H, c.Bp), st));
+  switch (c.hsl) {
+    case 1: return launch_coop(lstm_seq_bwd_kernel<1, LSTM_BW>, c, c.smem_b, a, st);
+    case 2: return launch_coop(lstm_seq_bwd_kernel<2, LSTM_BW>, c, c.smem_b, a, st);
+    default: return launch_coop(lstm_seq_bwd_kernel<4, LSTM_BW>, c, c.smem_b, a, st);
   }
 }
 

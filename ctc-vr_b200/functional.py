@@ -288,7 +288,7 @@ class _LstmSeq(torch.autograd.Function):
             raise RuntimeError("lstm_sequence: empty sequence")
         if not bool(query("ctcvr_lstm_seq_supported", B, H)):
             raise RuntimeError(f"lstm_sequence: hidden size {H} with batch {B} does not fit the persistent kernel "
-                               "(H <= 8 x SM count and the per-CTA shared memory)")
+                               "(H <= 16 x SM count and the per-CTA shared memory)")
         x2 = _f32c(x).view(B * U1, E)
         wi, wh = _f32c(w_ih), _f32c(w_hh)
         bias = None
