@@ -14,7 +14,8 @@ inside the timed region.  L2 is flushed (256 MiB write) before every timed step.
 Beside the contract keys the line carries (rank 0, N=1): `parity` - the CPU reference run on the SAME batch and
 weights, per-utterance costs compared with the GPU step; `gpu_reference` - the reference's own data flow on this GPU
 through the library kernels it would use (cuBLAS + torchaudio's rnnt_loss CUDA kernels, ATen ctc_loss); `fp32` - the
-reference-precision path; `eager` - the ungraphed ragged-batch public API; `decode` - the A4-A10 rows with RTF.
+reference-precision path; `eager` - the ungraphed ragged-batch public API; `predictor` - the LSTM sequence kernels of
+section 8f row 2 beside the library LSTM on the same GPU; `decode` - the A4-A10 rows with RTF.
 """
 import argparse
 import json
@@ -520,6 +521,7 @@ def run_ours(args):
             line["gpu_reference"] = gpu_reference(dev)
             line["gpu_reference"]["speedup_vs_fp32"] = line["value"] / line["gpu_reference"]["fp32"]["value"]
             line["gpu_reference"]["speedup_vs_autocast_bf16"] = line["value"] / line["gpu_reference"]["autocast_bf16"]["value"]
+            line["predictor"] = time_predictor(C, B, U + 1, D)
             if not args.no_decode:
                 import bench_decode
                 line["decode"] = bench_decode.run_rows(quick=True)
@@ -528,6 +530,86 @@ def run_ours(args):
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line))
+
+
+def time_predictor(C, B, U1, H, iters=20):
+    """the predictor's LSTM over the label sequence (model/component/predictor.py:58) at the
+    bench shape, forward + backward with gradients of the input and of all four parameters.  `ours` = the persistent
+    sequence kernels (csrc/lstm_seq.cu, fp32) + their four plain GEMMs; `library` = torch's nn.LSTM on this GPU (cuDNN,
+    TF32 allowed by torch's default).  Both eager and replayed from a CUDA graph; CUDA events, median.  Parity: both
+    outputs against torch's fp32 CPU LSTM - the arithmetic the reference runs - on the same weights and input."""
+    import torch
+    from ctcvr_b200 import functional as CF
+    g = torch.Generator().manual_seed(4321)
+    cpu = torch.nn.LSTM(H, H, 1, batch_first=True)
+    x_c = torch.randn(B, U1, H, generator=g)
+    with torch.no_grad():
+        want = cpu(x_c)[0]
+    lstm = torch.nn.LSTM(H, H, 1, batch_first=True).cuda()
+    lstm.load_state_dict(cpu.state_dict())
+    x = x_c.cuda().requires_grad_(True)
+    h0 = torch.zeros(1, B, H, device="cuda")
+    c0 = torch.zeros(1, B, H, device="cuda")
+    r = torch.randn(B, U1, H, device="cuda")
+    ps = [lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0]
+
+    def clear():
+        x.grad = None
+        for p in ps:
+            p.grad = None
+
+    def ours():
+        torch.autograd.backward(CF.lstm_sequence(x, *ps, h0[0], c0[0])[0], r)
+        clear()
+
+    def library():
+        torch.autograd.backward(lstm(x, (h0, c0))[0], r)
+        clear()
+
+    def timed(fn):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+        ev[0].record()
+        for i in range(iters):
+            fn()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
+        return ts[len(ts) // 2]
+
+    with torch.no_grad():
+        err_ours = float((CF.lstm_sequence(x, *ps, h0[0], c0[0])[0].cpu() - want).abs().max() / want.abs().max())
+        err_lib = float((lstm(x, (h0, c0))[0].cpu() - want).abs().max() / want.abs().max())
+    n0 = C._lib.lib().ctcvr_launch_count()
+    ours()
+    res = {"workload": f"LSTM layer fwd+bwd, B={B}, U+1={U1}, E=H={H}, fp32", "unit": "ms per fwd+bwd",
+           "kernel_launches_per_call": int(C._lib.lib().ctcvr_launch_count() - n0),
+           "max_abs_err_over_max_vs_cpu_fp32": {"ours": err_ours, "library_cudnn": err_lib}}
+    if err_ours > 1e-4:
+        raise RuntimeError(f"bench.py: the LSTM sequence kernels disagree with the CPU LSTM: {err_ours}")
+    for name, fn in (("ours", ours), ("library_cudnn", library)):
+        row = {"eager": round(timed(fn), 4)}
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fn()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        try:
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                fn()
+            row["graphed"] = round(timed(gr.replay), 4)
+            del gr
+        except Exception as e:  # noqa: BLE001
+            row["graphed"] = None
+            row["graph_error"] = type(e).__name__
+            torch.cuda.synchronize()
+        res[name] = row
+    res["utt_per_s_ours_graphed"] = B / (res["ours"]["graphed"] * 1e-3) if res["ours"].get("graphed") else None
+    return res
 
 
 def time_fp32_step(C, joint, B, T, U, blank, enc, pred, tgt, tl, ul, flush, reps=3):
