@@ -45,6 +45,7 @@ _SIGS = {
     "ctcvr_lstm_seq_ws_bytes": (Z, [I, I]),
     "ctcvr_lstm_seq_fwd": (I, [P] * 9 + [I, I, I, P, Z, P]),
     "ctcvr_lstm_seq_bwd": (I, [P] * 10 + [I, I, I, P, Z, P]),
+    "ctcvr_split_tf32": (I, [P, P, c_long, c_long, I, I, P]),
     "ctcvr_peer_create": (I, [I, I, Z, P, P]),
     "ctcvr_peer_connect": (I, [P, P, P]),
     "ctcvr_peer_local_buffer": (P, [P]),

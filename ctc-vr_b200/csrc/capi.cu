@@ -71,6 +71,8 @@ int lstm_seq_fwd(const float*, const float*, const float*, const float*, float*,
 int lstm_seq_bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, float*,
                  float*, float*, int, int, int, void*, size_t, cudaStream_t);
 
+int split_tf32(const float*, float*, long, long, int, int, cudaStream_t);
+
 int peer_create(int, int, size_t, void**, void*);
 int peer_connect(void*, const void*, void* const*);
 void* peer_local_buffer(void*);
@@ -242,6 +244,11 @@ int ctcvr_lstm_seq_bwd(const float* act, const float* cs, const float* c0, const
   CTCVR_REQUIRE(B > 0 && U1 > 0 && H > 0, "lstm_seq_bwd: bad dims");
   CTCVR_REQUIRE(act && cs && w_hh && dgates && d_h0 && d_c0 && ws, "lstm_seq_bwd: NULL pointer");
   return lstm_seq_bwd(act, cs, c0, w_hh, d_out, d_hn, d_cn, dgates, d_h0, d_c0, B, U1, H, ws, ws_bytes, ST(stream));
+}
+
+int ctcvr_split_tf32(const float* in, float* out, long rows, long cols, int stack_cols, int pattern, void* stream) {
+  CTCVR_REQUIRE(in && out && rows > 0 && cols > 0 && (pattern == 0 || pattern == 1), "split_tf32: bad arguments");
+  return split_tf32(in, out, rows, cols, stack_cols, pattern, ST(stream));
 }
 
 int ctcvr_peer_create(int rank, int world, size_t max_floats, void** out_ctx, void* out_handle64) {

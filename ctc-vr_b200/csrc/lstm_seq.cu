@@ -35,6 +35,9 @@ namespace {
 constexpr int LSTM_THREADS = 512;
 constexpr int LSTM_WARPS = 16;
 constexpr long long LSTM_TIMEOUT_NS = 2LL * 1000 * 1000 * 1000;
+constexpr int LF = 16;    // exchange rows a lane keeps in flight per batch, forward
+constexpr int LB = 16;    // ... backward (32 in flight measured slower: 349 against 284 us at cfg2, spills)
+constexpr int WPAD = 32;  // zero rows behind the shared-memory weights: a partial last batch reads them
 typedef unsigned long long u64;
 
 __device__ __forceinline__ u64 ld_relaxed_u64(const u64* p) {
@@ -98,29 +101,30 @@ struct LstmBwdArgs {
   int B, U1, H, Bp;
 };
 
-// Load rows r0 .. r0+15 (those below r1) of the exchange buffer for this lane's batch row, re-reading an element until
-// it carries `tag`.  All pending loads are issued before the first tag is looked at.  `dead` (shared memory) is set by
-// the first wait of this CTA that times out: later waits return at once, so a broken launch ends after ~2 s.
-__device__ __forceinline__ void load16(const u64* p, size_t stride, int r0, int r1, unsigned int tag, float (&v)[16],
-                                       unsigned int* err, int site, volatile int* dead) {
+// Load rows r0 .. r0+N-1 (those below r1) of the exchange buffer for this lane's batch row, re-reading an element until
+// it carries `tag`; out[i] = the raw word (value in the low half), 0 for rows at or beyond r1.  All pending loads are
+// issued before the first tag is looked at.  `dead` (shared memory) is set by the first wait of this CTA that times
+// out: later waits return at once, so a broken launch ends after ~2 s.
+template <int N>
+__device__ __forceinline__ void load_rows(const u64* p, size_t stride, int r0, int r1, unsigned int tag, u64 (&out)[N],
+                                          unsigned int* err, int site, volatile int* dead) {
   unsigned int pend = 0;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    v[i] = 0.f;
+  for (int i = 0; i < N; ++i) {
+    out[i] = 0ull;
     if (r0 + i < r1) pend |= 1u << i;
   }
   int spins = 0;
   long long t0 = 0;
   while (pend) {
-    u64 raw[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if ((pend >> i) & 1u) raw[i] = ld_relaxed_u64(p + (size_t)(r0 + i) * stride);
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (((pend >> i) & 1u) && (unsigned int)(raw[i] >> 32) == tag) {
-        v[i] = __uint_as_float((unsigned int)raw[i]);
-        pend &= ~(1u << i);
+    for (int i = 0; i < N; ++i)
+      if ((pend >> i) & 1u) {
+        const u64 raw = ld_relaxed_u64(p + (size_t)(r0 + i) * stride);
+        if ((unsigned int)(raw >> 32) == tag) {
+          out[i] = raw;
+          pend &= ~(1u << i);
+        }
       }
     if (pend && (++spins & 63) == 0) {
       if (t0 == 0) t0 = gtime_ns();
@@ -133,22 +137,20 @@ __device__ __forceinline__ void load16(const u64* p, size_t stride, int r0, int 
   }
 }
 
-// load16 for 16 full rows, the common case: one address add, one load and one tag compare per element; the whole batch
-// is re-read until every element carries the tag (re-reading an element that already arrived is harmless).
-__device__ __forceinline__ void load16_full(const u64* p, size_t stride, int r0, unsigned int tag, float (&v)[16],
-                                            unsigned int* err, int site, volatile int* dead) {
+// load_rows for N full rows, the common case: one address add, one load and one tag compare per element, all N loads in
+// flight; the whole batch is re-read until every element carries the tag (re-reading one that arrived is harmless).
+template <int N>
+__device__ __forceinline__ void load_rows_full(const u64* p, size_t stride, int r0, unsigned int tag, u64 (&raw)[N],
+                                               unsigned int* err, int site, volatile int* dead) {
   const u64* q = p + (size_t)r0 * stride;
   int spins = 0;
   long long t0 = 0;
   while (true) {
-    u64 raw[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) raw[i] = ld_relaxed_u64(q + (size_t)i * stride);
+    for (int i = 0; i < N; ++i) raw[i] = ld_relaxed_u64(q + (size_t)i * stride);
     bool ok = true;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) ok = ok && ((unsigned int)(raw[i] >> 32) == tag);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float((unsigned int)raw[i]);
+    for (int i = 0; i < N; ++i) ok = ok && ((unsigned int)(raw[i] >> 32) == tag);
     if (ok) break;
     if ((++spins & 63) == 0) {
       if (t0 == 0) t0 = gtime_ns();
@@ -179,6 +181,43 @@ __device__ __forceinline__ LaneMap lane_map(int lane) {
   return m;
 }
 
+// acc[u] += hv[i] * {W_i, W_f | W_g, W_o}(k + i, unit u of this lane's group): weights are shared-memory broadcasts
+template <int N, int HSL, int UG>
+__device__ __forceinline__ void fwd_fma(const u64 (&hv)[N], const ulonglong2* Wsm2, int k, int ug, u64 (&acc)[HSL][2]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float hf = __uint_as_float((unsigned int)hv[i]);
+    const u64 hh = pack2(hf, hf);
+#pragma unroll
+    for (int u = 0; u < HSL; ++u) {
+      const ulonglong2 wv = Wsm2[((size_t)(k + i) * HSL + u) * UG + ug];
+      acc[u][0] = fma2(hh, wv.x, acc[u][0]);
+      acc[u][1] = fma2(hh, wv.y, acc[u][1]);
+    }
+  }
+}
+// acc[u] += gv[i] * W_hh[j + i][unit u of this lane's group]
+template <int N, int HSL, int UG>
+__device__ __forceinline__ void bwd_fma(const u64 (&gv)[N], const float* Wc, int j, int ug, float (&acc)[HSL]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float* wr = Wc + ((size_t)(j + i) * UG + ug) * HSL;
+    const float gf = __uint_as_float((unsigned int)gv[i]);
+    if (HSL >= 2) {
+      const u64 gg2 = pack2(gf, gf);
+      const u64* wr2 = reinterpret_cast<const u64*>(wr);
+#pragma unroll
+      for (int u = 0; u < HSL / 2; ++u) {
+        u64 c2 = pack2(acc[2 * u], acc[2 * u + 1]);
+        c2 = fma2(gg2, wr2[u], c2);
+        unpack2(c2, acc[2 * u], acc[2 * u + 1]);
+      }
+    } else {
+      acc[0] = fmaf(gf, wr[0], acc[0]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------------
@@ -191,8 +230,8 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_fwd_kernel(const Lst
   const int H = a.H, B = a.B, Bp = a.Bp, U1 = a.U1;
   const int RG = Bp / BW, NBS = gridDim.y, bs = blockIdx.y;
   const int nch = (RG - bs + NBS - 1) / NBS;                            // row groups of this CTA: bs, bs + NBS, ...
-  float4* Wsm = reinterpret_cast<float4*>(lstm_smem);                    // [H + 16][HSL][UG] {i, f, g, o} weights of (k, unit)
-  float* red = reinterpret_cast<float*>(Wsm + (size_t)(H + 16) * UC);    // [16][4*HSL][32]
+  float4* Wsm = reinterpret_cast<float4*>(lstm_smem);                    // [H + WPAD][HSL][UG] {i, f, g, o} weights of (k, unit)
+  float* red = reinterpret_cast<float*>(Wsm + (size_t)(H + WPAD) * UC);    // [16][4*HSL][32]
   float* sums = red + LSTM_WARPS * 4 * HSL * 32;                         // [4*HSL][32]
   float* c_sm = sums + 4 * HSL * 32;                                     // [nch][32][HSL]
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
@@ -200,8 +239,8 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_fwd_kernel(const Lst
   const int unit0 = blockIdx.x * UC;
   const size_t H4 = (size_t)4 * H;
 
-  for (int idx = tid; idx < (H + 16) * UC; idx += LSTM_THREADS) {        // idx = uc * (H+16) + k: coalesced over k
-    const int uc = idx / (H + 16), k = idx - uc * (H + 16), unit = unit0 + uc;
+  for (int idx = tid; idx < (H + WPAD) * UC; idx += LSTM_THREADS) {        // idx = uc * (H+16) + k: coalesced over k
+    const int uc = idx / (H + WPAD), k = idx - uc * (H + WPAD), unit = unit0 + uc;
     const int ug = uc / HSL, ui = uc - ug * HSL;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k < H && unit < H) {
@@ -244,20 +283,16 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_fwd_kernel(const Lst
 #pragma unroll
       for (int u = 0; u < HSL; ++u) acc[u][0] = acc[u][1] = 0ull;
       const u64* hp = hprev + b;
-      for (int k = k0; k < k1; k += 16) {
-        float hv[16];
-        if (k + 16 <= k1) load16_full(hp, (size_t)Bp, k, (unsigned)(t + 1), hv, a.err, 1, &s_dead);
-        else load16(hp, (size_t)Bp, k, k1, (unsigned)(t + 1), hv, a.err, 1, &s_dead);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const u64 hh = pack2(hv[i], hv[i]);
-#pragma unroll
-          for (int u = 0; u < HSL; ++u) {
-            const ulonglong2 wv = Wsm2[((size_t)(k + i) * HSL + u) * UG + lm.ug];
-            acc[u][0] = fma2(hh, wv.x, acc[u][0]);
-            acc[u][1] = fma2(hh, wv.y, acc[u][1]);
-          }
-        }
+      int k = k0;
+      for (; k + LF <= k1; k += LF) {
+        u64 hv[LF];
+        load_rows_full<LF>(hp, (size_t)Bp, k, (unsigned)(t + 1), hv, a.err, 1, &s_dead);
+        fwd_fma<LF, HSL, UG>(hv, Wsm2, k, lm.ug, acc);
+      }
+      for (; k < k1; k += 8) {                               // tail of a slice that is not a multiple of LF rows
+        u64 hv[8];
+        load_rows<8>(hp, (size_t)Bp, k, k1, (unsigned)(t + 1), hv, a.err, 1, &s_dead);
+        fwd_fma<8, HSL, UG>(hv, Wsm2, k, lm.ug, acc);
       }
 #pragma unroll
       for (int u = 0; u < HSL; ++u) {
@@ -344,15 +379,15 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_bwd_kernel(const Lst
   const int RG = Bp / BW, NBS = gridDim.y, bs = blockIdx.y;
   const int nch = (RG - bs + NBS - 1) / NBS;
   const int J = 4 * H;
-  float* Wc = reinterpret_cast<float*>(lstm_smem);        // [4H + 16][UG][HSL]: W_hh[j][unit0 + ug * HSL + ui]
-  float* red = Wc + (size_t)(J + 16) * UC;                 // [16][HSL][32]
+  float* Wc = reinterpret_cast<float*>(lstm_smem);        // [4H + WPAD][UG][HSL]: W_hh[j][unit0 + ug * HSL + ui]
+  float* red = Wc + (size_t)(J + WPAD) * UC;                 // [16][HSL][32]
   float* dh_sm = red + LSTM_WARPS * HSL * 32;              // [nch][32][HSL] dL/dh_t arriving through the recurrence
   float* dc_sm = dh_sm + (size_t)nch * 32 * HSL;           // [nch][32][HSL] dL/dc_t arriving from step t+1
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const LaneMap lm = lane_map<BW>(lane);
   const int unit0 = blockIdx.x * UC;
 
-  for (int idx = tid; idx < (J + 16) * UC; idx += LSTM_THREADS) {
+  for (int idx = tid; idx < (J + WPAD) * UC; idx += LSTM_THREADS) {
     const int j = idx / UC, uc = idx - j * UC, unit = unit0 + uc;       // [ug][ui] order == unit order inside the CTA
     Wc[idx] = (j < J && unit < H) ? a.w_hh[(size_t)j * H + unit] : 0.f;
   }
@@ -415,26 +450,16 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_bwd_kernel(const Lst
 #pragma unroll
       for (int u = 0; u < HSL; ++u) acc[u] = 0.f;
       const u64* gp = dgx + b;
-      for (int j = j0; j < j1; j += 16) {
-        float gv[16];
-        if (j + 16 <= j1) load16_full(gp, (size_t)Bp, j, tag, gv, a.err, 2, &s_dead);
-        else load16(gp, (size_t)Bp, j, j1, tag, gv, a.err, 2, &s_dead);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float* wr = Wc + ((size_t)(j + i) * UG + lm.ug) * HSL;
-          if (HSL >= 2) {
-            const u64 gg2 = pack2(gv[i], gv[i]);
-            const u64* wr2 = reinterpret_cast<const u64*>(wr);
-#pragma unroll
-            for (int u = 0; u < HSL / 2; ++u) {
-              u64 c2 = pack2(acc[2 * u], acc[2 * u + 1]);
-              c2 = fma2(gg2, wr2[u], c2);
-              unpack2(c2, acc[2 * u], acc[2 * u + 1]);
-            }
-          } else {
-            acc[0] = fmaf(gv[i], wr[0], acc[0]);
-          }
-        }
+      int j = j0;
+      for (; j + LB <= j1; j += LB) {
+        u64 gv[LB];
+        load_rows_full<LB>(gp, (size_t)Bp, j, tag, gv, a.err, 2, &s_dead);
+        bwd_fma<LB, HSL, UG>(gv, Wc, j, lm.ug, acc);
+      }
+      for (; j < j1; j += 8) {
+        u64 gv[8];
+        load_rows<8>(gp, (size_t)Bp, j, j1, tag, gv, a.err, 2, &s_dead);
+        bwd_fma<8, HSL, UG>(gv, Wc, j, lm.ug, acc);
       }
 #pragma unroll
       for (int u = 0; u < HSL; ++u) red[(w * HSL + u) * 32 + lane] = acc[u];
@@ -488,8 +513,8 @@ LstmCfg pick_cfg(int B, int H) {
     const int gy = std::max(1, std::min(RG, sms / gx)), nch = (RG + gy - 1) / gy;
     LstmCfg c{};
     c.hsl = hsl; c.gx = gx; c.gy = gy; c.nch = nch; c.Bp = RG * LSTM_BW;
-    c.smem_f = (size_t)(H + 16) * uc * 16 + (size_t)LSTM_WARPS * 4 * hsl * 32 * 4 + (size_t)4 * hsl * 32 * 4 + (size_t)nch * 32 * hsl * 4;
-    c.smem_b = (size_t)(4 * H + 16) * uc * 4 + (size_t)LSTM_WARPS * hsl * 32 * 4 + (size_t)2 * nch * 32 * hsl * 4;
+    c.smem_f = (size_t)(H + WPAD) * uc * 16 + (size_t)LSTM_WARPS * 4 * hsl * 32 * 4 + (size_t)4 * hsl * 32 * 4 + (size_t)nch * 32 * hsl * 4;
+    c.smem_b = (size_t)(4 * H + WPAD) * uc * 4 + (size_t)LSTM_WARPS * hsl * 32 * 4 + (size_t)2 * nch * 32 * hsl * 4;
     c.ok = c.smem_f <= 232448 - 64 && c.smem_b <= 232448 - 64;
     if (!c.ok) continue;
     const long cost = (long)nch * (hsl + 2);       // per step: nch passes of (hsl units of arithmetic + a fixed latency)
@@ -579,6 +604,41 @@ int lstm_seq_bwd(const float* act, const float* cs, const float* c0, const float
     case 2: return launch_coop(lstm_seq_bwd_kernel<2, LSTM_BW>, c, c.smem_b, a, st);
     default: return launch_coop(lstm_seq_bwd_kernel<4, LSTM_BW>, c, c.smem_b, a, st);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Operand split for the plain GEMMs around the recurrence (x W_ih^T, dG^T x, dG^T h_prev, dG W_ih): an fp32 matrix A is
+// written as A_hi + A_lo with A_hi = A truncated to TF32's 10 mantissa bits (exact) and A_lo = A - A_hi (exact in fp32,
+// 13 significant bits), and A B ~= A_hi B_hi + A_hi B_lo + A_lo B_hi becomes ONE tensor-core GEMM with the three terms
+// stacked along K: the dropped A_lo B_lo term and the TF32 rounding of the low parts are ~2^-20 relative, against 2^-11
+// for a plain TF32 GEMM (what the library LSTM uses by default) and 60 - 90 us per product for cuBLAS's fp32 SIMT kernels.
+//   stack_cols = 1: out [R, 3C] = (p0 | p1 | p2) per row;  stack_cols = 0: out [3R, C] = p0 over p1 over p2
+//   pattern 0: (hi, hi, lo)   pattern 1: (hi, lo, hi)      - one operand of a product takes 0, the other 1
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, long rows,
+                                                         long cols, int stack_cols, int pattern) {
+  const long n = rows * cols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = in[i];
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    const float lo = v - hi;
+    const float p1 = pattern == 0 ? hi : lo, p2 = pattern == 0 ? lo : hi;
+    if (stack_cols) {
+      const long r = i / cols, c = i - r * cols;
+      float* q = out + r * 3 * cols + c;
+      q[0] = hi; q[cols] = p1; q[2 * cols] = p2;
+    } else {
+      out[i] = hi; out[n + i] = p1; out[2 * n + i] = p2;
+    }
+  }
+}
+
+int split_tf32(const float* in, float* out, long rows, long cols, int stack_cols, int pattern, cudaStream_t st) {
+  const long n = rows * cols;
+  const int grid = (int)std::min<long>((n + 255) / 256, 148L * 16);
+  split_tf32_kernel<<<grid, 256, 0, st>>>(in, out, rows, cols, stack_cols, pattern);
+  CTCVR_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace ctcvr

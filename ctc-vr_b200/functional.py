@@ -272,6 +272,61 @@ def ctc_loss_from_logits(logits, targets, input_lengths, target_lengths, blank: 
     return loss, lp
 
 
+class _tf32_matmul:
+    """cuBLAS fp32 matmuls inside the block run on the TF32 tensor cores (torch's `fp32_precision` switch of the cuBLAS
+    backend, restored on exit).  Only used on operands pre-split by `_split3`, where the result keeps fp32-level
+    accuracy.  `ok` is False when the switch cannot be set (a script that drives the legacy allow_tf32 flag): the
+    caller then multiplies the unsplit fp32 operands."""
+    def __enter__(self):
+        self.ok, self.old = True, None
+        try:
+            m = torch.backends.cuda.matmul
+            self.old = m.fp32_precision
+            m.fp32_precision = "tf32"
+        except Exception:  # noqa: BLE001
+            self.ok = False
+        return self
+
+    def __exit__(self, *exc):
+        if self.ok:
+            torch.backends.cuda.matmul.fp32_precision = self.old
+        return False
+
+
+def _split3(t2, stack_cols: bool, pattern: int):
+    """[R,C] fp32 -> the (hi, hi|lo, lo|hi) TF32 terms stacked along the columns ([R,3C]) or the rows ([3R,C])."""
+    R, Cc = t2.shape
+    out = torch.empty((R, 3 * Cc) if stack_cols else (3 * R, Cc), dtype=torch.float32, device=t2.device)
+    call("ctcvr_split_tf32", ptr(t2), ptr(out), R, Cc, int(stack_cols), int(pattern), stream())
+    return out
+
+
+def _mm3(a, b, out=None, a_t=False, b_t=False):
+    """a @ b in fp32 accuracy on the tensor cores: a is [M,K] (or [K,M] with a_t), b is [K,N] (or [N,K] with b_t), both
+    contiguous fp32.  Each operand is split along K into its TF32 terms (csrc/lstm_seq.cu::split_tf32_kernel) and the
+    three products are one GEMM with K tripled."""
+    with _tf32_matmul() as t:
+        if not t.ok:
+            aa, bb = (a.t() if a_t else a), (b.t() if b_t else b)
+            return torch.mm(aa, bb, out=out) if out is not None else torch.mm(aa, bb)
+        a3 = _split3(a, stack_cols=not a_t, pattern=0)           # K is the column index of a unless a is given transposed
+        b3 = _split3(b, stack_cols=b_t, pattern=1)
+        aa, bb = (a3.t() if a_t else a3), (b3.t() if b_t else b3)
+        return torch.mm(aa, bb, out=out) if out is not None else torch.mm(aa, bb)
+
+
+_SIDE = {}
+
+
+def _side_streams(dev):
+    """Two side streams per device for the independent GEMMs of the LSTM backward."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    st = _SIDE.get(key)
+    if st is None:
+        st = _SIDE[key] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+    return st
+
+
 class _LstmSeq(torch.autograd.Function):
     """One LSTM layer over [B,U1,*] (batch_first, fp32).  The sequential part runs in the two persistent kernels of
     csrc/lstm_seq.cu; the input projection and the three weight / input gradient products are plain library GEMMs
@@ -294,7 +349,10 @@ class _LstmSeq(torch.autograd.Function):
         bias = None
         if b_ih is not None:
             bias = _f32c(b_ih) + _f32c(b_hh)
-        xg = torch.addmm(bias, x2, wi.t()) if bias is not None else torch.mm(x2, wi.t())
+        with torch.cuda.device(dev):
+            xg = _mm3(x2, wi, b_t=True)                            # x W_ih^T
+        if bias is not None:
+            xg += bias
         h0c, c0c = _f32c(h0), _f32c(c0)
         keep = any(ctx.needs_input_grad)
         out = torch.empty((B, U1, H), dtype=torch.float32, device=dev)
@@ -329,13 +387,35 @@ class _LstmSeq(torch.autograd.Function):
                  ptr(d_h0), ptr(d_c0), B, U1, H, ptr(ws), ws.numel(), stream())
         dg2 = dg.view(B * U1, 4 * H)
         ng = ctx.needs_input_grad
-        dx = torch.mm(dg2, wi).view(B, U1, E) if ng[0] else None
-        d_wi = torch.mm(dg2.t(), x2) if ng[1] else None
-        d_wh = None
+        # dx, dW_ih (+ the bias column sum) and dW_hh are independent plain GEMMs of 44 - 64 output tiles each at the
+        # reference sizes - a third of the chip apiece - so they run side by side on three streams (parallel branches
+        # when the step is captured in a CUDA graph).  Outputs are allocated on the calling stream.
+        need_b = ctx.has_bias and (ng[3] or ng[4])
+        d_wi = torch.empty((4 * H, E), dtype=torch.float32, device=dev) if ng[1] else None
+        d_wh = torch.empty((4 * H, H), dtype=torch.float32, device=dev) if ng[2] else None
+        db = torch.empty((4 * H,), dtype=torch.float32, device=dev) if need_b else None
+        h_prev = torch.empty((B, U1, H), dtype=torch.float32, device=dev) if ng[2] else None
+        cur = torch.cuda.current_stream(dev)
+        s1, s2 = _side_streams(dev)
+        if ng[1] or need_b:
+            s1.wait_stream(cur)
+            with torch.cuda.stream(s1):
+                if ng[1]:
+                    _mm3(dg2, x2, out=d_wi, a_t=True)              # dG^T x
+                if need_b:
+                    torch.sum(dg2, 0, out=db)
         if ng[2]:
-            h_prev = torch.cat([h0c.unsqueeze(1), out[:, :-1]], dim=1).reshape(B * U1, H)
-            d_wh = torch.mm(dg2.t(), h_prev)
-        db = dg2.sum(0) if ctx.has_bias and (ng[3] or ng[4]) else None
+            s2.wait_stream(cur)
+            with torch.cuda.stream(s2):
+                h_prev[:, 0].copy_(h0c)
+                if U1 > 1:
+                    h_prev[:, 1:].copy_(out[:, :-1])
+                _mm3(dg2, h_prev.view(B * U1, H), out=d_wh, a_t=True)   # dG^T h_prev
+        dx = _mm3(dg2, wi).view(B, U1, E) if ng[0] else None          # dG W_ih
+        if ng[1] or need_b:
+            cur.wait_stream(s1)
+        if ng[2]:
+            cur.wait_stream(s2)
         return dx, d_wi, d_wh, (db if ctx.has_bias and ng[3] else None), (db if ctx.has_bias and ng[4] else None), \
             (d_h0 if ng[5] else None), (d_c0 if ng[6] else None)
 

@@ -133,6 +133,13 @@ int ctcvr_lstm_seq_bwd(const float* act, const float* cs, const float* c0, const
                        const float* d_hn, const float* d_cn, float* dgates, float* d_h0, float* d_c0, int B, int U1,
                        int H, void* ws, size_t ws_bytes, void* stream);
 
+/* Operand split for the plain fp32 products around the LSTM recurrence (x W_ih^T and the three gradient products): in
+ * [rows, cols] fp32 -> the three TF32 terms stacked along the reduction dimension, so that A B ~= A_hi B_hi + A_hi B_lo +
+ * A_lo B_hi is ONE tensor-core GEMM with fp32-level error (~2^-20).  stack_cols = 1: out [rows, 3*cols] (p0 | p1 | p2);
+ * stack_cols = 0: out [3*rows, cols] (p0 over p1 over p2).  pattern 0 = (hi, hi, lo), 1 = (hi, lo, hi): one operand of
+ * a product takes 0, the other 1. */
+int ctcvr_split_tf32(const float* in, float* out, long rows, long cols, int stack_cols, int pattern, void* stream);
+
 /* ---- section 8(f)4: calculate_cer (rnnt_eval.py:11-56) for N (hypothesis, reference) pairs: hyp [N,Lh], ref [N,Lr]
  * int32 padded, lengths [N]; out_sdin [N,4] int32 = substitutions, deletions, insertions, reference length, with the
  * reference's backtrace tie-breaking (match, substitution, deletion, insertion).  ws: ctcvr_cer_ws_bytes. */

@@ -1,6 +1,6 @@
 """Time the predictor LSTM sequence kernels (csrc/lstm_seq.cu) against the library LSTM (cuDNN) on the same GPU.
 
-    python tools/lstm_time.py            # cfg2 (B=32, U+1=41, H=512) and cfg1-like (B=32, U+1=25, H=256), fwd and fwd+bwd
+    python tools/lstm_time.py [B U1 H ...]   # default: cfg2 (B=32, U+1=41, H=512) and cfg1-like (B=32, U+1=25, H=256), fwd and fwd+bwd
 
 CUDA events on the current stream, 20 iterations after 5 warm-ups; prints one JSON line per shape."""
 import json
@@ -82,6 +82,7 @@ def predictor_times(B, U1, H):
 
 
 if __name__ == "__main__":
-    shapes = [(32, 41, 512), (32, 25, 256), (256, 41, 512)]
+    a = [int(v) for v in sys.argv[1:]]
+    shapes = [tuple(a[i:i + 3]) for i in range(0, len(a), 3)] or [(32, 41, 512), (32, 25, 256), (256, 41, 512)]
     for B, U1, H in shapes:
         print(json.dumps(predictor_times(B, U1, H)), flush=True)
