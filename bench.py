@@ -522,6 +522,8 @@ def run_ours(args):
             line["gpu_reference"]["speedup_vs_fp32"] = line["value"] / line["gpu_reference"]["fp32"]["value"]
             line["gpu_reference"]["speedup_vs_autocast_bf16"] = line["value"] / line["gpu_reference"]["autocast_bf16"]["value"]
             line["predictor"] = time_predictor(C, B, U + 1, D)
+            line["predictor"]["step_with_predictor"] = time_step_with_predictor(C, joint, B, T, U, D, V, blank, args.precision,
+                                                                                 enc, tgt, tl, ul, flush)
             if not args.no_decode:
                 import bench_decode
                 line["decode"] = bench_decode.run_rows(quick=True)
@@ -610,6 +612,36 @@ def time_predictor(C, B, U1, H, iters=20):
         res[name] = row
     res["utt_per_s_ours_graphed"] = B / (res["ours"]["graphed"] * 1e-3) if res["ours"].get("graphed") else None
     return res
+
+
+def time_step_with_predictor(C, joint, B, T, U, D, V, blank, precision, enc, tgt, tl, ul, flush, reps=10):
+    """The bench step with the label side inside the captured graph: add_blank -> RNNPredictor (embedding, LSTM sequence
+    kernels, projection) -> fused joint / loss -> backward through all of it (13 parameter tensors, 13.2 MB of
+    gradients: SURVEY.md section 8(e)'s data-parallel payload).  Same batch as the headline; L2 flushed before every
+    timed replay; CUDA events, median."""
+    import torch
+    pr = C.RNNPredictor(V, D, D, 0.0, D, 1, dropout=0.0).to(enc.device)
+    g = C.GraphedJointRnntStep(joint, B, T, U, blank, precision=precision, predictor=pr)
+    g.load(enc.detach(), None, tgt, tl, ul)
+    ts = []
+    for i in range(reps + 2):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = g.step()
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    ms = ts[len(ts) // 2]
+    nbytes = sum(p.numel() for p in g.parameters()) * 4
+    out = {"ms_per_step": ms, "value": B / (ms * 1e-3), "unit": UNIT, "loss": float(loss),
+           "gradient_bytes": nbytes, "precision": precision}
+    for p in pr.parameters():
+        p.grad = None
+    del g
+    return out
 
 
 def time_fp32_step(C, joint, B, T, U, blank, enc, pred, tgt, tl, ul, flush, reps=3):
