@@ -356,6 +356,157 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_fwd_kernel(const Lst
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// forward, register-resident weights (H = 32 * KPL; dispatched for H = 512, KPL = 16 - see lstm_seq_fwd)
+//
+// ncu on the kernel above: 4.4 k shared-memory wavefronts per step and CTA for the weight broadcasts (2.1 per LDS.128)
+// and two dependent L2 round trips per warp.  Here warp w owns ONE hidden unit (16 units per CTA) and lane l the k's
+// {i * 32 + l}: the 4 * KPL weights of (unit, those k's) live in registers for the whole sequence.  Per step the CTA
+// stages h_{t-1} for its 8 batch rows into shared memory once (all 512 threads poll their 4 - 8 {value, tag} words in one
+// round trip), every lane multiplies its k's for the 8 rows x 4 gates (32 accumulators, packed FFMA2; shared memory is
+// read conflict-free, 16 bytes per lane), and a 31-shuffle reduce-scatter over the lanes leaves lane l with the
+// pre-activation of (batch row l / 4, gate l % 4) - so the four activations of a cell are computed by four lanes in
+// parallel before lane 4b gathers them for c and h.  One __syncthreads per step (h staging is double buffered).
+// ---------------------------------------------------------------------------------------------------------------
+template <int KPL, int BPC>
+__global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_fwd_reg_kernel(const LstmFwdArgs a) {
+  constexpr int BW = 8, NE = KPL / 2;                      // NE staging elements per thread: H * 8 / 512
+  extern __shared__ __align__(16) unsigned char lstm_smem[];
+  __shared__ int s_dead;
+  if (threadIdx.x == 0) s_dead = 0;
+  const int H = a.H, B = a.B, Bp = BPC ? BPC : a.Bp, U1 = a.U1;
+  const int RG = Bp / BW, NBS = gridDim.y, bs = blockIdx.y;
+  const int nch = (RG - bs + NBS - 1) / NBS;
+  float4* h_s = reinterpret_cast<float4*>(lstm_smem);      // [2 buffers][2 planes: rows 0-3 / 4-7][H] float4
+  float* c_sm = reinterpret_cast<float*>(h_s + (size_t)4 * H);   // [nch][16 units][8 rows]
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int unit = blockIdx.x * 16 + w;                    // < H: the grid is exactly H / 16 wide
+  const int pb = lane >> 2, pg = lane & 3;                 // after the reduction: batch row and gate of this lane
+  const size_t H4 = (size_t)4 * H;
+
+  u64 wIF[KPL], wGO[KPL];                                  // {W_i, W_f}, {W_g, W_o} of (unit, k = i * 32 + lane)
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+    const int k = i * 32 + lane;
+    wIF[i] = pack2(a.w_hh[((size_t)0 * H + unit) * H + k], a.w_hh[((size_t)1 * H + unit) * H + k]);
+    wGO[i] = pack2(a.w_hh[((size_t)2 * H + unit) * H + k], a.w_hh[((size_t)3 * H + unit) * H + k]);
+  }
+  if (pg == 0) {
+    for (int c = 0; c < nch; ++c) {
+      const int b = (bs + c * NBS) * BW + pb;
+      const bool ok = b < B;
+      c_sm[(c * 16 + w) * 8 + pb] = (ok && a.c0) ? a.c0[(size_t)b * H + unit] : 0.f;
+      st_relaxed_u64(a.hx + (size_t)unit * Bp + b, tagged((ok && a.h0) ? a.h0[(size_t)b * H + unit] : 0.f, 1u));
+    }
+  }
+  __syncthreads();
+
+  int it = 0;
+  for (int t = 0; t < U1; ++t) {
+    const u64* hprev = a.hx + (size_t)(t & 1) * H * Bp;
+    u64* hnext = a.hx + (size_t)((t + 1) & 1) * H * Bp;
+    const unsigned int tag = (unsigned)(t + 1);
+    for (int c = 0; c < nch; ++c, ++it) {
+      const int b0 = (bs + c * NBS) * BW;
+      const int b = b0 + pb;
+      // this lane's input projection (row pb, gate pg of the warp's unit), ahead of the wait
+      const float xv = b < B ? __ldg(a.xg + ((size_t)b * U1 + t) * H4 + (size_t)pg * H + unit) : 0.f;
+      // stage h_{t-1}[all k][8 rows]: element e = tid + 512 * j -> k = e / 8, row = e % 8
+      {
+        u64 raw[NE];
+        int spins = 0;
+        long long t0 = 0;
+        while (true) {
+#pragma unroll
+          for (int j = 0; j < NE; ++j) {
+            const int e = tid + LSTM_THREADS * j;
+            raw[j] = ld_relaxed_u64(hprev + (size_t)(e >> 3) * Bp + b0 + (e & 7));
+          }
+          bool ok = true;
+#pragma unroll
+          for (int j = 0; j < NE; ++j) ok = ok && ((unsigned int)(raw[j] >> 32) == tag);
+          if (ok) break;
+          if ((++spins & 63) == 0) {
+            if (t0 == 0) t0 = gtime_ns();
+            if (s_dead || gtime_ns() - t0 > LSTM_TIMEOUT_NS) {
+              if (a.err) *reinterpret_cast<volatile unsigned int*>(a.err) = 0x80000000u | (3u << 24) | ((tag & 0xfffu) << 12) | (blockIdx.x & 0xfffu);
+              s_dead = 1;
+              break;
+            }
+          }
+        }
+        float* hs = reinterpret_cast<float*>(h_s + (size_t)(it & 1) * 2 * H);
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+          const int e = tid + LSTM_THREADS * j, k = e >> 3, r = e & 7;
+          hs[((size_t)(r >> 2) * H + k) * 4 + (r & 3)] = __uint_as_float((unsigned int)raw[j]);
+        }
+      }
+      __syncthreads();
+      const float4* hA = h_s + (size_t)(it & 1) * 2 * H;   // rows 0-3
+      const float4* hB = hA + H;                           // rows 4-7
+      u64 accIF[8], accGO[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) accIF[r] = accGO[r] = 0ull;
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        const float4 va = hA[i * 32 + lane], vb = hB[i * 32 + lane];
+        const float hv[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const u64 hh = pack2(hv[r], hv[r]);
+          accIF[r] = fma2(hh, wIF[i], accIF[r]);
+          accGO[r] = fma2(hh, wGO[i], accGO[r]);
+        }
+      }
+      // reduce-scatter over the 32 lanes: vals[row * 4 + gate]; lane l ends with the total of vals[l]
+      float vals[32];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        unpack2(accIF[r], vals[r * 4 + 0], vals[r * 4 + 1]);
+        unpack2(accGO[r], vals[r * 4 + 2], vals[r * 4 + 3]);
+      }
+#pragma unroll
+      for (int o = 16, n = 16; o >= 1; o >>= 1, n >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+          const float send = upper ? vals[j] : vals[j + n];
+          const float keep = upper ? vals[j + n] : vals[j];
+          vals[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      // lane (pb, pg): activation of gate pg of cell (unit, row pb)
+      const float pre = vals[0] + xv;
+      const float actv = pg == 2 ? tanhf(pre) : sigmoidf_(pre);
+      const size_t row = (size_t)b * U1 + t;
+      if (a.act && b < B) a.act[row * H4 + (size_t)pg * H + unit] = actv;
+      const int base = lane & ~3;
+      const float gi = __shfl_sync(0xffffffffu, actv, base + 0);
+      const float gf = __shfl_sync(0xffffffffu, actv, base + 1);
+      const float gg = __shfl_sync(0xffffffffu, actv, base + 2);
+      const float go = __shfl_sync(0xffffffffu, actv, base + 3);
+      if (pg == 0) {
+        if (b < B) {
+          float* cp = c_sm + (c * 16 + w) * 8 + pb;
+          const float cc = gf * *cp + gi * gg;
+          const float h = go * tanhf(cc);
+          *cp = cc;
+          st_relaxed_u64(hnext + (size_t)unit * Bp + b, tagged(h, tag + 1));      // first: the others wait for it
+          a.out[row * H + unit] = h;
+          if (a.cs) a.cs[row * H + unit] = cc;
+          if (t == U1 - 1) {
+            a.hn[(size_t)b * H + unit] = h;
+            a.cn[(size_t)b * H + unit] = cc;
+          }
+        } else {
+          st_relaxed_u64(hnext + (size_t)unit * Bp + b, tagged(0.f, tag + 1));    // padded batch rows
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // backward: dL/d(gates) of every step, dL/dh0, dL/dc0
 // ---------------------------------------------------------------------------------------------------------------
 struct BwdStepIn { float gi, gf, gg, go, c, cprev, dh; };
@@ -581,6 +732,23 @@ int lstm_seq_fwd(const float* xg, const float* w_hh, const float* h0, const floa
   a.hx = reinterpret_cast<u64*>(ws); a.B = B; a.U1 = U1; a.H = H; a.Bp = c.Bp;
   lstm_error_host_word(&a.err);
   CTCVR_CHECK_CUDA(cudaMemsetAsync(ws, 0, xch_bytes(H, c.Bp), st));
+  // register-resident forward (lstm_seq_fwd_reg_kernel) where it measured faster: H = 512 (152 against 180 us at B = 32,
+  // 270 against 353 us at B = 64); at H = 256 its 16-unit CTAs fill only 64 SMs and the shuffle reduction outweighs the
+  // saved shared-memory traffic (112 against 85 us), so that size stays on the shared-memory kernel
+  if (H == 512) {
+    LstmCfg r = c;
+    r.gx = H / 16;
+    r.gy = std::max(1, std::min(c.Bp / LSTM_BW, lstm_sm_count() / r.gx));
+    const int nchr = (c.Bp / LSTM_BW + r.gy - 1) / r.gy;
+    const size_t smem_r = (size_t)4 * H * 16 + (size_t)nchr * 16 * 8 * 4;
+#define LSTM_FWD_REG(KPL, BPC) return launch_coop(lstm_seq_fwd_reg_kernel<KPL, BPC>, r, smem_r, a, st)
+    if (smem_r <= 200 * 1024 && r.gx <= lstm_sm_count()) {
+      if (c.Bp == 32) LSTM_FWD_REG(16, 32);
+      if (c.Bp == 64) LSTM_FWD_REG(16, 64);
+      LSTM_FWD_REG(16, 0);
+    }
+#undef LSTM_FWD_REG
+  }
 #define LSTM_FWD(HSL, BPC) return launch_coop(lstm_seq_fwd_kernel<HSL, LSTM_BW, BPC>, c, c.smem_f, a, st)
 #define LSTM_FWD_BP(HSL) do { if (c.Bp == 32) LSTM_FWD(HSL, 32); if (c.Bp == 8) LSTM_FWD(HSL, 8); if (c.Bp == 64) LSTM_FWD(HSL, 64); \
                               if (c.Bp == 128) LSTM_FWD(HSL, 128); LSTM_FWD(HSL, 0); } while (0)
