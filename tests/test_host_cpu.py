@@ -217,3 +217,54 @@ def test_dp_step_matches_single_process_gloo():
     assert abs(total - loss.item()) < 1e-5 * abs(loss.item())
     for k, p in params.items():
         torch.testing.assert_close(torch.tensor(grads[k]), p.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_predictor_lstm_host_logic_without_gpu():
+    """Section 8f row 2 on a box without a GPU: the LSTM entry points are exported and validate their arguments before any
+    CUDA call, the shape predicate answers from the SM-count fallback, and the Python layer refuses CPU tensors loudly
+    (there is no library-LSTM fallback behind RNNPredictor)."""
+    import ctcvr_b200 as C
+    from ctcvr_b200 import functional as CF
+    from ctcvr_b200._lib import call, query
+    assert query("ctcvr_lstm_seq_supported", 32, 512) == 1 and query("ctcvr_lstm_seq_supported", 2, 256) == 1
+    assert query("ctcvr_lstm_seq_supported", 1, 1184) == 1
+    assert query("ctcvr_lstm_seq_supported", 32, 100000) == 0 and query("ctcvr_lstm_seq_supported", 0, 256) == 0
+    # exchange buffer: 2 x [4H][roundup(B, 8)] 8-byte {value, tag} words
+    assert query("ctcvr_lstm_seq_ws_bytes", 32, 512) == 2 * 4 * 512 * 32 * 8
+    assert query("ctcvr_lstm_seq_ws_bytes", 2, 256) == 2 * 4 * 256 * 8 * 8
+    assert query("ctcvr_lstm_seq_ws_bytes", 0, 256) == 0
+    with pytest.raises(RuntimeError, match="bad dims"):
+        call("ctcvr_lstm_seq_fwd", None, None, None, None, None, None, None, None, None, 0, 1, 8, None, 0, None)
+    with pytest.raises(RuntimeError, match="NULL pointer"):
+        call("ctcvr_lstm_seq_bwd", None, None, None, None, None, None, None, None, None, None, 2, 3, 8, None, 0, None)
+    with pytest.raises(RuntimeError, match="bad arguments"):
+        call("ctcvr_split_tf32", None, None, 4, 4, 1, 0, None)
+    pr = C.RNNPredictor(20, 16, 16, 0.0, 16, 2, dropout=0.0)
+    assert [k for k in pr.state_dict() if k.startswith("rnn.")] == [
+        "rnn.weight_ih_l0", "rnn.weight_hh_l0", "rnn.bias_ih_l0", "rnn.bias_hh_l0",
+        "rnn.weight_ih_l1", "rnn.weight_hh_l1", "rnn.bias_ih_l1", "rnn.bias_hh_l1"]
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pr(torch.zeros(2, 3, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pr.forward_step(torch.zeros(2, 1, dtype=torch.long), torch.zeros(2, 1), pr.init_state(2, torch.device("cpu")))
+    z = torch.zeros(2, 16)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        CF.lstm_sequence(torch.zeros(2, 3, 16), pr.rnn.weight_ih_l0, pr.rnn.weight_hh_l0, pr.rnn.bias_ih_l0,
+                         pr.rnn.bias_hh_l0, z, z)
+    with pytest.raises(RuntimeError):                       # the graphed step with a predictor needs a CUDA joint too
+        C.GraphedJointRnntStep(C.TransducerJoint(20, 16, 16, 16), 2, 4, 3, 5, predictor=pr)
+    # patch.install covers the reference predictor's forward / forward_step (model/component/predictor.py:43-63,79-98)
+    import types
+
+    class RNNPredictor(torch.nn.Module):
+        def forward(self, input_tensor, cache=None):
+            return "reference body"
+
+    ns = {"predictor": types.SimpleNamespace(RNNPredictor=RNNPredictor)}
+    done = C.patch.install(ns)
+    try:
+        assert done == {"predictor": ["RNNPredictor.forward/forward_step"]}
+        assert RNNPredictor.forward is not None and RNNPredictor.forward.__name__ == "_predictor_forward"
+    finally:
+        C.patch.uninstall()
+    assert RNNPredictor().forward(None) == "reference body" and not hasattr(RNNPredictor, "forward_step")
