@@ -521,9 +521,12 @@ def run_ours(args):
             line["gpu_reference"] = gpu_reference(dev)
             line["gpu_reference"]["speedup_vs_fp32"] = line["value"] / line["gpu_reference"]["fp32"]["value"]
             line["gpu_reference"]["speedup_vs_autocast_bf16"] = line["value"] / line["gpu_reference"]["autocast_bf16"]["value"]
-            line["predictor"] = time_predictor(C, B, U + 1, D)
-            line["predictor"]["step_with_predictor"] = time_step_with_predictor(C, joint, B, T, U, D, V, blank, args.precision,
-                                                                                 enc, tgt, tl, ul, flush)
+            try:        # a side row: it must not cost the record its headline
+                line["predictor"] = time_predictor(C, B, U + 1, D)
+                line["predictor"]["step_with_predictor"] = time_step_with_predictor(C, joint, B, T, U, D, V, blank, args.precision,
+                                                                                     enc, tgt, tl, ul, flush)
+            except Exception as e:  # noqa: BLE001
+                line.setdefault("predictor", {})["error"] = f"{type(e).__name__}: {e}"[:300]
             if not args.no_decode:
                 import bench_decode
                 line["decode"] = bench_decode.run_rows(quick=True)
