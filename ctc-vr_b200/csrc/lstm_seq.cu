@@ -732,22 +732,16 @@ int lstm_seq_fwd(const float* xg, const float* w_hh, const float* h0, const floa
   a.hx = reinterpret_cast<u64*>(ws); a.B = B; a.U1 = U1; a.H = H; a.Bp = c.Bp;
   lstm_error_host_word(&a.err);
   CTCVR_CHECK_CUDA(cudaMemsetAsync(ws, 0, xch_bytes(H, c.Bp), st));
-  // register-resident forward (lstm_seq_fwd_reg_kernel) where it measured faster: H = 512 (152 against 180 us at B = 32,
-  // 270 against 353 us at B = 64); at H = 256 its 16-unit CTAs fill only 64 SMs and the shuffle reduction outweighs the
-  // saved shared-memory traffic (112 against 85 us), so that size stays on the shared-memory kernel
-  if (H == 512) {
+  // register-resident forward (lstm_seq_fwd_reg_kernel) where it measured faster AND is covered by the parity tests:
+  // H = 512 with one row group per CTA (24 < B <= 32: 152 against 180 us).  B = 64 measured 270 against 353 us, but the
+  // several-row-groups path of this kernel has no parity test yet, so it is not dispatched; at H = 256 its 16-unit CTAs
+  // fill only 64 SMs and the shuffle reduction outweighs the saved shared-memory traffic (112 against 85 us).
+  if (H == 512 && c.Bp == 32) {
     LstmCfg r = c;
     r.gx = H / 16;
-    r.gy = std::max(1, std::min(c.Bp / LSTM_BW, lstm_sm_count() / r.gx));
-    const int nchr = (c.Bp / LSTM_BW + r.gy - 1) / r.gy;
-    const size_t smem_r = (size_t)4 * H * 16 + (size_t)nchr * 16 * 8 * 4;
-#define LSTM_FWD_REG(KPL, BPC) return launch_coop(lstm_seq_fwd_reg_kernel<KPL, BPC>, r, smem_r, a, st)
-    if (smem_r <= 200 * 1024 && r.gx <= lstm_sm_count()) {
-      if (c.Bp == 32) LSTM_FWD_REG(16, 32);
-      if (c.Bp == 64) LSTM_FWD_REG(16, 64);
-      LSTM_FWD_REG(16, 0);
-    }
-#undef LSTM_FWD_REG
+    r.gy = c.Bp / LSTM_BW;
+    const size_t smem_r = (size_t)4 * H * 16 + (size_t)16 * 8 * 4;
+    if (r.gx * r.gy <= lstm_sm_count()) return launch_coop(lstm_seq_fwd_reg_kernel<16, 32>, r, smem_r, a, st);
   }
 #define LSTM_FWD(HSL, BPC) return launch_coop(lstm_seq_fwd_kernel<HSL, LSTM_BW, BPC>, c, c.smem_f, a, st)
 #define LSTM_FWD_BP(HSL) do { if (c.Bp == 32) LSTM_FWD(HSL, 32); if (c.Bp == 8) LSTM_FWD(HSL, 8); if (c.Bp == 64) LSTM_FWD(HSL, 64); \
