@@ -7,24 +7,26 @@
 //
 // The input projection x_t W_ih^T + b_ih + b_hh of all steps is one plain GEMM done by the caller (`xg`); what is
 // sequential is h_{t-1} W_hh^T.  One persistent cooperative launch walks the sequence:
-//   * the H hidden units are dealt to G = ceil(H / HS) CTAs (HS = 1, 2, 4 or 8 so that G <= 148: one CTA per SM); a CTA
-//     keeps the 4*HS rows of W_hh that produce its units' gates resident in shared memory for the whole sequence
-//     (forward), or the HS columns it needs for dh_{t-1} (backward), so the 4 MB of W_hh are read from HBM once;
-//   * a step exchanges h_t (forward, [H][B]) or the gate gradients (backward, [4H][B]) through a ping-pong buffer in
+//   * a CTA owns UC = 4 * HSL hidden units (HSL = 1, 2 or 4) and one or more groups of 8 batch rows; the grid is
+//     ceil(H / UC) x (row groups), at most one CTA per SM (pick_cfg).  It keeps the 4 * UC rows of W_hh that produce its
+//     units' gates resident in shared memory for the whole sequence (forward; in registers in lstm_seq_fwd_reg_kernel),
+//     or the UC columns it needs for dh_{t-1} (backward), so the 4 MB of W_hh are read from HBM once per launch;
+//   * a step exchanges h_t (forward, [H][Bp]) or the gate gradients (backward, [4H][Bp]) through a ping-pong buffer in
 //     L2 whose elements validate themselves: every element is one 8-byte word {fp32 value, step tag} written and read
 //     with single 64-bit relaxed accesses (the pattern NCCL's LL protocol uses over NVLink).  A consumer simply re-reads
 //     an element until its tag is the step it waits for, so a step costs one store -> L2 -> load trip: there is no
 //     flag barrier, no fence and no atomic on the critical path (the first version of this kernel raised one release
-//     flag per CTA and step and polled all G of them: 7 us per step with nothing else to do);
+//     flag per CTA and step and polled all of them: 7 us per step with nothing else to do);
 //     the buffer is zeroed before the launch, tags start at 1;
-//   * inside a CTA warp w owns a 1/16 slice of the reduction dimension and lane b one batch row: the operand row
-//     exchange[k][b] is one coalesced 256-byte L2 load per warp, 16 of them in flight per warp, the weights are
-//     shared-memory broadcasts, and each lane keeps 4*HS (forward) or HS (backward) accumulators fed by packed
-//     fma.rn.f32x2 (two IEEE FMAs per issue slot); the 16 partial sums meet in shared memory;
+//   * inside a CTA warp w owns a 1/16 slice of the reduction dimension and lane = (batch row, unit group): a warp load
+//     of one exchange row touches the 8 words of the CTA's row group (one 64-byte segment), 16 rows in flight per lane
+//     with immediate offsets (the padded batch is a template constant), the weights are shared-memory broadcasts, and
+//     each lane keeps 4 * HSL (forward) or HSL (backward) accumulators fed by packed fma.rn.f32x2 (two IEEE FMAs per
+//     issue slot); the 16 partial sums meet in shared memory;
 //   * the per-step tensors that do not depend on the recurrence (xg; the saved gates, cell states and dL/dh_t) are
 //     loaded into registers BEFORE the first exchange load, so their latency hides under the wait.
-// Batches beyond 32 rows run as chunks of 32 inside a step.  Waits are bounded (2 s): a CTA that gives up writes a
-// mapped host word and the next call fails loudly.
+// More row groups than grid rows run as several passes inside a step.  Waits are bounded (2 s): a CTA that gives up
+// writes a mapped host word and the next call fails loudly.
 #include <algorithm>
 
 #include "common.cuh"
