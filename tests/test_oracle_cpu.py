@@ -198,3 +198,59 @@ def test_predictor_restated_matches_reference_golden():
         y, _ = lstm(pw["embed.weight"][T(ys)])
         y = y @ pw["projection.weight"].T + pw["projection.bias"]
         assert rel_l2(y.detach().numpy(), out.numpy()) < 1e-12
+
+
+def test_lstm_numpy_restatement_forward_backward():
+    """oracle/lstm_oracle.py (one layer, numpy, hand-derived backward with the kernels' decomposition) against torch's
+    nn.LSTM autograd in fp64 - the library call the reference makes (model/component/predictor.py:58) - with a non-zero
+    initial state and cotangents on out, h_n and c_n; and, composed with the embedding and the projection, against what
+    the reference RNNPredictor produced (predictor_small.npz, case p1)."""
+    from oracle import lstm_oracle as LO
+    rng = np.random.default_rng(3)
+    for B, U1, E, H in ((3, 6, 5, 7), (2, 1, 4, 4), (4, 9, 8, 8)):
+        lstm = torch.nn.LSTM(E, H, 1, batch_first=True).double()
+        x, h0, c0 = (T(rng.standard_normal(s)).requires_grad_(True) for s in ((B, U1, E), (1, B, H), (1, B, H)))
+        r, rh, rc = (T(rng.standard_normal(s)) for s in ((B, U1, H), (1, B, H), (1, B, H)))
+        y, (hn, cn) = lstm(x, (h0, c0))
+        ((y * r).sum() + (hn * rh).sum() + (cn * rc).sum()).backward()
+        w = [p.detach().numpy() for p in (lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0)]
+        out, hn_o, cn_o, cache = LO.lstm_layer_forward(x.detach().numpy(), *w, h0[0].detach().numpy(), c0[0].detach().numpy())
+        g = LO.lstm_layer_backward(cache, r.numpy(), rh[0].numpy(), rc[0].numpy())
+        for got, want in ((out, y), (hn_o, hn[0]), (cn_o, cn[0]), (g["dx"], x.grad), (g["dW_ih"], lstm.weight_ih_l0.grad),
+                          (g["dW_hh"], lstm.weight_hh_l0.grad), (g["db"], lstm.bias_ih_l0.grad), (g["db"], lstm.bias_hh_l0.grad),
+                          (g["dh0"], h0.grad[0]), (g["dc0"], c0.grad[0])):
+            assert rel_l2(got, want.detach().numpy()) < 1e-12
+    fx = load_golden("predictor_small.npz")
+    (V, H, L, B, U1), st, ys, r = predictor_case(fx, "p1")
+    w = {k: v.astype(np.float64) for k, v in st.items()}
+    emb = w["embed.weight"][ys]
+    z = np.zeros((B, H))
+    out, _, _, cache = LO.lstm_layer_forward(emb, w["rnn.weight_ih_l0"], w["rnn.weight_hh_l0"], w["rnn.bias_ih_l0"],
+                                             w["rnn.bias_hh_l0"], z, z)
+    proj = out @ w["projection.weight"].T + w["projection.bias"]
+    assert rel_l2(proj, fx["p1_out"]) < 1e-6
+    g = LO.lstm_layer_backward(cache, r.astype(np.float64) @ w["projection.weight"])
+    assert rel_l2(g["dW_hh"], fx["p1_d_rnn.weight_hh_l0"]) < 2e-6 and rel_l2(g["dW_ih"], fx["p1_d_rnn.weight_ih_l0"]) < 2e-6
+    assert rel_l2(g["db"], fx["p1_d_rnn.bias_ih_l0"]) < 2e-6
+    d_emb = np.zeros_like(w["embed.weight"])
+    np.add.at(d_emb, ys, g["dx"])
+    assert rel_l2(d_emb, fx["p1_d_embed.weight"]) < 2e-6
+
+
+def test_split_tf32_product_keeps_fp32_level_accuracy():
+    """The operand split in front of the plain GEMMs around the LSTM recurrence (split_tf32_kernel): three TF32 terms
+    stacked along K keep the product within ~2^-20 of the exact one, against ~2^-11 for a plain TF32 GEMM (what the
+    library LSTM uses by default) - on a product of the bench's shape class (K = 512) and on badly scaled operands."""
+    from oracle import lstm_oracle as LO
+    rng = np.random.default_rng(11)
+    for scale in (1.0, 1e-3):
+        a = (rng.standard_normal((64, 512)) * scale).astype(np.float32)
+        b = rng.standard_normal((512, 48)).astype(np.float32)
+        exact = a.astype(np.float64) @ b.astype(np.float64)
+        e3 = np.abs(LO.split_tf32_product(a, b, 3) - exact).max() / np.abs(exact).max()
+        e1 = np.abs(LO.split_tf32_product(a, b, 1) - exact).max() / np.abs(exact).max()
+        assert e3 < 4e-6 and e1 > 20 * e3, (scale, e3, e1)
+    # the stacked operands reproduce hi + lo exactly: nothing is lost before the GEMM
+    v = rng.standard_normal(1000).astype(np.float32)
+    hi = LO._tf32_trunc(v)
+    assert np.array_equal(hi + (v - hi), v) and np.all((hi.view(np.uint32) & np.uint32(0x1FFF)) == 0)
