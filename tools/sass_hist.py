@@ -5,12 +5,12 @@ import collections, os, re, subprocess, sys
 lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ctc-vr_b200", "libctcvr.so")
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 keys = ["UTCHMMA", "UTCQMMA", "UTCBAR", "UTCCP", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTMAPF", "SYNCS", "HMMA", "MUFU.TANH",
-        "MUFU.EX2", "MUFU.LG2", "STSM", "LDSM", "SHFL", "ATOMG", "REDG", "RED.", "ELECT", "UCGABAR"]
+        "MUFU.EX2", "MUFU.LG2", "STSM", "LDSM", "SHFL", "ATOMG", "REDG", "RED.", "ELECT", "UCGABAR", "FFMA2", "LDG.E.64.STRONG", "STG.E.64.STRONG"]
 cur, hist = None, collections.OrderedDict()
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
     if m:
-        cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
+        cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().replace("(anonymous namespace)::", "").split("(")[0]
         hist[cur] = collections.Counter()
         continue
     if cur is None:
