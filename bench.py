@@ -537,6 +537,28 @@ def run_ours(args):
         print(json.dumps(line))
 
 
+def cpu_lstm_baseline(B, U1, H, reps=3):
+    """The reference's own arithmetic for the predictor row: torch's nn.LSTM forward + backward on the host cores
+    (model/component/predictor.py:58 runs exactly this call), all threads, median of `reps` after one warm-up."""
+    import torch
+    g = torch.Generator().manual_seed(4321)
+    lstm = torch.nn.LSTM(H, H, 1, batch_first=True)
+    x = torch.randn(B, U1, H, generator=g, requires_grad=True)
+    r = torch.randn(B, U1, H, generator=g)
+    ts = []
+    for i in range(reps + 1):
+        t0 = time.perf_counter()
+        torch.autograd.backward(lstm(x)[0], r)
+        dt = time.perf_counter() - t0
+        x.grad = None
+        lstm.zero_grad(set_to_none=True)
+        if i:
+            ts.append(dt)
+    ts.sort()
+    return {"ms": ts[len(ts) // 2] * 1e3, "cores": torch.get_num_threads(), "kind": "reference arithmetic (torch CPU nn.LSTM)",
+            "sample": f"the full batch, median of {reps} after 1 warm-up"}
+
+
 def time_predictor(C, B, U1, H, iters=20):
     """the predictor's LSTM over the label sequence (model/component/predictor.py:58) at the
     bench shape, forward + backward with gradients of the input and of all four parameters.  `ours` = the persistent
@@ -614,6 +636,7 @@ def time_predictor(C, B, U1, H, iters=20):
             torch.cuda.synchronize()
         res[name] = row
     res["utt_per_s_ours_graphed"] = B / (res["ours"]["graphed"] * 1e-3) if res["ours"].get("graphed") else None
+    res["cpu_baseline"] = cpu_lstm_baseline(B, U1, H)
     return res
 
 
