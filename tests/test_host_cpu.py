@@ -268,3 +268,29 @@ def test_predictor_lstm_host_logic_without_gpu():
     finally:
         C.patch.uninstall()
     assert RNNPredictor().forward(None) == "reference body" and not hasattr(RNNPredictor, "forward_step")
+
+
+def test_mm3_fallback_and_precision_switch_restored(monkeypatch):
+    """functional._mm3: when torch's cuBLAS precision switch cannot be set (a script that drives the legacy allow_tf32
+    flag), the product falls back to a plain fp32 matmul of the UNSPLIT operands with the same transposition
+    conventions; and the switch is restored after a normal block."""
+    from ctcvr_b200 import functional as CF
+    before = torch.backends.cuda.matmul.fp32_precision
+    with CF._tf32_matmul() as t:
+        assert t.ok and torch.backends.cuda.matmul.fp32_precision == "tf32"
+    assert torch.backends.cuda.matmul.fp32_precision == before
+
+    def broken_enter(self):
+        self.ok, self.old = False, None
+        return self
+
+    monkeypatch.setattr(CF._tf32_matmul, "__enter__", broken_enter)
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(5, 7, generator=g), torch.randn(7, 3, generator=g)
+    assert torch.allclose(CF._mm3(a, b), a @ b)
+    assert torch.allclose(CF._mm3(a.t().contiguous(), b, a_t=True), a @ b)            # a given as [K, M]
+    assert torch.allclose(CF._mm3(a, b.t().contiguous(), b_t=True), a @ b)            # b given as [N, K]
+    out = torch.empty(5, 3)
+    CF._mm3(a.t().contiguous(), b.t().contiguous(), out=out, a_t=True, b_t=True)
+    assert torch.allclose(out, a @ b)
+    assert torch.backends.cuda.matmul.fp32_precision == before
